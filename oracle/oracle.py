@@ -1,0 +1,383 @@
+"""ctypes front end of the CPU oracle (oracle/groan_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (groan_rs_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OK, ENOBOX, ENOTORTHO, EEMPTY, ENOPOS, ENOMASS, EGROUPSIZE, EZEROBOX = range(8)
+DIM = {"None": 0, "X": 1, "Y": 2, "Z": 3, "XY": 4, "XZ": 5, "YZ": 6, "XYZ": 7}
+
+_f = C.POINTER(C.c_float)
+_d = C.POINTER(C.c_double)
+_u = C.POINTER(C.c_uint32)
+_i8 = C.POINTER(C.c_int8)
+_sz = C.c_size_t
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libgroan_oracle.so")
+    src = os.path.join(HERE, "groan_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "libgroan_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_wrap1.restype = C.c_float
+        L.orc_wrap1.argtypes = [C.c_float, C.c_float]
+        L.orc_minimg1.restype = C.c_float
+        L.orc_minimg1.argtypes = [C.c_float, C.c_float]
+        L.orc_floor_mod.restype = C.c_float
+        L.orc_floor_mod.argtypes = [C.c_float, C.c_float]
+        L.orc_distance.restype = C.c_float
+        L.orc_distance.argtypes = [_f, _f, C.c_int, _f]
+        L.orc_tric_distance.restype = C.c_float
+        L.orc_tric_distance.argtypes = [_f, _f, C.c_int, _f]
+        L.orc_tric_distance_brute64.restype = C.c_double
+        L.orc_tric_distance_brute64.argtypes = [_f, _f, C.c_int, _f, C.c_int]
+        L.orc_hash.restype = C.c_uint64
+        L.orc_hash.argtypes = [C.c_uint64] * 4
+        L.orc_baseline_traj.restype = C.c_double
+        L.orc_baseline_pairs.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _idx(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _L(box):
+    """accepts L[3] or a 3x3 / 9 matrix; returns (status, L[3])"""
+    b = _f32(box).reshape(-1)
+    if b.size == 3:
+        return OK, b.copy()
+    out = np.zeros(3, np.float32)
+    st = lib().orc_box_lengths(_fp(b), _fp(out))
+    return st, out
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        super().__init__("oracle status %d" % code)
+        self.code = code
+
+
+def _chk(st):
+    if st != OK:
+        raise OracleError(st)
+
+
+def wrap1(x, L):
+    return lib().orc_wrap1(np.float32(x), np.float32(L))
+
+
+def minimg1(d, L):
+    return lib().orc_minimg1(np.float32(d), np.float32(L))
+
+
+def floor_mod(x, y):
+    return lib().orc_floor_mod(np.float32(x), np.float32(y))
+
+
+def vector_to(c, p, box):
+    st, L = _L(box)
+    _chk(st)
+    out = np.zeros(3, np.float32)
+    lib().orc_vector_to(_fp(_f32(c)), _fp(_f32(p)), _fp(L), _fp(out))
+    return out
+
+
+def distance(a, b, dim, box):
+    st, L = _L(box)
+    _chk(st)
+    return np.float32(lib().orc_distance(_fp(_f32(a)), _fp(_f32(b)), DIM[dim], _fp(L)))
+
+
+def _grp(xyz, idx):
+    x = _f32(xyz).reshape(-1, 3)
+    i = _idx(idx)
+    return x, i
+
+
+def estimate_center(xyz, idx, box, mass=None):
+    st, L = _L(box)
+    _chk(st)
+    x, i = _grp(xyz, idx)
+    out = np.zeros(3, np.float32)
+    m = _f32(mass) if mass is not None else None
+    _chk(lib().orc_estimate_center(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(m) if m is not None else None,
+                                   _fp(L), _fp(out)))
+    return out
+
+
+def get_center(xyz, idx, box):
+    st, L = _L(box)
+    _chk(st)
+    x, i = _grp(xyz, idx)
+    if i.size == 0:
+        raise OracleError(EEMPTY)
+    out = np.zeros(3, np.float32)
+    _chk(lib().orc_get_center(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(L), _fp(out)))
+    return out
+
+
+def get_com(xyz, idx, mass, box):
+    st, L = _L(box)
+    _chk(st)
+    x, i = _grp(xyz, idx)
+    if i.size == 0:
+        raise OracleError(EEMPTY)
+    out = np.zeros(3, np.float32)
+    m = _f32(mass)
+    _chk(lib().orc_get_com(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(m), _fp(L), _fp(out)))
+    return out
+
+
+def get_center_naive(xyz, idx):
+    x, i = _grp(xyz, idx)
+    out = np.zeros(3, np.float32)
+    lib().orc_get_center_naive(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(out))
+    return out
+
+
+def group_distance(xyz, idx1, idx2, dim, box):
+    st, L = _L(box)
+    _chk(st)
+    x, i1 = _grp(xyz, idx1)
+    i2 = _idx(idx2)
+    out = C.c_float(0)
+    _chk(lib().orc_group_distance(_fp(x), _sz(3), i1.ctypes.data_as(_u), _sz(i1.size), i2.ctypes.data_as(_u), _sz(i2.size),
+                                  DIM[dim], _fp(L), C.byref(out)))
+    return np.float32(out.value)
+
+
+def all_distances(xyz, idx1, idx2, dim, box):
+    st, L = _L(box)
+    _chk(st)
+    x, i1 = _grp(xyz, idx1)
+    i2 = _idx(idx2)
+    out = np.zeros((i1.size, i2.size), np.float32)
+    _chk(lib().orc_all_distances(_fp(x), _sz(3), i1.ctypes.data_as(_u), _sz(i1.size), i2.ctypes.data_as(_u), _sz(i2.size),
+                                 DIM[dim], _fp(L), _fp(out)))
+    return out
+
+
+def all_distances_minmax(xyz, idx1, idx2, dim, box, cutoff=0.0):
+    st, L = _L(box)
+    _chk(st)
+    x, i1 = _grp(xyz, idx1)
+    i2 = _idx(idx2)
+    dmin, dmax = C.c_float(0), C.c_float(0)
+    imin, imax = np.zeros(2, np.uint32), np.zeros(2, np.uint32)
+    cnt = C.c_uint64(0)
+    _chk(lib().orc_all_distances_minmax(_fp(x), _sz(3), i1.ctypes.data_as(_u), _sz(i1.size), i2.ctypes.data_as(_u),
+                                        _sz(i2.size), DIM[dim], _fp(L), C.byref(dmin), imin.ctypes.data_as(_u),
+                                        C.byref(dmax), imax.ctypes.data_as(_u), C.c_float(cutoff), C.byref(cnt)))
+    return np.float32(dmin.value), imin, np.float32(dmax.value), imax, cnt.value
+
+
+def wrap(xyz, idx, box):
+    """returns (wrapped copy, shifts int8 [g,3])"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    i = _idx(idx)
+    sh = np.zeros((i.size, 3), np.int8)
+    _chk(lib().orc_wrap(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(L), sh.ctypes.data_as(_i8)))
+    return x, sh
+
+
+def translate(xyz, idx, t, box):
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    i = _idx(idx)
+    sh = np.zeros((i.size, 3), np.int8)
+    _chk(lib().orc_translate(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(_f32(t)), _fp(L), sh.ctypes.data_as(_i8)))
+    return x, sh
+
+
+def kabsch(p, q, w, cp, cq, sum_w):
+    p, q, w = _f32(p).reshape(-1, 3), _f32(q).reshape(-1, 3), _f32(w)
+    r, t = np.zeros(9, np.float32), np.zeros(3, np.float32)
+    rmsd = C.c_float(0)
+    lib().orc_kabsch(_fp(p), _fp(q), _fp(w), _sz(p.shape[0]), _fp(_f32(cp)), _fp(_f32(cq)), C.c_float(sum_w), _fp(r), _fp(t),
+                     C.byref(rmsd))
+    return r.reshape(3, 3), t, np.float32(rmsd.value)
+
+
+def calc_rmsd(ref_xyz, ref_idx, ref_box, mass, tgt_xyz, tgt_idx, tgt_box):
+    """returns (rmsd f32, r[3,3] row-major)"""
+    st, Lr = _L(ref_box)
+    _chk(st)
+    st, Lt = _L(tgt_box)
+    _chk(st)
+    rx, ri = _grp(ref_xyz, ref_idx)
+    tx, ti = _grp(tgt_xyz, tgt_idx)
+    if mass is None:
+        raise OracleError(ENOMASS)
+    m = _f32(mass)
+    r = np.zeros(9, np.float32)
+    rmsd = C.c_float(0)
+    _chk(lib().orc_calc_rmsd(_fp(rx), _sz(3), ri.ctypes.data_as(_u), _sz(ri.size), _fp(Lr), _fp(m), _fp(tx), _sz(3),
+                             ti.ctypes.data_as(_u), _sz(ti.size), _fp(Lt), _fp(r), C.byref(rmsd)))
+    return np.float32(rmsd.value), r.reshape(3, 3)
+
+
+def fit(xyz, r, com_tgt, com_ref, box):
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    lib().orc_fit(_fp(x), _sz(3), _sz(x.shape[0]), _fp(_f32(r).reshape(-1)), _fp(_f32(com_tgt)), _fp(_f32(com_ref)), _fp(L))
+    return x
+
+
+def calc_rmsd_and_fit(ref_xyz, ref_idx, ref_box, mass, tgt_xyz, tgt_idx, tgt_box):
+    """rmsd.rs:129-138: returns (rmsd, fitted copy of all target atoms)"""
+    rmsd, r = calc_rmsd(ref_xyz, ref_idx, ref_box, mass, tgt_xyz, tgt_idx, tgt_box)
+    com_ref = get_com(ref_xyz, ref_idx, mass, ref_box)
+    com_tgt = get_com(tgt_xyz, tgt_idx, mass, tgt_box)
+    return rmsd, fit(tgt_xyz, r, com_tgt, com_ref, tgt_box)
+
+
+# ---------------------------------------------------------------- exact64
+
+
+def estimate_center_x64(xyz, idx, box, mass=None):
+    st, L = _L(box)
+    _chk(st)
+    x, i = _grp(xyz, idx)
+    out = np.zeros(3, np.float64)
+    m = _f32(mass) if mass is not None else None
+    _chk(lib().orc_estimate_center_x64(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(m) if m is not None else None,
+                                       _fp(L), out.ctypes.data_as(_d)))
+    return out
+
+
+def get_center_x64(xyz, idx, box, mass=None):
+    st, L = _L(box)
+    _chk(st)
+    x, i = _grp(xyz, idx)
+    out = np.zeros(3, np.float64)
+    m = _f32(mass) if mass is not None else None
+    _chk(lib().orc_get_center_x64(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(m) if m is not None else None,
+                                  _fp(L), out.ctypes.data_as(_d)))
+    return out
+
+
+def calc_rmsd_x64(ref_xyz, ref_idx, ref_box, mass, tgt_xyz, tgt_idx, tgt_box):
+    st, Lr = _L(ref_box)
+    _chk(st)
+    st, Lt = _L(tgt_box)
+    _chk(st)
+    rx, ri = _grp(ref_xyz, ref_idx)
+    tx, ti = _grp(tgt_xyz, tgt_idx)
+    m = _f32(mass)
+    r = np.zeros(9, np.float64)
+    rmsd = C.c_double(0)
+    _chk(lib().orc_calc_rmsd_x64(_fp(rx), _sz(3), ri.ctypes.data_as(_u), _sz(ri.size), _fp(Lr), _fp(m), _fp(tx), _sz(3),
+                                 ti.ctypes.data_as(_u), _sz(ti.size), _fp(Lt), r.ctypes.data_as(_d), C.byref(rmsd)))
+    return rmsd.value, r.reshape(3, 3)
+
+
+# ---------------------------------------------------------------- triclinic extension (UNPINNED by the reference)
+
+
+def tric_wrap(xyz, idx, box9):
+    x = _f32(xyz).reshape(-1, 3).copy()
+    i = _idx(idx)
+    b = _f32(box9).reshape(-1)
+    sh = np.zeros((i.size, 3), np.int8)
+    _chk(lib().orc_tric_wrap(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(b), sh.ctypes.data_as(_i8)))
+    return x, sh
+
+
+def tric_distance(a, b, dim, box9):
+    return np.float32(lib().orc_tric_distance(_fp(_f32(a)), _fp(_f32(b)), DIM[dim], _fp(_f32(box9).reshape(-1))))
+
+
+def tric_distance_brute64(a, b, dim, box9, nimg=2):
+    return lib().orc_tric_distance_brute64(_fp(_f32(a)), _fp(_f32(b)), DIM[dim], _fp(_f32(box9).reshape(-1)), nimg)
+
+
+def tric_all_distances(xyz, idx1, idx2, dim, box9):
+    x, i1 = _grp(xyz, idx1)
+    i2 = _idx(idx2)
+    out = np.zeros((i1.size, i2.size), np.float32)
+    _chk(lib().orc_tric_all_distances(_fp(x), _sz(3), i1.ctypes.data_as(_u), _sz(i1.size), i2.ctypes.data_as(_u), _sz(i2.size),
+                                      DIM[dim], _fp(_f32(box9).reshape(-1)), _fp(out)))
+    return out
+
+
+# ---------------------------------------------------------------- synthetic workloads
+
+
+def synth_uniform(n, seed, frame, lo, span):
+    x = np.zeros((n, 3), np.float32)
+    lib().orc_synth_uniform(_fp(x), _sz(n), C.c_uint64(seed), C.c_uint64(frame), _fp(_f32(lo)), _fp(_f32(span)))
+    return x
+
+
+def synth_blob_ref(n, seed, scale, centre):
+    x = np.zeros((n, 3), np.float32)
+    lib().orc_synth_blob_ref(_fp(x), _sz(n), C.c_uint64(seed), C.c_float(scale), _fp(_f32(centre)))
+    return x
+
+
+def synth_blob_frame(n, seed, frame, scale, nscale, rot, centre, L, wrap=True):
+    x = np.zeros((n, 3), np.float32)
+    lib().orc_synth_blob_frame(_fp(x), _sz(n), C.c_uint64(seed), C.c_uint64(frame), C.c_float(scale), C.c_float(nscale),
+                               _fp(_f32(rot).reshape(-1)), _fp(_f32(centre)), _fp(_f32(L)), C.c_int(1 if wrap else 0))
+    return x
+
+
+# ---------------------------------------------------------------- restated CPU trajectory path (baseline)
+
+
+def baseline_traj(frames, boxes_L, idx, mass_all, ref_xyz, ref_L, ops, n_threads):
+    """ops bitmask: 1 group_get_center, 2 calc_rmsd, 4 fit, 8 atoms_wrap.  Returns (seconds, centers, rmsd)."""
+    fr = _f32(frames)
+    F, n = fr.shape[0], fr.shape[1]
+    bx = _f32(boxes_L).reshape(F, 3)
+    i = _idx(idx)
+    cen = np.zeros((F, 3), np.float32)
+    rm = np.zeros(F, np.float32)
+    m = _f32(mass_all) if mass_all is not None else None
+    rx = _f32(ref_xyz) if ref_xyz is not None else None
+    rl = _f32(ref_L) if ref_L is not None else None
+    sec = lib().orc_baseline_traj(_fp(fr), _fp(bx), _sz(F), _sz(n), i.ctypes.data_as(_u), _sz(i.size),
+                                  _fp(m) if m is not None else None, _fp(rx) if rx is not None else None,
+                                  _fp(rl) if rl is not None else None, C.c_int(ops), C.c_int(n_threads), _fp(cen), _fp(rm))
+    return sec, cen, rm
+
+
+def baseline_pairs(frames, boxes_L, idx1, idx2, dim, n_threads):
+    fr = _f32(frames)
+    F, n = fr.shape[0], fr.shape[1]
+    bx = _f32(boxes_L).reshape(F, 3)
+    i1, i2 = _idx(idx1), _idx(idx2)
+    dmin, dmax = np.zeros(F, np.float32), np.zeros(F, np.float32)
+    sec = lib().orc_baseline_pairs(_fp(fr), _fp(bx), _sz(F), _sz(n), i1.ctypes.data_as(_u), _sz(i1.size),
+                                   i2.ctypes.data_as(_u), _sz(i2.size), C.c_int(DIM[dim]), C.c_int(n_threads), _fp(dmin),
+                                   _fp(dmax))
+    return sec, dmin, dmax
