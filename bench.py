@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the PBC geometry hot path (group_get_center + calc_rmsd per frame) on B200.
+
+Workload (BASELINE.json configs[4], orthogonal box -- the reference rejects triclinic boxes for this path,
+SURVEY.md section 0.1): synthetic 4 000 000-atom system, box 34 nm, a compact rigid blob (extent < half box)
+that is randomly rotated, translated across the periodic boundary and perturbed by 0.05 nm noise per frame, so
+the RMSD to the reference structure is ~0.087 nm analytically.  A "step" is one batch of F frames (48 MB each;
+the batch is larger than the 126 MB L2) through System.group_get_center + System.calc_rmsd.
+
+One JSON line on stdout (rank 0).  `value` times device-resident frames with CUDA events; `e2e` pushes the same
+batch from pinned HOST memory through the public API every step (H2D + kernels + D2H of the results).
+`--impl reference` times the restated groan_rs CPU path (oracle/, the reference itself is Rust and cannot be
+built in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ATOMS = 4_000_000
+BOX = 34.0
+SEED = 20261018
+BLOB_SCALE = 5.5 / 131070.0        # blob support +-5.5 nm per axis: extent (rotated) stays below half the box (17 nm)
+NOISE_SCALE = 0.05 / 37837.23      # Irwin-Hall(4) of 16-bit fields has sigma 37837.23 -> 0.05 nm per axis
+METRIC = "frames/s (group_get_center + calc_rmsd per frame, 4M-atom group)"
+
+
+def frame_params(frame0, n_frames):
+    """per-frame random rigid motion: rotation (unit quaternion) and a centre anywhere in the box"""
+    rot = np.empty((n_frames, 9), np.float32)
+    cen = np.empty((n_frames, 3), np.float32)
+    for k in range(n_frames):
+        rng = np.random.default_rng([SEED, frame0 + k])
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        rot[k] = np.array([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                           2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                           2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], np.float32)
+        cen[k] = rng.uniform(0.0, BOX, size=3).astype(np.float32)
+    return rot, cen
+
+
+def masses(n):
+    return np.random.default_rng(SEED + 1).uniform(1.0, 100.0, n).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps, warmup, sample_frames=None, threads=None):
+    """Restated groan_rs CPU trajectory path (oracle/groan_oracle.c: orc_baseline_traj, following
+    parallel.rs:208-269,425-448): T threads, interleaved frames, AoS 240-byte atom records, f32 sequential sums."""
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    T = threads or max(1, min(cores, 32))
+    Fs = sample_frames or T
+    m = masses(N_ATOMS)
+    idx = np.arange(N_ATOMS, dtype=np.uint32)
+    L = np.array([BOX, BOX, BOX], np.float32)
+    ref_xyz = orc.synth_blob_ref(N_ATOMS, SEED, BLOB_SCALE, [BOX / 2] * 3)
+    rot, cen = frame_params(0, Fs)
+    frames = np.empty((Fs, N_ATOMS, 3), np.float32)
+    for f in range(Fs):
+        frames[f] = orc.synth_blob_frame(N_ATOMS, SEED, f, BLOB_SCALE, NOISE_SCALE, rot[f], cen[f], L, wrap=True)
+    boxes = np.tile(L, (Fs, 1))
+    times = []
+    for it in range(warmup + steps):
+        sec, _, _ = orc.baseline_traj(frames, boxes, idx, m, ref_xyz, L, ops=1 | 2, n_threads=T)
+        if it >= warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    return {"value": Fs / sec, "unit": "frames/s", "cores": T, "kind": "port",
+            "sample": "%d frames x %d atoms (group_get_center + calc_rmsd), %d threads, interleaved frames; restated groan_rs CPU "
+                      "path (oracle/), generation excluded" % (Fs, N_ATOMS, T), "ms_per_step": sec * 1e3, "frames": Fs}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(max(1, args.steps), min(args.warmup, 1), sample_frames=args.cpu_frames)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded generator shared with the GPU arm)",
+            "config": workload_config(r["frames"]),
+            "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(frames_per_step):
+    return {"workload": "configs[4] synthetic 4M-atom box 34 nm (orthogonal: the reference rejects triclinic for this path), "
+                        "group = all 4M atoms, per frame group_get_center + calc_rmsd vs reference structure",
+            "n_atoms": N_ATOMS, "group_atoms": N_ATOMS, "frames_per_step": frames_per_step, "box_nm": BOX,
+            "l2_policy": "inputs larger than L2: %d MB per step vs 126 MB L2" % (frames_per_step * N_ATOMS * 12 // 1000000)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import groan_rs_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F, K, W = args.frames, args.steps, max(3, args.warmup)
+
+    m = masses(N_ATOMS)
+    s = g.System(N_ATOMS, masses=m, device=local, max_frames=F)
+    ref = g.System(N_ATOMS, masses=m, device=local, max_frames=1)
+    idx = np.arange(N_ATOMS, dtype=np.uint32)
+    s.group_create_from_indices("G", idx)
+    ref.group_create_from_indices("G", idx)
+    stream = torch.cuda.current_stream()
+    s.set_stream(stream.cuda_stream)
+    ref_xyz = s.synth_blob_ref(SEED, BLOB_SCALE, [BOX / 2] * 3)
+    ref.set_frames(ref_xyz, [BOX] * 3)
+
+    # this rank's frames: contiguous shard of the global trajectory (parallel.py frame_range); weak scaling
+    frame0 = rank * F
+    rot, cen = frame_params(frame0, F)
+    s.synth_blob(SEED, frame0, F, BLOB_SCALE, NOISE_SCALE, rot, cen, [BOX] * 3, wrap=True)
+    d_cen = torch.empty((F, 3), dtype=torch.float32, device=dev)
+    d_rmsd = torch.empty((F,), dtype=torch.float32, device=dev)
+    g_cen = torch.empty((world * F, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    g_rmsd = torch.empty((world * F,), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        s.group_get_center("G", out=d_cen)
+        s.calc_rmsd(ref, "G", out=d_rmsd)
+        if world > 1:  # the one exchange of the path: the small per-frame results
+            dist.all_gather_into_tensor(g_cen, d_cen)
+            dist.all_gather_into_tensor(g_rmsd, d_rmsd)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    # correctness guard inside the bench: RMSD must be the analytic value of the generator
+    r0 = d_rmsd.cpu().numpy()
+    assert np.all(np.abs(r0 - 0.0866) < 2e-3), r0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = s.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * F * K / (ms * 1e-3)
+
+    # per-op device times (same resident batch, CUDA events on the launching stream)
+    def time_op(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peak, peak_src = measured_peak()
+    reps = max(3, K)
+    t_center = time_op(lambda: s.group_get_center("G", out=d_cen), reps)
+    t_rmsd = time_op(lambda: s.calc_rmsd(ref, "G", out=d_rmsd), reps)
+    gb = 1e-9
+    ops = {
+        "group_get_center": {"ms": t_center, "alg_bytes": 12 * N_ATOMS * F, "gbs": 12 * N_ATOMS * F * gb / (t_center * 1e-3)},
+        "calc_rmsd": {"ms": t_rmsd, "alg_bytes": 28 * N_ATOMS * F, "gbs": 28 * N_ATOMS * F * gb / (t_rmsd * 1e-3)},
+    }
+    dom = max(ops, key=lambda k: ops[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": ops[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ops[dom]["alg_bytes"], "ops": ops}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + kernels + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        h_in = [torch.empty((F, N_ATOMS, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        s.get_frames(out=h_in[0])
+        s.sync()
+        h_in[1].copy_(h_in[0])
+        h_cen = torch.empty((F, 3), dtype=torch.float32).pin_memory()
+        h_rmsd = torch.empty((F,), dtype=torch.float32).pin_memory()
+        boxes = np.tile(np.array([BOX, BOX, BOX], np.float32), (F, 1))
+
+        def e2e_step(k):
+            s.set_frames(h_in[k & 1], boxes)
+            s.group_get_center("G", out=h_cen)
+            s.calc_rmsd(ref, "G", out=h_rmsd)
+
+        for k in range(2):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            e2e_step(k)
+        s.sync()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert np.all(np.abs(h_rmsd.numpy() - 0.0866) < 2e-3)
+        e2e = {"value": world * F * K / dt, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 12 + F * 36,
+               "d2h_bytes_per_step": F * 16, "ms_per_step": dt * 1e3 / K, "timing": "host wall clock around K steps, sync both sides"}
+
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = run_extras(torch, g, local, peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(1, 0, sample_frames=args.cpu_frames)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic: seeded rigid blob + noise generated on the device, batch resident in HBM and reused every step",
+                "config": workload_config(F), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "extras": extras}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(torch, g, local, peak):
+    """secondary numbers of the same path: atoms_wrap (HBM) and all-pairs distances (configs[3])"""
+    out = {}
+    dev = torch.device("cuda", local)
+
+    def time_op(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # atoms_wrap on 4M atoms x 8 frames: 24 B per atom per frame
+    F = 8
+    w = g.System(N_ATOMS, device=local, max_frames=F)
+    w.set_stream(torch.cuda.current_stream().cuda_stream)
+    w.synth_uniform(SEED, 0, F, [-0.1 * BOX] * 3, [1.2 * BOX] * 3, [BOX] * 3)
+    t = time_op(lambda: w.atoms_wrap())
+    out["atoms_wrap"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "gbs": 24 * N_ATOMS * F * 1e-9 / (t * 1e-3),
+                         "frac_of_hbm_peak": 24 * N_ATOMS * F * 1e-9 / (t * 1e-3) / peak}
+    w.close()
+    # configs[3]: 1M atoms, box 21.5, 2 000 x 200 000 all-pairs
+    n1, n2, N = 2000, 200000, 1_000_000
+    p = g.System(N, device=local, max_frames=2)
+    p.set_stream(torch.cuda.current_stream().cuda_stream)
+    p.group_create_from_indices("A", np.arange(n1))
+    p.group_create_from_indices("B", np.arange(500000, 500000 + n2))
+    p.synth_uniform(SEED, 0, 2, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
+    t = time_op(lambda: p.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0), reps=3)
+    pairs = 2 * n1 * n2
+    out["all_pairs_fused_reduce"] = {"ms": t, "pairs_per_s": pairs / (t * 1e-3), "frames_per_s": 2 / (t * 1e-3)}
+    p.synth_uniform(SEED, 0, 1, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
+    mat = torch.empty((1, n1, n2), dtype=torch.float32, device=dev)
+    t = time_op(lambda: p.group_all_distances("A", "B", g.Dimension.XYZ, out=mat), reps=3)
+    out["all_pairs_materialise"] = {"ms": t, "pairs_per_s": n1 * n2 / (t * 1e-3), "write_gbs": 4 * n1 * n2 * 1e-9 / (t * 1e-3),
+                                    "frac_of_hbm_peak": 4 * n1 * n2 * 1e-9 / (t * 1e-3) / peak}
+    del mat
+    p.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=8, help="frames per step (48 MB each)")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="frames in the CPU sample (default: one per thread)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,244 @@
+// common.cuh -- device helpers shared by every kernel of libgroan_gpu (sm_100a).
+//
+// The library is compiled with -fmad=false: the reference (rustc) never contracts a*b+c into an
+// FMA, and the parity-critical per-atom arithmetic below must round exactly like it.  Where an
+// FMA is wanted for speed it is written explicitly (__fmaf_rn / fma()).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace groan {
+
+constexpr int kThreads = 256;           // CTA size of the streaming kernels
+constexpr int kSMs = 148;               // B200
+constexpr int kMaxBlocksPerFrame = 592; // 4 resident CTAs x 148 SMs
+
+// ---------------------------------------------------------------- reference scalar primitives
+// Vector3D::wrap_coordinate, vector3d.rs:401-417 (strict comparisons; x == L stays L, 0 stays 0)
+__device__ __forceinline__ float wrap_coordinate(float x, float L) {
+    while (x > L) x -= L;
+    while (x < 0.0f) x += L;
+    return x;
+}
+__device__ __forceinline__ float wrap_coordinate_count(float x, float L, int &k) {
+    k = 0;
+    while (x > L) { x -= L; k--; }
+    while (x < 0.0f) { x += L; k++; }
+    return x;
+}
+// Vector3D::min_image, vector3d.rs:575-592
+__device__ __forceinline__ float min_image(float d, float L) {
+    const float h = L / 2.0f;
+    while (d > h) d -= L;
+    while (d < -h) d += L;
+    return d;
+}
+// One-step form, bit-identical to the loops when |d| <= 1.5 L (proved in DESIGN.md "min-image").
+__device__ __forceinline__ float min_image_1step(float d, float L, float h) {
+    if (d > h) d -= L;
+    else if (d < -h) d += L;
+    return d;
+}
+// C fmodf(a, L) for L > 0: exact by construction for |a| < 2L (a - L is exact there, Sterbenz),
+// CUDA's fmodf (0 ulp) otherwise.
+__device__ __forceinline__ float fmod_exact(float a, float L) {
+    const float aa = fabsf(a);
+    if (aa < L) return a;
+    if (aa < L + L) return copysignf(aa - L, a);
+    return fmodf(a, L);
+}
+// floor_mod, vector3d.rs:28-30: (x % y + y) % y
+__device__ __forceinline__ float floor_mod(float x, float y) { return fmod_exact(fmod_exact(x, y) + y, y); }
+// one axis of Vector3D::vector_to, vector3d.rs:561-569: floor_mod(p - c + half, L) - half
+__device__ __forceinline__ float vector_to_1(float c, float p, float L) {
+    const float h = L / 2.0f;
+    return floor_mod(p - c + h, L) - h;
+}
+
+__device__ __forceinline__ float pi_x2() { return 3.14159265358979323846f * 2.0f; } // auxiliary.rs:15
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ double shfl_down_d(double v, int off) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_down_sync(0xffffffffu, lo, off);
+    hi = __shfl_down_sync(0xffffffffu, hi, off);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum K per-thread values over the CTA in f64; result valid in thread 0.  smem: K * (kThreads/32) doubles.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *smem) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) smem[k * nw + w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double s = 0.0;
+            for (int j = 0; j < nw; j++) s += smem[k * nw + j];
+            v[k] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// "Last CTA of the frame finishes the frame": thread 0 publishes this CTA's K partial sums, takes a
+// ticket; the CTA that draws the last ticket re-reads all partials in a FIXED order (deterministic
+// result, independent of scheduling) and returns true with the totals in tot[] (thread 0 only).
+template <int K>
+__device__ __forceinline__ bool frame_finish(const double (&v)[K], double *partials /* [blocks][K] of this frame */,
+                                             unsigned int *ticket, int blocks, double (&tot)[K], int *sh_flag) {
+    if (threadIdx.x == 0) {
+        const int b = blockIdx.x;
+#pragma unroll
+        for (int k = 0; k < K; k++) partials[(size_t)b * K + k] = v[k];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        int last = (t == (unsigned)(blocks - 1));
+        if (last) {
+            __threadfence();
+#pragma unroll
+            for (int k = 0; k < K; k++) tot[k] = 0.0;
+            for (int j = 0; j < blocks; j++) {
+#pragma unroll
+                for (int k = 0; k < K; k++) tot[k] += ((volatile double *)partials)[(size_t)j * K + k];
+            }
+            *ticket = 0u; // re-arm for the next launch on this frame
+        }
+        *sh_flag = last;
+    }
+    __syncthreads();
+    return *sh_flag != 0;
+}
+
+// ---------------------------------------------------------------- 3x3 SVD / Kabsch rotation (f64)
+// One-sided Jacobi; singular values sorted descending like nalgebra's Matrix3::svd (rmsd.rs:573).
+__device__ inline void svd3(const double A[9], double U[9], double S[3], double V[9]) {
+    double W[9];
+    for (int i = 0; i < 9; i++) { W[i] = A[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 64; sweep++) {
+        int rotated = 0;
+        for (int e = 0; e < 3; e++) {
+            const int p = (e == 2) ? 1 : 0, q = (e == 0) ? 1 : 2;
+            double al = 0, be = 0, ga = 0;
+            for (int i = 0; i < 3; i++) {
+                al += W[i * 3 + p] * W[i * 3 + p];
+                be += W[i * 3 + q] * W[i * 3 + q];
+                ga += W[i * 3 + p] * W[i * 3 + q];
+            }
+            if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+            rotated = 1;
+            const double ze = (be - al) / (2.0 * ga);
+            const double t = (ze >= 0 ? 1.0 : -1.0) / (fabs(ze) + sqrt(1.0 + ze * ze));
+            const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+            for (int i = 0; i < 3; i++) {
+                const double wp = W[i * 3 + p], wq = W[i * 3 + q];
+                W[i * 3 + p] = c * wp - s * wq;
+                W[i * 3 + q] = s * wp + c * wq;
+                const double vp = V[i * 3 + p], vq = V[i * 3 + q];
+                V[i * 3 + p] = c * vp - s * vq;
+                V[i * 3 + q] = s * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    for (int j = 0; j < 3; j++) S[j] = sqrt(W[j] * W[j] + W[3 + j] * W[3 + j] + W[6 + j] * W[6 + j]);
+    for (int a = 0; a < 2; a++)
+        for (int b = a + 1; b < 3; b++)
+            if (S[b] > S[a]) {
+                double ts = S[a]; S[a] = S[b]; S[b] = ts;
+                for (int i = 0; i < 3; i++) {
+                    double tw = W[i * 3 + a]; W[i * 3 + a] = W[i * 3 + b]; W[i * 3 + b] = tw;
+                    double tv = V[i * 3 + a]; V[i * 3 + a] = V[i * 3 + b]; V[i * 3 + b] = tv;
+                }
+            }
+    const double tiny = 1e-12 * (S[0] > 0 ? S[0] : 1.0);
+    const int rank = (S[0] > tiny) + (S[1] > tiny) + (S[2] > tiny);
+    for (int j = 0; j < rank; j++)
+        for (int i = 0; i < 3; i++) U[i * 3 + j] = W[i * 3 + j] / S[j];
+    if (rank == 0) {
+        for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    } else if (rank == 1) {
+        const double u0[3] = {U[0], U[3], U[6]};
+        const int m = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+        double u1[3];
+        for (int i = 0; i < 3; i++) u1[i] = ((i == m) ? 1.0 : 0.0) - u0[m] * u0[i];
+        const double n = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        for (int i = 0; i < 3; i++) { u1[i] /= n; U[i * 3 + 1] = u1[i]; }
+        U[2] = u0[1] * u1[2] - u0[2] * u1[1];
+        U[5] = u0[2] * u1[0] - u0[0] * u1[2];
+        U[8] = u0[0] * u1[1] - u0[1] * u1[0];
+    } else if (rank == 2) {
+        U[2] = U[3] * U[7] - U[6] * U[4];
+        U[5] = U[6] * U[1] - U[0] * U[7];
+        U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+}
+
+// r = U * diag(1, 1, sign det(U Vt)) * Vt, rmsd.rs:573-583 (row-major)
+__device__ inline void kabsch_rotation(const double H[9], double r[9]) {
+    double U[9], S[3], V[9], M[9];
+    svd3(H, U, S, V);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) M[i * 3 + j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + U[i * 3 + 2] * V[j * 3 + 2];
+    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    const double d = det < 0.0 ? -1.0 : 1.0;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r[i * 3 + j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + d * U[i * 3 + 2] * V[j * 3 + 2];
+}
+
+// ---------------------------------------------------------------- atom accessors
+// A group is either a contiguous index range (the common case: Group = list of ranges,
+// container.rs:13-31) or a general ascending index list.
+struct GroupView {
+    const uint32_t *idx; // null for a contiguous range
+    uint32_t first;      // first atom of a contiguous range
+    uint32_t n;          // atoms in the group
+    const float *mass;   // group order, nullable
+    __device__ __forceinline__ uint32_t atom(uint32_t i) const { return idx ? __ldg(idx + i) : first + i; }
+};
+
+struct FrameView {
+    const float *xyz; // F x N x 3
+    const float *box; // F x 9
+    size_t n_atoms;
+    __device__ __forceinline__ const float *frame(int f) const { return xyz + (size_t)f * n_atoms * 3; }
+    __device__ __forceinline__ void lengths(int f, float &lx, float &ly, float &lz) const {
+        lx = __ldg(box + f * 9 + 0);
+        ly = __ldg(box + f * 9 + 4);
+        lz = __ldg(box + f * 9 + 8);
+    }
+};
+
+// counter-based generator shared with oracle/groan_oracle.c (orc_splitmix64 / orc_hash)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t frame_key(uint64_t seed, uint64_t frame) {
+    return splitmix64(seed ^ (0xD1B54A32D192ED03ULL * (frame + 1)));
+}
+
+} // namespace groan

@@ -1,0 +1,1001 @@
+// groan_gpu.cu -- host side of libgroan_gpu.so: the C ABI declared in include/groan_gpu.h.
+//
+// One ctx = one GPU = one host thread.  Frames live in two device slots so that the host->device copy
+// of batch k+1 (copy stream, pinned staging) overlaps the kernels of batch k (compute stream).
+// Every op evaluates one groan_rs function for every frame of the current batch; host code here only
+// validates arguments exactly like the reference does (error order included), picks launch
+// geometry and delivers results.  There is no CPU fallback anywhere in this file.
+#include "../../include/groan_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_center.cuh"
+#include "kernels_pairs.cuh"
+#include "kernels_rmsd.cuh"
+#include "kernels_synth.cuh"
+
+using namespace groan;
+
+namespace {
+
+constexpr size_t kStageBytes = 32u << 20;  // pinned staging chunk for pageable sources
+constexpr size_t kPartialSlots = 8192;     // (blocks per frame) x (frames) upper bound for reductions
+constexpr int kMaxSums = 24;               // widest per-CTA partial record, in doubles
+
+struct Group {
+    bool set = false;
+    std::vector<uint32_t> idx;  // host copy (validity / error reporting)
+    uint32_t *d_idx = nullptr;
+    bool contiguous = false;
+    uint32_t first = 0;
+    size_t n = 0;
+    bool has_mass = false;
+    long no_mass_at = -1;  // position in the group of the first atom without mass
+    float *d_mass = nullptr;
+};
+
+enum PtrKind { PK_DEVICE, PK_PINNED, PK_PAGEABLE };
+
+PtrKind classify(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return PK_PAGEABLE;
+    }
+    switch (a.type) {
+    case cudaMemoryTypeDevice:
+    case cudaMemoryTypeManaged: return PK_DEVICE;
+    case cudaMemoryTypeHost: return PK_PINNED;
+    default: return PK_PAGEABLE;
+    }
+}
+
+}  // namespace
+
+struct groan_gpu_ctx {
+    int device = 0;
+    size_t n_atoms = 0, max_frames = 0;
+    unsigned flags = 0;
+    cudaStream_t own_compute = nullptr, compute = nullptr, copy = nullptr;
+
+    // frames
+    float *d_slot[2] = {nullptr, nullptr};
+    float *d_box[2] = {nullptr, nullptr};
+    int slot = 1;               // slot of the current batch (first push goes to 0)
+    float *cur_xyz = nullptr;   // slot buffer or attached caller buffer
+    bool attached = false;
+    bool have_frames = false, have_box = false;
+    size_t n_frames = 0;
+    std::vector<float> h_box;   // F x 9 of the current batch
+    std::vector<uint8_t> valid; // F x N, empty = all valid
+    cudaEvent_t ev_h2d = nullptr, ev_done[2] = {nullptr, nullptr};
+    bool done_recorded[2] = {false, false};
+    float *h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+
+    Group groups[GROAN_MAX_GROUPS];
+    Group all;  // GROAN_GROUP_ALL
+
+    // scratch
+    double *d_partials = nullptr;
+    void *d_pair_partials = nullptr;
+    unsigned int *d_tickets = nullptr;
+    float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+
+    // RMSD reference (per group id)
+    struct Ref {
+        bool set = false;
+        size_t n = 0;
+        float4 *d_pc = nullptr;
+        double sum_mpp = 0, sum_m = 0;
+        float com[3] = {0, 0, 0};
+    } refs[GROAN_MAX_GROUPS];
+
+    uint64_t launches = 0;
+    std::string cuda_err;
+    size_t err_a = 0, err_b = 0;
+};
+
+namespace {
+
+int cuda_fail(groan_gpu_ctx *c, cudaError_t e, const char *what) {
+    if (c) c->cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return GROAN_ECUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);     \
+    } while (0)
+#define LAUNCHED()                                                   \
+    do {                                                             \
+        ctx->launches++;                                             \
+        cudaError_t e_ = cudaGetLastError();                         \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, "kernel launch"); \
+    } while (0)
+
+const Group *get_group(groan_gpu_ctx *ctx, int gid) {
+    if (gid == GROAN_GROUP_ALL) return &ctx->all;
+    if (gid < 0 || gid >= GROAN_MAX_GROUPS || !ctx->groups[gid].set) return nullptr;
+    return &ctx->groups[gid];
+}
+
+GroupView view_of(const Group &g) {
+    GroupView v;
+    v.idx = g.contiguous ? nullptr : g.d_idx;
+    v.first = g.first;
+    v.n = (uint32_t)g.n;
+    v.mass = g.d_mass;
+    return v;
+}
+
+FrameView frames_of(groan_gpu_ctx *ctx) {
+    FrameView fv;
+    fv.xyz = ctx->cur_xyz;
+    fv.box = ctx->d_box[ctx->slot];
+    fv.n_atoms = ctx->n_atoms;
+    return fv;
+}
+
+// simbox_check (simbox.rs:230-236) over every frame of the batch; zero box = the reference's panic
+int check_box(groan_gpu_ctx *ctx, bool allow_triclinic, bool *any_triclinic) {
+    if (any_triclinic) *any_triclinic = false;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    if (!ctx->have_box) return GROAN_ENOBOX;
+    for (size_t f = 0; f < ctx->n_frames; f++) {
+        const float *b = &ctx->h_box[f * 9];
+        if (b[1] != 0.0f || b[2] != 0.0f || b[5] != 0.0f) return GROAN_EINVAL;  // matrix2simbox rejects (xdrfile.rs:171)
+        const bool tric = (b[3] != 0.0f || b[6] != 0.0f || b[7] != 0.0f);
+        if (tric) {
+            if (!allow_triclinic || !(ctx->flags & GROAN_FLAG_TRICLINIC)) return GROAN_ENOTORTHO;
+            if (any_triclinic) *any_triclinic = true;
+        }
+        if (b[0] == 0.0f || b[4] == 0.0f || b[8] == 0.0f) return GROAN_EZEROBOX;
+    }
+    return GROAN_OK;
+}
+
+// first atom of the group (group order) without a position, in the first frame that has one
+int check_positions(groan_gpu_ctx *ctx, const Group &g) {
+    if (ctx->valid.empty()) return GROAN_OK;
+    for (size_t f = 0; f < ctx->n_frames; f++) {
+        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
+        for (size_t i = 0; i < g.n; i++) {
+            const size_t a = g.contiguous ? g.first + i : g.idx[i];
+            if (!v[a]) {
+                ctx->err_a = f;
+                ctx->err_b = a;
+                return GROAN_ENOPOS;
+            }
+        }
+    }
+    return GROAN_OK;
+}
+
+int check_masses(groan_gpu_ctx *ctx, const Group &g) {
+    if (!g.has_mass) {
+        ctx->err_a = 0;
+        ctx->err_b = g.n ? (g.contiguous ? g.first : g.idx[0]) : 0;
+        return GROAN_ENOMASS;
+    }
+    if (g.no_mass_at >= 0) {
+        ctx->err_a = 0;
+        ctx->err_b = g.contiguous ? g.first + (size_t)g.no_mass_at : g.idx[(size_t)g.no_mass_at];
+        return GROAN_ENOMASS;
+    }
+    return GROAN_OK;
+}
+
+// blocks per frame for a streaming pass over g atoms of each of F frames
+int blocks_per_frame(size_t g, size_t F) {
+    size_t nb = (g + (size_t)kThreads * 8 - 1) / ((size_t)kThreads * 8);
+    nb = std::max<size_t>(nb, 1);
+    nb = std::min<size_t>(nb, kMaxBlocksPerFrame);
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
+    return (int)nb;
+}
+
+int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->tmp_bytes) return GROAN_OK;
+    if (ctx->d_tmp) {
+        CK(cudaStreamSynchronize(ctx->compute));
+        CK(cudaFree(ctx->d_tmp));
+        ctx->d_tmp = nullptr;
+        ctx->tmp_bytes = 0;
+    }
+    CK(cudaMalloc(&ctx->d_tmp, bytes));
+    ctx->tmp_bytes = bytes;
+    return GROAN_OK;
+}
+
+// copy a device result to wherever the caller wants it (device / pinned: async; pageable: blocking)
+int deliver(groan_gpu_ctx *ctx, void *out, const void *d_src, size_t bytes) {
+    if (!out || out == d_src || bytes == 0) return GROAN_OK;
+    const PtrKind k = classify(out);
+    CK(cudaMemcpyAsync(out, d_src, bytes, cudaMemcpyDefault, ctx->compute));
+    if (k == PK_PAGEABLE) CK(cudaStreamSynchronize(ctx->compute));
+    return GROAN_OK;
+}
+
+template <typename T>
+T *target_of(void *out, T *scratch) {
+    return (out && classify(out) == PK_DEVICE) ? reinterpret_cast<T *>(out) : scratch;
+}
+
+int ensure_slots(groan_gpu_ctx *ctx) {
+    if (ctx->d_slot[0]) return GROAN_OK;
+    const size_t bytes = ctx->max_frames * ctx->n_atoms * 3 * sizeof(float) + 256;
+    for (int s = 0; s < 2; s++) CK(cudaMalloc(&ctx->d_slot[s], bytes));
+    return GROAN_OK;
+}
+
+// switch to the other slot; the copy stream may only overwrite it once every kernel that used it is done
+int begin_batch(groan_gpu_ctx *ctx, size_t F, const float *box, bool use_slot) {
+    if (F == 0) return GROAN_EINVAL;
+    if (F > ctx->max_frames) return GROAN_ECAPACITY;
+    const int prev = ctx->slot, next = ctx->slot ^ 1;
+    if (ctx->have_frames) {
+        CK(cudaEventRecord(ctx->ev_done[prev], ctx->compute));
+        ctx->done_recorded[prev] = true;
+    }
+    if (use_slot) {
+        int rc = ensure_slots(ctx);
+        if (rc) return rc;
+        if (ctx->done_recorded[next]) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_done[next], 0));
+    }
+    ctx->slot = next;
+    ctx->n_frames = F;
+    ctx->have_frames = true;
+    ctx->valid.clear();
+    ctx->have_box = (box != nullptr);
+    ctx->h_box.assign(F * 9, 0.0f);
+    if (box) {
+        std::memcpy(ctx->h_box.data(), box, F * 9 * sizeof(float));
+        // the box slot is small; order it after the kernels that still read the same slot's previous content
+        if (ctx->done_recorded[next]) CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_done[next], 0));
+        CK(cudaMemcpyAsync(ctx->d_box[next], ctx->h_box.data(), F * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy));
+    } else {
+        CK(cudaMemsetAsync(ctx->d_box[next], 0, F * 9 * sizeof(float), ctx->copy));
+    }
+    return GROAN_OK;
+}
+
+int end_batch(groan_gpu_ctx *ctx) {
+    CK(cudaEventRecord(ctx->ev_h2d, ctx->copy));
+    CK(cudaStreamWaitEvent(ctx->compute, ctx->ev_h2d, 0));
+    return GROAN_OK;
+}
+
+// ---- centre passes -------------------------------------------------------------------------------
+int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out) {
+    const int nb = blocks_per_frame(g.n, ctx->n_frames);
+    dim3 grid(nb, (unsigned)ctx->n_frames);
+    if (weighted)
+        k_trig<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out);
+    else
+        k_trig<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c0, float *out) {
+    const int nb = blocks_per_frame(g.n, ctx->n_frames);
+    dim3 grid(nb, (unsigned)ctx->n_frames);
+    if (weighted)
+        k_unwrap<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out);
+    else
+        k_unwrap<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+// group_get_center / group_get_com: estimate (always geometric, iterators.rs:1407) then unwrap
+int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
+    int rc = run_trig(ctx, g, false, ctx->d_c0);
+    if (rc) return rc;
+    return run_unwrap(ctx, g, weighted, ctx->d_c0, out);
+}
+
+// validation shared by the centre ops, in the reference's order (analysis.rs:105-120, iterators.rs:1152-1191)
+int check_center_args(groan_gpu_ctx *ctx, int gid, bool weighted, const Group **gp) {
+    if (!ctx) return GROAN_EINVAL;
+    const Group *g = get_group(ctx, gid);
+    if (!g) return GROAN_ENOGROUP;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    if (g->n == 0) return GROAN_EEMPTY;
+    int rc = check_box(ctx, false, nullptr);
+    if (rc) return rc;
+    rc = check_positions(ctx, *g);
+    if (rc) return rc;
+    if (weighted) {
+        rc = check_masses(ctx, *g);
+        if (rc) return rc;
+    }
+    *gp = g;
+    return GROAN_OK;
+}
+
+template <int DIM, typename BOX>
+int launch_pairs(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_out) {
+    const bool vec = (b.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    dim3 grid((unsigned)((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)),
+              (unsigned)((a.n + kPairRows - 1) / kPairRows), (unsigned)ctx->n_frames);
+    if (vec)
+        k_pairs<DIM, BOX, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+    else
+        k_pairs<DIM, BOX, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+template <typename BOX>
+int dispatch_pairs(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float *d_out) {
+    switch (dim) {
+    case 0: return launch_pairs<0, BOX>(ctx, a, b, d_out);
+    case 1: return launch_pairs<1, BOX>(ctx, a, b, d_out);
+    case 2: return launch_pairs<2, BOX>(ctx, a, b, d_out);
+    case 3: return launch_pairs<3, BOX>(ctx, a, b, d_out);
+    case 4: return launch_pairs<4, BOX>(ctx, a, b, d_out);
+    case 5: return launch_pairs<5, BOX>(ctx, a, b, d_out);
+    case 6: return launch_pairs<6, BOX>(ctx, a, b, d_out);
+    case 7: return launch_pairs<7, BOX>(ctx, a, b, d_out);
+    default: return GROAN_EINVAL;
+    }
+}
+
+struct ReduceOut {
+    float *dmin;
+    uint32_t *imin;
+    float *dmax;
+    uint32_t *imax;
+    unsigned long long *count;
+};
+
+template <int DIM, typename BOX>
+int launch_pairs_reduce(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
+    size_t nb = (b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ);
+    nb = std::max<size_t>(1, std::min<size_t>(nb, kMaxBlocksPerFrame));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    k_pairs_reduce<DIM, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff,
+                                                                  (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
+                                                                  o.imin, o.dmax, o.imax, o.count);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+template <typename BOX>
+int dispatch_pairs_reduce(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
+    switch (dim) {
+    case 0: return launch_pairs_reduce<0, BOX>(ctx, a, b, cutoff, o);
+    case 1: return launch_pairs_reduce<1, BOX>(ctx, a, b, cutoff, o);
+    case 2: return launch_pairs_reduce<2, BOX>(ctx, a, b, cutoff, o);
+    case 3: return launch_pairs_reduce<3, BOX>(ctx, a, b, cutoff, o);
+    case 4: return launch_pairs_reduce<4, BOX>(ctx, a, b, cutoff, o);
+    case 5: return launch_pairs_reduce<5, BOX>(ctx, a, b, cutoff, o);
+    case 6: return launch_pairs_reduce<6, BOX>(ctx, a, b, cutoff, o);
+    case 7: return launch_pairs_reduce<7, BOX>(ctx, a, b, cutoff, o);
+    default: return GROAN_EINVAL;
+    }
+}
+
+// Atom::distance checks self first, then the other atom (atom.rs:780-790); scan order is row-major
+int check_pair_positions(groan_gpu_ctx *ctx, const Group &a, const Group &b) {
+    if (ctx->valid.empty() || a.n == 0 || b.n == 0) return GROAN_OK;
+    for (size_t f = 0; f < ctx->n_frames; f++) {
+        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
+        auto at = [](const Group &g, size_t i) { return g.contiguous ? (size_t)g.first + i : (size_t)g.idx[i]; };
+        if (!v[at(a, 0)]) { ctx->err_a = f; ctx->err_b = at(a, 0); return GROAN_ENOPOS; }
+        for (size_t j = 0; j < b.n; j++)
+            if (!v[at(b, j)]) { ctx->err_a = f; ctx->err_b = at(b, j); return GROAN_ENOPOS; }
+        for (size_t i = 1; i < a.n; i++)
+            if (!v[at(a, i)]) { ctx->err_a = f; ctx->err_b = at(a, i); return GROAN_ENOPOS; }
+    }
+    return GROAN_OK;
+}
+
+int run_wrap(groan_gpu_ctx *ctx, const Group &g, bool translate, const float t[3], int8_t *shifts, bool tric) {
+    int8_t *d_sh = nullptr;
+    const size_t sh_bytes = ctx->n_frames * g.n * 3;
+    if (shifts) {
+        if (classify(shifts) == PK_DEVICE) {
+            d_sh = shifts;
+        } else {
+            int rc = ensure_tmp(ctx, sh_bytes);
+            if (rc) return rc;
+            d_sh = (int8_t *)ctx->d_tmp;
+        }
+    }
+    size_t nb = (g.n + kThreads - 1) / kThreads;
+    nb = std::max<size_t>(1, std::min<size_t>(nb, (size_t)kMaxBlocksPerFrame * 4));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    const float tx = translate ? t[0] : 0.0f, ty = translate ? t[1] : 0.0f, tz = translate ? t[2] : 0.0f;
+    float *xyz = ctx->cur_xyz;
+    const float *box = ctx->d_box[ctx->slot];
+    const GroupView gv = view_of(g);
+#define WRAP_LAUNCH(K, TR, SH) K<TR, SH><<<grid, kThreads, 0, ctx->compute>>>(xyz, box, ctx->n_atoms, gv, tx, ty, tz, d_sh)
+    if (tric) {
+        if (translate) { if (d_sh) WRAP_LAUNCH(k_wrap_tric, true, true); else WRAP_LAUNCH(k_wrap_tric, true, false); }
+        else { if (d_sh) WRAP_LAUNCH(k_wrap_tric, false, true); else WRAP_LAUNCH(k_wrap_tric, false, false); }
+    } else {
+        if (translate) { if (d_sh) WRAP_LAUNCH(k_wrap, true, true); else WRAP_LAUNCH(k_wrap, true, false); }
+        else { if (d_sh) WRAP_LAUNCH(k_wrap, false, true); else WRAP_LAUNCH(k_wrap, false, false); }
+    }
+#undef WRAP_LAUNCH
+    LAUNCHED();
+    if (shifts && d_sh != shifts) return deliver(ctx, shifts, d_sh, sh_bytes);
+    return GROAN_OK;
+}
+
+int check_wrap_args(groan_gpu_ctx *ctx, int gid, const Group **gp, bool *tric) {
+    if (!ctx) return GROAN_EINVAL;
+    const Group *g = get_group(ctx, gid);
+    if (!g) return GROAN_ENOGROUP;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    int rc = check_box(ctx, true, tric);
+    if (rc) return rc;
+    rc = check_positions(ctx, *g);
+    if (rc) return rc;
+    *gp = g;
+    return GROAN_OK;
+}
+
+int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) {
+    if (!ctx) return GROAN_EINVAL;
+    const Group *g = get_group(ctx, gid);
+    if (!g || gid < 0) return GROAN_ENOGROUP;
+    if (!ctx->refs[gid].set) return GROAN_ENOREF;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    // extract_data_from_system(target): box first (rmsd.rs:430), then group_get_com's own checks
+    int rc = check_box(ctx, false, nullptr);
+    if (rc) return rc;
+    if (g->n == 0) return GROAN_EEMPTY;
+    rc = check_positions(ctx, *g);
+    if (rc) return rc;
+    rc = check_masses(ctx, *g);
+    if (rc) return rc;
+    const groan_gpu_ctx::Ref &R = ctx->refs[gid];
+    if (R.n != g->n) {  // number_of_positions_consistent, rmsd.rs:405-422
+        ctx->err_a = R.n;
+        ctx->err_b = g->n;
+        return GROAN_EGROUPSIZE;
+    }
+    // group_get_com of the target (geometric estimate, mass-weighted unwrap)
+    rc = run_get_center(ctx, *g, true, ctx->d_cen);
+    if (rc) return rc;
+    float *d_rmsd = target_of<float>(rmsd, ctx->d_res);
+    float *d_rot = target_of<float>(rot, ctx->d_rot);
+    RefView rv;
+    rv.pc = R.d_pc;
+    rv.sum_mpp = R.sum_mpp;
+    rv.sum_m = R.sum_m;
+    rv.com[0] = R.com[0]; rv.com[1] = R.com[1]; rv.com[2] = R.com[2];
+    const int nb = blocks_per_frame(g->n, ctx->n_frames);
+    dim3 grid(nb, (unsigned)ctx->n_frames);
+    k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
+                                                d_rot);
+    LAUNCHED();
+    if (fit) {
+        size_t fb = (ctx->n_atoms + kThreads - 1) / kThreads;
+        fb = std::max<size_t>(1, std::min<size_t>(fb, (size_t)kMaxBlocksPerFrame * 4));
+        dim3 fgrid((unsigned)fb, (unsigned)ctx->n_frames);
+        k_fit<<<fgrid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->d_box[ctx->slot], ctx->n_atoms, ctx->d_cen, d_rot, R.com[0],
+                                                     R.com[1], R.com[2]);
+        LAUNCHED();
+    }
+    rc = deliver(ctx, rmsd, d_rmsd, ctx->n_frames * sizeof(float));
+    if (rc) return rc;
+    return deliver(ctx, rot, d_rot, ctx->n_frames * 9 * sizeof(float));
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out) {
+    if (!out || n_atoms == 0 || max_frames == 0 || n_atoms > 0xFFFFFFF0ull) return GROAN_EINVAL;
+    *out = nullptr;
+    groan_gpu_ctx *ctx = new (std::nothrow) groan_gpu_ctx();
+    if (!ctx) return GROAN_EINVAL;
+    ctx->device = device;
+    ctx->n_atoms = n_atoms;
+    ctx->max_frames = max_frames;
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->own_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+        ctx->compute = ctx->own_compute;
+        CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+        for (int s = 0; s < 2; s++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_stage[s], cudaEventDisableTiming));
+            CK(cudaMalloc(&ctx->d_box[s], max_frames * 9 * sizeof(float)));
+        }
+        const size_t slots = std::max(max_frames, kPartialSlots) + kMaxBlocksPerFrame;
+        CK(cudaMalloc(&ctx->d_partials, slots * kMaxSums * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_pair_partials, slots * sizeof(PairPartial)));
+        CK(cudaMalloc(&ctx->d_tickets, (max_frames + 1) * sizeof(unsigned int)));
+        CK(cudaMemset(ctx->d_tickets, 0, (max_frames + 1) * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_c0, max_frames * 3 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_cen, max_frames * 3 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_cen2, max_frames * 3 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_res, max_frames * 8 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_rot, max_frames * 9 * sizeof(float)));
+        return GROAN_OK;
+    }();
+    if (rc) {
+        groan_gpu_destroy(ctx);
+        return rc;
+    }
+    ctx->all.set = true;
+    ctx->all.contiguous = true;
+    ctx->all.first = 0;
+    ctx->all.n = n_atoms;
+    *out = ctx;
+    return GROAN_OK;
+}
+
+void groan_gpu_destroy(groan_gpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; s++) {
+        if (ctx->d_slot[s]) cudaFree(ctx->d_slot[s]);
+        if (ctx->d_box[s]) cudaFree(ctx->d_box[s]);
+        if (ctx->h_stage[s]) cudaFreeHost(ctx->h_stage[s]);
+        if (ctx->ev_done[s]) cudaEventDestroy(ctx->ev_done[s]);
+        if (ctx->ev_stage[s]) cudaEventDestroy(ctx->ev_stage[s]);
+    }
+    for (auto &g : ctx->groups) {
+        if (g.d_idx) cudaFree(g.d_idx);
+        if (g.d_mass) cudaFree(g.d_mass);
+    }
+    for (auto &r : ctx->refs)
+        if (r.d_pc) cudaFree(r.d_pc);
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int groan_gpu_set_flags(groan_gpu_ctx *ctx, unsigned flags) {
+    if (!ctx) return GROAN_EINVAL;
+    ctx->flags = flags;
+    return GROAN_OK;
+}
+
+int groan_gpu_set_stream(groan_gpu_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return GROAN_EINVAL;
+    CK(cudaStreamSynchronize(ctx->compute));
+    ctx->compute = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_compute;
+    return GROAN_OK;
+}
+
+int groan_gpu_sync(groan_gpu_ctx *ctx) {
+    if (!ctx) return GROAN_EINVAL;
+    CK(cudaStreamSynchronize(ctx->copy));
+    CK(cudaStreamSynchronize(ctx->compute));
+    return GROAN_OK;
+}
+
+const char *groan_gpu_strerror(int status) {
+    switch (status) {
+    case GROAN_OK: return "ok";
+    case GROAN_ENOBOX: return "system has no simulation box";
+    case GROAN_ENOTORTHO: return "simulation box is not orthogonal";
+    case GROAN_EEMPTY: return "group is empty";
+    case GROAN_ENOPOS: return "atom has no position";
+    case GROAN_ENOMASS: return "atom has no mass";
+    case GROAN_EGROUPSIZE: return "group has an inconsistent number of atoms in reference and target";
+    case GROAN_EZEROBOX: return "box length is zero";
+    case GROAN_ENOGROUP: return "group does not exist";
+    case GROAN_EINVAL: return "invalid argument";
+    case GROAN_ECUDA: return "CUDA runtime failure";
+    case GROAN_ENOFRAMES: return "no frames pushed or attached";
+    case GROAN_ENOREF: return "RMSD reference not set";
+    case GROAN_ECAPACITY: return "more frames than the ctx was created for";
+    default: return "unknown status";
+    }
+}
+
+const char *groan_gpu_last_cuda_error(groan_gpu_ctx *ctx) { return ctx ? ctx->cuda_err.c_str() : ""; }
+
+int groan_gpu_error_detail(groan_gpu_ctx *ctx, size_t *a, size_t *b) {
+    if (!ctx) return GROAN_EINVAL;
+    if (a) *a = ctx->err_a;
+    if (b) *b = ctx->err_b;
+    return GROAN_OK;
+}
+
+uint64_t groan_gpu_launch_count(groan_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- groups ---------------------------------------------------------------------------------------
+int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t n, const float *mass) {
+    if (!ctx || gid < 0 || gid >= GROAN_MAX_GROUPS || (n && !idx)) return GROAN_EINVAL;
+    for (size_t i = 0; i < n; i++) {
+        if (idx[i] >= ctx->n_atoms) return GROAN_EINVAL;
+        if (i && idx[i] <= idx[i - 1]) return GROAN_EINVAL;  // container.rs:51-115: sorted, unique
+    }
+    Group &g = ctx->groups[gid];
+    CK(cudaStreamSynchronize(ctx->compute));
+    if (g.d_idx) { cudaFree(g.d_idx); g.d_idx = nullptr; }
+    if (g.d_mass) { cudaFree(g.d_mass); g.d_mass = nullptr; }
+    if (ctx->refs[gid].d_pc) { cudaFree(ctx->refs[gid].d_pc); ctx->refs[gid].d_pc = nullptr; }
+    ctx->refs[gid].set = false;
+    g.set = true;
+    g.n = n;
+    g.idx.assign(idx, idx + n);
+    g.contiguous = true;
+    g.first = n ? idx[0] : 0;
+    for (size_t i = 0; i < n; i++)
+        if (idx[i] != g.first + i) { g.contiguous = false; break; }
+    g.has_mass = (mass != nullptr);
+    g.no_mass_at = -1;
+    if (n) {
+        CK(cudaMalloc(&g.d_idx, n * sizeof(uint32_t)));
+        CK(cudaMemcpy(g.d_idx, idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (mass) {
+            for (size_t i = 0; i < n; i++)
+                if (mass[i] < 0.0f) { g.no_mass_at = (long)i; break; }
+            CK(cudaMalloc(&g.d_mass, n * sizeof(float)));
+            CK(cudaMemcpy(g.d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    if (g.contiguous) g.idx.clear();
+    return GROAN_OK;
+}
+
+// ---- frames ---------------------------------------------------------------------------------------
+int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box, size_t n_frames) {
+    if (!ctx || !xyz) return GROAN_EINVAL;
+    int rc = begin_batch(ctx, n_frames, box, true);
+    if (rc) return rc;
+    ctx->attached = false;
+    float *dst = ctx->d_slot[ctx->slot];
+    ctx->cur_xyz = dst;
+    const size_t bytes = n_frames * ctx->n_atoms * 3 * sizeof(float);
+    if (classify(xyz) != PK_PAGEABLE) {
+        CK(cudaMemcpyAsync(dst, xyz, bytes, cudaMemcpyDefault, ctx->copy));
+    } else {
+        // pageable source: bounce through two pinned chunks so that the host memcpy of chunk i+1 overlaps the DMA of chunk i
+        for (int s = 0; s < 2; s++)
+            if (!ctx->h_stage[s]) CK(cudaMallocHost(&ctx->h_stage[s], kStageBytes));
+        size_t off = 0;
+        int s = 0;
+        while (off < bytes) {
+            const size_t chunk = std::min(kStageBytes, bytes - off);
+            CK(cudaEventSynchronize(ctx->ev_stage[s]));
+            std::memcpy(ctx->h_stage[s], reinterpret_cast<const char *>(xyz) + off, chunk);
+            CK(cudaMemcpyAsync(reinterpret_cast<char *>(dst) + off, ctx->h_stage[s], chunk, cudaMemcpyHostToDevice, ctx->copy));
+            CK(cudaEventRecord(ctx->ev_stage[s], ctx->copy));
+            off += chunk;
+            s ^= 1;
+        }
+    }
+    return end_batch(ctx);
+}
+
+int groan_gpu_attach_frames(groan_gpu_ctx *ctx, float *d_xyz, const float *box, size_t n_frames) {
+    if (!ctx || !d_xyz || classify(d_xyz) != PK_DEVICE) return GROAN_EINVAL;
+    int rc = begin_batch(ctx, n_frames, box, false);
+    if (rc) return rc;
+    ctx->attached = true;
+    ctx->cur_xyz = d_xyz;
+    return end_batch(ctx);
+}
+
+int groan_gpu_set_valid(groan_gpu_ctx *ctx, const uint8_t *valid) {
+    if (!ctx) return GROAN_EINVAL;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    if (!valid) ctx->valid.clear();
+    else ctx->valid.assign(valid, valid + ctx->n_frames * ctx->n_atoms);
+    return GROAN_OK;
+}
+
+int groan_gpu_get_frames(groan_gpu_ctx *ctx, float *xyz_out) {
+    if (!ctx || !xyz_out) return GROAN_EINVAL;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    return deliver(ctx, xyz_out, ctx->cur_xyz, ctx->n_frames * ctx->n_atoms * 3 * sizeof(float));
+}
+
+// ---- centres --------------------------------------------------------------------------------------
+int groan_gpu_estimate_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out) {
+    const Group *g = nullptr;
+    int rc = check_center_args(ctx, gid, weighted != 0, &g);
+    if (rc) return rc;
+    if (!out) return GROAN_EINVAL;
+    float *d_out = target_of<float>(out, ctx->d_cen);
+    rc = run_trig(ctx, *g, weighted != 0, d_out);
+    if (rc) return rc;
+    return deliver(ctx, out, d_out, ctx->n_frames * 3 * sizeof(float));
+}
+
+int groan_gpu_get_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out) {
+    const Group *g = nullptr;
+    int rc = check_center_args(ctx, gid, weighted != 0, &g);
+    if (rc) return rc;
+    if (!out) return GROAN_EINVAL;
+    float *d_out = target_of<float>(out, ctx->d_cen);
+    rc = run_get_center(ctx, *g, weighted != 0, d_out);
+    if (rc) return rc;
+    return deliver(ctx, out, d_out, ctx->n_frames * 3 * sizeof(float));
+}
+
+int groan_gpu_get_center_naive(groan_gpu_ctx *ctx, int gid, float *out) {
+    if (!ctx || !out) return GROAN_EINVAL;
+    const Group *g = get_group(ctx, gid);
+    if (!g) return GROAN_ENOGROUP;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    if (g->n == 0) return GROAN_EEMPTY;
+    int rc = check_positions(ctx, *g);
+    if (rc) return rc;
+    float *d_out = target_of<float>(out, ctx->d_cen);
+    const int nb = blocks_per_frame(g->n, ctx->n_frames);
+    dim3 grid(nb, (unsigned)ctx->n_frames);
+    k_naive<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_out);
+    LAUNCHED();
+    return deliver(ctx, out, d_out, ctx->n_frames * 3 * sizeof(float));
+}
+
+// ---- distances ------------------------------------------------------------------------------------
+int groan_gpu_group_distance(groan_gpu_ctx *ctx, int g1, int g2, int dim, float *out) {
+    if (!ctx || !out || dim < 0 || dim > 7) return GROAN_EINVAL;
+    const Group *a = nullptr, *b = nullptr;
+    int rc = check_center_args(ctx, g1, false, &a);  // group_get_center(group1)? then group2 (analysis.rs:353-354)
+    if (rc) return rc;
+    rc = check_center_args(ctx, g2, false, &b);
+    if (rc) return rc;
+    rc = run_get_center(ctx, *a, false, ctx->d_cen);
+    if (rc) return rc;
+    rc = run_get_center(ctx, *b, false, ctx->d_cen2);
+    if (rc) return rc;
+    float *d_out = target_of<float>(out, ctx->d_res);
+    const unsigned F = (unsigned)ctx->n_frames;
+    k_center_distance<<<(F + 127) / 128, 128, 0, ctx->compute>>>(ctx->d_cen, ctx->d_cen2, frames_of(ctx), dim, (int)F, d_out);
+    LAUNCHED();
+    return deliver(ctx, out, d_out, F * sizeof(float));
+}
+
+int groan_gpu_all_distances(groan_gpu_ctx *ctx, int g1, int g2, int dim, float *out) {
+    if (!ctx || dim < 0 || dim > 7) return GROAN_EINVAL;
+    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
+    if (!a || !b) return GROAN_ENOGROUP;  // group_get_n_atoms (analysis.rs:407-408)
+    bool tric = false;
+    int rc = check_box(ctx, true, &tric);
+    if (rc) return rc;
+    if (a->n == 0 || b->n == 0) return GROAN_OK;  // empty matrix, not an error (analysis.rs:412)
+    if (!out) return GROAN_EINVAL;
+    rc = check_pair_positions(ctx, *a, *b);
+    if (rc) return rc;
+    const size_t bytes = ctx->n_frames * a->n * b->n * sizeof(float);
+    float *d_out = out;
+    if (classify(out) != PK_DEVICE) {
+        rc = ensure_tmp(ctx, bytes);
+        if (rc) return rc;
+        d_out = (float *)ctx->d_tmp;
+    }
+    rc = tric ? dispatch_pairs<BoxTric>(ctx, dim, *a, *b, d_out) : dispatch_pairs<BoxOrtho>(ctx, dim, *a, *b, d_out);
+    if (rc) return rc;
+    return deliver(ctx, out, d_out, bytes);
+}
+
+int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, float cutoff, float *dmin, uint32_t *imin,
+                                   float *dmax, uint32_t *imax, uint64_t *count) {
+    if (!ctx || dim < 0 || dim > 7) return GROAN_EINVAL;
+    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
+    if (!a || !b) return GROAN_ENOGROUP;
+    bool tric = false;
+    int rc = check_box(ctx, true, &tric);
+    if (rc) return rc;
+    if (a->n == 0 || b->n == 0) return GROAN_EEMPTY;  // min/max of an empty matrix: Option::unwrap panics in the documented consumer
+    rc = check_pair_positions(ctx, *a, *b);
+    if (rc) return rc;
+    const size_t F = ctx->n_frames;
+    // scratch layout inside d_res (8 floats per frame): dmin | dmax | imin(2) | imax(2) | count(u64)
+    float *s = ctx->d_res;
+    ReduceOut o;
+    o.dmin = target_of<float>(dmin, s);
+    o.dmax = target_of<float>(dmax, s + F);
+    o.imin = target_of<uint32_t>(imin, (uint32_t *)(s + 2 * F));
+    o.imax = target_of<uint32_t>(imax, (uint32_t *)(s + 4 * F));
+    o.count = target_of<unsigned long long>(count, (unsigned long long *)(s + 6 * F));
+    rc = tric ? dispatch_pairs_reduce<BoxTric>(ctx, dim, *a, *b, cutoff, o) : dispatch_pairs_reduce<BoxOrtho>(ctx, dim, *a, *b, cutoff, o);
+    if (rc) return rc;
+    if ((rc = deliver(ctx, dmin, o.dmin, F * sizeof(float)))) return rc;
+    if ((rc = deliver(ctx, dmax, o.dmax, F * sizeof(float)))) return rc;
+    if ((rc = deliver(ctx, imin, o.imin, F * 2 * sizeof(uint32_t)))) return rc;
+    if ((rc = deliver(ctx, imax, o.imax, F * 2 * sizeof(uint32_t)))) return rc;
+    return deliver(ctx, count, o.count, F * sizeof(uint64_t));
+}
+
+// ---- wrap / translate -----------------------------------------------------------------------------
+int groan_gpu_wrap(groan_gpu_ctx *ctx, int gid, int8_t *shifts) {
+    const Group *g = nullptr;
+    bool tric = false;
+    int rc = check_wrap_args(ctx, gid, &g, &tric);
+    if (rc) return rc;
+    if (g->n == 0) return GROAN_OK;
+    return run_wrap(ctx, *g, false, nullptr, shifts, tric);
+}
+
+int groan_gpu_translate(groan_gpu_ctx *ctx, int gid, const float t[3], int8_t *shifts) {
+    if (!t) return GROAN_EINVAL;
+    const Group *g = nullptr;
+    bool tric = false;
+    int rc = check_wrap_args(ctx, gid, &g, &tric);
+    if (rc) return rc;
+    if (g->n == 0) return GROAN_OK;
+    return run_wrap(ctx, *g, true, t, shifts, tric);
+}
+
+// ---- RMSD -----------------------------------------------------------------------------------------
+int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_xyz, size_t n_ref_atoms, const uint32_t *ref_idx,
+                                 size_t n_ref, const float ref_box[9], const float *ref_mass) {
+    if (!ctx || !ref_xyz || gid < 0 || gid >= GROAN_MAX_GROUPS) return GROAN_EINVAL;
+    const Group *g = get_group(ctx, gid);
+    if (!g) return GROAN_ENOGROUP;
+    if (!ref_box) return GROAN_ENOBOX;  // get_box_center (mod.rs:298-308) comes first in extract_data_from_system
+    if (ref_box[1] != 0.0f || ref_box[2] != 0.0f || ref_box[5] != 0.0f) return GROAN_EINVAL;
+    if (ref_box[3] != 0.0f || ref_box[6] != 0.0f || ref_box[7] != 0.0f) return GROAN_ENOTORTHO;
+    if (ref_box[0] == 0.0f || ref_box[4] == 0.0f || ref_box[8] == 0.0f) return GROAN_EZEROBOX;
+    if (n_ref == 0) return GROAN_EEMPTY;
+    if (!ref_idx) return GROAN_EINVAL;
+    for (size_t i = 0; i < n_ref; i++) {
+        if (ref_idx[i] >= n_ref_atoms) return GROAN_EINVAL;
+        if (i && ref_idx[i] <= ref_idx[i - 1]) return GROAN_EINVAL;
+    }
+    int rc = GROAN_OK;
+    if (ref_mass) {
+        // masses of the REFERENCE system's group: reference.group_get_com and the Kabsch weights (rmsd.rs:154,192)
+        for (size_t i = 0; i < n_ref; i++)
+            if (ref_mass[i] < 0.0f) {
+                ctx->err_a = 0;
+                ctx->err_b = ref_idx[i];
+                return GROAN_ENOMASS;
+            }
+    } else {
+        rc = check_masses(ctx, *g);
+        if (rc) return rc;
+        if (n_ref != g->n) {  // borrowing the target group's masses needs equal sizes
+            ctx->err_a = n_ref;
+            ctx->err_b = g->n;
+            return GROAN_EGROUPSIZE;
+        }
+    }
+    groan_gpu_ctx::Ref &R = ctx->refs[gid];
+    CK(cudaStreamSynchronize(ctx->compute));
+    if (R.d_pc) { cudaFree(R.d_pc); R.d_pc = nullptr; }
+    R.set = false;
+    float *d_ref = nullptr, *d_refbox = nullptr, *d_small = nullptr, *d_rmass = nullptr;
+    uint32_t *d_ridx = nullptr;
+    double *d_sums = nullptr;
+    rc = [&]() -> int {
+        CK(cudaMalloc(&d_ref, n_ref_atoms * 3 * sizeof(float)));
+        CK(cudaMalloc(&d_refbox, 9 * sizeof(float)));
+        CK(cudaMalloc(&d_small, 6 * sizeof(float)));
+        CK(cudaMalloc(&d_ridx, n_ref * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_sums, 2 * sizeof(double)));
+        CK(cudaMalloc(&R.d_pc, n_ref * sizeof(float4)));
+        CK(cudaMemcpyAsync(d_ref, ref_xyz, n_ref_atoms * 3 * sizeof(float), cudaMemcpyDefault, ctx->compute));
+        CK(cudaMemcpyAsync(d_refbox, ref_box, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+        CK(cudaMemcpyAsync(d_ridx, ref_idx, n_ref * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->compute));
+        if (ref_mass) {
+            CK(cudaMalloc(&d_rmass, n_ref * sizeof(float)));
+            CK(cudaMemcpyAsync(d_rmass, ref_mass, n_ref * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+        }
+        FrameView fv;
+        fv.xyz = d_ref;
+        fv.box = d_refbox;
+        fv.n_atoms = n_ref_atoms;
+        GroupView gv;
+        gv.idx = d_ridx;
+        gv.first = 0;
+        gv.n = (uint32_t)n_ref;
+        gv.mass = ref_mass ? d_rmass : g->d_mass;
+        const int nb = blocks_per_frame(n_ref, 1);
+        // reference.group_get_com(group): geometric estimate, then mass-weighted unwrap (iterators.rs:1404-1438)
+        k_trig<false><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, ctx->d_partials, ctx->d_tickets + ctx->max_frames, d_small);
+        LAUNCHED();
+        k_unwrap<true><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small, ctx->d_partials, ctx->d_tickets + ctx->max_frames,
+                                                                    d_small + 3);
+        LAUNCHED();
+        k_ref_prepare<<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small + 3, R.d_pc, ctx->d_partials,
+                                                                   ctx->d_tickets + ctx->max_frames, d_sums);
+        LAUNCHED();
+        double sums[2];
+        CK(cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaMemcpyAsync(R.com, d_small + 3, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaStreamSynchronize(ctx->compute));
+        R.sum_mpp = sums[0];
+        R.sum_m = sums[1];
+        return GROAN_OK;
+    }();
+    cudaFree(d_ref); cudaFree(d_refbox); cudaFree(d_small); cudaFree(d_ridx); cudaFree(d_sums); cudaFree(d_rmass);
+    if (rc) return rc;
+    R.n = n_ref;
+    R.set = true;
+    return GROAN_OK;
+}
+
+int groan_gpu_rmsd(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot) {
+    if (!rmsd) return GROAN_EINVAL;
+    return rmsd_common(ctx, gid, rmsd, rot, false);
+}
+
+int groan_gpu_rmsd_fit(groan_gpu_ctx *ctx, int gid, float *rmsd) {
+    if (!rmsd) return GROAN_EINVAL;
+    return rmsd_common(ctx, gid, rmsd, nullptr, true);
+}
+
+// ---- synthetic workloads ----------------------------------------------------------------------------
+int groan_gpu_synth_uniform(groan_gpu_ctx *ctx, uint64_t seed, uint64_t frame0, size_t n_frames, const float lo[3],
+                            const float span[3], const float *box) {
+    if (!ctx || !lo || !span) return GROAN_EINVAL;
+    int rc = begin_batch(ctx, n_frames, box, true);
+    if (rc) return rc;
+    ctx->attached = false;
+    ctx->cur_xyz = ctx->d_slot[ctx->slot];
+    rc = end_batch(ctx);
+    if (rc) return rc;
+    dim3 grid(kMaxBlocksPerFrame, (unsigned)n_frames);
+    k_synth_uniform<<<grid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->n_atoms, seed, frame0, lo[0], lo[1], lo[2], span[0],
+                                                          span[1], span[2]);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+int groan_gpu_synth_blob(groan_gpu_ctx *ctx, uint64_t seed, uint64_t frame0, size_t n_frames, float scale, float nscale,
+                         const float *rot, const float *centre, const float *box, int wrap) {
+    if (!ctx || !rot || !centre || !box) return GROAN_EINVAL;
+    int rc = begin_batch(ctx, n_frames, box, true);
+    if (rc) return rc;
+    ctx->attached = false;
+    ctx->cur_xyz = ctx->d_slot[ctx->slot];
+    rc = end_batch(ctx);
+    if (rc) return rc;
+    rc = ensure_tmp(ctx, n_frames * 12 * sizeof(float));
+    if (rc) return rc;
+    float *d_rot = (float *)ctx->d_tmp, *d_cen = d_rot + n_frames * 9;
+    CK(cudaMemcpyAsync(d_rot, rot, n_frames * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+    CK(cudaMemcpyAsync(d_cen, centre, n_frames * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+    dim3 grid(kMaxBlocksPerFrame, (unsigned)n_frames);
+    k_synth_blob<<<grid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->n_atoms, seed, frame0, scale, nscale, d_rot, d_cen,
+                                                       ctx->d_box[ctx->slot], wrap);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+// reference structure of the blob workload (n_atoms x 3), written to a caller buffer (host or device)
+int groan_gpu_synth_blob_ref(groan_gpu_ctx *ctx, uint64_t seed, float scale, const float centre[3], float *xyz_out) {
+    if (!ctx || !centre || !xyz_out) return GROAN_EINVAL;
+    const size_t bytes = ctx->n_atoms * 3 * sizeof(float);
+    float *d_out = xyz_out;
+    if (classify(xyz_out) != PK_DEVICE) {
+        int rc = ensure_tmp(ctx, bytes);
+        if (rc) return rc;
+        d_out = (float *)ctx->d_tmp;
+    }
+    k_synth_blob_ref<<<kMaxBlocksPerFrame, kThreads, 0, ctx->compute>>>(d_out, ctx->n_atoms, seed, scale, centre[0], centre[1],
+                                                                         centre[2]);
+    LAUNCHED();
+    return deliver(ctx, xyz_out, d_out, bytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// kernels_synth.cuh -- deterministic synthetic workloads, generated on the device.
+//
+// Bit-identical to oracle/groan_oracle.c (orc_synth_uniform / orc_synth_blob_ref / orc_synth_blob_frame):
+// counter-based splitmix64 keyed by (seed, frame, atom, axis), integer -> f32 conversions that are
+// exact, and f32 arithmetic without FMA contraction (the library is built with -fmad=false).
+// BASELINE.json configs 4 and 5 cannot be stored (4.8 TB of frames), so they are generated per batch.
+#pragma once
+#include "common.cuh"
+
+namespace groan {
+
+constexpr uint64_t kRefFrame = 0xFFFFFFFFULL;
+
+__device__ __forceinline__ uint64_t atom_hash(uint64_t key, uint64_t atom, uint64_t axis) {
+    return splitmix64(key + 4 * atom + axis);
+}
+// Irwin-Hall(4) of the four 16-bit fields of one hash: integer in [-131070, 131070], exact in f32
+__device__ __forceinline__ float ih4(uint64_t h) {
+    const int k = (int)(h & 0xFFFF) + (int)((h >> 16) & 0xFFFF) + (int)((h >> 32) & 0xFFFF) + (int)((h >> 48) & 0xFFFF);
+    return (float)(k - 131070);
+}
+
+// x = lo + u * span, u = (hash >> 40) * 2^-24
+__global__ void __launch_bounds__(kThreads) k_synth_uniform(float *xyz, size_t n_atoms, uint64_t seed, uint64_t frame0,
+                                                             float lox, float loy, float loz, float spx, float spy, float spz) {
+    const int f = blockIdx.y;
+    const uint64_t key = frame_key(seed, frame0 + (uint64_t)f);
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    const size_t total = n_atoms * 3;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / 3;
+        const int k = (int)(e - i * 3);
+        const float u = (float)(atom_hash(key, i, (uint64_t)k) >> 40) * 0x1p-24f;
+        const float lo = k == 0 ? lox : (k == 1 ? loy : loz);
+        const float sp = k == 0 ? spx : (k == 1 ? spy : spz);
+        const float t = u * sp;
+        fr[e] = lo + t;
+    }
+}
+
+// reference structure of the blob: p_i * scale + centre
+__global__ void __launch_bounds__(kThreads) k_synth_blob_ref(float *xyz, size_t n_atoms, uint64_t seed, float scale, float cx,
+                                                              float cy, float cz) {
+    const uint64_t key = frame_key(seed, kRefFrame);
+    const size_t total = n_atoms * 3;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / 3;
+        const int k = (int)(e - i * 3);
+        const float p = ih4(atom_hash(key, i, (uint64_t)k)) * scale;
+        xyz[e] = p + (k == 0 ? cx : (k == 1 ? cy : cz));
+    }
+}
+
+// frame f: x = R_f * p_i + c_f + noise_{f,i}, optionally folded once into [0, L]
+__global__ void __launch_bounds__(kThreads) k_synth_blob(float *xyz, size_t n_atoms, uint64_t seed, uint64_t frame0, float scale,
+                                                          float nscale, const float *rot, const float *centre, const float *box,
+                                                          int wrap) {
+    const int f = blockIdx.y;
+    const uint64_t kref = frame_key(seed, kRefFrame);
+    const uint64_t key = frame_key(seed, frame0 + (uint64_t)f);
+    float r[9], c[3], L[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = rot[f * 9 + k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c[k] = centre[f * 3 + k]; L[k] = box[f * 9 + 4 * k]; }
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_atoms; i += (size_t)gridDim.x * blockDim.x) {
+        float p[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = ih4(atom_hash(kref, i, (uint64_t)k)) * scale;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float t0 = r[k * 3 + 0] * p[0], t1 = r[k * 3 + 1] * p[1], t2 = r[k * 3 + 2] * p[2];
+            float s = (t0 + t1) + t2;
+            s = s + c[k];
+            const float nz = ih4(atom_hash(key, i, (uint64_t)k)) * nscale;
+            s = s + nz;
+            if (wrap) {
+                if (s < 0.0f) s = s + L[k];
+                else if (s > L[k]) s = s - L[k];
+            }
+            fr[i * 3 + k] = s;
+        }
+    }
+}
+
+} // namespace groan

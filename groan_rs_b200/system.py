@@ -1,0 +1,518 @@
+"""Host-side mirror of groan_rs's System / Group / SimBox / Dimension surface for the PBC geometry hot path.
+
+Same method names, argument meaning and error behaviour as the reference (citations per method), but
+every analysis method evaluates ALL frames of the current batch on the GPU and returns an array with a
+leading frame axis.  Everything here is plumbing around the C ABI (include/groan_gpu.h): argument
+marshalling, group bookkeeping, error translation.  No arithmetic of the hot path happens in Python and
+there is no CPU fallback.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------------------------- errors
+class GroanError(Exception):
+    """Base of the mirrored error enums; `variant` names the reference's enum variant."""
+
+    def __init__(self, variant, message, status=None, detail=None):
+        super().__init__("%s: %s" % (variant, message))
+        self.variant = variant
+        self.status = status
+        self.detail = detail
+
+
+class GroupError(GroanError):  # src/errors.rs GroupError
+    pass
+
+
+class SimBoxError(GroanError):  # src/errors.rs:556-582
+    pass
+
+
+class PositionError(GroanError):  # src/errors.rs:227-258
+    pass
+
+
+class MassError(GroanError):  # src/errors.rs:290-305
+    pass
+
+
+class RMSDError(GroanError):  # src/errors.rs:624-650
+    pass
+
+
+class GpuError(GroanError):
+    pass
+
+
+class Dimension(enum.IntEnum):
+    """src/structures/dimension.rs:15-25"""
+    None_ = 0
+    X = 1
+    Y = 2
+    Z = 3
+    XY = 4
+    XZ = 5
+    YZ = 6
+    XYZ = 7
+
+    @classmethod
+    def from_bools(cls, x, y, z):  # dimension.rs From<[bool;3]>
+        return {(0, 0, 0): cls.None_, (1, 0, 0): cls.X, (0, 1, 0): cls.Y, (0, 0, 1): cls.Z, (1, 1, 0): cls.XY,
+                (1, 0, 1): cls.XZ, (0, 1, 1): cls.YZ, (1, 1, 1): cls.XYZ}[(int(bool(x)), int(bool(y)), int(bool(z)))]
+
+
+class SimBox:
+    """src/structures/simbox.rs:13-52.  Nine floats in GROMACS order v1x v2y v3z v1y v1z v2x v2z v3x v3y."""
+
+    def __init__(self, values):
+        v = np.asarray(values, dtype=np.float32).reshape(-1)
+        if v.size == 3:
+            v = np.concatenate([v, np.zeros(6, np.float32)])
+        if v.size != 9:
+            raise ValueError("SimBox takes 3 or 9 floats")
+        if v[3] != 0 or v[4] != 0 or v[6] != 0:  # simbox.rs:28-52 panics
+            raise ValueError("SimBox: v1y, v1z and v2z must be zero")
+        self.v = v.astype(np.float32)
+
+    @classmethod
+    def from_matrix(cls, m):
+        """io/xdrfile.rs:170-187: row-major 3x3, box[i][j] = component j of box vector i"""
+        m = np.asarray(m, dtype=np.float32).reshape(3, 3)
+        return cls([m[0, 0], m[1, 1], m[2, 2], m[0, 1], m[0, 2], m[1, 0], m[1, 2], m[2, 0], m[2, 1]])
+
+    def matrix(self):
+        v = self.v
+        return np.array([v[0], v[3], v[4], v[5], v[1], v[6], v[7], v[8], v[2]], dtype=np.float32)
+
+    @property
+    def x(self):
+        return self.v[0]
+
+    @property
+    def y(self):
+        return self.v[1]
+
+    @property
+    def z(self):
+        return self.v[2]
+
+    def is_orthogonal(self):  # simbox.rs:185
+        return self.v[5] == 0 and self.v[7] == 0 and self.v[8] == 0
+
+
+def _boxes_to_matrices(boxes, n_frames):
+    """Accepts None, a SimBox, [3], [9] (row-major matrix), [3,3], [F,3], [F,9], [F,3,3]; returns F x 9 f32 or None."""
+    if boxes is None:
+        return None
+    if isinstance(boxes, SimBox):
+        return np.ascontiguousarray(np.tile(boxes.matrix(), (n_frames, 1)), dtype=np.float32)
+    b = np.asarray(boxes, dtype=np.float32)
+    if b.ndim == 1 and b.size == 3:
+        b = np.tile(b, (n_frames, 1))
+    elif b.ndim == 1 and b.size == 9:
+        b = np.tile(b, (n_frames, 1))
+    elif b.ndim == 2 and b.shape == (3, 3) and n_frames != 3:
+        b = np.tile(b.reshape(1, 9), (n_frames, 1))
+    if b.ndim == 3:
+        b = b.reshape(b.shape[0], 9)
+    if b.shape[0] != n_frames:
+        raise ValueError("boxes: expected %d frames, got %r" % (n_frames, b.shape))
+    if b.shape[1] == 3:
+        m = np.zeros((n_frames, 9), np.float32)
+        m[:, 0], m[:, 4], m[:, 8] = b[:, 0], b[:, 1], b[:, 2]
+        b = m
+    return np.ascontiguousarray(b, dtype=np.float32)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+class Group:
+    """src/structures/group.rs, container.rs:51-115: sorted, de-duplicated atom indices; iteration ascending."""
+
+    def __init__(self, indices, n_atoms):
+        idx = np.unique(np.asarray(indices, dtype=np.int64).reshape(-1))
+        if idx.size and (idx[0] < 0 or idx[-1] >= n_atoms):
+            raise ValueError("group index out of range")
+        self.indices = np.ascontiguousarray(idx, dtype=np.uint32)
+        self.gid = None
+
+    def __len__(self):
+        return int(self.indices.size)
+
+
+class System:
+    """A molecular system whose per-frame PBC geometry runs on one B200 (src/system/mod.rs:38-73).
+
+    Frames are given in batches (`set_frames`, the FrameData::update_system tap of xdrfile_xtc.rs:88-104);
+    every analysis method returns one result per frame.
+    """
+
+    def __init__(self, n_atoms, masses=None, device=0, max_frames=1, triclinic=False):
+        self.n_atoms = int(n_atoms)
+        self.max_frames = int(max_frames)
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        self._check(self._lib.groan_gpu_create(int(device), self.n_atoms, self.max_frames, C.byref(h)), "create")
+        self._h = h
+        self.device = int(device)
+        self.masses = None if masses is None else np.ascontiguousarray(masses, dtype=np.float32)
+        self._groups = {}
+        self._next_gid = 0
+        self.n_frames = 0
+        self._host_frames = None
+        self._boxes = None
+        self._version = 0
+        self._ref_cache = {}
+        self._keep = []
+        if triclinic:
+            self.set_flags(_lib.FLAG_TRICLINIC)
+
+    # ------------------------------------------------------------------ lifetime / errors
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.groan_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_flags(self, flags):
+        self._check(self._lib.groan_gpu_set_flags(self._h, int(flags)), "set_flags")
+
+    def set_stream(self, cuda_stream):
+        """Run all kernels on a caller-owned CUDA stream (an int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.groan_gpu_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)), "set_stream")
+
+    def sync(self):
+        self._check(self._lib.groan_gpu_sync(self._h), "sync")
+
+    def launch_count(self):
+        return int(self._lib.groan_gpu_launch_count(self._h))
+
+    def _detail(self):
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        self._lib.groan_gpu_error_detail(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def _check(self, st, what, group=None, rmsd=False):
+        if st == _lib.OK:
+            return
+        msg = _lib.strerror(st)
+        L = _lib
+        if st == L.ECUDA:
+            raise GpuError("CudaError", self._lib.groan_gpu_last_cuda_error(self._h).decode(), st)
+        if st in (L.ENOBOX, L.ENOTORTHO, L.EZEROBOX):
+            variant = {L.ENOBOX: "SimBoxError::DoesNotExist", L.ENOTORTHO: "SimBoxError::NotOrthogonal",
+                       L.EZEROBOX: "panic: Box len should not be zero"}[st]
+            outer = RMSDError if rmsd else (GroupError if group is not None else SimBoxError)
+            e = outer("InvalidSimBox(%s)" % variant, msg, st)
+            e.inner = SimBoxError(variant, msg, st)
+            raise e
+        if st == L.EEMPTY:
+            raise (RMSDError if rmsd else GroupError)("EmptyGroup", "%s (%s)" % (msg, group), st)
+        if st == L.ENOGROUP:
+            raise (RMSDError("NonexistentGroup", "%s (%s)" % (msg, group), st) if rmsd
+                   else GroupError("NotFound", "%s (%s)" % (msg, group), st))
+        if st == L.ENOPOS:
+            f, a = self._detail()
+            e = (RMSDError if rmsd else GroupError)("InvalidPosition(PositionError::NoPosition(%d))" % a, msg, st, (f, a))
+            e.inner = PositionError("NoPosition", "atom %d has no position (frame %d)" % (a, f), st, (f, a))
+            raise e
+        if st == L.ENOMASS:
+            f, a = self._detail()
+            e = (RMSDError if rmsd else GroupError)("InvalidMass(MassError::NoMass(%d))" % a, msg, st, (f, a))
+            e.inner = MassError("NoMass", "atom %d has no mass" % a, st, (f, a))
+            raise e
+        if st == L.EGROUPSIZE:
+            a, b = self._detail()
+            raise RMSDError("InconsistentGroup", "%s: %d atoms in reference, %d in target (%s)" % (msg, a, b, group), st, (a, b))
+        raise GpuError({L.EINVAL: "InvalidArgument", L.ENOFRAMES: "NoFrames", L.ENOREF: "NoReference",
+                        L.ECAPACITY: "Capacity"}.get(st, "Unknown"), "%s in %s" % (msg, what), st)
+
+    # ------------------------------------------------------------------ groups (src/system/groups.rs)
+    def group_create_from_indices(self, name, indices):
+        """Group::from_indices (group.rs:94): sorted + de-duplicated.  Re-creating a name overwrites it."""
+        g = Group(indices, self.n_atoms)
+        if name in self._groups:
+            g.gid = self._groups[name].gid
+        else:
+            if self._next_gid >= _lib.MAX_GROUPS:
+                raise GpuError("Capacity", "too many groups")
+            g.gid = self._next_gid
+            self._next_gid += 1
+        gm = None
+        if self.masses is not None:
+            gm = np.ascontiguousarray(self.masses[g.indices.astype(np.int64)], dtype=np.float32)
+            gm = np.where(np.isnan(gm), np.float32(-1.0), gm).astype(np.float32)
+        g.mass = gm
+        self._check(self._lib.groan_gpu_set_group(self._h, g.gid, _ptr(g.indices) if len(g) else None, len(g),
+                                                  _ptr(gm) if gm is not None and len(g) else None), "set_group", name)
+        self._groups[name] = g
+        self._ref_cache = {k: v for k, v in self._ref_cache.items() if k[1] != name}
+        return g
+
+    def group_create_from_ranges(self, name, ranges):
+        """container.rs:13-31: inclusive (start, end) ranges"""
+        idx = np.concatenate([np.arange(a, b + 1) for a, b in ranges]) if ranges else np.zeros(0, np.int64)
+        return self.group_create_from_indices(name, idx)
+
+    def group_exists(self, name):
+        return name in ("all", "All") or name in self._groups
+
+    def group_get_n_atoms(self, name):
+        return self.n_atoms if name in ("all", "All") and name not in self._groups else len(self._group(name))
+
+    def group_isempty(self, name):
+        return self.group_get_n_atoms(name) == 0
+
+    def _group(self, name, rmsd=False):
+        if name not in self._groups:
+            if rmsd:
+                raise RMSDError("NonexistentGroup", name, _lib.ENOGROUP)
+            raise GroupError("NotFound", name, _lib.ENOGROUP)
+        return self._groups[name]
+
+    def _gid(self, name, rmsd=False):
+        if name in ("all", "All") and name not in self._groups:
+            return _lib.GROUP_ALL
+        return self._group(name, rmsd).gid
+
+    # ------------------------------------------------------------------ frames
+    def set_frames(self, xyz, boxes):
+        """Stage a batch: xyz [F, N, 3] (or [N, 3]) f32 as read_xtc emits; boxes per frame (see _boxes_to_matrices).
+
+        numpy / pinned torch input is copied host->device on the copy stream (overlapping kernels still running on
+        the previous batch); a CUDA torch tensor is attached zero-copy and modified in place by wrap / fit.
+        """
+        if _is_torch(xyz):
+            t = xyz if xyz.dim() == 3 else xyz.unsqueeze(0)
+            if str(t.dtype) != "torch.float32" or not t.is_contiguous():
+                raise ValueError("frames must be contiguous float32")
+            F = int(t.shape[0])
+            if tuple(t.shape[1:]) != (self.n_atoms, 3):
+                raise ValueError("frames must be [F, %d, 3]" % self.n_atoms)
+            bm = _boxes_to_matrices(boxes, F)
+            fn = self._lib.groan_gpu_attach_frames if t.is_cuda else self._lib.groan_gpu_push_frames
+            self._check(fn(self._h, _ptr(t), _ptr(bm), F), "set_frames")
+            self._keep = [t]
+            self._host_frames = None
+        else:
+            a = np.ascontiguousarray(xyz, dtype=np.float32)
+            if a.ndim == 2:
+                a = a[None]
+            F = int(a.shape[0])
+            if a.shape[1:] != (self.n_atoms, 3):
+                raise ValueError("frames must be [F, %d, 3]" % self.n_atoms)
+            bm = _boxes_to_matrices(boxes, F)
+            self._check(self._lib.groan_gpu_push_frames(self._h, _ptr(a), _ptr(bm), F), "set_frames")
+            self._host_frames = a
+            self._keep = [a]
+        self.n_frames = F
+        self._boxes = bm
+        self._version += 1
+
+    def set_valid(self, valid):
+        """Option<Vector3D> positions (atom.rs:23-71): valid[f, i] == 0 means atom i has no position in frame f."""
+        v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8).reshape(self.n_frames, self.n_atoms)
+        self._check(self._lib.groan_gpu_set_valid(self._h, _ptr(v)), "set_valid")
+
+    def get_frames(self, out=None):
+        if out is None:
+            out = np.empty((self.n_frames, self.n_atoms, 3), np.float32)
+        self._check(self._lib.groan_gpu_get_frames(self._h, _ptr(out)), "get_frames")
+        return out
+
+    def synth_uniform(self, seed, frame0, n_frames, lo, span, boxes):
+        bm = _boxes_to_matrices(boxes, n_frames)
+        lo3 = (C.c_float * 3)(*[float(v) for v in lo])
+        sp3 = (C.c_float * 3)(*[float(v) for v in span])
+        self._check(self._lib.groan_gpu_synth_uniform(self._h, seed, frame0, n_frames, lo3, sp3, _ptr(bm)), "synth_uniform")
+        self.n_frames, self._boxes, self._host_frames = n_frames, bm, None
+        self._version += 1
+
+    def synth_blob(self, seed, frame0, n_frames, scale, nscale, rot, centre, boxes, wrap=True):
+        bm = _boxes_to_matrices(boxes, n_frames)
+        r = np.ascontiguousarray(rot, dtype=np.float32).reshape(n_frames, 9)
+        c = np.ascontiguousarray(centre, dtype=np.float32).reshape(n_frames, 3)
+        self._check(self._lib.groan_gpu_synth_blob(self._h, seed, frame0, n_frames, scale, nscale, _ptr(r), _ptr(c), _ptr(bm),
+                                                   1 if wrap else 0), "synth_blob")
+        self.n_frames, self._boxes, self._host_frames = n_frames, bm, None
+        self._version += 1
+
+    def synth_blob_ref(self, seed, scale, centre, out=None):
+        if out is None:
+            out = np.empty((self.n_atoms, 3), np.float32)
+        c3 = (C.c_float * 3)(*[float(v) for v in centre])
+        self._check(self._lib.groan_gpu_synth_blob_ref(self._h, seed, scale, c3, _ptr(out)), "synth_blob_ref")
+        return out
+
+    def get_box_center(self):
+        """System::get_box_center (mod.rs:298-308), per frame"""
+        if self._boxes is None:
+            raise SimBoxError("SimBoxError::DoesNotExist", "no box", _lib.ENOBOX)
+        b = self._boxes
+        if np.any(b[:, [3, 6, 7]] != 0):
+            raise SimBoxError("SimBoxError::NotOrthogonal", "box not orthogonal", _lib.ENOTORTHO)
+        return np.stack([b[:, 0] / np.float32(2), b[:, 4] / np.float32(2), b[:, 8] / np.float32(2)], axis=1)
+
+    # ------------------------------------------------------------------ outputs
+    def _out(self, out, shape, dtype=np.float32):
+        if out is None:
+            return np.empty(shape, dtype)
+        return out
+
+    # ------------------------------------------------------------------ centres (src/system/analysis.rs)
+    def group_estimate_center(self, name, out=None):
+        """analysis.rs:52 -> iterators.rs:1152-1191 (plain Bai-Breen)"""
+        out = self._out(out, (self.n_frames, 3))
+        self._check(self._lib.groan_gpu_estimate_center(self._h, self._gid(name), 0, _ptr(out)), "group_estimate_center", name)
+        return out
+
+    def group_estimate_com(self, name, out=None):
+        """iterators.rs:1314-1357"""
+        out = self._out(out, (self.n_frames, 3))
+        self._check(self._lib.groan_gpu_estimate_center(self._h, self._gid(name), 1, _ptr(out)), "group_estimate_com", name)
+        return out
+
+    def group_get_center(self, name, out=None):
+        """analysis.rs:105-120 -> iterators.rs:1237-1266 (refined Bai-Breen)"""
+        out = self._out(out, (self.n_frames, 3))
+        self._check(self._lib.groan_gpu_get_center(self._h, self._gid(name), 0, _ptr(out)), "group_get_center", name)
+        return out
+
+    def group_get_com(self, name, out=None):
+        """analysis.rs:258 -> iterators.rs:1404-1438"""
+        out = self._out(out, (self.n_frames, 3))
+        self._check(self._lib.groan_gpu_get_center(self._h, self._gid(name), 1, _ptr(out)), "group_get_com", name)
+        return out
+
+    def group_get_center_naive(self, name, out=None):
+        """iterators.rs:886-903"""
+        out = self._out(out, (self.n_frames, 3))
+        self._check(self._lib.groan_gpu_get_center_naive(self._h, self._gid(name), _ptr(out)), "group_get_center_naive", name)
+        return out
+
+    # ------------------------------------------------------------------ distances
+    def group_distance(self, group1, group2, dim, out=None):
+        """analysis.rs:348-360"""
+        g1, g2 = self._gid(group1), self._gid(group2)
+        out = self._out(out, (self.n_frames,))
+        self._check(self._lib.groan_gpu_group_distance(self._h, g1, g2, int(dim), _ptr(out)), "group_distance",
+                    "%s/%s" % (group1, group2))
+        return out
+
+    def group_all_distances(self, group1, group2, dim, out=None):
+        """analysis.rs:401-427: [F, n1, n2] row-major"""
+        g1, g2 = self._gid(group1), self._gid(group2)
+        n1, n2 = self.group_get_n_atoms(group1), self.group_get_n_atoms(group2)
+        out = self._out(out, (self.n_frames, n1, n2))
+        self._check(self._lib.groan_gpu_all_distances(self._h, g1, g2, int(dim), _ptr(out) if n1 * n2 else None),
+                    "group_all_distances", "%s/%s" % (group1, group2))
+        return out
+
+    def group_all_distances_reduce(self, group1, group2, dim, cutoff=0.0):
+        """The documented consumer of the matrix (analysis.rs:390-399) fused on the device:
+        returns dict(min, argmin [F,2], max, argmax [F,2], count) without materialising the matrix."""
+        g1, g2 = self._gid(group1), self._gid(group2)
+        F = self.n_frames
+        r = {"min": np.empty(F, np.float32), "argmin": np.empty((F, 2), np.uint32), "max": np.empty(F, np.float32),
+             "argmax": np.empty((F, 2), np.uint32), "count": np.empty(F, np.uint64)}
+        self._check(self._lib.groan_gpu_all_distances_reduce(self._h, g1, g2, int(dim), float(cutoff), _ptr(r["min"]),
+                                                             _ptr(r["argmin"]), _ptr(r["max"]), _ptr(r["argmax"]),
+                                                             _ptr(r["count"])), "group_all_distances_reduce",
+                    "%s/%s" % (group1, group2))
+        return r
+
+    # ------------------------------------------------------------------ wrap / translate (src/system/modifying.rs)
+    def atoms_wrap(self, shifts=False):
+        """modifying.rs:201"""
+        return self.group_wrap("all", shifts)
+
+    def group_wrap(self, name, shifts=False):
+        """modifying.rs:215; shifts=True also returns the int8 image shifts [F, G, 3]"""
+        gid = self._gid(name)
+        sh = np.empty((self.n_frames, self.group_get_n_atoms(name), 3), np.int8) if shifts is True else (shifts or None)
+        self._check(self._lib.groan_gpu_wrap(self._h, gid, _ptr(sh) if sh is not None else None), "group_wrap", name)
+        self._host_frames = None
+        return sh
+
+    def atoms_translate(self, t, shifts=False):
+        """modifying.rs:73"""
+        return self.group_translate("all", t, shifts)
+
+    def group_translate(self, name, t, shifts=False):
+        gid = self._gid(name)
+        t3 = (C.c_float * 3)(*[float(v) for v in t])
+        sh = np.empty((self.n_frames, self.group_get_n_atoms(name), 3), np.int8) if shifts is True else (shifts or None)
+        self._check(self._lib.groan_gpu_translate(self._h, gid, t3, _ptr(sh) if sh is not None else None), "group_translate", name)
+        self._host_frames = None
+        return sh
+
+    # ------------------------------------------------------------------ RMSD (src/system/rmsd.rs)
+    def _frame0(self):
+        if self._host_frames is not None:
+            return self._host_frames[0]
+        return self.get_frames()[0]
+
+    def _set_reference(self, reference, group):
+        key = (id(reference), group, reference._version)
+        if self._ref_cache.get("cur") == key:
+            return
+        # extract_data_from_system(reference) runs first (rmsd.rs:146-147): box, then the group in the REFERENCE
+        if reference._boxes is None:
+            raise RMSDError("InvalidSimBox(SimBoxError::DoesNotExist)", "reference has no box", _lib.ENOBOX)
+        rg = reference._group(group, rmsd=True)
+        gid = self._gid(group, rmsd=True)
+        if gid < 0:
+            raise RMSDError("NonexistentGroup", group, _lib.ENOGROUP)
+        rmass = getattr(rg, "mass", None)
+        if rmass is None and len(rg):
+            e = RMSDError("InvalidMass(MassError::NoMass(%d))" % int(rg.indices[0]), "reference atom has no mass", _lib.ENOMASS)
+            raise e
+        ref_xyz = np.ascontiguousarray(reference._frame0(), dtype=np.float32)
+        ref_box = np.ascontiguousarray(reference._boxes[0], dtype=np.float32)
+        self._check(self._lib.groan_gpu_rmsd_set_reference(self._h, gid, _ptr(ref_xyz), reference.n_atoms,
+                                                           _ptr(rg.indices) if len(rg) else None, len(rg), _ptr(ref_box),
+                                                           _ptr(rmass) if len(rg) else None),
+                    "rmsd_set_reference", group, rmsd=True)
+        self._ref_cache["cur"] = key
+
+    def calc_rmsd(self, reference, group, out=None, rot=None):
+        """System::calc_rmsd / RMSDTrajRead::calc_rmsd (rmsd.rs:75,315): RMSD of every frame to `reference` (its frame 0)."""
+        self._set_reference(reference, group)
+        out = self._out(out, (self.n_frames,))
+        self._check(self._lib.groan_gpu_rmsd(self._h, self._gid(group, True), _ptr(out), _ptr(rot) if rot is not None else None),
+                    "calc_rmsd", group, rmsd=True)
+        return out
+
+    def calc_rmsd_and_fit(self, reference, group, out=None):
+        """System::calc_rmsd_and_fit (rmsd.rs:129; fit_structure :508-528): also fits ALL atoms of every frame in place."""
+        self._set_reference(reference, group)
+        out = self._out(out, (self.n_frames,))
+        self._check(self._lib.groan_gpu_rmsd_fit(self._h, self._gid(group, True), _ptr(out)), "calc_rmsd_and_fit", group, rmsd=True)
+        self._host_frames = None
+        return out

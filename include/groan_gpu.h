@@ -1,0 +1,152 @@
+/*
+ * groan_gpu.h -- C ABI of libgroan_gpu.so: groan_rs's per-frame PBC geometry hot path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary a groan_rs maintainer binds from Rust (see INTEGRATION.md for the
+ * extern "C" block and the safe wrapper).  Conventions mirror the reference's only existing FFI,
+ * the xdrfile binding (src/io/xdrfile.rs:27-100): opaque handle, caller-owned buffers, plain
+ * pointers and sizes, `int` status (0 = ok), no exceptions or panics across the boundary.
+ *
+ * Data model (one ctx = one GPU = one host thread; multi-GPU = one ctx per rank):
+ *   - a ctx is created for a System of `n_atoms` atoms and batches of up to `max_frames` frames;
+ *   - groups are ascending, unique atom-index lists, exactly what Group/AtomContainer iterate
+ *     (src/structures/container.rs:51-115,415-436), optionally with per-atom masses in group order;
+ *   - a batch of frames is pushed as the xtc reader emits it: coordinates F x N x 3 f32 AoS
+ *     (src/io/xtc_io/xdrfile_xtc.rs:25-31) and one 3x3 row-major box matrix per frame, box[i][j] =
+ *     component j of box vector i (src/io/xdrfile.rs:170-187);
+ *   - every op below evaluates one reference function for EVERY frame of the current batch.
+ *
+ * Output pointers may be device memory, pinned host memory (both: the call is asynchronous on the
+ * ctx's compute stream; use groan_gpu_sync) or pageable host memory (the call blocks until the
+ * result is there).  There is no CPU fallback: every op runs CUDA kernels or fails.
+ */
+#ifndef GROAN_GPU_H
+#define GROAN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct groan_gpu_ctx groan_gpu_ctx;
+
+/* Status codes.  1..8 map 1:1 onto the reference's error enums so a Rust wrapper can rebuild them. */
+enum groan_status {
+    GROAN_OK = 0,
+    GROAN_ENOBOX = 1,     /* SimBoxError::DoesNotExist          src/errors.rs:556-582, simbox.rs:230-236 */
+    GROAN_ENOTORTHO = 2,  /* SimBoxError::NotOrthogonal         simbox.rs:185,230-236 */
+    GROAN_EEMPTY = 3,     /* GroupError::EmptyGroup / RMSDError::EmptyGroup   analysis.rs:106-108 */
+    GROAN_ENOPOS = 4,     /* PositionError::NoPosition(index)   errors.rs:227-258; index via groan_gpu_error_detail */
+    GROAN_ENOMASS = 5,    /* MassError::NoMass(index)           errors.rs:290-305 */
+    GROAN_EGROUPSIZE = 6, /* RMSDError::InconsistentGroup(n_ref, n_target)    rmsd.rs:405-422 */
+    GROAN_EZEROBOX = 7,   /* reference panics "Box len should not be zero"    vector3d.rs:402,576 */
+    GROAN_ENOGROUP = 8,   /* GroupError::NotFound */
+    GROAN_EINVAL = 9,     /* bad argument (null pointer, unsorted indices, index >= n_atoms, ...) */
+    GROAN_ECUDA = 10,     /* CUDA runtime failure; groan_gpu_last_cuda_error() has the text */
+    GROAN_ENOFRAMES = 11, /* no batch pushed / attached */
+    GROAN_ENOREF = 12,    /* groan_gpu_rmsd* before groan_gpu_rmsd_set_reference */
+    GROAN_ECAPACITY = 13  /* more frames than max_frames */
+};
+
+/* Dimension, numerically the reference's enum order (src/structures/dimension.rs:15-25). */
+enum groan_dim {
+    GROAN_DIM_NONE = 0, GROAN_DIM_X = 1, GROAN_DIM_Y = 2, GROAN_DIM_Z = 3,
+    GROAN_DIM_XY = 4, GROAN_DIM_XZ = 5, GROAN_DIM_YZ = 6, GROAN_DIM_XYZ = 7
+};
+
+#define GROAN_GROUP_ALL (-1) /* "all": every atom of the system (System::atoms_wrap, atoms_translate) */
+#define GROAN_MAX_GROUPS 64
+
+/* ctx flags */
+#define GROAN_FLAG_TRICLINIC 1u  /* enable the triclinic EXTENSION (wrap, min-image distances); without it a
+                                    non-orthogonal box returns GROAN_ENOTORTHO exactly like the reference */
+#define GROAN_FLAG_EXACT_ONLY 2u /* disable the single-pass fast paths; always run the reference-order passes */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out);
+void groan_gpu_destroy(groan_gpu_ctx *ctx);
+int groan_gpu_set_flags(groan_gpu_ctx *ctx, unsigned flags);
+/* run all kernels on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = ctx's own */
+int groan_gpu_set_stream(groan_gpu_ctx *ctx, void *cuda_stream);
+int groan_gpu_sync(groan_gpu_ctx *ctx);
+const char *groan_gpu_strerror(int status);
+const char *groan_gpu_last_cuda_error(groan_gpu_ctx *ctx);
+/* frame and atom index behind the last GROAN_ENOPOS / GROAN_ENOMASS / GROAN_EGROUPSIZE (a = n_ref, b = n_target) */
+int groan_gpu_error_detail(groan_gpu_ctx *ctx, size_t *a, size_t *b);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t groan_gpu_launch_count(groan_gpu_ctx *ctx);
+
+/* ---- groups: Group::from_indices, container.rs:51-115 ---------------------------------------- */
+/* idx ascending and unique, each < n_atoms; mass nullable (ops that need masses then fail GROAN_ENOMASS,
+ * mass[i] < 0 marks "atom idx[i] has no mass") */
+int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t n, const float *mass);
+
+/* ---- frames: FrameData::update_system, xdrfile_xtc.rs:88-104 ---------------------------------- */
+/* host -> device staging of a batch: chunks go through pinned buffers with cudaMemcpyAsync on the ctx's
+ * copy stream into the slot NOT used by the previous batch, so the copy overlaps kernels still running
+ * on the previous batch.  box: F x 9 row-major matrices, NULL = system has no box. */
+int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box, size_t n_frames);
+/* zero-copy: operate in place on a caller-owned DEVICE buffer of F x N x 3 floats (16-byte aligned) */
+int groan_gpu_attach_frames(groan_gpu_ctx *ctx, float *d_xyz, const float *box, size_t n_frames);
+/* Option<Vector3D> positions: valid[f*N + i] == 0 marks "atom i has no position in frame f" (host array,
+ * NULL = all valid, the default after every push/attach) */
+int groan_gpu_set_valid(groan_gpu_ctx *ctx, const uint8_t *valid);
+/* read the (possibly wrapped / translated / fitted) current batch back: F x N x 3 */
+int groan_gpu_get_frames(groan_gpu_ctx *ctx, float *xyz_out);
+
+/* ---- centres ---------------------------------------------------------------------------------- */
+/* System::group_estimate_center / group_estimate_com  (analysis.rs:52; iterators.rs:1152-1191,1314-1357) */
+int groan_gpu_estimate_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out /* F x 3 */);
+/* System::group_get_center / group_get_com            (analysis.rs:105,258; iterators.rs:1237-1266,1404-1438) */
+int groan_gpu_get_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out /* F x 3 */);
+/* System::group_get_center_naive (iterators.rs:886-903) */
+int groan_gpu_get_center_naive(groan_gpu_ctx *ctx, int gid, float *out /* F x 3 */);
+
+/* ---- distances -------------------------------------------------------------------------------- */
+/* System::group_distance (analysis.rs:348-360) */
+int groan_gpu_group_distance(groan_gpu_ctx *ctx, int g1, int g2, int dim, float *out /* F */);
+/* System::group_all_distances (analysis.rs:401-427): F x n1 x n2 row-major */
+int groan_gpu_all_distances(groan_gpu_ctx *ctx, int g1, int g2, int dim, float *out);
+/* the documented consumer of that matrix (analysis.rs:390-399), fused so the matrix is never written:
+ * per frame min (FIRST minimum in row-major order, Iterator::min_by) and max (LAST maximum,
+ * Iterator::max_by) with their (i, j) positions inside the groups, and the number of pairs with
+ * distance < cutoff.  Any output pointer may be NULL. */
+int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, float cutoff, float *dmin /* F */,
+                                   uint32_t *imin /* F x 2 */, float *dmax /* F */, uint32_t *imax /* F x 2 */,
+                                   uint64_t *count /* F */);
+
+/* ---- wrap / translate (in place on the current batch) ------------------------------------------ */
+/* System::atoms_wrap / group_wrap (modifying.rs:201,215; vector3d.rs:380-417).  shifts (nullable):
+ * F x G x 3 int8, net number of +L steps per axis (for the triclinic extension: multiples of box vectors) */
+int groan_gpu_wrap(groan_gpu_ctx *ctx, int gid, int8_t *shifts);
+/* System::atoms_translate / group_translate (modifying.rs:73; atom.rs:498-511) */
+int groan_gpu_translate(groan_gpu_ctx *ctx, int gid, const float t[3], int8_t *shifts);
+
+/* ---- RMSD / Kabsch ----------------------------------------------------------------------------- */
+/* RMSDConverterAnalyzer::new (rmsd.rs:186-203): the reference may be a different System (own atom count,
+ * own index list for the same group name, rmsd.rs:823-841).  ref_mass: the n_ref masses of the REFERENCE
+ * system's group (they weight the RMSD sum and reference.group_get_com, rmsd.rs:154,192); NULL = use the
+ * masses given to groan_gpu_set_group (then n_ref must equal the group's size).  The target's own
+ * group_get_com always uses the set_group masses. */
+int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_xyz, size_t n_ref_atoms,
+                                 const uint32_t *ref_idx, size_t n_ref, const float ref_box[9], const float *ref_mass);
+/* System::calc_rmsd / RMSDTrajRead::calc_rmsd (rmsd.rs:75,315): rmsd F; rot (nullable) F x 9 row-major r */
+int groan_gpu_rmsd(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot);
+/* System::calc_rmsd_and_fit / RMSDTrajRead::calc_rmsd_and_fit (rmsd.rs:129,390; fit_structure :508-528):
+ * also fits ALL atoms of every frame in place */
+int groan_gpu_rmsd_fit(groan_gpu_ctx *ctx, int gid, float *rmsd);
+
+/* ---- synthetic workloads (bench / test support; bit-identical to oracle/groan_oracle.c) -------- */
+/* fills the ctx's current device slot with F generated frames and makes it the current batch */
+int groan_gpu_synth_uniform(groan_gpu_ctx *ctx, uint64_t seed, uint64_t frame0, size_t n_frames, const float lo[3],
+                            const float span[3], const float *box);
+int groan_gpu_synth_blob(groan_gpu_ctx *ctx, uint64_t seed, uint64_t frame0, size_t n_frames, float scale, float nscale,
+                         const float *rot /* F x 9 */, const float *centre /* F x 3 */, const float *box, int wrap);
+/* the blob's reference structure (n_atoms x 3) into a caller buffer (host or device) */
+int groan_gpu_synth_blob_ref(groan_gpu_ctx *ctx, uint64_t seed, float scale, const float centre[3], float *xyz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROAN_GPU_H */

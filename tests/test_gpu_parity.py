@@ -1,0 +1,461 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (groan_rs_b200.System -> libgroan_gpu.so), against
+the CPU oracle and the reference's own golden numbers (file:line cited per test).
+
+Tolerances (BASELINE.json north_star): atom indices and wrap image shifts bit-exact; distances and centres
+within 1e-5 nm; RMSD within 1e-4 nm.  All-pairs distances and wrapped positions are additionally required to
+be BIT-identical to the ref32 oracle, because the per-pair / per-atom arithmetic is the reference's, f32, no FMA.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_CENTER = 1e-5
+TOL_DIST = 1e-5
+TOL_RMSD = 1e-4
+DIMS = ["None", "X", "Y", "Z", "XY", "XZ", "YZ", "XYZ"]
+
+
+def _sys(n_atoms, **kw):
+    import groan_rs_b200 as g
+    return g.System(n_atoms, **kw)
+
+
+def _dim(name):
+    import groan_rs_b200 as g
+    return g.Dimension.None_ if name == "None" else g.Dimension[name]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ------------------------------------------------------------------ distances: vector3d.rs:1040-1207
+@pytest.mark.parametrize("dim,exp", [("X", 1.5), ("Y", -0.2), ("Z", -1.8), ("XY", 1.51327), ("XZ", 2.34307),
+                                     ("YZ", 1.81108), ("XYZ", 2.351595), ("None", 0.0)])
+def test_distance_kat(dim, exp):
+    s = _sys(2)
+    s.group_create_from_indices("a", [0])
+    s.group_create_from_indices("b", [1])
+    s.set_frames(np.array([[1.0, 3.9, 2.6], [3.5, 0.1, 0.4]], np.float32), [4.0, 4.0, 4.0])
+    d = s.group_all_distances("a", "b", _dim(dim))
+    assert d.shape == (1, 1, 1)
+    assert abs(d[0, 0, 0] - exp) <= 1e-5
+    sign = -1.0 if dim in ("X", "Y", "Z") else 1.0
+    assert abs(s.group_all_distances("b", "a", _dim(dim))[0, 0, 0] - sign * exp) <= 1e-5
+    # out-of-box points, vector3d.rs:1148-1207
+    s.set_frames(np.array([[-1.0, 4.5, 2.3], [3.5, -0.5, 4.2]], np.float32), [4.0, 4.0, 4.0])
+    for dn, e in (("X", -0.5), ("Y", 1.0), ("Z", -1.9)):
+        assert abs(s.group_all_distances("a", "b", _dim(dn))[0, 0, 0] - e) <= 1e-6
+
+
+def test_min_image_ties_and_far_images():
+    """strict comparisons (vector3d.rs:583-589): d == +L/2 stays +L/2; many box lengths away still folds"""
+    s = _sys(4)
+    s.group_create_from_indices("a", [0, 2])
+    s.group_create_from_indices("b", [1, 3])
+    xyz = np.array([[3.0, 0, 0], [1.0, 0, 0], [-41.5, 77.0, 1.0], [2.0, -35.25, 9.5]], np.float32)
+    s.set_frames(xyz, [4.0, 4.0, 4.0])
+    for dn in DIMS:
+        got = s.group_all_distances("a", "b", _dim(dn))[0]
+        exp = orc.all_distances(xyz, [0, 2], [1, 3], dn, [4.0, 4.0, 4.0])
+        assert np.array_equal(bits(got), bits(exp)), dn
+    assert s.group_all_distances("a", "b", _dim("X"))[0, 0, 0] == 2.0
+
+
+# ------------------------------------------------------------------ centres: analysis.rs:488-629, 846-988
+def test_center_artificial_kats():
+    s = _sys(5, masses=[10.3, 5.4, 3.8, 10.1, 7.6])
+    s.group_create_from_indices("g", range(5))
+    five = np.array([[3.3, 0.3, 2.5], [4.3, 1.2, 9.8], [3.2, 5.6, 0.5], [0.2, 9.0, 6.6], [8.7, 5.0, 2.4]], np.float32)
+    out = np.array([[3.3, 10.3, 2.5], [4.3, 1.2, -0.2], [13.2, 15.6, 0.5], [10.2, -1.0, 6.6], [-1.3, 5.0, 2.4]], np.float32)
+    s2 = _sys(5, masses=[10.3, 5.4, 3.8, 10.1, 7.6], max_frames=2)
+    s2.group_create_from_indices("g", range(5))
+    s2.set_frames(np.stack([five, out]), [10.0, 10.0, 10.0])
+    c = s2.group_estimate_center("g")
+    for f in range(2):
+        assert np.allclose(c[f], [2.634386, 9.775156, 1.1748], atol=1e-4)  # the reference's own epsilon
+    assert np.allclose(c[0], orc.estimate_center(five, range(5), [10.0] * 3), atol=TOL_CENTER)
+    cm = s2.group_estimate_com("g")
+    assert np.allclose(cm[0], [1.9526, 9.7567, 1.8812], atol=1e-4)  # analysis.rs:930-988
+    assert np.allclose(cm[0], orc.estimate_center(five, range(5), [10.0] * 3, mass=s2.masses), atol=TOL_CENTER)
+
+    p = _sys(2, masses=[12.8, 0.4])
+    p.group_create_from_indices("g", [0, 1])
+    pbc = np.array([[4.5, 3.2, 1.7], [9.8, 9.5, 3.0]], np.float32)
+    p.set_frames(pbc, [10.0, 10.0, 10.0])
+    assert np.allclose(p.group_estimate_center("g")[0], [2.15, 1.35, 2.35], atol=TOL_CENTER)
+    assert np.allclose(p.group_get_center("g")[0], [2.15, 1.35, 2.35], atol=TOL_CENTER)
+    assert np.allclose(p.group_get_com("g")[0], [4.3575745, 3.0878792, 1.7393947], atol=TOL_CENTER)
+
+
+def test_center_real_system(example):
+    """analysis.rs:631-647, 749-763: example.gro + index.ndx"""
+    xyz, box = example["xyz"], example["box"]
+    s = _sys(xyz.shape[0])
+    s.group_create_from_indices("Protein", example["Protein"])
+    s.group_create_from_indices("Membrane", example["Membrane"])
+    s.set_frames(xyz, box.reshape(1, 9))
+    for name in ("Protein", "Membrane"):
+        idx = example[name]
+        assert np.allclose(s.group_get_center_naive(name)[0], orc.get_center_naive(xyz, idx), atol=TOL_CENTER)
+        assert np.allclose(s.group_estimate_center(name)[0], orc.estimate_center(xyz, idx, box), atol=TOL_CENTER)
+        got, exp = s.group_get_center(name)[0], orc.get_center(xyz, idx, box)
+        x64 = orc.get_center_x64(xyz, idx, box)
+        assert np.allclose(got, exp, atol=TOL_CENTER), (name, got, exp)
+        assert np.allclose(got, x64, atol=TOL_CENTER), (name, got, x64)
+    assert np.allclose(s.group_get_center_naive("Membrane")[0], [6.47077, 6.52237, 5.77978], atol=1e-4)
+    assert np.allclose(s.group_get_center("Protein")[0], [9.85718, 2.46213, 5.45931], atol=1e-4)
+
+
+def test_center_trajectory_cfg1(protein):
+    """BASELINE config 1: protein.gro + short_trajectory_protein.xtc, per-frame group_get_center / group_get_com"""
+    fr, bx, m = protein["frames"], protein["boxes"], protein["mass"]
+    s = _sys(61, masses=m, max_frames=11)
+    s.group_create_from_indices("Protein", range(61))
+    s.set_frames(fr, bx)
+    c, com = s.group_get_center("Protein"), s.group_get_com("Protein")
+    for f in range(11):
+        assert np.allclose(c[f], orc.get_center(fr[f], range(61), bx[f]), atol=TOL_CENTER)
+        assert np.allclose(com[f], orc.get_com(fr[f], range(61), m, bx[f]), atol=TOL_CENTER)
+
+
+def test_group_distance_kats(example):
+    """analysis.rs:1269-1354 (Protein-Membrane, all dims) -- values from SURVEY 8c"""
+    xyz, box = example["xyz"], example["box"]
+    s = _sys(xyz.shape[0])
+    s.group_create_from_indices("Protein", example["Protein"])
+    s.group_create_from_indices("Membrane", example["Membrane"])
+    s.set_frames(xyz, box.reshape(1, 9))
+    kat = {"X": 6.3029766, "Y": -5.566175, "Z": -0.32046986, "XYZ": 8.415017}
+    for dn in DIMS:
+        got = s.group_distance("Protein", "Membrane", _dim(dn))[0]
+        exp = orc.group_distance(xyz, example["Protein"], example["Membrane"], dn, box)
+        assert abs(got - exp) <= TOL_DIST, (dn, got, exp)
+        if dn in kat:
+            assert abs(got - kat[dn]) <= 1e-4
+
+
+# ------------------------------------------------------------------ all-pairs: analysis.rs:1420-1530
+def test_all_distances_example_bitexact(example):
+    xyz, box = example["xyz"], example["box"]
+    s = _sys(xyz.shape[0])
+    s.group_create_from_indices("Protein", example["Protein"])
+    s.group_create_from_indices("Membrane", example["Membrane"])
+    s.set_frames(xyz, box.reshape(1, 9))
+    for dn in DIMS:
+        got = s.group_all_distances("Protein", "Membrane", _dim(dn))[0]
+        exp = orc.all_distances(xyz, example["Protein"], example["Membrane"], dn, box)
+        assert np.array_equal(bits(got), bits(exp)), dn
+    d = s.group_all_distances("Protein", "Protein", _dim("XY"))[0]
+    assert np.all(np.diag(d) == 0) and np.array_equal(d, d.T)  # analysis.rs:1420-1470
+    assert abs(d.max() - 4.597961) <= 1e-5
+    # reduce == the documented consumer of the matrix, with Rust's tie rules
+    for dn in DIMS:
+        r = s.group_all_distances_reduce("Protein", "Membrane", _dim(dn), cutoff=1.0)
+        mn, imn, mx, imx, cnt = orc.all_distances_minmax(xyz, example["Protein"], example["Membrane"], dn, box, cutoff=1.0)
+        assert bits(r["min"])[0] == bits(mn) and bits(r["max"])[0] == bits(mx), dn
+        assert tuple(r["argmin"][0]) == tuple(imn) and tuple(r["argmax"][0]) == tuple(imx), dn
+        assert int(r["count"][0]) == cnt, dn
+
+
+def test_all_distances_cfg2_trajectory(aa_pep):
+    """BASELINE config 2: aa_membrane_peptide, peptide -> membrane phosphates, 21 frames, orthogonal box"""
+    fr, bx = aa_pep["frames"], aa_pep["boxes"]
+    pep, pho = aa_pep["Peptide"], aa_pep["Phosphates"]
+    s = _sys(fr.shape[1], max_frames=fr.shape[0])
+    s.group_create_from_indices("Peptide", pep)
+    s.group_create_from_indices("P", pho)
+    s.set_frames(fr, bx)
+    got = s.group_all_distances("Peptide", "P", _dim("XYZ"))
+    assert got.shape == (21, 363, 128)
+    red = s.group_all_distances_reduce("Peptide", "P", _dim("XYZ"), cutoff=0.8)
+    gd = s.group_distance("Peptide", "P", _dim("Z"))
+    for f in range(fr.shape[0]):
+        exp = orc.all_distances(fr[f], pep, pho, "XYZ", bx[f])
+        assert np.array_equal(bits(got[f]), bits(exp)), f
+        mn, imn, mx, imx, cnt = orc.all_distances_minmax(fr[f], pep, pho, "XYZ", bx[f], cutoff=0.8)
+        assert bits(red["min"][f]) == bits(mn) and bits(red["max"][f]) == bits(mx)
+        assert tuple(red["argmin"][f]) == tuple(imn) and tuple(red["argmax"][f]) == tuple(imx)
+        assert int(red["count"][f]) == cnt
+        assert abs(gd[f] - orc.group_distance(fr[f], pep, pho, "Z", bx[f])) <= TOL_DIST
+
+
+def test_all_distances_ragged_and_empty():
+    rng = np.random.default_rng(5)
+    n = 1037
+    xyz = (rng.random((3, n, 3), dtype=np.float32) * 12 - 1).astype(np.float32)
+    L = np.array([[9.5, 10.25, 8.75]] * 3, np.float32)
+    s = _sys(n, max_frames=3)
+    a = np.arange(3, 3 + 77)            # contiguous, odd size
+    b = np.sort(rng.choice(n, 333, replace=False))
+    s.group_create_from_indices("a", a)
+    s.group_create_from_indices("b", b)
+    s.group_create_from_indices("e", [])
+    s.set_frames(xyz, L)
+    for dn in ("XYZ", "XZ", "Y"):
+        got = s.group_all_distances("a", "b", _dim(dn))
+        for f in range(3):
+            assert np.array_equal(bits(got[f]), bits(orc.all_distances(xyz[f], a, b, dn, L[f]))), (dn, f)
+    assert s.group_all_distances("a", "e", _dim("XYZ")).shape == (3, 77, 0)  # empty matrix, not an error
+    assert s.group_all_distances("e", "b", _dim("XYZ")).shape == (3, 0, 333)
+
+
+# ------------------------------------------------------------------ wrap / translate
+def test_wrap_kat_and_shifts(example):
+    """vector3d.rs:1017-1037 and modifying.rs:688-734"""
+    s = _sys(3)
+    pts = np.array([[-1.0, 1.5, 3.0], [2.0, 2.2, -0.3], [-54.2, 77.8, 124.5]], np.float32)
+    s.set_frames(pts, [2.0, 2.0, 2.0])
+    sh = s.atoms_wrap(shifts=True)
+    w = s.get_frames()[0]
+    exp, esh = orc.wrap(pts, range(3), [2.0, 2.0, 2.0])
+    assert np.array_equal(bits(w), bits(exp)) and np.array_equal(sh[0], esh)
+    assert w[1, 0] == 2.0  # x == L stays L (strict '>')
+    assert np.allclose(w, [[1, 1.5, 1], [2.0, 0.2, 1.7], [1.8, 1.8, 0.5]], atol=1e-5)
+
+    xyz, box = example["xyz"].copy(), example["box"]
+    L = np.array([box[0, 0], box[1, 1], box[2, 2]], np.float32)
+    rng = np.random.default_rng(11)
+    k = rng.integers(-3, 4, size=xyz.shape).astype(np.float32)
+    moved = (xyz + k * L).astype(np.float32)
+    t = _sys(xyz.shape[0])
+    t.group_create_from_indices("Membrane", example["Membrane"])
+    t.set_frames(moved, box.reshape(1, 9))
+    sh = t.group_wrap("Membrane", shifts=True)
+    exp, esh = orc.wrap(moved, example["Membrane"], box)
+    got = t.get_frames()[0]
+    assert np.array_equal(bits(got), bits(exp))          # untouched atoms included
+    assert np.array_equal(sh[0], esh)
+    assert np.allclose(got[example["Membrane"]], xyz[example["Membrane"]], atol=1e-4)
+    # idempotence
+    sh2 = t.group_wrap("Membrane", shifts=True)
+    assert not sh2.any() and np.array_equal(bits(t.get_frames()[0]), bits(got))
+
+
+def test_translate(example):
+    """modifying.rs:504-524, atom.rs:1335-1361"""
+    xyz, box = example["xyz"], example["box"]
+    s = _sys(xyz.shape[0])
+    s.group_create_from_indices("Protein", example["Protein"])
+    s.set_frames(xyz, box.reshape(1, 9))
+    tv = [3.5, -1.1, 5.4]
+    sh = s.atoms_translate(tv, shifts=True)
+    exp, esh = orc.translate(xyz, range(xyz.shape[0]), tv, box)
+    assert np.array_equal(bits(s.get_frames()[0]), bits(exp)) and np.array_equal(sh[0], esh)
+    s.group_translate("Protein", [-20.0, 0.25, 31.0])
+    exp2, _ = orc.translate(exp, example["Protein"], [-20.0, 0.25, 31.0], box)
+    assert np.array_equal(bits(s.get_frames()[0]), bits(exp2))
+
+
+# ------------------------------------------------------------------ RMSD: rmsd.rs:796-866, 952-1073
+GOLDEN_RMSD = [0.23669721, 0.2634763, 0.26021627, 0.21364464, 0.22166993, 0.19383307, 0.26422343, 0.27013618, 0.26398134,
+               0.23475659, 0.24208021]
+
+
+def test_rmsd_cfg1(protein):
+    """BASELINE config 1: calc_rmsd of Protein vs the gro frame; golden vector rmsd.rs:811-814"""
+    m = protein["mass"]
+    ref = _sys(61, masses=m)
+    ref.group_create_from_indices("Protein", range(61))
+    ref.set_frames(protein["xyz"], protein["box"].reshape(1, 9))
+    s = _sys(61, masses=m, max_frames=11)
+    s.group_create_from_indices("Protein", range(61))
+    s.set_frames(protein["frames"], protein["boxes"])
+    rot = np.empty((11, 9), np.float32)
+    got = s.calc_rmsd(ref, "Protein", rot=rot)
+    for f in range(11):
+        e, r = orc.calc_rmsd(protein["xyz"], range(61), protein["box"], m, protein["frames"][f], range(61), protein["boxes"][f])
+        assert abs(got[f] - e) <= TOL_RMSD, (f, got[f], e)
+        assert np.allclose(rot[f].reshape(3, 3), r, atol=1e-4)
+    # the gro reference carries 3 decimals, the tpr reference of the reference's test more: 2e-3 covers that
+    assert np.allclose(got, GOLDEN_RMSD, atol=2e-3)
+
+
+def test_rmsd_and_fit_short_trajectory(example, short_traj):
+    """rmsd.rs:952-1073: fit every frame of short_trajectory.xtc to example.gro; golden short_trajectory_fit.xtc"""
+    xyz, box = example["xyz"], example["box"]
+    n = xyz.shape[0]
+    prot = example["Protein"]
+    masses = np.full(n, np.nan, np.float32)
+    masses[prot] = short_traj["protein_mass"]
+    ref = _sys(n, masses=masses)
+    ref.group_create_from_indices("Protein", prot)
+    ref.set_frames(xyz, box.reshape(1, 9))
+    fr, bx = short_traj["frames"], short_traj["boxes"]
+    s = _sys(n, masses=masses, max_frames=fr.shape[0])
+    s.group_create_from_indices("Protein", prot)
+    s.set_frames(fr, bx)
+    rm = s.calc_rmsd(ref, "Protein")
+    assert np.allclose(rm, GOLDEN_RMSD, atol=2e-3)
+    rm2 = s.calc_rmsd_and_fit(ref, "Protein")
+    assert np.array_equal(rm, rm2)
+    fitted = s.get_frames()
+    for f in range(fr.shape[0]):
+        e, ef = orc.calc_rmsd_and_fit(xyz, prot, box, short_traj["protein_mass"], fr[f], prot, bx[f])
+        assert abs(rm[f] - e) <= TOL_RMSD
+        assert np.abs(fitted[f] - ef).max() <= 2e-4, f
+        # golden fitted trajectory, quantised to 0.01 nm (half quantum + 7e-5 with the gro reference)
+        assert np.abs(fitted[f] - short_traj["fit"][f]).max() <= 0.0052, f
+
+
+def test_rmsd_identity_and_broken_reference(protein):
+    """rmsd.rs:844-866: a PBC-broken copy of the same structure has RMSD 0"""
+    m = protein["mass"]
+    L = np.array([protein["box"][0, 0], protein["box"][1, 1], protein["box"][2, 2]], np.float32)
+    ref = _sys(61, masses=m)
+    ref.group_create_from_indices("Protein", range(61))
+    ref.set_frames(protein["xyz"], protein["box"].reshape(1, 9))
+    broken = protein["xyz"].copy()
+    broken[::2] += L
+    broken[1::3] -= L
+    s = _sys(61, masses=m, max_frames=2)
+    s.group_create_from_indices("Protein", range(61))
+    s.set_frames(np.stack([protein["xyz"], broken]), np.stack([protein["box"]] * 2))
+    got = s.calc_rmsd(ref, "Protein")
+    assert np.all(np.abs(got) <= 1e-4), got
+
+
+# ------------------------------------------------------------------ triclinic EXTENSION (config 3; unpinned by the reference)
+@pytest.mark.parametrize("name", ["triclinic", "dodecahedron", "octahedron"])
+def test_triclinic_cfg3(tric, name):
+    import groan_rs_b200 as g
+    fr, bx = tric[name + "_frames"], tric[name + "_boxes"]
+    n = fr.shape[1]
+    # without the extension flag the behaviour is the reference's: NotOrthogonal (simbox.rs:230-236)
+    plain = _sys(n, max_frames=fr.shape[0])
+    plain.set_frames(fr, bx)
+    with pytest.raises(g.GroanError) as ei:
+        plain.atoms_wrap()
+    assert "NotOrthogonal" in ei.value.variant
+    with pytest.raises(g.GroanError):
+        plain.group_all_distances("all", "all", g.Dimension.XYZ)
+
+    s = _sys(n, max_frames=fr.shape[0], triclinic=True)
+    s.set_frames(fr, bx)
+    for dn in ("XYZ", "XY", "Z"):
+        got = s.group_all_distances("all", "all", _dim(dn))
+        for f in range(fr.shape[0]):
+            exp = orc.tric_all_distances(fr[f], range(n), range(n), dn, bx[f])
+            assert np.array_equal(bits(got[f]), bits(exp)), (dn, f)
+    # self-pin: f64 brute force over 5^3 images
+    got = s.group_all_distances("all", "all", _dim("XYZ"))
+    for f in (0, 5, 10):
+        for i in range(0, n, 7):
+            for j in range(n):
+                b = orc.tric_distance_brute64(fr[f, i], fr[f, j], "XYZ", bx[f], 2)
+                assert abs(got[f, i, j] - b) <= TOL_DIST
+    # wrap after moving atoms by random integer combinations of box vectors: shifts bit-exact vs the ref32 oracle
+    rng = np.random.default_rng(3)
+    k = rng.integers(-2, 3, size=(fr.shape[0], n, 3)).astype(np.float32)
+    moved = fr.copy()
+    for f in range(fr.shape[0]):
+        B = bx[f].reshape(3, 3)
+        moved[f] = (fr[f] + k[f] @ B).astype(np.float32)
+    s.set_frames(moved, bx)
+    sh = s.atoms_wrap(shifts=True)
+    w = s.get_frames()
+    for f in range(fr.shape[0]):
+        exp, esh = orc.tric_wrap(moved[f], range(n), bx[f])
+        assert np.array_equal(sh[f], esh), f
+        assert np.array_equal(bits(w[f]), bits(exp)), f
+    # centre / RMSD stay the reference's behaviour on a triclinic box
+    with pytest.raises(g.GroanError) as ei:
+        s.group_get_center("all")
+    assert "NotOrthogonal" in ei.value.variant
+
+
+def test_triclinic_code_on_orthogonal_box_is_identical(example):
+    """self-pin (i): with the flag set, an orthogonal box goes through the orthogonal kernels and matches bit for bit"""
+    xyz, box = example["xyz"], example["box"]
+    s = _sys(xyz.shape[0], triclinic=True)
+    s.group_create_from_indices("Protein", example["Protein"])
+    s.set_frames(xyz, box.reshape(1, 9))
+    got = s.group_all_distances("Protein", "Protein", _dim("XYZ"))[0]
+    assert np.array_equal(bits(got), bits(orc.all_distances(xyz, example["Protein"], example["Protein"], "XYZ", box)))
+    assert np.array_equal(bits(got), bits(orc.tric_all_distances(xyz, example["Protein"], example["Protein"], "XYZ", box)))
+
+
+# ------------------------------------------------------------------ errors: analysis.rs:650-746, rmsd.rs:1076-1183
+def test_error_paths(protein):
+    import groan_rs_b200 as g
+    m = protein["mass"]
+    s = _sys(61, masses=m, max_frames=2)
+    s.group_create_from_indices("Protein", range(61))
+    s.group_create_from_indices("Empty", [])
+    with pytest.raises(g.GpuError):  # no frames yet
+        s.group_get_center("Protein")
+    s.set_frames(protein["frames"][:2], None)
+    with pytest.raises(g.GroupError) as ei:
+        s.group_get_center("Protein")
+    assert "DoesNotExist" in ei.value.variant
+    s.set_frames(protein["frames"][:2], protein["boxes"][:2])
+    with pytest.raises(g.GroupError) as ei:
+        s.group_get_center("Nonexistent")
+    assert ei.value.variant == "NotFound"
+    with pytest.raises(g.GroupError) as ei:
+        s.group_get_center("Empty")
+    assert ei.value.variant == "EmptyGroup"
+    with pytest.raises(g.GroupError) as ei:
+        s.group_distance("Protein", "Empty", g.Dimension.XYZ)
+    assert ei.value.variant == "EmptyGroup"
+    valid = np.ones((2, 61), np.uint8)
+    valid[1, 17] = 0
+    s.set_valid(valid)
+    with pytest.raises(g.GroupError) as ei:
+        s.group_get_center("Protein")
+    assert "NoPosition(17)" in ei.value.variant and ei.value.detail == (1, 17)
+    with pytest.raises(g.GroupError):
+        s.atoms_wrap()
+    s.set_valid(None)
+    s.group_get_center("Protein")
+    # zero box: the reference panics "Box len should not be zero"
+    zb = protein["boxes"][:2].copy()
+    zb[1, 2, 2] = 0.0
+    s.set_frames(protein["frames"][:2], zb)
+    with pytest.raises(g.GroanError):
+        s.group_get_center("Protein")
+    # masses
+    nm = _sys(61, max_frames=1)
+    nm.group_create_from_indices("Protein", range(61))
+    nm.set_frames(protein["frames"][:1], protein["boxes"][:1])
+    with pytest.raises(g.GroupError) as ei:
+        nm.group_get_com("Protein")
+    assert "NoMass" in ei.value.variant
+    # RMSD: inconsistent group sizes (rmsd.rs:1110-1130), missing group, missing masses
+    ref = _sys(61, masses=m)
+    ref.group_create_from_indices("Protein", range(60))
+    ref.set_frames(protein["xyz"], protein["box"].reshape(1, 9))
+    s.set_frames(protein["frames"][:2], protein["boxes"][:2])
+    with pytest.raises(g.RMSDError) as ei:
+        s.calc_rmsd(ref, "Protein")
+    assert ei.value.variant == "InconsistentGroup" and ei.value.detail == (60, 61)
+    with pytest.raises(g.RMSDError) as ei:
+        s.calc_rmsd(ref, "Nope")
+    assert ei.value.variant == "NonexistentGroup"
+    with pytest.raises(g.GpuError):  # capacity
+        s.set_frames(protein["frames"][:3], protein["boxes"][:3])
+
+
+# ------------------------------------------------------------------ synthetic generators == oracle generators
+def test_synth_generators_match_oracle():
+    n = 5000
+    s = _sys(n, max_frames=3)
+    lo, span = [-2.15, -2.15, -2.15], [25.8, 25.8, 25.8]
+    s.synth_uniform(20261018, 7, 3, lo, span, [21.5, 21.5, 21.5])
+    got = s.get_frames()
+    for f in range(3):
+        assert np.array_equal(bits(got[f]), bits(orc.synth_uniform(n, 20261018, 7 + f, lo, span)))
+    rot = np.stack([np.eye(3, dtype=np.float32)] * 3)
+    th = 0.3
+    rot[1] = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+    cen = np.array([[3, 4, 5], [33.5, 0.2, 17], [10, 20, 30]], np.float32)
+    L = [34.0, 34.0, 34.0]
+    s.synth_blob(99, 100, 3, 2.5e-5, 1e-7, rot, cen, L, wrap=True)
+    got = s.get_frames()
+    for f in range(3):
+        exp = orc.synth_blob_frame(n, 99, 100 + f, 2.5e-5, 1e-7, rot[f], cen[f], L, wrap=True)
+        assert np.array_equal(bits(got[f]), bits(exp)), f
+    assert np.array_equal(bits(s.synth_blob_ref(99, 2.5e-5, [17, 17, 17])), bits(orc.synth_blob_ref(n, 99, 2.5e-5, [17, 17, 17])))
