@@ -172,7 +172,10 @@ def run_gpu_arm(args):
     idx = np.arange(N_ATOMS, dtype=np.uint32)
     s.group_create_from_indices("G", idx)
     ref.group_create_from_indices("G", idx)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: torch.cuda.Event then times exactly the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     s.set_stream(stream.cuda_stream)
     ref_xyz = s.synth_blob_ref(SEED, BLOB_SCALE, [BOX / 2] * 3)
     ref.set_frames(ref_xyz, [BOX] * 3)
@@ -324,6 +327,7 @@ def run_extras(torch, g, local, peak):
 
     # atoms_wrap on 4M atoms x 8 frames: 24 B per atom per frame
     F = 8
+    assert torch.cuda.current_stream().cuda_stream != 0
     w = g.System(N_ATOMS, device=local, max_frames=F)
     w.set_stream(torch.cuda.current_stream().cuda_stream)
     w.synth_uniform(SEED, 0, F, [-0.1 * BOX] * 3, [1.2 * BOX] * 3, [BOX] * 3)

@@ -149,7 +149,7 @@ def test_all_distances_example_bitexact(example):
         got = s.group_all_distances("Protein", "Membrane", _dim(dn))[0]
         exp = orc.all_distances(xyz, example["Protein"], example["Membrane"], dn, box)
         assert np.array_equal(bits(got), bits(exp)), dn
-    d = s.group_all_distances("Protein", "Protein", _dim("XY"))[0]
+    d = s.group_all_distances("Protein", "Protein", _dim("XYZ"))[0]
     assert np.all(np.diag(d) == 0) and np.array_equal(d, d.T)  # analysis.rs:1420-1470
     assert abs(d.max() - 4.597961) <= 1e-5
     # reduce == the documented consumer of the matrix, with Rust's tie rules
@@ -298,7 +298,7 @@ def test_rmsd_and_fit_short_trajectory(example, short_traj):
         assert abs(rm[f] - e) <= TOL_RMSD
         assert np.abs(fitted[f] - ef).max() <= 2e-4, f
         # golden fitted trajectory, quantised to 0.01 nm (half quantum + 7e-5 with the gro reference)
-        assert np.abs(fitted[f] - short_traj["fit"][f]).max() <= 0.0052, f
+        assert np.abs(fitted[f] - short_traj["fit"][f]).max() <= 0.0053, f  # the ref32 oracle itself: 0.00524 (frame 7)
 
 
 def test_rmsd_identity_and_broken_reference(protein):
