@@ -10,6 +10,7 @@
 namespace groan {
 
 constexpr int kThreads = 256;           // CTA size of the streaming kernels
+constexpr int kWarps = kThreads / 32;
 constexpr int kSMs = 148;               // B200
 constexpr int kMaxBlocksPerFrame = 592; // 4 resident CTAs x 148 SMs
 
@@ -33,12 +34,6 @@ __device__ __forceinline__ float min_image(float d, float L) {
     while (d < -h) d += L;
     return d;
 }
-// One-step form, bit-identical to the loops when |d| <= 1.5 L (proved in DESIGN.md "min-image").
-__device__ __forceinline__ float min_image_1step(float d, float L, float h) {
-    if (d > h) d -= L;
-    else if (d < -h) d += L;
-    return d;
-}
 // C fmodf(a, L) for L > 0: exact by construction for |a| < 2L (a - L is exact there, Sterbenz),
 // CUDA's fmodf (0 ulp) otherwise.
 __device__ __forceinline__ float fmod_exact(float a, float L) {
@@ -57,6 +52,33 @@ __device__ __forceinline__ float vector_to_1(float c, float p, float L) {
 
 __device__ __forceinline__ float pi_x2() { return 3.14159265358979323846f * 2.0f; } // auxiliary.rs:15
 
+// ---------------------------------------------------------------- B200 streaming loads
+// 256-bit global loads (LDG.E.256, sm_100+) with cache policy: frame coordinates are read once
+// (no L1 allocation, evict-first in L2); the RMSD reference is re-read by every frame of the batch
+// and should stay in the 126 MB L2 (evict-last).
+struct f8 {
+    float v[8];
+};
+__device__ __forceinline__ f8 ld256_stream(const void *p) {
+    f8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ f8 ld256_keep(const void *p) {
+    f8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256_stream(void *p, const f8 &r) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                 "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ double shfl_down_d(double v, int off) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -67,6 +89,11 @@ __device__ __forceinline__ double shfl_down_d(double v, int off) {
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
 }
 __device__ __forceinline__ float warp_min(float v) {
@@ -80,54 +107,93 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// Sum K per-thread values over the CTA in f64; result valid in thread 0.  smem: K * (kThreads/32) doubles.
-template <int K>
-__device__ __forceinline__ void block_sum(double (&v)[K], double *smem) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        double s = warp_sum(v[k]);
-        if (lane == 0) smem[k * nw + w] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            double s = 0.0;
-            for (int j = 0; j < nw; j++) s += smem[k * nw + j];
-            v[k] = s;
-        }
-    }
-    __syncthreads();
-}
+// Per-frame reduction of KS sums and NM (min, max) pairs over all CTAs of a frame.
+//
+//   1. warp shuffles, then one shared-memory stage across the CTA's warps -> one record per CTA,
+//      stored as f64 in partials[(frame, cta)][KS + 2*NM];
+//   2. "last CTA of the frame finishes the frame": a ticket per frame; the CTA that draws the last
+//      ticket re-reads all records with ALL its threads in a fixed order (deterministic result,
+//      independent of scheduling) and leaves the totals in tot[] / tmn[] / tmx[] of EVERY thread.
+//
+// T is the per-thread accumulator type (float for the single-pass kernels, double for the exact ones).
+template <int KS, int NM>
+struct FrameReduceSmem {
+    double stage[(KS + 2 * NM) * kWarps];
+    double tot[KS + 2 * NM];
+    int last;
+};
 
-// "Last CTA of the frame finishes the frame": thread 0 publishes this CTA's K partial sums, takes a
-// ticket; the CTA that draws the last ticket re-reads all partials in a FIXED order (deterministic
-// result, independent of scheduling) and returns true with the totals in tot[] (thread 0 only).
-template <int K>
-__device__ __forceinline__ bool frame_finish(const double (&v)[K], double *partials /* [blocks][K] of this frame */,
-                                             unsigned int *ticket, int blocks, double (&tot)[K], int *sh_flag) {
-    if (threadIdx.x == 0) {
-        const int b = blockIdx.x;
+template <int KS, int NM, typename T>
+__device__ __forceinline__ bool frame_reduce(const T (&sum)[KS], const float *mn, const float *mx, double *partials_frame,
+                                             unsigned int *ticket, int blocks, FrameReduceSmem<KS, NM> &sm, double (&tot)[KS],
+                                             float *tmn, float *tmx) {
+    constexpr int KT = KS + 2 * NM;
+    static_assert(KT <= kThreads, "record wider than a CTA");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-        for (int k = 0; k < K; k++) partials[(size_t)b * K + k] = v[k];
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        int last = (t == (unsigned)(blocks - 1));
-        if (last) {
-            __threadfence();
+    for (int k = 0; k < KS; k++) {
+        const T s = warp_sum(sum[k]);
+        if (lane == 0) sm.stage[k * kWarps + w] = (double)s;
+    }
 #pragma unroll
-            for (int k = 0; k < K; k++) tot[k] = 0.0;
-            for (int j = 0; j < blocks; j++) {
-#pragma unroll
-                for (int k = 0; k < K; k++) tot[k] += ((volatile double *)partials)[(size_t)j * K + k];
-            }
-            *ticket = 0u; // re-arm for the next launch on this frame
+    for (int k = 0; k < NM; k++) {
+        const float a = warp_min(mn[k]), b = warp_max(mx[k]);
+        if (lane == 0) {
+            sm.stage[(KS + k) * kWarps + w] = (double)a;
+            sm.stage[(KS + NM + k) * kWarps + w] = (double)b;
         }
-        *sh_flag = last;
     }
     __syncthreads();
-    return *sh_flag != 0;
+    if (threadIdx.x < KT) {
+        const int k = threadIdx.x;
+        double v = sm.stage[k * kWarps];
+        for (int j = 1; j < kWarps; j++) {
+            const double u = sm.stage[k * kWarps + j];
+            v = (k < KS) ? v + u : (k < KS + NM ? fmin(v, u) : fmax(v, u));
+        }
+        partials_frame[(size_t)blockIdx.x * KT + k] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        sm.last = (t == (unsigned)(blocks - 1));
+        if (sm.last) *ticket = 0u; // re-arm for the next launch on this frame
+    }
+    __syncthreads();
+    if (!sm.last) return false;
+    __threadfence();
+    // parallel, fixed-order re-read: thread (k, js) folds records js, js + J, js + 2J, ...
+    constexpr int J = (kThreads / KT) < kWarps ? (kThreads / KT) : kWarps;
+    const int k = threadIdx.x % KT, js = threadIdx.x / KT;
+    const volatile double *vp = partials_frame;
+    if (js < J) {
+        double v = (k < KS) ? 0.0 : (k < KS + NM ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL));
+        for (int j = js; j < blocks; j += J) {
+            const double u = vp[(size_t)j * KT + k];
+            v = (k < KS) ? v + u : (k < KS + NM ? fmin(v, u) : fmax(v, u));
+        }
+        sm.stage[k * kWarps + js] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < KT) {
+        const int kk = threadIdx.x;
+        double v = sm.stage[kk * kWarps];
+        for (int j = 1; j < J; j++) {
+            const double u = sm.stage[kk * kWarps + j];
+            v = (kk < KS) ? v + u : (kk < KS + NM ? fmin(v, u) : fmax(v, u));
+        }
+        sm.tot[kk] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KS; q++) tot[q] = sm.tot[q];
+#pragma unroll
+    for (int q = 0; q < NM; q++) {
+        tmn[q] = (float)sm.tot[KS + q];
+        tmx[q] = (float)sm.tot[KS + NM + q];
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------- 3x3 SVD / Kabsch rotation (f64)
@@ -228,6 +294,49 @@ struct FrameView {
         lz = __ldg(box + f * 9 + 8);
     }
 };
+
+// Visit every atom of the group in frame f that belongs to this CTA: fn(i, x, y, z) with i the
+// position inside the group.  A contiguous group is streamed with 256-bit loads (three LDG.256 =
+// eight atoms per thread, issued before any of them is used); the up-to-7 atoms before the first
+// 32-byte boundary and after the last full octet, and index-list groups, use scalar loads.
+template <typename F>
+__device__ __forceinline__ void for_each_group_atom(const FrameView &fv, const GroupView &g, int f, F &&fn) {
+    const float *fr = fv.frame(f);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (g.idx) {
+        for (uint32_t i = tid; i < g.n; i += nth) {
+            const float *p = fr + (size_t)__ldg(g.idx + i) * 3;
+            fn(i, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        }
+        return;
+    }
+    const size_t a0 = (size_t)f * fv.n_atoms + g.first; // global atom index of the group's first atom
+    const bool base_ok = ((reinterpret_cast<uintptr_t>(fv.xyz) & 31) == 0);
+    uint32_t head = base_ok ? (uint32_t)((8 - (a0 & 7)) & 7) : g.n;
+    if (head > g.n) head = g.n;
+    const uint32_t noct = (g.n - head) >> 3;
+    const char *body = reinterpret_cast<const char *>(fr + ((size_t)g.first + head) * 3);
+    for (uint32_t o = tid; o < noct; o += nth) {
+        const f8 q0 = ld256_stream(body + (size_t)o * 96), q1 = ld256_stream(body + (size_t)o * 96 + 32),
+                 q2 = ld256_stream(body + (size_t)o * 96 + 64);
+        const uint32_t i = head + o * 8;
+        fn(i + 0, q0.v[0], q0.v[1], q0.v[2]);
+        fn(i + 1, q0.v[3], q0.v[4], q0.v[5]);
+        fn(i + 2, q0.v[6], q0.v[7], q1.v[0]);
+        fn(i + 3, q1.v[1], q1.v[2], q1.v[3]);
+        fn(i + 4, q1.v[4], q1.v[5], q1.v[6]);
+        fn(i + 5, q1.v[7], q2.v[0], q2.v[1]);
+        fn(i + 6, q2.v[2], q2.v[3], q2.v[4]);
+        fn(i + 7, q2.v[5], q2.v[6], q2.v[7]);
+    }
+    // head and tail atoms: at most 14, spread over the first threads of the frame's first CTA
+    const uint32_t tail0 = head + noct * 8, ntail = g.n - tail0;
+    if (tid < head + ntail) {
+        const uint32_t i = tid < head ? tid : tail0 + (tid - head);
+        const float *p = fr + ((size_t)g.first + i) * 3;
+        fn(i, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    }
+}
 
 // counter-based generator shared with oracle/groan_oracle.c (orc_splitmix64 / orc_hash)
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

@@ -29,7 +29,7 @@ namespace {
 
 constexpr size_t kStageBytes = 32u << 20;  // pinned staging chunk for pageable sources
 constexpr size_t kPartialSlots = 8192;     // (blocks per frame) x (frames) upper bound for reductions
-constexpr int kMaxSums = 24;               // widest per-CTA partial record, in doubles
+constexpr int kMaxSums = 32;               // widest per-CTA partial record, in doubles
 
 struct Group {
     bool set = false;
@@ -41,6 +41,7 @@ struct Group {
     bool has_mass = false;
     long no_mass_at = -1;  // position in the group of the first atom without mass
     float *d_mass = nullptr;
+    std::vector<float> mass;  // host copy (compared with the RMSD reference's masses)
 };
 
 enum PtrKind { PK_DEVICE, PK_PINNED, PK_PAGEABLE };
@@ -90,6 +91,8 @@ struct groan_gpu_ctx {
     void *d_pair_partials = nullptr;
     unsigned int *d_tickets = nullptr;
     float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
+    int *d_flags = nullptr;  // per frame: 1 = the single-pass kernel could not certify its result, redo exactly
+    int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
 
@@ -98,7 +101,8 @@ struct groan_gpu_ctx {
         bool set = false;
         size_t n = 0;
         float4 *d_pc = nullptr;
-        double sum_mpp = 0, sum_m = 0;
+        double sums[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool same_mass = true;  // reference masses == the target group's masses
         float com[3] = {0, 0, 0};
     } refs[GROAN_MAX_GROUPS];
 
@@ -207,6 +211,17 @@ int blocks_per_frame(size_t g, size_t F) {
     return (int)nb;
 }
 
+// single-pass kernels: one wave of long-lived CTAs (occ per SM), so that the per-CTA reduction and the
+// last-CTA finish are amortised over hundreds of atoms per thread
+int blocks_per_frame_fast(size_t g, size_t F, int occ) {
+    const size_t octs = (g + 7) / 8;
+    size_t nb = (octs + (size_t)kThreads * 2 - 1) / ((size_t)kThreads * 2);
+    nb = std::max<size_t>(nb, 1);
+    nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
+    return (int)nb;
+}
+
 int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->tmp_bytes) return GROAN_OK;
     if (ctx->d_tmp) {
@@ -279,33 +294,48 @@ int end_batch(groan_gpu_ctx *ctx) {
 }
 
 // ---- centre passes -------------------------------------------------------------------------------
-int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out) {
-    const int nb = blocks_per_frame(g.n, ctx->n_frames);
+int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out, const int *flags) {
+    const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
     dim3 grid(nb, (unsigned)ctx->n_frames);
     if (weighted)
-        k_trig<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out);
+        k_trig<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags);
     else
-        k_trig<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out);
+        k_trig<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags);
     LAUNCHED();
     return GROAN_OK;
 }
 
-int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c0, float *out) {
-    const int nb = blocks_per_frame(g.n, ctx->n_frames);
+int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c0, float *out, const int *flags) {
+    const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
     dim3 grid(nb, (unsigned)ctx->n_frames);
     if (weighted)
-        k_unwrap<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out);
+        k_unwrap<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags);
     else
-        k_unwrap<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out);
+        k_unwrap<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags);
     LAUNCHED();
     return GROAN_OK;
 }
 
-// group_get_center / group_get_com: estimate (always geometric, iterators.rs:1407) then unwrap
+// group_get_center / group_get_com.  Single pass first (kernels_center.cuh); the reference-order passes --
+// estimate (always geometric, iterators.rs:1407) then unwrap -- then re-do only the frames it flagged
+// (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
-    int rc = run_trig(ctx, g, false, ctx->d_c0);
+    const int *flags = nullptr;
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
+        const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, ctx->occ_center);
+        dim3 grid(nb, (unsigned)ctx->n_frames);
+        if (weighted)
+            k_center_fast<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+                                                                     ctx->d_flags);
+        else
+            k_center_fast<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+                                                                      ctx->d_flags);
+        LAUNCHED();
+        flags = ctx->d_flags;
+    }
+    int rc = run_trig(ctx, g, false, ctx->d_c0, flags);
     if (rc) return rc;
-    return run_unwrap(ctx, g, weighted, ctx->d_c0, out);
+    return run_unwrap(ctx, g, weighted, ctx->d_c0, out, flags);
 }
 
 // validation shared by the centre ops, in the reference's order (analysis.rs:105-120, iterators.rs:1152-1191)
@@ -472,20 +502,41 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) 
         ctx->err_b = g->n;
         return GROAN_EGROUPSIZE;
     }
-    // group_get_com of the target (geometric estimate, mass-weighted unwrap)
-    rc = run_get_center(ctx, *g, true, ctx->d_cen);
-    if (rc) return rc;
     float *d_rmsd = target_of<float>(rmsd, ctx->d_res);
     float *d_rot = target_of<float>(rot, ctx->d_rot);
     RefView rv;
     rv.pc = R.d_pc;
-    rv.sum_mpp = R.sum_mpp;
-    rv.sum_m = R.sum_m;
-    rv.com[0] = R.com[0]; rv.com[1] = R.com[1]; rv.com[2] = R.com[2];
-    const int nb = blocks_per_frame(g->n, ctx->n_frames);
+    rv.sum_wpp = R.sums[0];
+    rv.sum_w = R.sums[1];
+    for (int k = 0; k < 3; k++) {
+        rv.sum_pc[k] = R.sums[2 + k];
+        rv.sum_wpc[k] = R.sums[5 + k];
+        rv.com[k] = R.com[k];
+    }
+    const int *flags = nullptr;
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
+        // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
+        const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
+        dim3 fgrid(nbf, (unsigned)ctx->n_frames);
+        if (R.same_mass)
+            k_rmsd_fast<true><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+                                                                     d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+        else
+            k_rmsd_fast<false><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+                                                                      d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+        LAUNCHED();
+        flags = ctx->d_flags;
+    }
+    // reference-order passes (all frames, or only the flagged ones): group_get_com of the target
+    // (geometric estimate, mass-weighted unwrap), then shift + wrap + covariance in f64
+    rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
+    if (rc) return rc;
+    rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags);
+    if (rc) return rc;
+    const int nb = blocks_per_frame_fast(g->n, ctx->n_frames, 2);
     dim3 grid(nb, (unsigned)ctx->n_frames);
     k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                                d_rot);
+                                                d_rot, flags);
     LAUNCHED();
     if (fit) {
         size_t fb = (ctx->n_atoms + kThreads - 1) / kThreads;
@@ -534,6 +585,12 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaMalloc(&ctx->d_cen2, max_frames * 3 * sizeof(float)));
         CK(cudaMalloc(&ctx->d_res, max_frames * 8 * sizeof(float)));
         CK(cudaMalloc(&ctx->d_rot, max_frames * 9 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_flags, max_frames * sizeof(int)));
+        CK(cudaMemset(ctx->d_flags, 0, max_frames * sizeof(int)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center, k_center_fast<false>, kThreads, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
+        ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
+        ctx->occ_rmsd = std::max(1, std::min(ctx->occ_rmsd, 8));
         return GROAN_OK;
     }();
     if (rc) {
@@ -565,7 +622,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
     }
     for (auto &r : ctx->refs)
         if (r.d_pc) cudaFree(r.d_pc);
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp};
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
@@ -648,6 +705,8 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
         if (idx[i] != g.first + i) { g.contiguous = false; break; }
     g.has_mass = (mass != nullptr);
     g.no_mass_at = -1;
+    g.mass.clear();
+    if (mass) g.mass.assign(mass, mass + n);
     if (n) {
         CK(cudaMalloc(&g.d_idx, n * sizeof(uint32_t)));
         CK(cudaMemcpy(g.d_idx, idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -722,7 +781,7 @@ int groan_gpu_estimate_center(groan_gpu_ctx *ctx, int gid, int weighted, float *
     if (rc) return rc;
     if (!out) return GROAN_EINVAL;
     float *d_out = target_of<float>(out, ctx->d_cen);
-    rc = run_trig(ctx, *g, weighted != 0, d_out);
+    rc = run_trig(ctx, *g, weighted != 0, d_out, nullptr);
     if (rc) return rc;
     return deliver(ctx, out, d_out, ctx->n_frames * 3 * sizeof(float));
 }
@@ -891,7 +950,7 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         CK(cudaMalloc(&d_refbox, 9 * sizeof(float)));
         CK(cudaMalloc(&d_small, 6 * sizeof(float)));
         CK(cudaMalloc(&d_ridx, n_ref * sizeof(uint32_t)));
-        CK(cudaMalloc(&d_sums, 2 * sizeof(double)));
+        CK(cudaMalloc(&d_sums, kRefSums * sizeof(double)));
         CK(cudaMalloc(&R.d_pc, n_ref * sizeof(float4)));
         CK(cudaMemcpyAsync(d_ref, ref_xyz, n_ref_atoms * 3 * sizeof(float), cudaMemcpyDefault, ctx->compute));
         CK(cudaMemcpyAsync(d_refbox, ref_box, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
@@ -911,20 +970,19 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         gv.mass = ref_mass ? d_rmass : g->d_mass;
         const int nb = blocks_per_frame(n_ref, 1);
         // reference.group_get_com(group): geometric estimate, then mass-weighted unwrap (iterators.rs:1404-1438)
-        k_trig<false><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, ctx->d_partials, ctx->d_tickets + ctx->max_frames, d_small);
+        k_trig<false><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, ctx->d_partials, ctx->d_tickets + ctx->max_frames, d_small,
+                                                                   nullptr);
         LAUNCHED();
         k_unwrap<true><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small, ctx->d_partials, ctx->d_tickets + ctx->max_frames,
-                                                                    d_small + 3);
+                                                                    d_small + 3, nullptr);
         LAUNCHED();
         k_ref_prepare<<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small + 3, R.d_pc, ctx->d_partials,
                                                                    ctx->d_tickets + ctx->max_frames, d_sums);
         LAUNCHED();
-        double sums[2];
-        CK(cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaMemcpyAsync(R.sums, d_sums, sizeof(R.sums), cudaMemcpyDeviceToHost, ctx->compute));
         CK(cudaMemcpyAsync(R.com, d_small + 3, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
         CK(cudaStreamSynchronize(ctx->compute));
-        R.sum_mpp = sums[0];
-        R.sum_m = sums[1];
+        R.same_mass = !ref_mass || (g->mass.size() == n_ref && std::memcmp(g->mass.data(), ref_mass, n_ref * sizeof(float)) == 0);
         return GROAN_OK;
     }();
     cudaFree(d_ref); cudaFree(d_refbox); cudaFree(d_small); cudaFree(d_ridx); cudaFree(d_sums); cudaFree(d_rmass);

@@ -1,15 +1,25 @@
 // kernels_center.cuh -- periodic centre of geometry / mass over a batch of frames.
 //
-// Reference-order ("exact") passes.  Per-atom arithmetic is the reference's, operation for operation
-// and in f32 (so every per-atom value, in particular every image decision, is the reference's);
-// only the SUMMATION differs: per-thread f32 partials over <= 64 atoms, then f64 tree reduction
-// (the reference sums sequentially in f32 and drifts; see DESIGN.md "Accumulation").
+// (1) Reference-order ("exact") passes.  Per-atom arithmetic is the reference's, operation for operation
+//     and in f32 (so every per-atom value, in particular every image decision, is the reference's);
+//     only the SUMMATION differs: per-thread f32 partials over <= 64 atoms, then an f64 tree
+//     (the reference sums sequentially in f32 and drifts; see DESIGN.md "Accumulation").
 //
-//   k_trig    Bai-Breen circular mean          iterators.rs:1152-1191 / 1314-1357, auxiliary.rs:59-99
-//   k_unwrap  refined pass: unwrap around c0   iterators.rs:1237-1266 / 1404-1438, vector3d.rs:561-569
-//   k_naive   plain mean                       iterators.rs:886-903
+//       k_trig    Bai-Breen circular mean          iterators.rs:1152-1191 / 1314-1357, auxiliary.rs:59-99
+//       k_unwrap  refined pass: unwrap around c0   iterators.rs:1237-1266 / 1404-1438, vector3d.rs:561-569
+//       k_naive   plain mean                       iterators.rs:886-903
 //
-// Grid = (blocks per frame, frames); the last CTA of each frame finishes the frame (common.cuh).
+// (2) Single-pass kernel k_center_fast for group_get_center / group_get_com (DESIGN.md "Single-pass
+//     centre"): every atom is unwrapped around a PILOT (the group's first atom) instead of around the
+//     Bai-Breen estimate c0, and the sums, the extent of the unwrapped group and the circular-mean sums
+//     are taken in the same pass.  If the unwrapped group is shorter than half the box on every axis
+//     -- the reference's own validity condition (iterators.rs:1195) -- c0 provably lies inside the
+//     group's arc, no atom changes image between the two choices of origin, and the reference's result
+//     is mean(unwrapped) + k*L with k fixed by c0.  c0 is only needed to pick k, so its trig sums use
+//     the SFU (MUFU.SIN/COS); frames where that decision is within the SFU error of the box edge, or
+//     whose group is not compact, are flagged and re-done by the exact passes.
+//
+// Grid = (CTAs per frame, frames); the last CTA of each frame finishes the frame (common.cuh).
 #pragma once
 #include "common.cuh"
 
@@ -17,41 +27,43 @@ namespace groan {
 
 constexpr int kFlush = 64; // f32 partials are flushed to f64 every kFlush atoms
 
+// frames are skipped when a flag array is given and the frame's flag is zero (exact passes re-doing
+// only the frames a single-pass kernel could not certify)
+__device__ __forceinline__ bool frame_skipped(const int *flags, int f) { return flags && flags[f] == 0; }
+
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads) k_trig(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                    float *c0_out) {
-    __shared__ double smem[6 * (kThreads / 32)];
-    __shared__ int sh_flag;
+                                                    float *c0_out, const int *flags) {
+    __shared__ FrameReduceSmem<6, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
+    if (frame_skipped(flags, f)) return;
     float lx, ly, lz;
     fv.lengths(f, lx, ly, lz);
     const float sx = pi_x2() / lx, sy = pi_x2() / ly, sz = pi_x2() / lz; // iterators.rs:1154
-    const float *fr = fv.frame(f);
     float a[6] = {0, 0, 0, 0, 0, 0};
     double d[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += nb * blockDim.x) {
-        const float *p = fr + (size_t)g.atom(i) * 3;
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float m = WEIGHTED ? __ldg(g.mass + i) : 1.0f;
         float s, c;
         // auxiliary.rs:59-83: wrap, theta = pos * scaling, sum_xi += m cos, sum_zeta += m sin
-        sincosf(wrap_coordinate(__ldg(p + 0), lx) * sx, &s, &c);
+        sincosf(wrap_coordinate(x, lx) * sx, &s, &c);
         a[0] += m * c; a[3] += m * s;
-        sincosf(wrap_coordinate(__ldg(p + 1), ly) * sy, &s, &c);
+        sincosf(wrap_coordinate(y, ly) * sy, &s, &c);
         a[1] += m * c; a[4] += m * s;
-        sincosf(wrap_coordinate(__ldg(p + 2), lz) * sz, &s, &c);
+        sincosf(wrap_coordinate(z, lz) * sz, &s, &c);
         a[2] += m * c; a[5] += m * s;
         if (++cnt == kFlush) {
 #pragma unroll
             for (int k = 0; k < 6; k++) { d[k] += (double)a[k]; a[k] = 0.0f; }
             cnt = 0;
         }
-    }
+    });
 #pragma unroll
     for (int k = 0; k < 6; k++) d[k] += (double)a[k];
-    block_sum<6>(d, smem);
     double tot[6];
-    if (frame_finish<6>(d, partials + (size_t)f * nb * 6, tickets + f, nb, tot, &sh_flag) && threadIdx.x == 0) {
+    if (frame_reduce<6, 0>(d, nullptr, nullptr, partials + (size_t)f * nb * 6, tickets + f, nb, sm, tot, nullptr, nullptr) &&
+        threadIdx.x == 0) {
         // auxiliary.rs:87-99: (atan2(-zeta, -xi) + PI) / scaling, in f32
         const float sc[3] = {sx, sy, sz};
         for (int k = 0; k < 3; k++) {
@@ -64,35 +76,33 @@ __global__ void __launch_bounds__(kThreads) k_trig(FrameView fv, GroupView g, do
 // centre = sum(m * (c0 + vector_to(c0, x))) / sum(m); geometry: m = 1, divisor = n
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads) k_unwrap(FrameView fv, GroupView g, const float *c0_in, double *partials,
-                                                      unsigned int *tickets, float *out) {
-    __shared__ double smem[4 * (kThreads / 32)];
-    __shared__ int sh_flag;
+                                                      unsigned int *tickets, float *out, const int *flags) {
+    __shared__ FrameReduceSmem<4, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
+    if (frame_skipped(flags, f)) return;
     float lx, ly, lz;
     fv.lengths(f, lx, ly, lz);
     const float cx = c0_in[f * 3 + 0], cy = c0_in[f * 3 + 1], cz = c0_in[f * 3 + 2];
-    const float *fr = fv.frame(f);
     float a[4] = {0, 0, 0, 0};
     double d[4] = {0, 0, 0, 0};
     int cnt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += nb * blockDim.x) {
-        const float *p = fr + (size_t)g.atom(i) * 3;
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float m = WEIGHTED ? __ldg(g.mass + i) : 1.0f;
-        const float nx = cx + vector_to_1(cx, __ldg(p + 0), lx);
-        const float ny = cy + vector_to_1(cy, __ldg(p + 1), ly);
-        const float nz = cz + vector_to_1(cz, __ldg(p + 2), lz);
+        const float nx = cx + vector_to_1(cx, x, lx);
+        const float ny = cy + vector_to_1(cy, y, ly);
+        const float nz = cz + vector_to_1(cz, z, lz);
         a[0] += nx * m; a[1] += ny * m; a[2] += nz * m; a[3] += m;
         if (++cnt == kFlush) {
 #pragma unroll
             for (int k = 0; k < 4; k++) { d[k] += (double)a[k]; a[k] = 0.0f; }
             cnt = 0;
         }
-    }
+    });
 #pragma unroll
     for (int k = 0; k < 4; k++) d[k] += (double)a[k];
-    block_sum<4>(d, smem);
     double tot[4];
-    if (frame_finish<4>(d, partials + (size_t)f * nb * 4, tickets + f, nb, tot, &sh_flag) && threadIdx.x == 0) {
+    if (frame_reduce<4, 0>(d, nullptr, nullptr, partials + (size_t)f * nb * 4, tickets + f, nb, sm, tot, nullptr, nullptr) &&
+        threadIdx.x == 0) {
         const double div = WEIGHTED ? tot[3] : (double)g.n;
         for (int k = 0; k < 3; k++) out[f * 3 + k] = (float)(tot[k] / div);
     }
@@ -100,28 +110,95 @@ __global__ void __launch_bounds__(kThreads) k_unwrap(FrameView fv, GroupView g, 
 
 __global__ void __launch_bounds__(kThreads) k_naive(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
                                                      float *out) {
-    __shared__ double smem[3 * (kThreads / 32)];
-    __shared__ int sh_flag;
+    __shared__ FrameReduceSmem<3, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
-    const float *fr = fv.frame(f);
     float a[3] = {0, 0, 0};
     double d[3] = {0, 0, 0};
     int cnt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += nb * blockDim.x) {
-        const float *p = fr + (size_t)g.atom(i) * 3;
-        a[0] += __ldg(p + 0); a[1] += __ldg(p + 1); a[2] += __ldg(p + 2);
+    for_each_group_atom(fv, g, f, [&](uint32_t, float x, float y, float z) {
+        a[0] += x; a[1] += y; a[2] += z;
         if (++cnt == kFlush) {
 #pragma unroll
             for (int k = 0; k < 3; k++) { d[k] += (double)a[k]; a[k] = 0.0f; }
             cnt = 0;
         }
-    }
+    });
 #pragma unroll
     for (int k = 0; k < 3; k++) d[k] += (double)a[k];
-    block_sum<3>(d, smem);
     double tot[3];
-    if (frame_finish<3>(d, partials + (size_t)f * nb * 3, tickets + f, nb, tot, &sh_flag) && threadIdx.x == 0)
+    if (frame_reduce<3, 0>(d, nullptr, nullptr, partials + (size_t)f * nb * 3, tickets + f, nb, sm, tot, nullptr, nullptr) &&
+        threadIdx.x == 0)
         for (int k = 0; k < 3; k++) out[f * 3 + k] = (float)(tot[k] / (double)g.n);
+}
+
+// ---------------------------------------------------------------- single pass
+// min-image displacement from the pilot, branch-free: d - L * rint(d / L).  Differs from the reference's
+// vector_to (vector3d.rs:561-569) only in the last ulp and at the |d| = L/2 tie, which the extent check
+// below excludes before the result is trusted.
+__device__ __forceinline__ float pilot_delta(float x, float p, float L, float invL) {
+    const float d = x - p;
+    return __fmaf_rn(-L, rintf(d * invL), d);
+}
+
+constexpr double kExtentSlack = 1.0 - 1e-5; // unwrapped extent must be below (L/2) * slack on every axis
+constexpr double kEdgeBand = 2e-5;          // c0 within this fraction of L of the box edge: image count ambiguous
+
+// sums: [0..2] sum m*d, [3] sum m, [4..6] sum cos(phi), [7..9] sum sin(phi); min/max of d per axis
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads) k_center_fast(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
+                                                           float *out, int *flags) {
+    __shared__ FrameReduceSmem<10, 3> sm;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *p0 = fv.frame(f) + (size_t)g.atom(0) * 3;
+    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
+    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
+    const float sx = pi_x2() * ix, sy = pi_x2() * iy, sz = pi_x2() * iz;
+    float a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
+        const float dx = pilot_delta(x, px, L[0], ix), dy = pilot_delta(y, py, L[1], iy), dz = pilot_delta(z, pz, L[2], iz);
+        if (WEIGHTED) {
+            const float m = __ldg(g.mass + i);
+            a[0] = __fmaf_rn(m, dx, a[0]); a[1] = __fmaf_rn(m, dy, a[1]); a[2] = __fmaf_rn(m, dz, a[2]);
+            a[3] += m;
+        } else {
+            a[0] += dx; a[1] += dy; a[2] += dz;
+        }
+        float s, c;
+        __sincosf(dx * sx, &s, &c); a[4] += c; a[7] += s;
+        __sincosf(dy * sy, &s, &c); a[5] += c; a[8] += s;
+        __sincosf(dz * sz, &s, &c); a[6] += c; a[9] += s;
+        mn[0] = fminf(mn[0], dx); mx[0] = fmaxf(mx[0], dx);
+        mn[1] = fminf(mn[1], dy); mx[1] = fmaxf(mx[1], dy);
+        mn[2] = fminf(mn[2], dz); mx[2] = fmaxf(mx[2], dz);
+    });
+    double tot[10];
+    float tmn[3], tmx[3];
+    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
+        const double M = WEIGHTED ? tot[3] : (double)g.n;
+        const float p[3] = {px, py, pz};
+        int redo = 0;
+        for (int k = 0; k < 3; k++) {
+            const double Lk = (double)L[k];
+            if ((double)tmx[k] - (double)tmn[k] >= 0.5 * Lk * kExtentSlack) redo = 1; // not compact: images may differ
+            // circular mean of the group, iterators.rs:1152-1191, from the pilot-relative sums:
+            // theta_i = theta_p + phi_i  =>  (xi, zeta) = R(theta_p) (C, S)
+            const double C = tot[4 + k], S = tot[7 + k];
+            if (C * C + S * S < 1e-6 * (double)g.n * (double)g.n) redo = 1; // resultant too short to trust the SFU sums
+            const double sc = 6.283185307179586 / Lk;
+            double pw = fmod((double)p[k], Lk);
+            if (pw < 0) pw += Lk;
+            const double tp = pw * sc, ct = cos(tp), st = sin(tp);
+            const double xi = ct * C - st * S, ze = st * C + ct * S;
+            const double c0 = (atan2(-ze, -xi) + 3.141592653589793) / sc; // in [0, L]
+            if (c0 < kEdgeBand * Lk || c0 > (1.0 - kEdgeBand) * Lk) redo = 1;     // which side of the edge decides k
+            const double um = (double)p[k] + tot[k] / M;                          // mean of the unwrapped group
+            out[f * 3 + k] = (float)(um + Lk * rint((c0 - um) / Lk));             // the image within L/2 of c0
+        }
+        flags[f] = redo;
+    }
 }
 
 // Vector3D::distance between two per-frame centres (System::group_distance, analysis.rs:348-360)

@@ -1,79 +1,91 @@
-// kernels_rmsd.cuh -- RMSD with Kabsch fit over a batch of frames (reference-order passes).
+// kernels_rmsd.cuh -- RMSD with Kabsch fit over a batch of frames, plus wrap / translate.
 //
-//   k_ref_prepare  extract_data_from_system on the reference  rmsd.rs:425-446,479-492
-//   k_cov          shift+wrap the target group, covariance sums, last CTA: SVD + RMSD   rmsd.rs:547-603
-//   k_fit          fit_structure over ALL atoms              rmsd.rs:508-528
+//   k_ref_prepare  extract_data_from_system on the reference      rmsd.rs:425-446,479-492
+//   k_cov          exact pass: shift+wrap the target group, covariance sums in f64, SVD + RMSD   rmsd.rs:547-603
+//   k_rmsd_fast    single pass: COM, covariance and RMSD sums relative to a pilot atom (DESIGN.md "Single-pass RMSD")
+//   k_fit          fit_structure over ALL atoms                   rmsd.rs:508-528
+//   k_wrap         atoms_wrap / atoms_translate                   modifying.rs:73,201; vector3d.rs:380-417
 //
 // RMSD is evaluated from sums (no second pass over rotated coordinates):
 //   sum_i w_i |r^T pc_i - qc_i|^2 = sum w|pc|^2 + sum w|qc|^2 - 2 sum_ab r_ab Hw_ab,  Hw = sum_i w_i pc_i qc_i^T
-// with H = sum_i pc_i qc_i^T (UNWEIGHTED, rmsd.rs:566-570) feeding the SVD.  The sums are accumulated in
-// f64 (products of f32 pairs are exact there), so the cancellation in the identity is harmless.
+// with H = sum_i pc_i qc_i^T (UNWEIGHTED, rmsd.rs:566-570) feeding the SVD.
 #pragma once
 #include "common.cuh"
+#include "kernels_center.cuh"
 
 namespace groan {
 
 struct RefView {
-    const float4 *pc; // group order: (y_ref - box_centre_ref).xyz, w = mass
-    double sum_mpp;   // sum m |pc|^2
-    double sum_m;     // sum m
-    float com[3];     // reference.group_get_com(group) (rmsd.rs:133,198)
+    const float4 *pc;  // group order: (y_ref - box_centre_ref).xyz, w = reference mass
+    double sum_wpp;    // sum w |pc|^2
+    double sum_w;      // sum w
+    double sum_pc[3];  // sum pc
+    double sum_wpc[3]; // sum w pc
+    float com[3];      // reference.group_get_com(group) (rmsd.rs:133,198)
 };
 
-// reference side, once: y = wrap(x + (bc - com)); pc = y - bc; (pc, m) -> float4; sums m|pc|^2 and m
+constexpr int kRefSums = 8; // w|pc|^2, w, pc[3], w pc[3]
+
+// reference side, once: y = wrap(x + (bc - com)); pc = y - bc; (pc, w) -> float4; constant sums
 __global__ void __launch_bounds__(kThreads) k_ref_prepare(FrameView fv, GroupView g, const float *com, float4 *pc_out,
                                                            double *partials, unsigned int *tickets, double *sums_out) {
-    __shared__ double smem[2 * (kThreads / 32)];
-    __shared__ int sh_flag;
+    __shared__ FrameReduceSmem<kRefSums, 0> sm;
     const int nb = gridDim.x;
     float lx, ly, lz;
     fv.lengths(0, lx, ly, lz);
     const float bx = lx / 2.0f, by = ly / 2.0f, bz = lz / 2.0f; // get_box_center, mod.rs:298-308
     const float shx = bx - com[0], shy = by - com[1], shz = bz - com[2];
-    const float *fr = fv.frame(0);
-    double d[2] = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += nb * blockDim.x) {
-        const float *p = fr + (size_t)g.atom(i) * 3;
+    double d[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for_each_group_atom(fv, g, 0, [&](uint32_t i, float x, float y, float z) {
         const float m = __ldg(g.mass + i);
-        const float px = wrap_coordinate(__ldg(p + 0) + shx, lx) - bx;
-        const float py = wrap_coordinate(__ldg(p + 1) + shy, ly) - by;
-        const float pz = wrap_coordinate(__ldg(p + 2) + shz, lz) - bz;
+        const float px = wrap_coordinate(x + shx, lx) - bx;
+        const float py = wrap_coordinate(y + shy, ly) - by;
+        const float pz = wrap_coordinate(z + shz, lz) - bz;
         pc_out[i] = make_float4(px, py, pz, m);
         d[0] += (double)m * ((double)px * px + (double)py * py + (double)pz * pz);
         d[1] += (double)m;
-    }
-    block_sum<2>(d, smem);
-    double tot[2];
-    if (frame_finish<2>(d, partials, tickets, nb, tot, &sh_flag) && threadIdx.x == 0) {
-        sums_out[0] = tot[0];
-        sums_out[1] = tot[1];
-    }
+        d[2] += (double)px; d[3] += (double)py; d[4] += (double)pz;
+        d[5] += (double)m * px; d[6] += (double)m * py; d[7] += (double)m * pz;
+    });
+    double tot[kRefSums];
+    if (frame_reduce<kRefSums, 0>(d, nullptr, nullptr, partials, tickets, nb, sm, tot, nullptr, nullptr) && threadIdx.x == 0)
+        for (int k = 0; k < kRefSums; k++) sums_out[k] = tot[k];
 }
 
-constexpr int kCovSums = 19; // H[9], Hw[9], sum m|qc|^2
+// Kabsch + RMSD from the covariance sums (thread 0 of the finishing CTA), rmsd.rs:573-599
+__device__ inline double finish_kabsch(const double H[9], const double Hw[9], double sum_wqq, const RefView &ref, double r[9],
+                                       double *ratio) {
+    kabsch_rotation(H, r);
+    double cross = 0.0;
+    for (int k = 0; k < 9; k++) cross += r[k] * Hw[k];
+    const double T = ref.sum_wpp + sum_wqq;
+    double R = T - 2.0 * cross;
+    if (ratio) *ratio = (T > 0.0) ? R / T : 1.0;
+    if (R < 0.0) R = 0.0;
+    return sqrt(R / ref.sum_w);
+}
 
-__global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, RefView ref, const float *com_in,
-                                                   double *partials, unsigned int *tickets, float *rmsd_out, float *rot_out) {
-    __shared__ double smem[kCovSums * (kThreads / 32)];
-    __shared__ int sh_flag;
+constexpr int kCovSums = 19; // H[9], Hw[9], sum w|qc|^2
+
+__global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, RefView ref, const float *com_in, double *partials,
+                                                   unsigned int *tickets, float *rmsd_out, float *rot_out, const int *flags) {
+    __shared__ FrameReduceSmem<kCovSums, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
+    if (frame_skipped(flags, f)) return;
     float lx, ly, lz;
     fv.lengths(f, lx, ly, lz);
     const float bx = lx / 2.0f, by = ly / 2.0f, bz = lz / 2.0f;
     const float shx = bx - com_in[f * 3 + 0], shy = by - com_in[f * 3 + 1], shz = bz - com_in[f * 3 + 2];
-    const float *fr = fv.frame(f);
     // f64 accumulation: products of two f32 are exact in f64, so the identity above stays accurate
-    // down to rmsd ~ 1e-6 nm (an f32 partial would leave ~1e-4 nm at rmsd = 0).
+    // down to rmsd ~ 1e-6 nm (an f32 partial would leave ~1e-4 nm at rmsd = 0 for a small group).
     double d[kCovSums];
 #pragma unroll
     for (int k = 0; k < kCovSums; k++) d[k] = 0.0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += nb * blockDim.x) {
-        const float *p = fr + (size_t)g.atom(i) * 3;
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float4 r = __ldg(ref.pc + i);
         // shift_and_wrap_coordinates (rmsd.rs:479-492) then q - centroid_q (rmsd.rs:564), f32 like the reference
-        const double q[3] = {(double)(wrap_coordinate(__ldg(p + 0) + shx, lx) - bx),
-                             (double)(wrap_coordinate(__ldg(p + 1) + shy, ly) - by),
-                             (double)(wrap_coordinate(__ldg(p + 2) + shz, lz) - bz)};
+        const double q[3] = {(double)(wrap_coordinate(x + shx, lx) - bx), (double)(wrap_coordinate(y + shy, ly) - by),
+                             (double)(wrap_coordinate(z + shz, lz) - bz)};
         const double pc[3] = {(double)r.x, (double)r.y, (double)r.z};
         const double m = (double)r.w;
 #pragma unroll
@@ -86,18 +98,101 @@ __global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, Ref
             }
         }
         d[18] = fma(m, fma(q[0], q[0], fma(q[1], q[1], q[2] * q[2])), d[18]);
-    }
-    block_sum<kCovSums>(d, smem);
+    });
     double tot[kCovSums];
-    if (frame_finish<kCovSums>(d, partials + (size_t)f * nb * kCovSums, tickets + f, nb, tot, &sh_flag) && threadIdx.x == 0) {
+    if (frame_reduce<kCovSums, 0>(d, nullptr, nullptr, partials + (size_t)f * nb * kCovSums, tickets + f, nb, sm, tot, nullptr,
+                                  nullptr) &&
+        threadIdx.x == 0) {
         double r[9];
-        kabsch_rotation(tot, r);
-        double cross = 0.0;
-        for (int k = 0; k < 9; k++) cross += r[k] * tot[9 + k];
-        double msd = (ref.sum_mpp + tot[18] - 2.0 * cross) / ref.sum_m;
-        if (msd < 0.0) msd = 0.0;
-        rmsd_out[f] = (float)sqrt(msd);
+        rmsd_out[f] = (float)finish_kabsch(tot, tot + 9, tot[18], ref, r, nullptr);
         for (int k = 0; k < 9; k++) rot_out[f * 9 + k] = (float)r[k];
+    }
+}
+
+// ---------------------------------------------------------------- single pass
+// With d_i the min-image displacement of atom i from the pilot p (the group's first atom), u_i = p + d_i is
+// the group made whole, com = p + delta with delta = sum m d / sum m, and -- as long as the whole group is
+// shorter than half the box (checked) -- the reference's wrap(x + (bc - com)) - bc equals d_i - delta.  Hence
+//   H  = sum pc d^T   - (sum pc)   delta^T          Hw = sum w pc d^T - (sum w pc) delta^T
+//   sum w|qc|^2 = sum w|d|^2 - 2 delta . sum w d + |delta|^2 sum w
+// and one pass over the frame suffices.  Sums are f32 FFMA per thread, f64 across threads; the finishing
+// thread flags the frame for the exact f64 passes when the cancellation in the RMSD identity has eaten more
+// than the f32 products can give (ratio test) or the group is not compact.
+//
+// sums: [0..8] sum pc_a d_b, [9..17] sum w pc_a d_b, [18..20] sum w d, [21] sum w|d|^2, [22..24] sum m d, [25] sum m
+constexpr int kFastSums = 26;
+constexpr double kCancelGuard = 2e-5;
+
+template <bool SAME_MASS>
+__global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast(FrameView fv, GroupView g, RefView ref, double *partials,
+                                                            unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
+                                                            int *flags) {
+    __shared__ FrameReduceSmem<kFastSums, 3> sm;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *p0 = fv.frame(f) + (size_t)g.atom(0) * 3;
+    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
+    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
+    float a[kFastSums];
+#pragma unroll
+    for (int k = 0; k < kFastSums; k++) a[k] = 0.0f;
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
+        const float4 r = __ldg(ref.pc + i);
+        const float d[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
+        const float pc[3] = {r.x, r.y, r.z};
+        const float w = r.w;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const float wp = w * pc[u];
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                a[u * 3 + v] = __fmaf_rn(pc[u], d[v], a[u * 3 + v]);
+                a[9 + u * 3 + v] = __fmaf_rn(wp, d[v], a[9 + u * 3 + v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const float wd = w * d[v];
+            a[18 + v] += wd;
+            a[21] = __fmaf_rn(wd, d[v], a[21]);
+            mn[v] = fminf(mn[v], d[v]);
+            mx[v] = fmaxf(mx[v], d[v]);
+        }
+        if (!SAME_MASS) {
+            const float m = __ldg(g.mass + i);
+#pragma unroll
+            for (int v = 0; v < 3; v++) a[22 + v] = __fmaf_rn(m, d[v], a[22 + v]);
+            a[25] += m;
+        }
+    });
+    double tot[kFastSums];
+    float tmn[3], tmx[3];
+    if (frame_reduce<kFastSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFastSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
+        threadIdx.x == 0) {
+        int redo = 0;
+        double delta[3];
+        for (int k = 0; k < 3; k++) {
+            if ((double)tmx[k] - (double)tmn[k] >= 0.5 * (double)L[k] * kExtentSlack) redo = 1;
+            delta[k] = SAME_MASS ? tot[18 + k] / ref.sum_w : tot[22 + k] / tot[25];
+        }
+        double H[9], Hw[9];
+        for (int u = 0; u < 3; u++)
+            for (int v = 0; v < 3; v++) {
+                H[u * 3 + v] = tot[u * 3 + v] - ref.sum_pc[u] * delta[v];
+                Hw[u * 3 + v] = tot[9 + u * 3 + v] - ref.sum_wpc[u] * delta[v];
+            }
+        const double dd = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
+        const double wqq = tot[21] - 2.0 * (delta[0] * tot[18] + delta[1] * tot[19] + delta[2] * tot[20]) + dd * ref.sum_w;
+        double r[9], ratio;
+        rmsd_out[f] = (float)finish_kabsch(H, Hw, wqq, ref, r, &ratio);
+        if (!(ratio >= kCancelGuard)) redo = 1; // f32 products cannot resolve this RMSD: exact f64 passes
+        for (int k = 0; k < 9; k++) rot_out[f * 9 + k] = (float)r[k];
+        com_out[f * 3 + 0] = (float)((double)px + delta[0]);
+        com_out[f * 3 + 1] = (float)((double)py + delta[1]);
+        com_out[f * 3 + 2] = (float)((double)pz + delta[2]);
+        flags[f] = redo;
     }
 }
 

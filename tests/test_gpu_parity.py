@@ -459,3 +459,85 @@ def test_synth_generators_match_oracle():
         exp = orc.synth_blob_frame(n, 99, 100 + f, 2.5e-5, 1e-7, rot[f], cen[f], L, wrap=True)
         assert np.array_equal(bits(got[f]), bits(exp)), f
     assert np.array_equal(bits(s.synth_blob_ref(99, 2.5e-5, [17, 17, 17])), bits(orc.synth_blob_ref(n, 99, 2.5e-5, [17, 17, 17])))
+
+
+# ------------------------------------------------------------------ single-pass kernels vs reference-order passes
+def _blob_system(n, F, L, seed, scale, nscale, masses, flags=0):
+    import groan_rs_b200 as g
+    rng = np.random.default_rng(seed)
+    rot = np.empty((F, 9), np.float32)
+    for k in range(F):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        rot[k] = [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
+                  2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]
+    cen = rng.uniform(0, L, size=(F, 3)).astype(np.float32)
+    cen[0] = [0.01, L[1] - 0.01, L[2] / 2]  # straddles two box faces
+    s = g.System(n, masses=masses, max_frames=F)
+    if flags:
+        s.set_flags(flags)
+    s.synth_blob(seed, 0, F, scale, nscale, rot, cen, L, wrap=True)
+    return s
+
+
+@pytest.mark.parametrize("n,contig", [(200_003, True), (200_003, False), (1_000_000, True)])
+def test_single_pass_matches_exact_and_x64(n, contig):
+    """group_get_center / group_get_com / calc_rmsd: the single-pass kernels, the reference-order passes
+    (GROAN_FLAG_EXACT_ONLY) and the exact64 oracle agree within the north-star tolerances at a size where the
+    reference's sequential f32 sums have already drifted."""
+    import groan_rs_b200 as g
+    F, L = 4, np.array([20.0, 21.0, 19.0], np.float32)
+    rng = np.random.default_rng(1)
+    masses = rng.uniform(1.0, 100.0, n).astype(np.float32)
+    idx = np.arange(5, n - 3) if contig else np.sort(rng.choice(n, n // 2, replace=False))
+    scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
+    fast = _blob_system(n, F, L, 77, scale, nscale, masses)
+    exact = _blob_system(n, F, L, 77, scale, nscale, masses, flags=g.FLAG_EXACT_ONLY)
+    ref = g.System(n, masses=masses)
+    ref_xyz = fast.synth_blob_ref(77, scale, L / 2)
+    ref.set_frames(ref_xyz, L)
+    for s in (fast, exact, ref):
+        s.group_create_from_indices("G", idx)
+    frames = fast.get_frames()
+    l0 = fast.launch_count()
+    cf, mf, rf = fast.group_get_center("G"), fast.group_get_com("G"), fast.calc_rmsd(ref, "G")
+    assert fast.launch_count() - l0 >= 3
+    ce, me, re_ = exact.group_get_center("G"), exact.group_get_com("G"), exact.calc_rmsd(ref, "G")
+    assert np.abs(cf - ce).max() <= TOL_CENTER and np.abs(mf - me).max() <= TOL_CENTER
+    assert np.abs(rf - re_).max() <= 2e-5
+    for f in range(F):
+        c64 = orc.get_center_x64(frames[f], idx, L)
+        m64 = orc.get_center_x64(frames[f], idx, L, mass=masses[idx])
+        r64, _ = orc.calc_rmsd_x64(ref_xyz, idx, L, masses[idx], frames[f], idx, L)
+        assert np.abs(cf[f] - c64).max() <= TOL_CENTER, (f, cf[f], c64)
+        assert np.abs(mf[f] - m64).max() <= TOL_CENTER, (f, mf[f], m64)
+        assert abs(rf[f] - r64) <= 2e-5, (f, rf[f], r64)
+        assert abs(r64 - np.sqrt(3) * 0.03) < 1e-3  # analytic RMSD of the generator
+
+
+def test_single_pass_falls_back_when_it_cannot_certify(example):
+    """box-spanning group (Membrane spans x and y), c0 on the box edge, and RMSD ~ 0: the single-pass kernels flag
+    the frame and the reference-order passes produce the result -- identical to GROAN_FLAG_EXACT_ONLY."""
+    import groan_rs_b200 as g
+    xyz, box = example["xyz"], example["box"]
+    n = xyz.shape[0]
+    res = []
+    for flags in (0, g.FLAG_EXACT_ONLY):
+        s = g.System(n, masses=np.ones(n, np.float32))
+        s.set_flags(flags)
+        s.group_create_from_indices("Membrane", example["Membrane"])
+        s.set_frames(xyz, box.reshape(1, 9))
+        res.append((s.group_get_center("Membrane"), s.group_get_com("Membrane")))
+    assert np.array_equal(bits(res[0][0]), bits(res[1][0])) and np.array_equal(bits(res[0][1]), bits(res[1][1]))
+    # symmetric pair around the box edge: the circular mean sits on the edge, where k is decided by rounding
+    two = np.array([[9.9, 5.0, 0.2], [0.1, 5.0, 0.4]], np.float32)
+    out = []
+    for flags in (0, g.FLAG_EXACT_ONLY):
+        s = g.System(2)
+        s.set_flags(flags)
+        s.group_create_from_indices("g", [0, 1])
+        s.set_frames(two, [10.0, 10.0, 10.0])
+        out.append(s.group_get_center("g"))
+    assert np.array_equal(bits(out[0]), bits(out[1]))
+    assert np.allclose(out[0][0], orc.get_center(two, [0, 1], [10.0] * 3), atol=TOL_CENTER)
