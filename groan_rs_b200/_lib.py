@@ -16,6 +16,7 @@ GROUP_ALL = -1
 MAX_GROUPS = 64
 FLAG_TRICLINIC = 1
 FLAG_EXACT_ONLY = 2
+FLAG_NO_TMA = 4
 
 _vp = C.c_void_p
 _sz = C.c_size_t

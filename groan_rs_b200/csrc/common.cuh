@@ -116,41 +116,42 @@ __device__ __forceinline__ float warp_max(float v) {
 //      independent of scheduling) and leaves the totals in tot[] / tmn[] / tmx[] of EVERY thread.
 //
 // T is the per-thread accumulator type (float for the single-pass kernels, double for the exact ones).
-template <int KS, int NM>
+template <int KS, int NM, int NW = kWarps>
 struct FrameReduceSmem {
-    double stage[(KS + 2 * NM) * kWarps];
+    double stage[(KS + 2 * NM) * NW];
     double tot[KS + 2 * NM];
     int last;
 };
 
-template <int KS, int NM, typename T>
+__device__ __forceinline__ double fold(double v, double u, int k, int ks, int nm) {
+    return (k < ks) ? v + u : (k < ks + nm ? fmin(v, u) : fmax(v, u));
+}
+
+template <int KS, int NM, typename T, int NW>
 __device__ __forceinline__ bool frame_reduce(const T (&sum)[KS], const float *mn, const float *mx, double *partials_frame,
-                                             unsigned int *ticket, int blocks, FrameReduceSmem<KS, NM> &sm, double (&tot)[KS],
+                                             unsigned int *ticket, int blocks, FrameReduceSmem<KS, NM, NW> &sm, double (&tot)[KS],
                                              float *tmn, float *tmx) {
     constexpr int KT = KS + 2 * NM;
-    static_assert(KT <= kThreads, "record wider than a CTA");
+    static_assert(KT <= NW * 32, "record wider than a CTA");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < KS; k++) {
         const T s = warp_sum(sum[k]);
-        if (lane == 0) sm.stage[k * kWarps + w] = (double)s;
+        if (lane == 0) sm.stage[k * NW + w] = (double)s;
     }
 #pragma unroll
     for (int k = 0; k < NM; k++) {
         const float a = warp_min(mn[k]), b = warp_max(mx[k]);
         if (lane == 0) {
-            sm.stage[(KS + k) * kWarps + w] = (double)a;
-            sm.stage[(KS + NM + k) * kWarps + w] = (double)b;
+            sm.stage[(KS + k) * NW + w] = (double)a;
+            sm.stage[(KS + NM + k) * NW + w] = (double)b;
         }
     }
     __syncthreads();
     if (threadIdx.x < KT) {
         const int k = threadIdx.x;
-        double v = sm.stage[k * kWarps];
-        for (int j = 1; j < kWarps; j++) {
-            const double u = sm.stage[k * kWarps + j];
-            v = (k < KS) ? v + u : (k < KS + NM ? fmin(v, u) : fmax(v, u));
-        }
+        double v = sm.stage[k * NW];
+        for (int j = 1; j < NW; j++) v = fold(v, sm.stage[k * NW + j], k, KS, NM);
         partials_frame[(size_t)blockIdx.x * KT + k] = v;
         __threadfence();
     }
@@ -164,25 +165,19 @@ __device__ __forceinline__ bool frame_reduce(const T (&sum)[KS], const float *mn
     if (!sm.last) return false;
     __threadfence();
     // parallel, fixed-order re-read: thread (k, js) folds records js, js + J, js + 2J, ...
-    constexpr int J = (kThreads / KT) < kWarps ? (kThreads / KT) : kWarps;
+    constexpr int J = (NW * 32 / KT) < NW ? (NW * 32 / KT) : NW;
     const int k = threadIdx.x % KT, js = threadIdx.x / KT;
     const volatile double *vp = partials_frame;
     if (js < J) {
         double v = (k < KS) ? 0.0 : (k < KS + NM ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL));
-        for (int j = js; j < blocks; j += J) {
-            const double u = vp[(size_t)j * KT + k];
-            v = (k < KS) ? v + u : (k < KS + NM ? fmin(v, u) : fmax(v, u));
-        }
-        sm.stage[k * kWarps + js] = v;
+        for (int j = js; j < blocks; j += J) v = fold(v, vp[(size_t)j * KT + k], k, KS, NM);
+        sm.stage[k * NW + js] = v;
     }
     __syncthreads();
     if (threadIdx.x < KT) {
         const int kk = threadIdx.x;
-        double v = sm.stage[kk * kWarps];
-        for (int j = 1; j < J; j++) {
-            const double u = sm.stage[kk * kWarps + j];
-            v = (kk < KS) ? v + u : (kk < KS + NM ? fmin(v, u) : fmax(v, u));
-        }
+        double v = sm.stage[kk * NW];
+        for (int j = 1; j < J; j++) v = fold(v, sm.stage[kk * NW + j], kk, KS, NM);
         sm.tot[kk] = v;
     }
     __syncthreads();

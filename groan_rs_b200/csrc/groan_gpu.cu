@@ -22,6 +22,7 @@
 #include "kernels_pairs.cuh"
 #include "kernels_rmsd.cuh"
 #include "kernels_synth.cuh"
+#include "kernels_tma.cuh"
 
 using namespace groan;
 
@@ -93,6 +94,7 @@ struct groan_gpu_ctx {
     float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
     int *d_flags = nullptr;  // per frame: 1 = the single-pass kernel could not certify its result, redo exactly
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
+    int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
 
@@ -222,6 +224,21 @@ int blocks_per_frame_fast(size_t g, size_t F, int occ) {
     return (int)nb;
 }
 
+// TMA-fed kernels need a contiguous group (one byte range per frame), enough atoms to fill the ring, and a
+// 16-byte aligned coordinate buffer (cudaMalloc'ed slots always are; attached buffers are checked)
+bool tma_ok(const groan_gpu_ctx *ctx, const Group &g, int occ) {
+    return occ > 0 && g.contiguous && g.n >= 4 * (size_t)kChunk && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
+           !(ctx->flags & GROAN_FLAG_NO_TMA);
+}
+
+int blocks_per_frame_tma(size_t g, size_t F, int occ) {
+    size_t nb = (g + kChunk - 1) / kChunk;  // at least one chunk per CTA
+    nb = std::max<size_t>(nb, 1);
+    nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
+    return (int)nb;
+}
+
 int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->tmp_bytes) return GROAN_OK;
     if (ctx->d_tmp) {
@@ -321,7 +338,18 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
 // (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
+        dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
+        const size_t smem = TmaSmem<false>::kBytes;
+        if (weighted)
+            k_center_tma<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+                                                                          out, ctx->d_flags);
+        else
+            k_center_tma<false><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+                                                                           out, ctx->d_flags);
+        LAUNCHED();
+        flags = ctx->d_flags;
+    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, ctx->occ_center);
         dim3 grid(nb, (unsigned)ctx->n_frames);
         if (weighted)
@@ -514,7 +542,19 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) 
         rv.com[k] = R.com[k];
     }
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
+        // single pass, TMA-fed (kernels_tma.cuh)
+        dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
+        const size_t smem = TmaSmem<true>::kBytes;
+        if (R.same_mass)
+            k_rmsd_tma<true><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,
+                                                                          ctx->d_tickets, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+        else
+            k_rmsd_tma<false><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,
+                                                                           ctx->d_tickets, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+        LAUNCHED();
+        flags = ctx->d_flags;
+    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
         const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
         dim3 fgrid(nbf, (unsigned)ctx->n_frames);
@@ -591,6 +631,16 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
         ctx->occ_rmsd = std::max(1, std::min(ctx->occ_rmsd, 8));
+        // TMA-fed versions: dynamic shared memory ring (48 KB centre, 112 KB RMSD)
+        const int sc = (int)TmaSmem<false>::kBytes, sr = (int)TmaSmem<true>::kBytes;
+        CK(cudaFuncSetAttribute(k_center_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
+        CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
+        CK(cudaFuncSetAttribute(k_rmsd_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaFuncSetAttribute(k_rmsd_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd_tma, k_rmsd_tma<true>, kTmaThreads, sr));
+        ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
+        ctx->occ_rmsd_tma = std::min(ctx->occ_rmsd_tma, 2);
         return GROAN_OK;
     }();
     if (rc) {

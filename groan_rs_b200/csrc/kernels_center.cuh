@@ -135,13 +135,46 @@ __global__ void __launch_bounds__(kThreads) k_naive(FrameView fv, GroupView g, d
 // min-image displacement from the pilot, branch-free: d - L * rint(d / L).  Differs from the reference's
 // vector_to (vector3d.rs:561-569) only in the last ulp and at the |d| = L/2 tie, which the extent check
 // below excludes before the result is trusted.
+// rint for |x| < 2^22 on the FMA pipe (two FADDs) instead of FRND, which shares the XU pipe with the SFU trig
+__device__ __forceinline__ float rint_fadd(float x) {
+    const float magic = 12582912.0f; // 1.5 * 2^23
+    return (x + magic) - magic;
+}
 __device__ __forceinline__ float pilot_delta(float x, float p, float L, float invL) {
     const float d = x - p;
-    return __fmaf_rn(-L, rintf(d * invL), d);
+    // |d / L| >= 2^22 would defeat rint_fadd; such a frame fails the extent check and is re-done exactly
+    return __fmaf_rn(-L, rint_fadd(d * invL), d);
 }
 
 constexpr double kExtentSlack = 1.0 - 1e-5; // unwrapped extent must be below (L/2) * slack on every axis
 constexpr double kEdgeBand = 2e-5;          // c0 within this fraction of L of the box edge: image count ambiguous
+
+// finishing thread of the single-pass centre: certify the pass and place the mean in the reference's image
+template <bool WEIGHTED>
+__device__ inline void finish_center(const double (&tot)[10], const float *tmn, const float *tmx, float px, float py, float pz,
+                                     const float *L, uint32_t n, float *out3, int *flag) {
+    const double M = WEIGHTED ? tot[3] : (double)n;
+    const float p[3] = {px, py, pz};
+    int redo = 0;
+    for (int k = 0; k < 3; k++) {
+        const double Lk = (double)L[k];
+        if (!((double)tmx[k] - (double)tmn[k] < 0.5 * Lk * kExtentSlack)) redo = 1; // not compact: images may differ
+        // circular mean of the group, iterators.rs:1152-1191, from the pilot-relative sums:
+        // theta_i = theta_p + phi_i  =>  (xi, zeta) = R(theta_p) (C, S)
+        const double C = tot[4 + k], S = tot[7 + k];
+        if (!(C * C + S * S >= 1e-6 * (double)n * (double)n)) redo = 1; // resultant too short to trust the SFU sums
+        const double sc = 6.283185307179586 / Lk;
+        double pw = fmod((double)p[k], Lk);
+        if (pw < 0) pw += Lk;
+        const double tp = pw * sc, ct = cos(tp), st = sin(tp);
+        const double xi = ct * C - st * S, ze = st * C + ct * S;
+        const double c0 = (atan2(-ze, -xi) + 3.141592653589793) / sc; // in [0, L]
+        if (!(c0 >= kEdgeBand * Lk && c0 <= (1.0 - kEdgeBand) * Lk)) redo = 1;  // which side of the edge decides k
+        const double um = (double)p[k] + tot[k] / M;                           // mean of the unwrapped group
+        out3[k] = (float)(um + Lk * rint((c0 - um) / Lk));                      // the image within L/2 of c0
+    }
+    *flag = redo;
+}
 
 // sums: [0..2] sum m*d, [3] sum m, [4..6] sum cos(phi), [7..9] sum sin(phi); min/max of d per axis
 template <bool WEIGHTED>
@@ -176,29 +209,8 @@ __global__ void __launch_bounds__(kThreads) k_center_fast(FrameView fv, GroupVie
     });
     double tot[10];
     float tmn[3], tmx[3];
-    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
-        const double M = WEIGHTED ? tot[3] : (double)g.n;
-        const float p[3] = {px, py, pz};
-        int redo = 0;
-        for (int k = 0; k < 3; k++) {
-            const double Lk = (double)L[k];
-            if ((double)tmx[k] - (double)tmn[k] >= 0.5 * Lk * kExtentSlack) redo = 1; // not compact: images may differ
-            // circular mean of the group, iterators.rs:1152-1191, from the pilot-relative sums:
-            // theta_i = theta_p + phi_i  =>  (xi, zeta) = R(theta_p) (C, S)
-            const double C = tot[4 + k], S = tot[7 + k];
-            if (C * C + S * S < 1e-6 * (double)g.n * (double)g.n) redo = 1; // resultant too short to trust the SFU sums
-            const double sc = 6.283185307179586 / Lk;
-            double pw = fmod((double)p[k], Lk);
-            if (pw < 0) pw += Lk;
-            const double tp = pw * sc, ct = cos(tp), st = sin(tp);
-            const double xi = ct * C - st * S, ze = st * C + ct * S;
-            const double c0 = (atan2(-ze, -xi) + 3.141592653589793) / sc; // in [0, L]
-            if (c0 < kEdgeBand * Lk || c0 > (1.0 - kEdgeBand) * Lk) redo = 1;     // which side of the edge decides k
-            const double um = (double)p[k] + tot[k] / M;                          // mean of the unwrapped group
-            out[f * 3 + k] = (float)(um + Lk * rint((c0 - um) / Lk));             // the image within L/2 of c0
-        }
-        flags[f] = redo;
-    }
+    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0)
+        finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, flags + f);
 }
 
 // Vector3D::distance between two per-frame centres (System::group_distance, analysis.rs:348-360)

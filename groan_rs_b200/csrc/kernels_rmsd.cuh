@@ -124,6 +124,62 @@ constexpr int kFastSums = 26;
 constexpr double kCancelGuard = 2e-5;
 
 template <bool SAME_MASS>
+__device__ __forceinline__ void rmsd_accumulate(float (&a)[kFastSums], float (&mn)[3], float (&mx)[3], const float (&d)[3],
+                                                const float4 &r, float m) {
+    const float pc[3] = {r.x, r.y, r.z};
+    const float w = r.w;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const float wp = w * pc[u];
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            a[u * 3 + v] = __fmaf_rn(pc[u], d[v], a[u * 3 + v]);
+            a[9 + u * 3 + v] = __fmaf_rn(wp, d[v], a[9 + u * 3 + v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        const float wd = w * d[v];
+        a[18 + v] += wd;
+        a[21] = __fmaf_rn(wd, d[v], a[21]);
+        mn[v] = fminf(mn[v], d[v]);
+        mx[v] = fmaxf(mx[v], d[v]);
+    }
+    if (!SAME_MASS) {
+#pragma unroll
+        for (int v = 0; v < 3; v++) a[22 + v] = __fmaf_rn(m, d[v], a[22 + v]);
+        a[25] += m;
+    }
+}
+
+template <bool SAME_MASS>
+__device__ inline void finish_rmsd(const double (&tot)[kFastSums], const float *tmn, const float *tmx, float px, float py, float pz,
+                                   const float *L, const RefView &ref, float *rmsd_out, float *rot9, float *com3, int *flag) {
+    int redo = 0;
+    double delta[3];
+    for (int k = 0; k < 3; k++) {
+        if (!((double)tmx[k] - (double)tmn[k] < 0.5 * (double)L[k] * kExtentSlack)) redo = 1;
+        delta[k] = SAME_MASS ? tot[18 + k] / ref.sum_w : tot[22 + k] / tot[25];
+    }
+    double H[9], Hw[9];
+    for (int u = 0; u < 3; u++)
+        for (int v = 0; v < 3; v++) {
+            H[u * 3 + v] = tot[u * 3 + v] - ref.sum_pc[u] * delta[v];
+            Hw[u * 3 + v] = tot[9 + u * 3 + v] - ref.sum_wpc[u] * delta[v];
+        }
+    const double dd = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
+    const double wqq = tot[21] - 2.0 * (delta[0] * tot[18] + delta[1] * tot[19] + delta[2] * tot[20]) + dd * ref.sum_w;
+    double r[9], ratio;
+    *rmsd_out = (float)finish_kabsch(H, Hw, wqq, ref, r, &ratio);
+    if (!(ratio >= kCancelGuard)) redo = 1; // f32 products cannot resolve this RMSD: exact f64 passes
+    for (int k = 0; k < 9; k++) rot9[k] = (float)r[k];
+    com3[0] = (float)((double)px + delta[0]);
+    com3[1] = (float)((double)py + delta[1]);
+    com3[2] = (float)((double)pz + delta[2]);
+    *flag = redo;
+}
+
+template <bool SAME_MASS>
 __global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast(FrameView fv, GroupView g, RefView ref, double *partials,
                                                             unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
                                                             int *flags) {
@@ -141,59 +197,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast(FrameView fv, GroupVi
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float4 r = __ldg(ref.pc + i);
         const float d[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
-        const float pc[3] = {r.x, r.y, r.z};
-        const float w = r.w;
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const float wp = w * pc[u];
-#pragma unroll
-            for (int v = 0; v < 3; v++) {
-                a[u * 3 + v] = __fmaf_rn(pc[u], d[v], a[u * 3 + v]);
-                a[9 + u * 3 + v] = __fmaf_rn(wp, d[v], a[9 + u * 3 + v]);
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-            const float wd = w * d[v];
-            a[18 + v] += wd;
-            a[21] = __fmaf_rn(wd, d[v], a[21]);
-            mn[v] = fminf(mn[v], d[v]);
-            mx[v] = fmaxf(mx[v], d[v]);
-        }
-        if (!SAME_MASS) {
-            const float m = __ldg(g.mass + i);
-#pragma unroll
-            for (int v = 0; v < 3; v++) a[22 + v] = __fmaf_rn(m, d[v], a[22 + v]);
-            a[25] += m;
-        }
+        rmsd_accumulate<SAME_MASS>(a, mn, mx, d, r, SAME_MASS ? 0.0f : __ldg(g.mass + i));
     });
     double tot[kFastSums];
     float tmn[3], tmx[3];
     if (frame_reduce<kFastSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFastSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
-        threadIdx.x == 0) {
-        int redo = 0;
-        double delta[3];
-        for (int k = 0; k < 3; k++) {
-            if ((double)tmx[k] - (double)tmn[k] >= 0.5 * (double)L[k] * kExtentSlack) redo = 1;
-            delta[k] = SAME_MASS ? tot[18 + k] / ref.sum_w : tot[22 + k] / tot[25];
-        }
-        double H[9], Hw[9];
-        for (int u = 0; u < 3; u++)
-            for (int v = 0; v < 3; v++) {
-                H[u * 3 + v] = tot[u * 3 + v] - ref.sum_pc[u] * delta[v];
-                Hw[u * 3 + v] = tot[9 + u * 3 + v] - ref.sum_wpc[u] * delta[v];
-            }
-        const double dd = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
-        const double wqq = tot[21] - 2.0 * (delta[0] * tot[18] + delta[1] * tot[19] + delta[2] * tot[20]) + dd * ref.sum_w;
-        double r[9], ratio;
-        rmsd_out[f] = (float)finish_kabsch(H, Hw, wqq, ref, r, &ratio);
-        if (!(ratio >= kCancelGuard)) redo = 1; // f32 products cannot resolve this RMSD: exact f64 passes
-        for (int k = 0; k < 9; k++) rot_out[f * 9 + k] = (float)r[k];
-        com_out[f * 3 + 0] = (float)((double)px + delta[0]);
-        com_out[f * 3 + 1] = (float)((double)py + delta[1]);
-        com_out[f * 3 + 2] = (float)((double)pz + delta[2]);
-        flags[f] = redo;
-    }
+        threadIdx.x == 0)
+        finish_rmsd<SAME_MASS>(tot, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, flags + f);
 }
 
 // fit_structure, rmsd.rs:508-528, every atom of every frame:

@@ -62,6 +62,7 @@ enum groan_dim {
 #define GROAN_FLAG_TRICLINIC 1u  /* enable the triclinic EXTENSION (wrap, min-image distances); without it a
                                     non-orthogonal box returns GROAN_ENOTORTHO exactly like the reference */
 #define GROAN_FLAG_EXACT_ONLY 2u /* disable the single-pass fast paths; always run the reference-order passes */
+#define GROAN_FLAG_NO_TMA 4u     /* single-pass kernels with register-staged 256-bit loads instead of the TMA-fed ring */
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
 int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out);
