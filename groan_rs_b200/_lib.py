@@ -35,6 +35,7 @@ SIGNATURES = {
     "groan_gpu_last_cuda_error": (C.c_char_p, [_vp]),
     "groan_gpu_error_detail": (_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "groan_gpu_launch_count": (_u64, [_vp]),
+    "groan_gpu_fallback_frames": (_int, [_vp, C.POINTER(_sz)]),
     "groan_gpu_set_group": (_int, [_vp, _int, _vp, _sz, _vp]),
     "groan_gpu_push_frames": (_int, [_vp, _vp, _vp, _sz]),
     "groan_gpu_attach_frames": (_int, [_vp, _vp, _vp, _sz]),

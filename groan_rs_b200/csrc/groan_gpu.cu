@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -102,7 +103,7 @@ struct groan_gpu_ctx {
     struct Ref {
         bool set = false;
         size_t n = 0;
-        float4 *d_pc = nullptr;
+        float *d_pc = nullptr;  // block-SoA prepared reference (kernels_rmsd.cuh)
         double sums[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
         bool same_mass = true;  // reference masses == the target group's masses
         float com[3] = {0, 0, 0};
@@ -340,7 +341,7 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
     const int *flags = nullptr;
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
         dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaSmem<false>::kBytes;
+        const size_t smem = TmaSmem<false, kCenterStages>::kBytes;
         if (weighted)
             k_center_tma<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
                                                                           out, ctx->d_flags);
@@ -545,7 +546,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) 
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // single pass, TMA-fed (kernels_tma.cuh)
         dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaSmem<true>::kBytes;
+        const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
         if (R.same_mass)
             k_rmsd_tma<true><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,
                                                                           ctx->d_tickets, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
@@ -632,13 +633,17 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
         ctx->occ_rmsd = std::max(1, std::min(ctx->occ_rmsd, 8));
         // TMA-fed versions: dynamic shared memory ring (48 KB centre, 112 KB RMSD)
-        const int sc = (int)TmaSmem<false>::kBytes, sr = (int)TmaSmem<true>::kBytes;
+        const int sc = (int)TmaSmem<false, kCenterStages>::kBytes, sr = (int)TmaSmem<true, kRmsdStages>::kBytes;
         CK(cudaFuncSetAttribute(k_center_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
         CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
         CK(cudaFuncSetAttribute(k_rmsd_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
         CK(cudaFuncSetAttribute(k_rmsd_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd_tma, k_rmsd_tma<true>, kTmaThreads, sr));
+        if (const char *e = std::getenv("GROAN_DEBUG_SKIP_REF")) {
+            const int v = std::atoi(e);
+            CK(cudaMemcpyToSymbol(g_debug_skip_ref, &v, sizeof(int)));
+        }
         ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
         ctx->occ_rmsd_tma = std::min(ctx->occ_rmsd_tma, 2);
         return GROAN_OK;
@@ -732,6 +737,17 @@ int groan_gpu_error_detail(groan_gpu_ctx *ctx, size_t *a, size_t *b) {
 }
 
 uint64_t groan_gpu_launch_count(groan_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n) {
+    if (!ctx || !n) return GROAN_EINVAL;
+    *n = 0;
+    if (!ctx->have_frames) return GROAN_OK;
+    std::vector<int> h(ctx->n_frames);
+    CK(cudaMemcpyAsync(h.data(), ctx->d_flags, ctx->n_frames * sizeof(int), cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    for (int v : h) *n += (v != 0);
+    return GROAN_OK;
+}
 
 // ---- groups ---------------------------------------------------------------------------------------
 int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t n, const float *mass) {
@@ -1001,7 +1017,8 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         CK(cudaMalloc(&d_small, 6 * sizeof(float)));
         CK(cudaMalloc(&d_ridx, n_ref * sizeof(uint32_t)));
         CK(cudaMalloc(&d_sums, kRefSums * sizeof(double)));
-        CK(cudaMalloc(&R.d_pc, n_ref * sizeof(float4)));
+        CK(cudaMalloc(&R.d_pc, ref_floats(n_ref) * sizeof(float)));
+        CK(cudaMemsetAsync(R.d_pc, 0, ref_floats(n_ref) * sizeof(float), ctx->compute));
         CK(cudaMemcpyAsync(d_ref, ref_xyz, n_ref_atoms * 3 * sizeof(float), cudaMemcpyDefault, ctx->compute));
         CK(cudaMemcpyAsync(d_refbox, ref_box, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
         CK(cudaMemcpyAsync(d_ridx, ref_idx, n_ref * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->compute));

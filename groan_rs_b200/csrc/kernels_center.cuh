@@ -135,15 +135,13 @@ __global__ void __launch_bounds__(kThreads) k_naive(FrameView fv, GroupView g, d
 // min-image displacement from the pilot, branch-free: d - L * rint(d / L).  Differs from the reference's
 // vector_to (vector3d.rs:561-569) only in the last ulp and at the |d| = L/2 tie, which the extent check
 // below excludes before the result is trusted.
-// rint for |x| < 2^22 on the FMA pipe (two FADDs) instead of FRND, which shares the XU pipe with the SFU trig
-__device__ __forceinline__ float rint_fadd(float x) {
-    const float magic = 12582912.0f; // 1.5 * 2^23
-    return (x + magic) - magic;
-}
+// rint on the FMA pipe instead of FRND (which shares the XU pipe with the SFU trig): adding 1.5 * 2^23 rounds
+// |q| < 2^22 to an integer, and that add rides on the FFMA that forms q = (x - p) / L.
+// |q| >= 2^22 would defeat it; such a frame fails the extent check and is re-done by the exact passes.
 __device__ __forceinline__ float pilot_delta(float x, float p, float L, float invL) {
     const float d = x - p;
-    // |d / L| >= 2^22 would defeat rint_fadd; such a frame fails the extent check and is re-done exactly
-    return __fmaf_rn(-L, rint_fadd(d * invL), d);
+    const float k = __fmaf_rn(d, invL, 12582912.0f) - 12582912.0f; // rint(d / L)
+    return __fmaf_rn(-L, k, d);
 }
 
 constexpr double kExtentSlack = 1.0 - 1e-5; // unwrapped extent must be below (L/2) * slack on every axis

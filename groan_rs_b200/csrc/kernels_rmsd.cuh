@@ -15,8 +15,20 @@
 
 namespace groan {
 
+// The prepared reference lives in blocks of kRefBlock atoms, structure-of-arrays inside a block:
+// [pc.x * 256][pc.y * 256][pc.z * 256][w * 256] with pc = y_ref - box_centre_ref and w the reference mass.
+// A bulk copy of whole blocks therefore lands in shared memory in a layout that consecutive lanes read
+// without bank conflicts and straight into the register pairs of the packed f32x2 arithmetic.
+constexpr int kRefBlock = 256;
+__host__ __device__ inline size_t ref_floats(size_t n) { return ((n + kRefBlock - 1) / kRefBlock) * (size_t)(4 * kRefBlock); }
+__device__ __forceinline__ size_t ref_word(uint32_t i) { return (size_t)(i >> 8) * (4 * kRefBlock) + (i & (kRefBlock - 1)); }
+__device__ __forceinline__ float4 ref_at(const float *ref, uint32_t i) {
+    const float *b = ref + ref_word(i);
+    return make_float4(__ldg(b), __ldg(b + kRefBlock), __ldg(b + 2 * kRefBlock), __ldg(b + 3 * kRefBlock));
+}
+
 struct RefView {
-    const float4 *pc;  // group order: (y_ref - box_centre_ref).xyz, w = reference mass
+    const float *pc;   // block-SoA (see above), group order
     double sum_wpp;    // sum w |pc|^2
     double sum_w;      // sum w
     double sum_pc[3];  // sum pc
@@ -27,7 +39,7 @@ struct RefView {
 constexpr int kRefSums = 8; // w|pc|^2, w, pc[3], w pc[3]
 
 // reference side, once: y = wrap(x + (bc - com)); pc = y - bc; (pc, w) -> float4; constant sums
-__global__ void __launch_bounds__(kThreads) k_ref_prepare(FrameView fv, GroupView g, const float *com, float4 *pc_out,
+__global__ void __launch_bounds__(kThreads) k_ref_prepare(FrameView fv, GroupView g, const float *com, float *pc_out,
                                                            double *partials, unsigned int *tickets, double *sums_out) {
     __shared__ FrameReduceSmem<kRefSums, 0> sm;
     const int nb = gridDim.x;
@@ -41,7 +53,8 @@ __global__ void __launch_bounds__(kThreads) k_ref_prepare(FrameView fv, GroupVie
         const float px = wrap_coordinate(x + shx, lx) - bx;
         const float py = wrap_coordinate(y + shy, ly) - by;
         const float pz = wrap_coordinate(z + shz, lz) - bz;
-        pc_out[i] = make_float4(px, py, pz, m);
+        float *o = pc_out + ref_word(i);
+        o[0] = px; o[kRefBlock] = py; o[2 * kRefBlock] = pz; o[3 * kRefBlock] = m;
         d[0] += (double)m * ((double)px * px + (double)py * py + (double)pz * pz);
         d[1] += (double)m;
         d[2] += (double)px; d[3] += (double)py; d[4] += (double)pz;
@@ -82,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, Ref
 #pragma unroll
     for (int k = 0; k < kCovSums; k++) d[k] = 0.0;
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
-        const float4 r = __ldg(ref.pc + i);
+        const float4 r = ref_at(ref.pc, i);
         // shift_and_wrap_coordinates (rmsd.rs:479-492) then q - centroid_q (rmsd.rs:564), f32 like the reference
         const double q[3] = {(double)(wrap_coordinate(x + shx, lx) - bx), (double)(wrap_coordinate(y + shy, ly) - by),
                              (double)(wrap_coordinate(z + shz, lz) - bz)};
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast(FrameView fv, GroupVi
     for (int k = 0; k < kFastSums; k++) a[k] = 0.0f;
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
-        const float4 r = __ldg(ref.pc + i);
+        const float4 r = ref_at(ref.pc, i);
         const float d[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
         rmsd_accumulate<SAME_MASS>(a, mn, mx, d, r, SAME_MASS ? 0.0f : __ldg(g.mass + i));
     });

@@ -7,10 +7,11 @@
 // kernels (profiles/r1_v2_*.md) showed exactly that limit: 75 % of the warp stalls were long-scoreboard
 // waits with 16 resident warps per SM.
 //
-//   CTA = 8 consumer warps + 1 producer warp (one elected lane).  Ring of kStages stages; a stage holds one
-//   chunk of kChunk atoms: 12 KB of coordinates (+ 16 KB of the RMSD reference, float4 per atom).
-//   full[s]  (count 1 + tx bytes): producer arms it, the TMA completes it.
-//   empty[s] (count 8): one arrival per consumer warp after its last read of the stage.
+//   CTA = 8 warps, all consumers.  Ring of 3-4 stages; a stage holds one chunk of kChunk atoms: 12 KB of
+//   coordinates (+ 16 KB of the RMSD reference, float4 per atom).  full[s] (count 1 + tx bytes) is armed by
+//   whoever issues the copies and completed by the TMA; the last warp to finish reading a stage (an atomic
+//   counter in shared memory) re-arms it and issues the copies for the chunk one ring ahead, so no warp is
+//   spent polling for free stages.
 //   Coordinates are read from shared memory with stride-3 LDS.32 (3 is coprime to 32: conflict-free), the
 //   reference with LDS.128.  Frame bytes carry an L2 evict-first policy, reference bytes evict-last, so the
 //   64 MB reference of the 4M-atom workload stays in the 126 MB L2 while 48 MB frames stream through.
@@ -24,10 +25,8 @@
 
 namespace groan {
 
-constexpr int kChunk = 1024;                 // atoms per stage
-constexpr int kStages = 4;                   // ring depth
-constexpr int kTmaThreads = kThreads + 32;   // 8 consumer warps + the producer warp
-constexpr int kTmaWarps = kTmaThreads / 32;
+constexpr int kChunk = 1024;          // atoms per stage
+constexpr int kTmaThreads = kThreads; // 8 warps, all consumers; the last warp to leave a stage refills it
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -42,9 +41,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    // the suspend-time hint lets the hardware park the warp until the phase completes instead of spinning on issue slots
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
                  : "memory");
     return ok != 0;
 }
@@ -52,7 +52,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) __trap();
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -73,12 +73,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-template <bool WITH_REF>
+template <bool WITH_REF, int STAGES>
 struct TmaSmem {
     static constexpr size_t kFrameBytes = (size_t)kChunk * 12;
-    static constexpr size_t kRefBytes = WITH_REF ? (size_t)kChunk * 16 : 0;
+    // reference: whole blocks of kRefBlock atoms; a chunk that does not start on a block boundary touches one more
+    static constexpr size_t kRefBytes = WITH_REF ? (size_t)(kChunk / kRefBlock + 1) * kRefBlock * 16 : 0;
     static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
-    static constexpr size_t kBytes = kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 128;
+    static constexpr size_t kBytes = STAGES * kStageBytes + 128;
+};
+constexpr int kCenterStages = 4; // 48 KB of ring: 4 CTAs per SM
+constexpr int kRmsdStages = 3;   // 96 KB of ring: 2 CTAs per SM
+
+template <int STAGES>
+struct TmaCtl {
+    uint64_t full[STAGES];     // count 1 + tx bytes: armed by whoever issues the copies, completed by the TMA
+    unsigned int done[STAGES]; // consumer warps that have finished reading the stage
 };
 
 // Geometry of a contiguous group inside frame f: `head` atoms before the first 16-byte boundary, a body whose
@@ -97,141 +106,264 @@ __device__ __forceinline__ BodyGeom body_geom(const FrameView &fv, const GroupVi
     return b;
 }
 
-// Stream the group's atoms of frame f through the ring.  Consumers call fn(i, x, y, z, ref) for each of their atoms
-// (i = position in the group; ref = reference float4, undefined when !WITH_REF); the producer warp only issues copies.
-template <bool WITH_REF, typename F>
-__device__ __forceinline__ void stream_group_tma(const FrameView &fv, const GroupView &g, int f, const float4 *ref_pc,
-                                                 unsigned char *smem_raw, F &&fn) {
-    typedef TmaSmem<WITH_REF> S;
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);
-    uint64_t *empty = full + kStages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const BodyGeom bg = body_geom(fv, g, f);
+// Stream the body of the group in frame f through the ring, two atoms per call:
+//   fn(i0, i1, X, Y, Z, ref)   with X = (x of atom i0, x of atom i1) etc. and ref the reference (pc.xyz, w) of the
+// two atoms, component-wise paired (zero when !WITH_REF).  Pairs feed the packed f32x2 arithmetic of sm_100 (FADD2 / FMUL2 / FFMA2: one
+// issue slot for two lanes of work), which is what lifts these kernels from issue-bound to HBM-bound
+// (profiles/r1_v4_*).  The two atoms of a pair sit half a chunk apart, so every LDS.32 of a warp walks
+// consecutive atoms (stride 3 words, conflict-free) and lands in a register pair the packed ops can use.
+// The up-to-3 atoms before and after the 16-byte aligned body are NOT visited; the finishing thread adds them.
+//
+// There is no producer warp and nobody polls for a free stage: a warp that has read its share of a stage bumps
+// done[s]; the warp that brings it to 8 is the last reader, so it re-arms full[s] and issues the copies of the
+// chunk STAGES ahead into the stage it has just emptied.  Consumers only ever wait on full[s].
+// profiling experiment only (GROAN_DEBUG_SKIP_REF=1): do not copy the reference into the ring, to measure how much
+// of the RMSD kernel's time is its L2 -> SM traffic.  Results are garbage with it set; never set in tests or bench.
+__device__ int g_debug_skip_ref = 0;
+
+struct RefPair {
+    float2 x, y, z, w; // (atom i0, atom i1) per component
+};
+
+template <bool WITH_REF, int STAGES, typename F>
+__device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg,
+                                                 const float *ref_pc, unsigned char *smem, TmaCtl<STAGES> &ctl, F &&fn) {
+    typedef TmaSmem<WITH_REF, STAGES> S;
+    const int lane = threadIdx.x & 31;
     const float *fr = fv.frame(f);
+    const char *src = reinterpret_cast<const char *>(fr + ((size_t)g.first + bg.head) * 3);
+    const uint32_t my_chunks = bg.chunks > blockIdx.x ? (bg.chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
+    auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES
+        const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
+        const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
+        // reference blocks covering group atoms [i0, i0 + atoms)
+        const uint32_t i0 = bg.head + c * kChunk, b0 = i0 >> 8, b1 = (i0 + atoms - 1) >> 8;
+        const uint32_t ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (b1 - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
+        mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
+        unsigned char *dst = smem + s * S::kStageBytes;
+        bulk_g2s(dst, src + (size_t)c * kChunk * 12, atoms * 12u, ctl.full + s, pol_frame);
+        if (WITH_REF && ref_bytes) bulk_g2s(dst + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);
+    };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, kWarps);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(ctl.full + s, 1);
+            ctl.done[s] = 0;
         }
         fence_mbar_init();
+        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
     }
     __syncthreads();
-    const uint32_t my_chunks = bg.chunks > blockIdx.x ? (bg.chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if (warp == kWarps) {
-        // ---------------- producer
-        if (lane == 0) {
-            const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
-            const char *src = reinterpret_cast<const char *>(fr + ((size_t)g.first + bg.head) * 3);
-            for (uint32_t it = 0; it < my_chunks; it++) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                const uint32_t c = blockIdx.x + it * gridDim.x;
-                const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, atoms * (WITH_REF ? 28u : 12u));
-                unsigned char *dst = smem + s * S::kStageBytes;
-                bulk_g2s(dst, src + (size_t)c * kChunk * 12, atoms * 12u, full + s, pol_frame);
-                if (WITH_REF)
-                    bulk_g2s(dst + S::kFrameBytes, reinterpret_cast<const char *>(ref_pc + bg.head + (size_t)c * kChunk), atoms * 16u,
-                             full + s, pol_ref);
+    for (uint32_t it = 0; it < my_chunks; it++) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        const uint32_t c = blockIdx.x + it * gridDim.x;
+        const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk); // a multiple of 4
+        const float *sf = reinterpret_cast<const float *>(smem + s * S::kStageBytes);
+        const float *sr = reinterpret_cast<const float *>(smem + s * S::kStageBytes + S::kFrameBytes);
+        const uint32_t i0 = bg.head + c * kChunk;
+        const uint32_t lo = i0 & (kRefBlock - 1); // position of the chunk's first atom inside its reference block
+        mbar_wait(ctl.full + s, ph);
+        auto pair = [&](uint32_t j0, uint32_t j1) {
+            const float2 X = make_float2(sf[3 * j0], sf[3 * j1]), Y = make_float2(sf[3 * j0 + 1], sf[3 * j1 + 1]),
+                         Z = make_float2(sf[3 * j0 + 2], sf[3 * j1 + 2]);
+            RefPair r;
+            if (WITH_REF) {
+                const uint32_t w0 = (uint32_t)ref_word(lo + j0), w1 = (uint32_t)ref_word(lo + j1);
+                r.x = make_float2(sr[w0], sr[w1]);
+                r.y = make_float2(sr[w0 + kRefBlock], sr[w1 + kRefBlock]);
+                r.z = make_float2(sr[w0 + 2 * kRefBlock], sr[w1 + 2 * kRefBlock]);
+                r.w = make_float2(sr[w0 + 3 * kRefBlock], sr[w1 + 3 * kRefBlock]);
+            } else {
+                r.x = r.y = r.z = r.w = make_float2(0.f, 0.f);
             }
+            fn(i0 + j0, i0 + j1, X, Y, Z, r);
+        };
+        if (atoms == kChunk) {
+#pragma unroll
+            for (int u = 0; u < kChunk / 2 / kThreads; u++) pair(threadIdx.x + u * kThreads, threadIdx.x + u * kThreads + kChunk / 2);
+        } else {
+            const uint32_t half = atoms >> 1;
+            for (uint32_t j = threadIdx.x; j < half; j += kThreads) pair(j, j + half);
         }
         __syncwarp();
-    } else {
-        // ---------------- consumers
-        for (uint32_t it = 0; it < my_chunks; it++) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            const uint32_t c = blockIdx.x + it * gridDim.x;
-            const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
-            const float *sf = reinterpret_cast<const float *>(smem + s * S::kStageBytes);
-            const float4 *sr = reinterpret_cast<const float4 *>(smem + s * S::kStageBytes + S::kFrameBytes);
-            mbar_wait(full + s, ph);
-#pragma unroll
-            for (int u = 0; u < kChunk / kThreads; u++) {
-                const uint32_t j = threadIdx.x + u * kThreads;
-                if (j < atoms) {
-                    const float4 r = WITH_REF ? sr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    fn(bg.head + c * kChunk + j, sf[3 * j], sf[3 * j + 1], sf[3 * j + 2], r);
-                }
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&ctl.done[s], 1u) == (unsigned)(kWarps - 1)) { // last reader of the stage: refill it
+                ctl.done[s] = 0;
+                __threadfence_block();
+                if (it + STAGES < my_chunks) issue(it + STAGES);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
-        }
-        // the up-to-3 atoms before and after the 16-byte-aligned body
-        if (blockIdx.x == 0 && threadIdx.x < bg.head + bg.tail) {
-            const uint32_t i = threadIdx.x < bg.head ? threadIdx.x : bg.head + bg.body + (threadIdx.x - bg.head);
-            const float *p = fr + ((size_t)g.first + i) * 3;
-            const float4 r = WITH_REF ? __ldg(ref_pc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            fn(i, __ldg(p), __ldg(p + 1), __ldg(p + 2), r);
         }
     }
+}
+
+// packed helpers (sm_100 f32x2 pipe)
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+// min-image displacement from the pilot for two atoms at once; same arithmetic as pilot_delta (kernels_center.cuh)
+__device__ __forceinline__ float2 pilot_delta2(float2 x, float negp, float L, float invL) {
+    const float2 d = __fadd2_rn(x, splat(negp));
+    const float2 k = __fadd2_rn(__ffma2_rn(d, splat(invL), splat(12582912.0f)), splat(-12582912.0f));
+    return __ffma2_rn(splat(-L), k, d);
 }
 
 // ---------------------------------------------------------------- group_get_center / group_get_com, single pass
+// per-thread sums (float2 = one partial per atom of the pair): [0..2] sum m d, [3] sum m, [4..6] sum cos, [7..9] sum sin
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(kTmaThreads) k_center_tma(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                             float *out, int *flags) {
-    extern __shared__ unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<10, 3, kTmaWarps> sm;
+__global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
+                                                                float *out, int *flags) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ FrameReduceSmem<10, 3> sm;
+    __shared__ TmaCtl<kCenterStages> ctl;
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
-    const float *p0 = fv.frame(f) + (size_t)g.first * 3;
+    const float *fr = fv.frame(f);
+    const float *p0 = fr + (size_t)g.first * 3;
     const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
     const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
     const float sx = pi_x2() * ix, sy = pi_x2() * iy, sz = pi_x2() * iz;
-    float a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const BodyGeom bg = body_geom(fv, g, f);
+    float2 a2[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_group_tma<false>(fv, g, f, nullptr, dyn_smem, [&](uint32_t i, float x, float y, float z, const float4 &) {
-        const float dx = pilot_delta(x, px, L[0], ix), dy = pilot_delta(y, py, L[1], iy),
-                    dz = pilot_delta(z, pz, L[2], iz);
+    stream_pairs_tma<false, kCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl,
+                                            [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &) {
+        const float2 dx = pilot_delta2(X, -px, L[0], ix), dy = pilot_delta2(Y, -py, L[1], iy), dz = pilot_delta2(Z, -pz, L[2], iz);
         if (WEIGHTED) {
-            const float m = __ldg(g.mass + i);
-            a[0] = __fmaf_rn(m, dx, a[0]); a[1] = __fmaf_rn(m, dy, a[1]); a[2] = __fmaf_rn(m, dz, a[2]);
-            a[3] += m;
+            const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
+            a2[0] = __ffma2_rn(m, dx, a2[0]); a2[1] = __ffma2_rn(m, dy, a2[1]); a2[2] = __ffma2_rn(m, dz, a2[2]);
+            a2[3] = __fadd2_rn(a2[3], m);
         } else {
-            a[0] += dx; a[1] += dy; a[2] += dz;
+            a2[0] = __fadd2_rn(a2[0], dx); a2[1] = __fadd2_rn(a2[1], dy); a2[2] = __fadd2_rn(a2[2], dz);
         }
-        float s, c;
-        __sincosf(dx * sx, &s, &c); a[4] += c; a[7] += s;
-        __sincosf(dy * sy, &s, &c); a[5] += c; a[8] += s;
-        __sincosf(dz * sz, &s, &c); a[6] += c; a[9] += s;
-        mn[0] = fminf(mn[0], dx); mx[0] = fmaxf(mx[0], dx);
-        mn[1] = fminf(mn[1], dy); mx[1] = fmaxf(mx[1], dy);
-        mn[2] = fminf(mn[2], dz); mx[2] = fmaxf(mx[2], dz);
+        const float2 tx = __fmul2_rn(dx, splat(sx)), ty = __fmul2_rn(dy, splat(sy)), tz = __fmul2_rn(dz, splat(sz));
+        float2 s, c;
+        __sincosf(tx.x, &s.x, &c.x); __sincosf(tx.y, &s.y, &c.y);
+        a2[4] = __fadd2_rn(a2[4], c); a2[7] = __fadd2_rn(a2[7], s);
+        __sincosf(ty.x, &s.x, &c.x); __sincosf(ty.y, &s.y, &c.y);
+        a2[5] = __fadd2_rn(a2[5], c); a2[8] = __fadd2_rn(a2[8], s);
+        __sincosf(tz.x, &s.x, &c.x); __sincosf(tz.y, &s.y, &c.y);
+        a2[6] = __fadd2_rn(a2[6], c); a2[9] = __fadd2_rn(a2[9], s);
+        mn[0] = fminf(mn[0], fminf(dx.x, dx.y)); mx[0] = fmaxf(mx[0], fmaxf(dx.x, dx.y));
+        mn[1] = fminf(mn[1], fminf(dy.x, dy.y)); mx[1] = fmaxf(mx[1], fmaxf(dy.x, dy.y));
+        mn[2] = fminf(mn[2], fminf(dz.x, dz.y)); mx[2] = fmaxf(mx[2], fmaxf(dz.x, dz.y));
     });
+    float a[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) a[k] = a2[k].x + a2[k].y;
     double tot[10];
     float tmn[3], tmx[3];
-    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0)
+    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
+        // the up-to-6 atoms outside the 16-byte aligned body, in f64 with the same definitions
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const float pp[3] = {px, py, pz};
+            const double m = WEIGHTED ? (double)__ldg(g.mass + i) : 1.0;
+            if (WEIGHTED) tot[3] += m;
+            for (int k = 0; k < 3; k++) {
+                const float d = pilot_delta(__ldg(q + k), pp[k], L[k], 1.0f / L[k]);
+                tot[k] += m * (double)d;
+                const double th = (double)d * 6.283185307179586 / (double)L[k];
+                tot[4 + k] += cos(th);
+                tot[7 + k] += sin(th);
+                tmn[k] = fminf(tmn[k], d);
+                tmx[k] = fmaxf(tmx[k], d);
+            }
+        }
         finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, flags + f);
+    }
 }
 
 // ---------------------------------------------------------------- calc_rmsd, single pass
+// per-thread sums as float2 (one partial per atom of the pair), same meaning as kFastSums of kernels_rmsd.cuh
 template <bool SAME_MASS>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
                                                               unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
                                                               int *flags) {
-    extern __shared__ unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<kFastSums, 3, kTmaWarps> sm;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ FrameReduceSmem<kFastSums, 3> sm;
+    __shared__ TmaCtl<kRmsdStages> ctl;
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
-    const float *p0 = fv.frame(f) + (size_t)g.first * 3;
+    const float *fr = fv.frame(f);
+    const float *p0 = fr + (size_t)g.first * 3;
     const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
     const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
+    const BodyGeom bg = body_geom(fv, g, f);
+    float2 a2[kFastSums];
+#pragma unroll
+    for (int k = 0; k < kFastSums; k++) a2[k] = make_float2(0.f, 0.f);
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl,
+                                         [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
+        const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
+        const float2 pc[3] = {r.x, r.y, r.z};
+        const float2 w = r.w;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const float2 wp = __fmul2_rn(w, pc[u]);
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                a2[u * 3 + v] = __ffma2_rn(pc[u], d[v], a2[u * 3 + v]);
+                a2[9 + u * 3 + v] = __ffma2_rn(wp, d[v], a2[9 + u * 3 + v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const float2 wd = __fmul2_rn(w, d[v]);
+            a2[18 + v] = __fadd2_rn(a2[18 + v], wd);
+            a2[21] = __ffma2_rn(wd, d[v], a2[21]);
+            mn[v] = fminf(mn[v], fminf(d[v].x, d[v].y));
+            mx[v] = fmaxf(mx[v], fmaxf(d[v].x, d[v].y));
+        }
+        if (!SAME_MASS) {
+            const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
+#pragma unroll
+            for (int v = 0; v < 3; v++) a2[22 + v] = __ffma2_rn(m, d[v], a2[22 + v]);
+            a2[25] = __fadd2_rn(a2[25], m);
+        }
+    });
     float a[kFastSums];
 #pragma unroll
-    for (int k = 0; k < kFastSums; k++) a[k] = 0.0f;
-    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_group_tma<true>(fv, g, f, ref.pc, dyn_smem, [&](uint32_t i, float x, float y, float z, const float4 &r) {
-        const float d[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
-        rmsd_accumulate<SAME_MASS>(a, mn, mx, d, r, SAME_MASS ? 0.0f : __ldg(g.mass + i));
-    });
+    for (int k = 0; k < kFastSums; k++) a[k] = a2[k].x + a2[k].y;
     double tot[kFastSums];
     float tmn[3], tmx[3];
     if (frame_reduce<kFastSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFastSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
-        threadIdx.x == 0)
+        threadIdx.x == 0) {
+        // the up-to-6 atoms outside the 16-byte aligned body, in f64 with the same definitions
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const float4 r = ref_at(ref.pc, i);
+            const float pp[3] = {px, py, pz};
+            const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
+            double d[3];
+            for (int k = 0; k < 3; k++) {
+                const float dk = pilot_delta(__ldg(q + k), pp[k], L[k], 1.0f / L[k]);
+                d[k] = (double)dk;
+                tmn[k] = fminf(tmn[k], dk);
+                tmx[k] = fmaxf(tmx[k], dk);
+            }
+            for (int u = 0; u < 3; u++)
+                for (int v = 0; v < 3; v++) {
+                    tot[u * 3 + v] += pcd[u] * d[v];
+                    tot[9 + u * 3 + v] += w * pcd[u] * d[v];
+                }
+            for (int v = 0; v < 3; v++) {
+                tot[18 + v] += w * d[v];
+                tot[21] += w * d[v] * d[v];
+            }
+            if (!SAME_MASS) {
+                const double m = (double)__ldg(g.mass + i);
+                for (int v = 0; v < 3; v++) tot[22 + v] += m * d[v];
+                tot[25] += m;
+            }
+        }
         finish_rmsd<SAME_MASS>(tot, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, flags + f);
+    }
 }
 
 } // namespace groan

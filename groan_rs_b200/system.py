@@ -213,6 +213,12 @@ class System:
     def launch_count(self):
         return int(self._lib.groan_gpu_launch_count(self._h))
 
+    def fallback_frames(self):
+        """frames of the last centre / RMSD call that the single-pass kernel handed to the reference-order passes"""
+        n = C.c_size_t(0)
+        self._check(self._lib.groan_gpu_fallback_frames(self._h, C.byref(n)), "fallback_frames")
+        return int(n.value)
+
     def _detail(self):
         a, b = C.c_size_t(0), C.c_size_t(0)
         self._lib.groan_gpu_error_detail(self._h, C.byref(a), C.byref(b))

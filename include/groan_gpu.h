@@ -77,6 +77,9 @@ const char *groan_gpu_last_cuda_error(groan_gpu_ctx *ctx);
 int groan_gpu_error_detail(groan_gpu_ctx *ctx, size_t *a, size_t *b);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t groan_gpu_launch_count(groan_gpu_ctx *ctx);
+/* diagnostics (synchronises): how many frames of the last get_center / get_com / rmsd call the single-pass kernel could
+ * not certify and handed to the reference-order passes (non-compact group, centre on the box edge, RMSD below f32 resolution) */
+int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n);
 
 /* ---- groups: Group::from_indices, container.rs:51-115 ---------------------------------------- */
 /* idx ascending and unique, each < n_atoms; mass nullable (ops that need masses then fail GROAN_ENOMASS,

@@ -501,7 +501,12 @@ def test_single_pass_matches_exact_and_x64(n, contig):
         s.group_create_from_indices("G", idx)
     frames = fast.get_frames()
     l0 = fast.launch_count()
-    cf, mf, rf = fast.group_get_center("G"), fast.group_get_com("G"), fast.calc_rmsd(ref, "G")
+    cf = fast.group_get_center("G")
+    assert fast.fallback_frames() == 0  # compact group, centre away from the box edge: certified by the single pass
+    mf = fast.group_get_com("G")
+    assert fast.fallback_frames() == 0
+    rf = fast.calc_rmsd(ref, "G")
+    assert fast.fallback_frames() == 0
     assert fast.launch_count() - l0 >= 3
     ce, me, re_ = exact.group_get_center("G"), exact.group_get_com("G"), exact.calc_rmsd(ref, "G")
     assert np.abs(cf - ce).max() <= TOL_CENTER and np.abs(mf - me).max() <= TOL_CENTER
@@ -530,6 +535,7 @@ def test_single_pass_falls_back_when_it_cannot_certify(example):
         s.set_frames(xyz, box.reshape(1, 9))
         res.append((s.group_get_center("Membrane"), s.group_get_com("Membrane")))
     assert np.array_equal(bits(res[0][0]), bits(res[1][0])) and np.array_equal(bits(res[0][1]), bits(res[1][1]))
+    assert s.fallback_frames() == 0  # EXACT_ONLY never flags
     # symmetric pair around the box edge: the circular mean sits on the edge, where k is decided by rounding
     two = np.array([[9.9, 5.0, 0.2], [0.1, 5.0, 0.4]], np.float32)
     out = []
@@ -539,5 +545,6 @@ def test_single_pass_falls_back_when_it_cannot_certify(example):
         s.group_create_from_indices("g", [0, 1])
         s.set_frames(two, [10.0, 10.0, 10.0])
         out.append(s.group_get_center("g"))
+        assert s.fallback_frames() == (1 if flags == 0 else 0)
     assert np.array_equal(bits(out[0]), bits(out[1]))
     assert np.allclose(out[0][0], orc.get_center(two, [0, 1], [10.0] * 3), atol=TOL_CENTER)
