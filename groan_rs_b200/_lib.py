@@ -51,6 +51,7 @@ SIGNATURES = {
     "groan_gpu_translate": (_int, [_vp, _int, C.POINTER(_f), _vp]),
     "groan_gpu_rmsd_set_reference": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
     "groan_gpu_rmsd": (_int, [_vp, _int, _vp, _vp]),
+    "groan_gpu_center_rmsd": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "groan_gpu_rmsd_fit": (_int, [_vp, _int, _vp]),
     "groan_gpu_synth_uniform": (_int, [_vp, _u64, _u64, _sz, C.POINTER(_f), C.POINTER(_f), _vp]),
     "groan_gpu_synth_blob": (_int, [_vp, _u64, _u64, _sz, _f, _f, _vp, _vp, _vp, _int]),

@@ -31,7 +31,7 @@ namespace {
 
 constexpr size_t kStageBytes = 32u << 20;  // pinned staging chunk for pageable sources
 constexpr size_t kPartialSlots = 8192;     // (blocks per frame) x (frames) upper bound for reductions
-constexpr int kMaxSums = 32;               // widest per-CTA partial record, in doubles
+constexpr int kMaxSums = 48;               // widest per-CTA partial record, in doubles
 
 struct Group {
     bool set = false;
@@ -511,7 +511,8 @@ int check_wrap_args(groan_gpu_ctx *ctx, int gid, const Group **gp, bool *tric) {
     return GROAN_OK;
 }
 
-int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) {
+// center != nullptr: also produce group_get_center (center_weighted = 0) or group_get_com (1) of the same group
+int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, float *center = nullptr, int center_weighted = 0) {
     if (!ctx) return GROAN_EINVAL;
     const Group *g = get_group(ctx, gid);
     if (!g || gid < 0) return GROAN_ENOGROUP;
@@ -543,7 +544,23 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) 
         rv.com[k] = R.com[k];
     }
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
+    float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
+    bool center_done = false;
+    if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
+        // centre + RMSD from one read of the frame (kernels_tma.cuh)
+        dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
+        const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
+#define FUSED_LAUNCH(SM, WC)                                                                                                      \
+    k_center_rmsd_tma<SM, WC><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,      \
+                                                                           ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,  \
+                                                                           ctx->d_flags)
+        if (R.same_mass) { if (center_weighted) FUSED_LAUNCH(true, true); else FUSED_LAUNCH(true, false); }
+        else { if (center_weighted) FUSED_LAUNCH(false, true); else FUSED_LAUNCH(false, false); }
+#undef FUSED_LAUNCH
+        LAUNCHED();
+        flags = ctx->d_flags;
+        center_done = true;
+    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // single pass, TMA-fed (kernels_tma.cuh)
         dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
         const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
@@ -586,6 +603,19 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit) 
         k_fit<<<fgrid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->d_box[ctx->slot], ctx->n_atoms, ctx->d_cen, d_rot, R.com[0],
                                                      R.com[1], R.com[2]);
         LAUNCHED();
+    }
+    if (center) {
+        if (center_done) {
+            // frames the fused pass flagged: reference-order centre passes for those frames only (d_c0 already
+            // holds their Bai-Breen estimate from the RMSD fallback above)
+            rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
+            if (rc) return rc;
+        } else {
+            rc = run_get_center(ctx, *g, center_weighted != 0, d_center);
+            if (rc) return rc;
+        }
+        rc = deliver(ctx, center, d_center, ctx->n_frames * 3 * sizeof(float));
+        if (rc) return rc;
     }
     rc = deliver(ctx, rmsd, d_rmsd, ctx->n_frames * sizeof(float));
     if (rc) return rc;
@@ -638,6 +668,10 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
         CK(cudaFuncSetAttribute(k_rmsd_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
         CK(cudaFuncSetAttribute(k_rmsd_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaFuncSetAttribute(k_center_rmsd_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaFuncSetAttribute(k_center_rmsd_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaFuncSetAttribute(k_center_rmsd_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
+        CK(cudaFuncSetAttribute(k_center_rmsd_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd_tma, k_rmsd_tma<true>, kTmaThreads, sr));
         if (const char *e = std::getenv("GROAN_DEBUG_SKIP_REF")) {
@@ -1062,6 +1096,11 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
 int groan_gpu_rmsd(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot) {
     if (!rmsd) return GROAN_EINVAL;
     return rmsd_common(ctx, gid, rmsd, rot, false);
+}
+
+int groan_gpu_center_rmsd(groan_gpu_ctx *ctx, int gid, int weighted, float *center, float *rmsd, float *rot) {
+    if (!rmsd || !center) return GROAN_EINVAL;
+    return rmsd_common(ctx, gid, rmsd, rot, false, center, weighted);
 }
 
 int groan_gpu_rmsd_fit(groan_gpu_ctx *ctx, int gid, float *rmsd) {

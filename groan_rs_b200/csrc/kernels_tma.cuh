@@ -366,4 +366,123 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
     }
 }
 
+// ---------------------------------------------------------------- group_get_center (or group_get_com) + calc_rmsd in ONE pass
+// A trajectory analysis usually wants several per-frame quantities of the same group; each extra pass costs
+// another 12 B/atom of HBM.  This kernel produces the refined centre (geometric, or mass-weighted = the COM the
+// RMSD needs anyway) and the Kabsch RMSD from a single read of the frame.
+// sums: [0..25] as k_rmsd_tma, [26..28] sum d (geometric centre), [29..31] sum cos, [32..34] sum sin
+constexpr int kFusedSums = kFastSums + 9;
+
+template <bool SAME_MASS, bool WEIGHTED_CENTER>
+__global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
+                                                                     unsigned int *tickets, float *center_out, float *rmsd_out,
+                                                                     float *rot_out, float *com_out, int *flags) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ FrameReduceSmem<kFusedSums, 3> sm;
+    __shared__ TmaCtl<kRmsdStages> ctl;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *fr = fv.frame(f);
+    const float *p0 = fr + (size_t)g.first * 3;
+    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
+    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
+    const float sc[3] = {pi_x2() * ix, pi_x2() * iy, pi_x2() * iz};
+    const BodyGeom bg = body_geom(fv, g, f);
+    float2 a2[kFusedSums];
+#pragma unroll
+    for (int k = 0; k < kFusedSums; k++) a2[k] = make_float2(0.f, 0.f);
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl,
+                                         [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
+        const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
+        const float2 pc[3] = {r.x, r.y, r.z};
+        const float2 w = r.w;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const float2 wp = __fmul2_rn(w, pc[u]);
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                a2[u * 3 + v] = __ffma2_rn(pc[u], d[v], a2[u * 3 + v]);
+                a2[9 + u * 3 + v] = __ffma2_rn(wp, d[v], a2[9 + u * 3 + v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const float2 wd = __fmul2_rn(w, d[v]);
+            a2[18 + v] = __fadd2_rn(a2[18 + v], wd);
+            a2[21] = __ffma2_rn(wd, d[v], a2[21]);
+            mn[v] = fminf(mn[v], fminf(d[v].x, d[v].y));
+            mx[v] = fmaxf(mx[v], fmaxf(d[v].x, d[v].y));
+            if (!WEIGHTED_CENTER) a2[26 + v] = __fadd2_rn(a2[26 + v], d[v]);
+            const float2 th = __fmul2_rn(d[v], splat(sc[v]));
+            float2 s, c;
+            __sincosf(th.x, &s.x, &c.x);
+            __sincosf(th.y, &s.y, &c.y);
+            a2[29 + v] = __fadd2_rn(a2[29 + v], c);
+            a2[32 + v] = __fadd2_rn(a2[32 + v], s);
+        }
+        if (!SAME_MASS) {
+            const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
+#pragma unroll
+            for (int v = 0; v < 3; v++) a2[22 + v] = __ffma2_rn(m, d[v], a2[22 + v]);
+            a2[25] = __fadd2_rn(a2[25], m);
+        }
+    });
+    float a[kFusedSums];
+#pragma unroll
+    for (int k = 0; k < kFusedSums; k++) a[k] = a2[k].x + a2[k].y;
+    double tot[kFusedSums];
+    float tmn[3], tmx[3];
+    if (frame_reduce<kFusedSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFusedSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
+        threadIdx.x == 0) {
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) { // atoms outside the 16-byte aligned body, in f64
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const float4 r = ref_at(ref.pc, i);
+            const float pp[3] = {px, py, pz};
+            const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
+            double d[3];
+            for (int k = 0; k < 3; k++) {
+                const float dk = pilot_delta(__ldg(q + k), pp[k], L[k], 1.0f / L[k]);
+                d[k] = (double)dk;
+                tmn[k] = fminf(tmn[k], dk);
+                tmx[k] = fmaxf(tmx[k], dk);
+                const double th = d[k] * 6.283185307179586 / (double)L[k];
+                if (!WEIGHTED_CENTER) tot[26 + k] += d[k];
+                tot[29 + k] += cos(th);
+                tot[32 + k] += sin(th);
+            }
+            for (int u = 0; u < 3; u++)
+                for (int v = 0; v < 3; v++) {
+                    tot[u * 3 + v] += pcd[u] * d[v];
+                    tot[9 + u * 3 + v] += w * pcd[u] * d[v];
+                }
+            for (int v = 0; v < 3; v++) {
+                tot[18 + v] += w * d[v];
+                tot[21] += w * d[v] * d[v];
+            }
+            if (!SAME_MASS) {
+                const double m = (double)__ldg(g.mass + i);
+                for (int v = 0; v < 3; v++) tot[22 + v] += m * d[v];
+                tot[25] += m;
+            }
+        }
+        double rt[kFastSums];
+        for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
+        int flag_r = 0, flag_c = 0;
+        finish_rmsd<SAME_MASS>(rt, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, &flag_r);
+        // centre: geometric (sum d / n) or mass-weighted with the target group's masses (= the COM of the RMSD)
+        double ct[10];
+        for (int k = 0; k < 3; k++) {
+            ct[k] = WEIGHTED_CENTER ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[26 + k];
+            ct[4 + k] = tot[29 + k];
+            ct[7 + k] = tot[32 + k];
+        }
+        ct[3] = SAME_MASS ? ref.sum_w : tot[25];
+        finish_center<WEIGHTED_CENTER>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
+        flags[f] = flag_r | (flag_c << 1);
+    }
+}
+
 } // namespace groan

@@ -515,6 +515,17 @@ class System:
                     "calc_rmsd", group, rmsd=True)
         return out
 
+    def group_center_and_rmsd(self, reference, group, weighted=False, center_out=None, rmsd_out=None, rot=None):
+        """group_get_center (or group_get_com when weighted) AND calc_rmsd of `group` from one read of every frame;
+        same results as calling the two methods one after the other.  Returns (centre [F,3], rmsd [F])."""
+        self._set_reference(reference, group)
+        center_out = self._out(center_out, (self.n_frames, 3))
+        rmsd_out = self._out(rmsd_out, (self.n_frames,))
+        self._check(self._lib.groan_gpu_center_rmsd(self._h, self._gid(group, True), 1 if weighted else 0, _ptr(center_out),
+                                                    _ptr(rmsd_out), _ptr(rot) if rot is not None else None),
+                    "group_center_and_rmsd", group, rmsd=True)
+        return center_out, rmsd_out
+
     def calc_rmsd_and_fit(self, reference, group, out=None):
         """System::calc_rmsd_and_fit (rmsd.rs:129; fit_structure :508-528): also fits ALL atoms of every frame in place."""
         self._set_reference(reference, group)

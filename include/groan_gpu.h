@@ -137,6 +137,11 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
                                  const uint32_t *ref_idx, size_t n_ref, const float ref_box[9], const float *ref_mass);
 /* System::calc_rmsd / RMSDTrajRead::calc_rmsd (rmsd.rs:75,315): rmsd F; rot (nullable) F x 9 row-major r */
 int groan_gpu_rmsd(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot);
+/* group_get_center (weighted = 0) or group_get_com (weighted = 1) AND calc_rmsd of the same group from ONE read of every
+ * frame: what a FrameAnalyze implementor that needs both (traj_convert.rs:76-83) would call per batch.  Results are those
+ * of groan_gpu_get_center + groan_gpu_rmsd. */
+int groan_gpu_center_rmsd(groan_gpu_ctx *ctx, int gid, int weighted, float *center /* F x 3 */, float *rmsd /* F */,
+                          float *rot /* nullable */);
 /* System::calc_rmsd_and_fit / RMSDTrajRead::calc_rmsd_and_fit (rmsd.rs:129,390; fit_structure :508-528):
  * also fits ALL atoms of every frame in place */
 int groan_gpu_rmsd_fit(groan_gpu_ctx *ctx, int gid, float *rmsd);

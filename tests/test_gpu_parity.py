@@ -508,7 +508,15 @@ def test_single_pass_matches_exact_and_x64(n, contig):
     rf = fast.calc_rmsd(ref, "G")
     assert fast.fallback_frames() == 0
     assert fast.launch_count() - l0 >= 3
+    # centre + RMSD from one read of the frame == the two separate calls
+    for weighted, sep in ((False, cf), (True, mf)):
+        c2, r2 = fast.group_center_and_rmsd(ref, "G", weighted=weighted)
+        assert fast.fallback_frames() == 0
+        assert np.abs(c2 - sep).max() <= 4e-6, np.abs(c2 - sep).max()  # 2 ulp of a 20 nm coordinate
+        assert np.abs(r2 - rf).max() <= 2e-6, np.abs(r2 - rf).max()
     ce, me, re_ = exact.group_get_center("G"), exact.group_get_com("G"), exact.calc_rmsd(ref, "G")
+    c3, r3 = exact.group_center_and_rmsd(ref, "G")
+    assert np.array_equal(bits(c3), bits(ce)) and np.array_equal(bits(r3), bits(re_))
     assert np.abs(cf - ce).max() <= TOL_CENTER and np.abs(mf - me).max() <= TOL_CENTER
     assert np.abs(rf - re_).max() <= 2e-5
     for f in range(F):
