@@ -240,6 +240,58 @@ int blocks_per_frame_tma(size_t g, size_t F, int occ) {
     return (int)nb;
 }
 
+// Cluster size along the frame axis for the reference multicast: the CTAs of a cluster must walk identical chunk
+// sequences, i.e. every frame must put the group at the same offset modulo 4 atoms (n_atoms % 4 == 0), and the
+// cluster size must divide the number of frames.
+int multicast_cluster_size(const groan_gpu_ctx *ctx) {
+    // Opt-in: measured on B200 (profiles/r1_multicast_experiment.md) the cluster version halves the reference's L2 traffic
+    // but runs 1.6-1.8x slower than the plain ring (warps wait on the shared stage), so it is off by default.
+    if (!(ctx->flags & GROAN_FLAG_MULTICAST)) return 1;
+    if (ctx->n_atoms % 4 != 0) return 1;
+    int cap = 8;
+    if (const char *e = std::getenv("GROAN_MULTICAST_MAX")) cap = std::max(1, std::atoi(e));  // tuning knob
+    for (int cs = std::min(8, cap); cs > 1; cs >>= 1)
+        if (ctx->n_frames % (size_t)cs == 0) return cs;
+    return 1;
+}
+
+// launch a TMA-fed RMSD-type kernel on grid (nb, F) with clusters (1, cs, 1); nb is capped by the number of
+// co-resident clusters so that the launch stays a single wave
+template <typename... KArgs, typename... Args>
+int launch_rmsd_tma(groan_gpu_ctx *ctx, void (*kernel)(KArgs...), const Group &g, int cs, Args... args) {
+    const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
+    int nb = blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_rmsd_tma);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->compute;
+    if (cs > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = (unsigned)cs;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)nb, (unsigned)ctx->n_frames);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters <= 0) {
+            cudaGetLastError();
+            cs = 1;
+            cfg.attrs = nullptr;
+            cfg.numAttrs = 0;
+        } else {
+            const int per_x = (int)(ctx->n_frames / (size_t)cs);  // clusters per grid column
+            nb = std::max(1, std::min(nb, max_clusters / std::max(per_x, 1)));
+        }
+    }
+    cfg.gridDim = dim3((unsigned)nb, (unsigned)ctx->n_frames);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args..., cs);
+    ctx->launches++;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cluster launch");
+    return GROAN_OK;
+}
+
 int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->tmp_bytes) return GROAN_OK;
     if (ctx->d_tmp) {
@@ -548,29 +600,26 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     bool center_done = false;
     if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
-        dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
-#define FUSED_LAUNCH(SM, WC)                                                                                                      \
-    k_center_rmsd_tma<SM, WC><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,      \
-                                                                           ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,  \
-                                                                           ctx->d_flags)
+        const int cs = multicast_cluster_size(ctx);
+#define FUSED_LAUNCH(SM, WC)                                                                                                  \
+    rc = launch_rmsd_tma(ctx, k_center_rmsd_tma<SM, WC>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, \
+                         d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags)
         if (R.same_mass) { if (center_weighted) FUSED_LAUNCH(true, true); else FUSED_LAUNCH(true, false); }
         else { if (center_weighted) FUSED_LAUNCH(false, true); else FUSED_LAUNCH(false, false); }
 #undef FUSED_LAUNCH
-        LAUNCHED();
+        if (rc) return rc;
         flags = ctx->d_flags;
         center_done = true;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // single pass, TMA-fed (kernels_tma.cuh)
-        dim3 fgrid(blocks_per_frame_tma(g->n, ctx->n_frames, ctx->occ_rmsd_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
+        const int cs = multicast_cluster_size(ctx);
         if (R.same_mass)
-            k_rmsd_tma<true><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,
-                                                                          ctx->d_tickets, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+            rc = launch_rmsd_tma(ctx, k_rmsd_tma<true>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
+                                 d_rot, ctx->d_cen, ctx->d_flags);
         else
-            k_rmsd_tma<false><<<fgrid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials,
-                                                                           ctx->d_tickets, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
-        LAUNCHED();
+            rc = launch_rmsd_tma(ctx, k_rmsd_tma<false>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
+                                 d_rot, ctx->d_cen, ctx->d_flags);
+        if (rc) return rc;
         flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)

@@ -73,6 +73,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// ---- thread-block cluster helpers: the CTAs that process the same chunks of DIFFERENT frames form a cluster along y,
+// and the reference chunk they all need is fetched from L2 once and multicast into every CTA's ring.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// atomic add on the counter at the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory);
+// acq_rel at cluster scope: every CTA's reads of a stage happen-before the copies issued by the CTA that arrives last
+__device__ __forceinline__ uint32_t atomic_add_remote(unsigned int *ctr, uint32_t rank, uint32_t v) {
+    uint32_t raddr, old;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(ctr)), "r"(rank));
+    asm volatile("atom.acq_rel.cluster.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(raddr), "r"(v) : "memory");
+    return old;
+}
+// bulk copy delivered to the same offset of every CTA in `mask`, completing on each CTA's own mbarrier at that offset
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask,
+                                                   uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask), "l"(policy)
+        : "memory");
+}
+
 template <bool WITH_REF, int STAGES>
 struct TmaSmem {
     static constexpr size_t kFrameBytes = (size_t)kChunk * 12;
@@ -87,7 +116,8 @@ constexpr int kRmsdStages = 3;   // 96 KB of ring: 2 CTAs per SM
 template <int STAGES>
 struct TmaCtl {
     uint64_t full[STAGES];     // count 1 + tx bytes: armed by whoever issues the copies, completed by the TMA
-    unsigned int done[STAGES]; // consumer warps that have finished reading the stage
+    unsigned int done[STAGES];  // consumer warps that have finished reading the stage
+    unsigned int cdone[STAGES]; // cluster rank 0's copy only: CTAs of the cluster that have finished reading the stage
 };
 
 // Geometry of a contiguous group inside frame f: `head` atoms before the first 16-byte boundary, a body whose
@@ -127,33 +157,62 @@ struct RefPair {
 
 template <bool WITH_REF, int STAGES, typename F>
 __device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg,
-                                                 const float *ref_pc, unsigned char *smem, TmaCtl<STAGES> &ctl, F &&fn) {
+                                                 const float *ref_pc, unsigned char *smem, TmaCtl<STAGES> &ctl, int cs, F &&fn) {
+    // cs = cluster size along y (frames).  cs > 1: all CTAs of the cluster walk the same chunk sequence (same blockIdx.x,
+    // same body geometry -- the host guarantees it) and share one L2 read of each reference chunk: the CTA that is the
+    // LAST of the cluster to finish a stage (a counter in rank 0's shared memory) multicasts the next chunk into it.
     typedef TmaSmem<WITH_REF, STAGES> S;
     const int lane = threadIdx.x & 31;
+    const bool mc = WITH_REF && cs > 1;
+    const uint32_t rank = mc ? cluster_rank() : 0u;
     const float *fr = fv.frame(f);
     const char *src = reinterpret_cast<const char *>(fr + ((size_t)g.first + bg.head) * 3);
     const uint32_t my_chunks = bg.chunks > blockIdx.x ? (bg.chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
-    auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES
-        const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
-        const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
-        // reference blocks covering group atoms [i0, i0 + atoms)
-        const uint32_t i0 = bg.head + c * kChunk, b0 = i0 >> 8, b1 = (i0 + atoms - 1) >> 8;
-        const uint32_t ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (b1 - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
+    // byte counts of this CTA's chunk `it`
+    auto geom = [&](uint32_t it, uint32_t &c, uint32_t &atoms, uint32_t &b0, uint32_t &ref_bytes) {
+        c = blockIdx.x + it * gridDim.x;
+        atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
+        const uint32_t i0 = bg.head + c * kChunk;
+        b0 = i0 >> 8; // reference blocks covering group atoms [i0, i0 + atoms)
+        ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (((i0 + atoms - 1) >> 8) - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
+    };
+    // arm full[s] for everything that will land in the stage and copy this CTA's own frame chunk (+ reference if not multicast)
+    auto issue_own = [&](uint32_t it) {
+        uint32_t c, atoms, b0, ref_bytes;
+        geom(it, c, atoms, b0, ref_bytes);
+        const uint32_t s = it % STAGES;
         mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
         unsigned char *dst = smem + s * S::kStageBytes;
         bulk_g2s(dst, src + (size_t)c * kChunk * 12, atoms * 12u, ctl.full + s, pol_frame);
-        if (WITH_REF && ref_bytes) bulk_g2s(dst + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);
+        if (WITH_REF && !mc && ref_bytes)
+            bulk_g2s(dst + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);
+    };
+    // one L2 read of the reference chunk, delivered to every CTA of the cluster
+    auto issue_multicast = [&](uint32_t it) {
+        uint32_t c, atoms, b0, ref_bytes;
+        geom(it, c, atoms, b0, ref_bytes);
+        const uint32_t s = it % STAGES;
+        if (ref_bytes)
+            bulk_g2s_multicast(smem + s * S::kStageBytes + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes,
+                               ctl.full + s, (uint16_t)((1u << cs) - 1u), pol_ref);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(ctl.full + s, 1);
             ctl.done[s] = 0;
+            ctl.cdone[s] = 0;
         }
         fence_mbar_init();
-        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
     }
-    __syncthreads();
+    if (mc) cluster_sync_all(); // every CTA's barriers exist before any multicast can signal them
+    else __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) {
+            issue_own(it);
+            if (mc && rank == 0) issue_multicast(it);
+        }
+    }
     for (uint32_t it = 0; it < my_chunks; it++) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         const uint32_t c = blockIdx.x + it * gridDim.x;
@@ -191,10 +250,15 @@ __device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const Grou
             if (atomicAdd(&ctl.done[s], 1u) == (unsigned)(kWarps - 1)) { // last reader of the stage: refill it
                 ctl.done[s] = 0;
                 __threadfence_block();
-                if (it + STAGES < my_chunks) issue(it + STAGES);
+                if (it + STAGES < my_chunks) {
+                    issue_own(it + STAGES);
+                    // this CTA no longer reads the stage's reference and has armed full[s]; the last CTA to say so multicasts
+                    if (mc && atomic_add_remote(&ctl.cdone[s], 0, 1u) % (uint32_t)cs == (uint32_t)(cs - 1)) issue_multicast(it + STAGES);
+                }
             }
         }
     }
+    if (mc) cluster_sync_all(); // no CTA may exit while a peer can still signal its barriers
 }
 
 // packed helpers (sm_100 f32x2 pipe)
@@ -227,7 +291,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
 #pragma unroll
     for (int k = 0; k < 10; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<false, kCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl,
+    stream_pairs_tma<false, kCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl, 1,
                                             [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &) {
         const float2 dx = pilot_delta2(X, -px, L[0], ix), dy = pilot_delta2(Y, -py, L[1], iy), dz = pilot_delta2(Z, -pz, L[2], iz);
         if (WEIGHTED) {
@@ -281,7 +345,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
 template <bool SAME_MASS>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
                                                               unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
-                                                              int *flags) {
+                                                              int *flags, int cs) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ FrameReduceSmem<kFastSums, 3> sm;
     __shared__ TmaCtl<kRmsdStages> ctl;
@@ -297,7 +361,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
 #pragma unroll
     for (int k = 0; k < kFastSums; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl,
+    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl, cs,
                                          [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
         const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
         const float2 pc[3] = {r.x, r.y, r.z};
@@ -376,7 +440,7 @@ constexpr int kFusedSums = kFastSums + 9;
 template <bool SAME_MASS, bool WEIGHTED_CENTER>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
                                                                      unsigned int *tickets, float *center_out, float *rmsd_out,
-                                                                     float *rot_out, float *com_out, int *flags) {
+                                                                     float *rot_out, float *com_out, int *flags, int cs) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ FrameReduceSmem<kFusedSums, 3> sm;
     __shared__ TmaCtl<kRmsdStages> ctl;
@@ -393,7 +457,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv
 #pragma unroll
     for (int k = 0; k < kFusedSums; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl,
+    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl, cs,
                                          [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
         const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
         const float2 pc[3] = {r.x, r.y, r.z};

@@ -556,3 +556,23 @@ def test_single_pass_falls_back_when_it_cannot_certify(example):
         assert s.fallback_frames() == (1 if flags == 0 else 0)
     assert np.array_equal(bits(out[0]), bits(out[1]))
     assert np.allclose(out[0][0], orc.get_center(two, [0, 1], [10.0] * 3), atol=TOL_CENTER)
+
+
+def test_multicast_clusters_match_plain_ring():
+    """opt-in thread-block-cluster multicast of the reference chunk (GROAN_FLAG_MULTICAST): same results as the plain ring"""
+    import groan_rs_b200 as g
+    n, F, L = 400_000, 8, np.array([20.0, 21.0, 19.0], np.float32)
+    masses = np.random.default_rng(2).uniform(1.0, 100.0, n).astype(np.float32)
+    scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
+    plain = _blob_system(n, F, L, 5, scale, nscale, masses)
+    multi = _blob_system(n, F, L, 5, scale, nscale, masses, flags=g.FLAG_MULTICAST)
+    ref = g.System(n, masses=masses)
+    ref.set_frames(plain.synth_blob_ref(5, scale, L / 2), L)
+    idx = np.arange(n)
+    for s in (plain, multi, ref):
+        s.group_create_from_indices("G", idx)
+    r0, r1 = plain.calc_rmsd(ref, "G"), multi.calc_rmsd(ref, "G")
+    assert multi.fallback_frames() == 0
+    c0, q0 = plain.group_center_and_rmsd(ref, "G")
+    c1, q1 = multi.group_center_and_rmsd(ref, "G")
+    assert np.abs(r0 - r1).max() <= 2e-6 and np.abs(q0 - q1).max() <= 2e-6 and np.abs(c0 - c1).max() <= 4e-6
