@@ -16,6 +16,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -451,8 +452,41 @@ int launch_pairs(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_ou
     return GROAN_OK;
 }
 
+// orthogonal box, 2-D / 3-D distance: packed one-step min-image (kernels_pairs.cuh "fast paths")
+template <int DIM>
+int launch_pairs_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_out) {
+    const bool vec = (b.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    dim3 grid((unsigned)((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)),
+              (unsigned)((a.n + kFastRows - 1) / kFastRows), (unsigned)ctx->n_frames);
+    if (vec)
+        k_pairs_fast<DIM, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+    else
+        k_pairs_fast<DIM, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+// smallest float t with sqrtf(t) >= c: (d2 < t) <=> (sqrtf(d2) < c) for every float d2 >= 0
+float cutoff_squared_threshold(float c) {
+    if (!(c > 0.0f)) return 0.0f;
+    float t = c * c;
+    if (std::isinf(t)) return t;
+    while (std::sqrt(t) >= c && t > 0.0f) t = std::nextafter(t, 0.0f);
+    while (std::sqrt(t) < c) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
 template <typename BOX>
 int dispatch_pairs(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float *d_out) {
+    if (std::is_same<BOX, BoxOrtho>::value) {
+        switch (dim) {
+        case 4: return launch_pairs_fast<4>(ctx, a, b, d_out);
+        case 5: return launch_pairs_fast<5>(ctx, a, b, d_out);
+        case 6: return launch_pairs_fast<6>(ctx, a, b, d_out);
+        case 7: return launch_pairs_fast<7>(ctx, a, b, d_out);
+        default: break;
+        }
+    }
     switch (dim) {
     case 0: return launch_pairs<0, BOX>(ctx, a, b, d_out);
     case 1: return launch_pairs<1, BOX>(ctx, a, b, d_out);
@@ -487,8 +521,37 @@ int launch_pairs_reduce(groan_gpu_ctx *ctx, const Group &a, const Group &b, floa
     return GROAN_OK;
 }
 
+template <int DIM>
+int launch_pairs_reduce_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
+    // one wave of CTAs over (B chunks) x frames: every CTA walks all of group A for its B atoms
+    size_t nb = (b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ);
+    nb = std::max<size_t>(1, std::min<size_t>(nb, kMaxBlocksPerFrame));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    const float c2 = cutoff_squared_threshold(cutoff);
+    if (o.count)
+        k_pairs_reduce_fast<DIM, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
+                                                                            (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
+                                                                            o.imin, o.dmax, o.imax, o.count);
+    else
+        k_pairs_reduce_fast<DIM, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
+                                                                             (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
+                                                                             o.imin, o.dmax, o.imax, o.count);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
 template <typename BOX>
 int dispatch_pairs_reduce(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
+    if (std::is_same<BOX, BoxOrtho>::value) {
+        switch (dim) {
+        case 4: return launch_pairs_reduce_fast<4>(ctx, a, b, cutoff, o);
+        case 5: return launch_pairs_reduce_fast<5>(ctx, a, b, cutoff, o);
+        case 6: return launch_pairs_reduce_fast<6>(ctx, a, b, cutoff, o);
+        case 7: return launch_pairs_reduce_fast<7>(ctx, a, b, cutoff, o);
+        default: break;
+        }
+    }
     switch (dim) {
     case 0: return launch_pairs_reduce<0, BOX>(ctx, a, b, cutoff, o);
     case 1: return launch_pairs_reduce<1, BOX>(ctx, a, b, cutoff, o);
@@ -1023,7 +1086,7 @@ int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, 
     o.dmax = target_of<float>(dmax, s + F);
     o.imin = target_of<uint32_t>(imin, (uint32_t *)(s + 2 * F));
     o.imax = target_of<uint32_t>(imax, (uint32_t *)(s + 4 * F));
-    o.count = target_of<unsigned long long>(count, (unsigned long long *)(s + 6 * F));
+    o.count = count ? target_of<unsigned long long>(count, (unsigned long long *)(s + 6 * F)) : nullptr;
     rc = tric ? dispatch_pairs_reduce<BoxTric>(ctx, dim, *a, *b, cutoff, o) : dispatch_pairs_reduce<BoxOrtho>(ctx, dim, *a, *b, cutoff, o);
     if (rc) return rc;
     if ((rc = deliver(ctx, dmin, o.dmin, F * sizeof(float)))) return rc;

@@ -576,3 +576,64 @@ def test_multicast_clusters_match_plain_ring():
     c0, q0 = plain.group_center_and_rmsd(ref, "G")
     c1, q1 = multi.group_center_and_rmsd(ref, "G")
     assert np.abs(r0 - r1).max() <= 2e-6 and np.abs(q0 - q1).max() <= 2e-6 and np.abs(c0 - c1).max() <= 4e-6
+
+
+# ------------------------------------------------------------------ all-pairs fast paths (packed one-step min-image)
+@pytest.mark.parametrize("far", [False, True])
+def test_all_pairs_fast_paths_bitexact(far):
+    """2-D / 3-D all-pairs on an orthogonal box: coordinates up to 10 % outside the box take the packed one-step fold,
+    a few atoms many box lengths away force the loop version for their tiles; both must equal the ref32 oracle bit for bit,
+    matrix and fused reduction (first minimum / last maximum / count below cutoff)."""
+    n, F = 6000, 2
+    L = np.array([7.5, 8.25, 6.75], np.float32)
+    s = _sys(n, max_frames=F)
+    s.synth_uniform(123, 0, F, -0.1 * L, 1.2 * L, L)
+    frames = s.get_frames()
+    if far:
+        frames[0, 17] += np.float32(5) * L
+        frames[1, 4100] -= np.float32(9) * L
+        frames[1, 4101, 1] += np.float32(1.6) * L[1]
+        s.set_frames(frames, L)
+    a = np.arange(0, 1900)          # not a multiple of the row tile
+    b = np.arange(3000, 3000 + 2603)  # odd size: scalar stores, ragged last thread
+    s.group_create_from_indices("A", a)
+    s.group_create_from_indices("B", b)
+    s.group_create_from_indices("B4", b[:2600])  # multiple of 4: float4 stores
+    for dn in ("XYZ", "XY", "XZ", "YZ"):
+        got = s.group_all_distances("A", "B", _dim(dn))
+        got4 = s.group_all_distances("A", "B4", _dim(dn))
+        red = s.group_all_distances_reduce("A", "B", _dim(dn), cutoff=0.35)
+        for f in range(F):
+            exp = orc.all_distances(frames[f], a, b, dn, L)
+            assert np.array_equal(bits(got[f]), bits(exp)), (dn, f)
+            assert np.array_equal(bits(got4[f]), bits(exp[:, :2600])), (dn, f)
+            mn, imn, mx, imx, cnt = orc.all_distances_minmax(frames[f], a, b, dn, L, cutoff=0.35)
+            assert bits(red["min"][f]) == bits(mn) and bits(red["max"][f]) == bits(mx), (dn, f)
+            assert tuple(red["argmin"][f]) == tuple(imn) and tuple(red["argmax"][f]) == tuple(imx), (dn, f)
+            assert int(red["count"][f]) == cnt, (dn, f)
+
+
+def test_all_pairs_reduce_ties_and_many_chunks():
+    """ties: duplicated atoms give equal distances at several (i, j); the fused reduction must return the FIRST minimum
+    and the LAST maximum of the row-major scan even when a CTA sweeps group B in several chunks (64 frames cap the grid)."""
+    n, F = 140_000, 64
+    L = np.array([9.0, 9.0, 9.0], np.float32)
+    s = _sys(n, max_frames=F)
+    s.synth_uniform(7, 0, F, [0, 0, 0], L, L)
+    frames = s.get_frames()
+    # plant ties: copies of A atoms inside B (distance 0 at several positions) and mirrored far pairs
+    frames[:, 200] = frames[:, 3]
+    frames[:, 139_000] = frames[:, 3]
+    frames[:, 70_000] = frames[:, 1]
+    s.set_frames(frames, L)
+    a = np.arange(0, 6)
+    b = np.arange(100, n)
+    s.group_create_from_indices("A", a)
+    s.group_create_from_indices("B", b)
+    red = s.group_all_distances_reduce("A", "B", _dim("XYZ"), cutoff=0.5)
+    for f in (0, 31, 63):
+        mn, imn, mx, imx, cnt = orc.all_distances_minmax(frames[f], a, b, "XYZ", L, cutoff=0.5)
+        assert mn == 0.0 and red["min"][f] == 0.0
+        assert tuple(red["argmin"][f]) == tuple(imn), (f, red["argmin"][f], imn)
+        assert bits(red["max"][f]) == bits(mx) and tuple(red["argmax"][f]) == tuple(imx)
+        assert int(red["count"][f]) == cnt
