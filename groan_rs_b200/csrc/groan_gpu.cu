@@ -523,10 +523,11 @@ int launch_pairs_reduce(groan_gpu_ctx *ctx, const Group &a, const Group &b, floa
 
 template <int DIM>
 int launch_pairs_reduce_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
-    // one wave of CTAs over (B chunks) x frames: every CTA walks all of group A for its B atoms
-    size_t nb = (b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ);
-    nb = std::max<size_t>(1, std::min<size_t>(nb, kMaxBlocksPerFrame));
-    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
+    // persistent CTAs (4 per SM in total) striding over work units of (1024 B atoms) x (256 A atoms)
+    const size_t units = ((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)) * ((a.n + kSliceA - 1) / kSliceA);
+    size_t nb = std::max<size_t>(1, ((size_t)kSMs * 4) / ctx->n_frames);
+    nb = std::min<size_t>(nb, units);
+    nb = std::max<size_t>(1, std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames)));
     dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
     const float c2 = cutoff_squared_threshold(cutoff);
     if (o.count)
