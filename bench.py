@@ -101,6 +101,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(frames_per_step):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the last `ncu --set full`
+    capture of this workload (profiles/r1_dominant_kernel.json); None if the capture was made with another batch size"""
+    p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
+    try:
+        d = json.load(open(p))
+        if d.get("frames_per_step") == frames_per_step:
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_run(steps, warmup, sample_frames=None, threads=None):
     """Restated groan_rs CPU trajectory path (oracle/groan_oracle.c: orc_baseline_traj, following
@@ -265,7 +278,7 @@ def run_gpu_arm(args):
     }
     dom = "group_center_and_rmsd"  # the kernel the timed step runs (k_center_rmsd_tma)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": ops[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ops[dom]["gbs"] / peak, "traffic": ncu_traffic(F), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ops[dom]["alg_bytes"], "ops": ops,
                 "fallback_frames": fallback}
 
@@ -357,7 +370,10 @@ def run_extras(torch, g, local, peak):
     p.synth_uniform(SEED, 0, 2, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
     t = time_op(lambda: p.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0), reps=3)
     pairs = 2 * n1 * n2
-    out["all_pairs_fused_reduce"] = {"ms": t, "pairs_per_s": pairs / (t * 1e-3), "frames_per_s": 2 / (t * 1e-3)}
+    # FP32 roofline of SURVEY 8d: 18 reference FP32 ops per pair against 148 SM x 128 lanes x 1.965 GHz = 37.2 T op/s (non-FMA)
+    out["all_pairs_fused_reduce"] = {"ms": t, "pairs_per_s": pairs / (t * 1e-3), "frames_per_s": 2 / (t * 1e-3),
+                                     "ref_fp32_ops_per_s": 18 * pairs / (t * 1e-3),
+                                     "frac_of_fp32_peak": 18 * pairs / (t * 1e-3) / (148 * 128 * 1.965e9)}
     p.synth_uniform(SEED, 0, 1, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
     mat = torch.empty((1, n1, n2), dtype=torch.float32, device=dev)
     t = time_op(lambda: p.group_all_distances("A", "B", g.Dimension.XYZ, out=mat), reps=3)
