@@ -33,6 +33,15 @@ NOISE_SCALE = 0.05 / 37837.23      # Irwin-Hall(4) of 16-bit fields has sigma 37
 METRIC = "frames/s (group_get_center + calc_rmsd per frame, 4M-atom group)"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def frame_params(frame0, n_frames):
     """per-frame random rigid motion: rotation (unit quaternion) and a centre anywhere in the box"""
     rot = np.empty((n_frames, 9), np.float32)
@@ -154,7 +163,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(frames_per_step):
@@ -197,17 +206,34 @@ def run_gpu_arm(args):
     frame0 = rank * F
     rot, cen = frame_params(frame0, F)
     s.synth_blob(SEED, frame0, F, BLOB_SCALE, NOISE_SCALE, rot, cen, [BOX] * 3, wrap=True)
+    # per-frame results, double-buffered so that the gather of batch k overlaps the kernels of batch k+1
     d_cen = torch.empty((F, 3), dtype=torch.float32, device=dev)
     d_rmsd = torch.empty((F,), dtype=torch.float32, device=dev)
-    g_cen = torch.empty((world * F, 3), dtype=torch.float32, device=dev) if world > 1 else None
-    g_rmsd = torch.empty((world * F,), dtype=torch.float32, device=dev) if world > 1 else None
+    bufs = [(torch.empty((F, 4), dtype=torch.float32, device=dev), torch.empty((world * F, 4), dtype=torch.float32, device=dev))
+            for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    step_no = [0]
 
     def step():
         # group_get_center + calc_rmsd of the same group: one read of every frame (groan_gpu_center_rmsd)
         s.group_center_and_rmsd(ref, "G", center_out=d_cen, rmsd_out=d_rmsd)
-        if world > 1:  # the one exchange of the path: the small per-frame results
-            dist.all_gather_into_tensor(g_cen, d_cen)
-            dist.all_gather_into_tensor(g_rmsd, d_rmsd)
+        if world > 1:
+            # the one exchange of the path: 16 B per frame, all ranks get the whole trajectory's results.
+            # Issued asynchronously on NCCL's stream; the slot is reused two steps later, after its gather has completed.
+            k = step_no[0] & 1
+            if pending[k] is not None:
+                pending[k].wait()
+            loc, glob = bufs[k]
+            loc[:, :3].copy_(d_cen)
+            loc[:, 3].copy_(d_rmsd)
+            pending[k] = dist.all_gather_into_tensor(glob, loc, async_op=True)
+            step_no[0] += 1
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -216,6 +242,7 @@ def run_gpu_arm(args):
 
     for _ in range(W):
         step()
+    drain()
     barrier()
     # correctness guard inside the bench: RMSD must be the analytic value of the generator
     r0 = d_rmsd.cpu().numpy()
@@ -238,6 +265,7 @@ def run_gpu_arm(args):
     e0.record()
     for _ in range(K):
         step()
+    drain()  # every batch's results have been gathered before the clock stops
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -331,7 +359,7 @@ def run_gpu_arm(args):
                 "data": "synthetic: seeded rigid blob + noise generated on the device, batch resident in HBM and reused every step",
                 "config": workload_config(F), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extras": extras}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -387,6 +415,11 @@ def run_extras(torch, g, local, peak):
 
 
 def main():
+    # stdout carries exactly one JSON line: route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
