@@ -255,14 +255,55 @@ __device__ inline void svd3(const double A[9], double U[9], double S[3], double 
     }
 }
 
-// r = U * diag(1, 1, sign det(U Vt)) * Vt, rmsd.rs:573-583 (row-major)
+// r = U * diag(1, 1, sign det(U Vt)) * Vt, rmsd.rs:573-583 (row-major).
+//
+// For det(H) > 0 (every non-degenerate, non-reflected case) that matrix is the orthogonal polar factor of H, which a
+// scaled Newton iteration X <- (g X + X^-T / g) / 2 reaches in ~8 steps of plain f64 multiply-adds -- about 10x
+// fewer dependent operations than the one-sided Jacobi SVD, and this code runs in ONE thread at the very end of a
+// frame while the rest of the GPU waits (profiles/r1_summary.md: the serial finish was ~25 % of the kernel).
+// Reflections (det < 0) and near-singular H (planar / collinear groups) keep the SVD path.
 __device__ inline void kabsch_rotation(const double H[9], double r[9]) {
+    double n2 = 0.0;
+    for (int i = 0; i < 9; i++) n2 += H[i] * H[i];
+    const double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+    const double n = sqrt(n2);
+    if (n2 > 0.0 && det > 1e-7 * n2 * n) {
+        double X[9];
+        const double inv_n = 1.0 / n;
+        for (int i = 0; i < 9; i++) X[i] = H[i] * inv_n;
+        bool ok = false;
+        for (int it = 0; it < 40; it++) {
+            // Y = X^-T = cofactor(X) / det(X)
+            double C[9];
+            C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
+            C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
+            C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
+            const double dx = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+            if (!(dx > 0.0)) break;
+            const double idx = 1.0 / dx;
+            double nx = 0.0, ny = 0.0;
+            for (int i = 0; i < 9; i++) { C[i] *= idx; nx += X[i] * X[i]; ny += C[i] * C[i]; }
+            const double g = sqrt(sqrt(ny / nx)); // Frobenius-norm scaling
+            const double a = 0.5 * g, b = 0.5 / g;
+            double diff = 0.0;
+            for (int i = 0; i < 9; i++) {
+                const double v = a * X[i] + b * C[i];
+                diff += (v - X[i]) * (v - X[i]);
+                X[i] = v;
+            }
+            if (diff < 1e-30) { ok = true; break; }
+        }
+        if (ok) {
+            for (int i = 0; i < 9; i++) r[i] = X[i];
+            return;
+        }
+    }
     double U[9], S[3], V[9], M[9];
     svd3(H, U, S, V);
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) M[i * 3 + j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + U[i * 3 + 2] * V[j * 3 + 2];
-    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
-    const double d = det < 0.0 ? -1.0 : 1.0;
+    const double dm = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    const double d = dm < 0.0 ? -1.0 : 1.0;
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) r[i * 3 + j] = U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1] + d * U[i * 3 + 2] * V[j * 3 + 2];
 }

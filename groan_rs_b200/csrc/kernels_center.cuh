@@ -161,12 +161,15 @@ __device__ inline void finish_center(const double (&tot)[10], const float *tmn, 
         // theta_i = theta_p + phi_i  =>  (xi, zeta) = R(theta_p) (C, S)
         const double C = tot[4 + k], S = tot[7 + k];
         if (!(C * C + S * S >= 1e-6 * (double)n * (double)n)) redo = 1; // resultant too short to trust the SFU sums
-        const double sc = 6.283185307179586 / Lk;
-        double pw = fmod((double)p[k], Lk);
-        if (pw < 0) pw += Lk;
-        const double tp = pw * sc, ct = cos(tp), st = sin(tp);
+        // f32 library trig is plenty here (c0 only decides an integer, guarded by the edge band) and keeps this serial
+        // section short: f64 sin/cos/atan2 cost thousands of cycles each in a single thread
+        const float scf = 6.2831853f / L[k];
+        const float pwf = p[k] - L[k] * floorf(p[k] / L[k]);
+        float stf, ctf;
+        sincosf(pwf * scf, &stf, &ctf);
+        const double ct = (double)ctf, st = (double)stf;
         const double xi = ct * C - st * S, ze = st * C + ct * S;
-        const double c0 = (atan2(-ze, -xi) + 3.141592653589793) / sc; // in [0, L]
+        const double c0 = ((double)atan2f((float)(-ze), (float)(-xi)) + 3.141592653589793) / (double)scf; // in [0, L]
         if (!(c0 >= kEdgeBand * Lk && c0 <= (1.0 - kEdgeBand) * Lk)) redo = 1;  // which side of the edge decides k
         const double um = (double)p[k] + tot[k] / M;                           // mean of the unwrapped group
         out3[k] = (float)(um + Lk * rint((c0 - um) / Lk));                      // the image within L/2 of c0
