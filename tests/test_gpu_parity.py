@@ -637,3 +637,84 @@ def test_all_pairs_reduce_ties_and_many_chunks():
         assert tuple(red["argmin"][f]) == tuple(imn), (f, red["argmin"][f], imn)
         assert bits(red["max"][f]) == bits(mx) and tuple(red["argmax"][f]) == tuple(imx)
         assert int(red["count"][f]) == cnt
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties (BASELINE configs[3], [4])
+def test_full_size_properties_cfg4_cfg5():
+    """At BASELINE.json's full sizes the oracle is too slow, so the CUDA path is checked through properties:
+    translation by box vectors leaves centre (mod L) and RMSD unchanged; a rigidly rotated noise-free copy has RMSD 0 and
+    the rotation is recovered; wrap is idempotent and undoes integer box shifts; the fused all-pairs reduction equals the
+    reduction of the materialised matrix; single-pass and reference-order passes agree."""
+    import groan_rs_b200 as g
+    import torch
+    # ---- configs[4]: 4M atoms, box 34 nm, centre + RMSD
+    n, F, L = 4_000_000, 4, np.array([34.0, 34.0, 34.0], np.float32)
+    scale = 5.5 / 131070.0
+    masses = np.random.default_rng(3).uniform(1.0, 100.0, n).astype(np.float32)
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+    rot = np.stack([np.eye(3, dtype=np.float32), R, R.T, R @ R]).reshape(F, 9)
+    cen = np.array([[17, 17, 17], [0.5, 33.8, 10.0], [33.9, 0.1, 0.2], [8.0, 25.0, 31.0]], np.float32)
+    s = g.System(n, masses=masses, max_frames=F)
+    ref = g.System(n, masses=masses)
+    ref.set_frames(s.synth_blob_ref(11, scale, L / 2), L)
+    idx = np.arange(n)
+    s.group_create_from_indices("G", idx)
+    ref.group_create_from_indices("G", idx)
+    s.synth_blob(11, 0, F, scale, 0.0, rot, cen, L, wrap=True)   # noise-free rigid copies
+    rotm = np.empty((F, 9), np.float32)
+    c, r = s.group_center_and_rmsd(ref, "G", rot=rotm)
+    # RMSD ~ 0 is below what f32 products can resolve: the cancellation guard hands every frame to the f64 passes
+    assert s.fallback_frames() == F
+    assert np.all(r <= 2e-4), r                                   # rigid copy: RMSD ~ 0 (f32 coordinates of a rotated blob)
+    # kabsch returns r with p_rotated = r^T p (rmsd.rs:586): frames were built as x = R p + c, so r^T = R
+    for f in range(F):
+        assert np.abs(rotm[f].reshape(3, 3).T - rot[f].reshape(3, 3)).max() <= 1e-4, f
+    # the blob is symmetric about its centre up to sampling: the PBC centre is the generator's centre (mod L)
+    dc = (c - cen + L / 2) % L - L / 2
+    assert np.abs(dc).max() <= 5e-3, dc
+    c_sep, r_sep = s.group_get_center("G"), s.calc_rmsd(ref, "G")
+    assert np.abs(c - c_sep).max() <= 8e-6 and np.abs(r - r_sep).max() <= 2e-5
+    # translate every atom by integer box vectors: wrapped coordinates, centre and RMSD are unchanged
+    before = torch.empty((F, n, 3), dtype=torch.float32, device="cuda")
+    s.get_frames(out=before)
+    s.sync()
+    s.atoms_translate([34.0 * 2, -34.0, 34.0 * 3])
+    after = torch.empty_like(before)
+    s.get_frames(out=after)
+    s.sync()
+    dlt = (after - before).abs()
+    dlt = torch.minimum(dlt, (dlt - 34.0).abs())                  # x = 0 may come back as x = L (closed interval, strict compares)
+    assert float(dlt.max()) <= 2e-5                               # back in the same box image
+    s.atoms_wrap()
+    again = torch.empty_like(before)
+    s.get_frames(out=again)
+    s.sync()
+    assert torch.equal(again, after)                              # idempotent
+    c2, r2 = s.group_center_and_rmsd(ref, "G")
+    assert np.abs(((c2 - c + L / 2) % L) - L / 2).max() <= 2e-5 and np.abs(r2 - r).max() <= 2e-4
+    del before, after, again
+    s.close()
+    ref.close()
+    # ---- configs[3]: 1M atoms, 2 000 x 200 000 all-pairs
+    N, n1, n2 = 1_000_000, 2000, 200_000
+    p = g.System(N, max_frames=1)
+    p.group_create_from_indices("A", np.arange(n1))
+    p.group_create_from_indices("B", np.arange(500_000, 500_000 + n2))
+    p.synth_uniform(20261018, 0, 1, [-2.15] * 3, [25.8] * 3, [21.5] * 3)
+    mat = torch.empty((1, n1, n2), dtype=torch.float32, device="cuda")
+    p.group_all_distances("A", "B", g.Dimension.XYZ, out=mat)
+    red = p.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0)
+    p.sync()
+    flat = mat.view(-1)
+    assert float(flat.min()) == float(red["min"][0]) and float(flat.max()) == float(red["max"][0])
+    first_min = int((flat == flat.min()).nonzero()[0])            # first minimum of the row-major scan
+    last_max = int((flat == flat.max()).nonzero()[-1])            # last maximum
+    assert (first_min // n2, first_min % n2) == tuple(int(v) for v in red["argmin"][0])
+    assert (last_max // n2, last_max % n2) == tuple(int(v) for v in red["argmax"][0])
+    assert int((flat < 1.0).sum()) == int(red["count"][0])
+    assert float(flat.max()) <= 0.5 * np.sqrt(3) * 21.5 + 1e-4     # no distance beyond half the box diagonal
+    # a 64 x 4096 sub-block against the ref32 oracle, bit for bit (SURVEY 8d cfg4)
+    fr = p.get_frames()[0]
+    sub = orc.all_distances(fr, np.arange(64), np.arange(500_000, 500_000 + 4096), "XYZ", [21.5] * 3)
+    assert np.array_equal(bits(mat[0, :64, :4096].cpu().numpy()), bits(sub))
