@@ -18,6 +18,7 @@ FLAG_TRICLINIC = 1
 FLAG_EXACT_ONLY = 2
 FLAG_NO_TMA = 4
 FLAG_MULTICAST = 8
+FLAG_HOST_FALLBACK = 16
 
 _vp = C.c_void_p
 _sz = C.c_size_t

@@ -15,6 +15,8 @@ LIB = os.path.join(HERE, "libgroan_gpu.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
+    # relocatable device code + device runtime: the single-pass kernels tail-launch their fallback passes from the device
+    "-rdc=true", "-lcudadevrt",
 ]
 
 

@@ -95,6 +95,7 @@ struct groan_gpu_ctx {
     unsigned int *d_tickets = nullptr;
     float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
     int *d_flags = nullptr;  // per frame: 1 = the single-pass kernel could not certify its result, redo exactly
+    unsigned int *d_frames_done = nullptr;  // device-side fallback launch: frames finished by the running single-pass kernel
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
     int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
     void *d_tmp = nullptr;
@@ -293,6 +294,24 @@ int launch_rmsd_tma(groan_gpu_ctx *ctx, void (*kernel)(KArgs...), const Group &g
     return GROAN_OK;
 }
 
+FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
+                           float *rmsd_out, float *rot_out) {
+    FallbackPlan fp;
+    fp.enabled = (ctx->flags & GROAN_FLAG_HOST_FALLBACK) ? 0 : 1;
+    fp.nb_exact = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
+    fp.nb_cov = blocks_per_frame_fast(g.n, ctx->n_frames, 2);
+    fp.frames_done = ctx->d_frames_done;
+    fp.c0 = ctx->d_c0;
+    fp.want_center = want_center;
+    fp.center_weighted = center_weighted;
+    fp.want_rmsd = want_rmsd;
+    fp.center_out = center_out;
+    fp.com = ctx->d_cen;
+    fp.rmsd_out = rmsd_out;
+    fp.rot_out = rot_out;
+    return fp;
+}
+
 int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->tmp_bytes) return GROAN_OK;
     if (ctx->d_tmp) {
@@ -395,13 +414,15 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
         dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
         const size_t smem = TmaSmem<false, kCenterStages>::kBytes;
+        const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
         if (weighted)
             k_center_tma<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                          out, ctx->d_flags);
+                                                                          out, ctx->d_flags, fp);
         else
             k_center_tma<false><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                           out, ctx->d_flags);
+                                                                           out, ctx->d_flags, fp);
         LAUNCHED();
+        if (fp.enabled) return GROAN_OK;  // the kernel launches the reference-order passes itself when a frame needs them
         flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, ctx->occ_center);
@@ -661,13 +682,15 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     }
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
-    bool center_done = false;
+    bool center_done = false, device_fallback = false;
     if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
         const int cs = multicast_cluster_size(ctx);
+        const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
+        device_fallback = fp.enabled != 0;
 #define FUSED_LAUNCH(SM, WC)                                                                                                  \
     rc = launch_rmsd_tma(ctx, k_center_rmsd_tma<SM, WC>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, \
-                         d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags)
+                         d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags, fp)
         if (R.same_mass) { if (center_weighted) FUSED_LAUNCH(true, true); else FUSED_LAUNCH(true, false); }
         else { if (center_weighted) FUSED_LAUNCH(false, true); else FUSED_LAUNCH(false, false); }
 #undef FUSED_LAUNCH
@@ -677,12 +700,14 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // single pass, TMA-fed (kernels_tma.cuh)
         const int cs = multicast_cluster_size(ctx);
+        const FallbackPlan fp = fallback_plan(ctx, *g, false, false, nullptr, true, d_rmsd, d_rot);
+        device_fallback = fp.enabled != 0;
         if (R.same_mass)
             rc = launch_rmsd_tma(ctx, k_rmsd_tma<true>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                 d_rot, ctx->d_cen, ctx->d_flags);
+                                 d_rot, ctx->d_cen, ctx->d_flags, fp);
         else
             rc = launch_rmsd_tma(ctx, k_rmsd_tma<false>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                 d_rot, ctx->d_cen, ctx->d_flags);
+                                 d_rot, ctx->d_cen, ctx->d_flags, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
@@ -699,16 +724,19 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         flags = ctx->d_flags;
     }
     // reference-order passes (all frames, or only the flagged ones): group_get_com of the target
-    // (geometric estimate, mass-weighted unwrap), then shift + wrap + covariance in f64
-    rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
-    if (rc) return rc;
-    rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags);
-    if (rc) return rc;
-    const int nb = blocks_per_frame_fast(g->n, ctx->n_frames, 2);
-    dim3 grid(nb, (unsigned)ctx->n_frames);
-    k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                                d_rot, flags);
-    LAUNCHED();
+    // (geometric estimate, mass-weighted unwrap), then shift + wrap + covariance in f64.  Skipped here when the
+    // single-pass kernel tail-launches them itself for the frames that need them.
+    if (!device_fallback) {
+        rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
+        if (rc) return rc;
+        rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags);
+        if (rc) return rc;
+        const int nb = blocks_per_frame_fast(g->n, ctx->n_frames, 2);
+        dim3 grid(nb, (unsigned)ctx->n_frames);
+        k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
+                                                    d_rot, flags);
+        LAUNCHED();
+    }
     if (fit) {
         size_t fb = (ctx->n_atoms + kThreads - 1) / kThreads;
         fb = std::max<size_t>(1, std::min<size_t>(fb, (size_t)kMaxBlocksPerFrame * 4));
@@ -721,8 +749,10 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         if (center_done) {
             // frames the fused pass flagged: reference-order centre passes for those frames only (d_c0 already
             // holds their Bai-Breen estimate from the RMSD fallback above)
-            rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
-            if (rc) return rc;
+            if (!device_fallback) {
+                rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
+                if (rc) return rc;
+            }
         } else {
             rc = run_get_center(ctx, *g, center_weighted != 0, d_center);
             if (rc) return rc;
@@ -769,6 +799,8 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaMalloc(&ctx->d_cen2, max_frames * 3 * sizeof(float)));
         CK(cudaMalloc(&ctx->d_res, max_frames * 8 * sizeof(float)));
         CK(cudaMalloc(&ctx->d_rot, max_frames * 9 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_frames_done, sizeof(unsigned int)));
+        CK(cudaMemset(ctx->d_frames_done, 0, sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_flags, max_frames * sizeof(int)));
         CK(cudaMemset(ctx->d_flags, 0, max_frames * sizeof(int)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center, k_center_fast<false>, kThreads, 0));
@@ -824,7 +856,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
     }
     for (auto &r : ctx->refs)
         if (r.d_pc) cudaFree(r.d_pc);
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags};
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);

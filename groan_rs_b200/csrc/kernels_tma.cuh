@@ -270,11 +270,50 @@ __device__ __forceinline__ float2 pilot_delta2(float2 x, float negp, float L, fl
     return __ffma2_rn(splat(-L), k, d);
 }
 
+// ---------------------------------------------------------------- device-side launch of the fallback passes
+// The reference-order passes are needed only for frames the single pass could not certify -- usually none.  Launching
+// them from the host every time costs four grids of early-exiting CTAs per call (~17 us of a 145 us step,
+// profiles/r1_launches.csv).  Instead the thread that finishes the LAST frame of the launch looks at the flags and,
+// only if one is set, tail-launches the passes from the device (CUDA dynamic parallelism, cudaStreamTailLaunch: they
+// run in order after this grid, before anything the host enqueues next on the stream).
+struct FallbackPlan {
+    int enabled;              // 0: the host launches the fallback passes itself
+    int nb_exact, nb_cov;     // CTAs per frame of k_trig / k_unwrap and of k_cov
+    unsigned int *frames_done;
+    float *c0;                // Bai-Breen estimates of the flagged frames
+    int want_center, center_weighted, want_rmsd;
+    float *center_out;        // want_center
+    float *com, *rmsd_out, *rot_out; // want_rmsd
+};
+
+__device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, const FrameView &fv, const GroupView &g, const RefView &ref,
+                                                      double *partials, unsigned int *tickets, const int *flags) {
+    if (!fp.enabled) return;
+    __threadfence();
+    const unsigned int done = atomicAdd(fp.frames_done, 1u);
+    if (done != gridDim.y - 1) return;
+    *fp.frames_done = 0u; // re-arm
+    __threadfence();
+    int any = 0;
+    for (unsigned int f = 0; f < gridDim.y; f++) any |= ((const volatile int *)flags)[f];
+    if (!any) return;
+    const dim3 ge(fp.nb_exact, gridDim.y), gc(fp.nb_cov, gridDim.y);
+    k_trig<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.c0, flags);
+    if (fp.want_rmsd) {
+        k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.com, flags);
+        k_cov<<<gc, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, ref, fp.com, partials, tickets, fp.rmsd_out, fp.rot_out, flags);
+    }
+    if (fp.want_center) {
+        if (fp.center_weighted) k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
+        else k_unwrap<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
+    }
+}
+
 // ---------------------------------------------------------------- group_get_center / group_get_com, single pass
 // per-thread sums (float2 = one partial per atom of the pair): [0..2] sum m d, [3] sum m, [4..6] sum cos, [7..9] sum sin
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                                float *out, int *flags) {
+                                                                float *out, int *flags, FallbackPlan fp) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ FrameReduceSmem<10, 3> sm;
     __shared__ TmaCtl<kCenterStages> ctl;
@@ -337,6 +376,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
             }
         }
         finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, flags + f);
+        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags);
     }
 }
 
@@ -345,7 +385,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
 template <bool SAME_MASS>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
                                                               unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
-                                                              int *flags, int cs) {
+                                                              int *flags, FallbackPlan fp, int cs) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ FrameReduceSmem<kFastSums, 3> sm;
     __shared__ TmaCtl<kRmsdStages> ctl;
@@ -427,6 +467,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
             }
         }
         finish_rmsd<SAME_MASS>(tot, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, flags + f);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
     }
 }
 
@@ -440,7 +481,7 @@ constexpr int kFusedSums = kFastSums + 9;
 template <bool SAME_MASS, bool WEIGHTED_CENTER>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
                                                                      unsigned int *tickets, float *center_out, float *rmsd_out,
-                                                                     float *rot_out, float *com_out, int *flags, int cs) {
+                                                                     float *rot_out, float *com_out, int *flags, FallbackPlan fp, int cs) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ FrameReduceSmem<kFusedSums, 3> sm;
     __shared__ TmaCtl<kRmsdStages> ctl;
@@ -546,6 +587,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv
         ct[3] = SAME_MASS ? ref.sum_w : tot[25];
         finish_center<WEIGHTED_CENTER>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
         flags[f] = flag_r | (flag_c << 1);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
     }
 }
 

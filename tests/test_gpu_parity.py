@@ -718,3 +718,34 @@ def test_full_size_properties_cfg4_cfg5():
     fr = p.get_frames()[0]
     sub = orc.all_distances(fr, np.arange(64), np.arange(500_000, 500_000 + 4096), "XYZ", [21.5] * 3)
     assert np.array_equal(bits(mat[0, :64, :4096].cpu().numpy()), bits(sub))
+
+
+def test_device_side_fallback_matches_exact_only():
+    """A large contiguous group that is NOT compact (uniform in the box) goes through the TMA-fed single-pass kernel, which
+    flags every frame and tail-launches the reference-order passes from the device; results must be bit-identical to
+    GROAN_FLAG_EXACT_ONLY and to the host-launched fallback (GROAN_FLAG_HOST_FALLBACK)."""
+    import groan_rs_b200 as g
+    n, F = 120_000, 3
+    L = np.array([11.0, 12.0, 13.0], np.float32)
+    masses = np.random.default_rng(8).uniform(1.0, 50.0, n).astype(np.float32)
+    res = {}
+    for name, flags in (("device", 0), ("host", g.FLAG_HOST_FALLBACK), ("exact", g.FLAG_EXACT_ONLY)):
+        s = g.System(n, masses=masses, max_frames=F)
+        s.set_flags(flags)
+        s.synth_uniform(99, 0, F, [0, 0, 0], L, L)
+        ref = g.System(n, masses=masses)
+        ref.set_frames(s.get_frames()[0], L)
+        for x in (s, ref):
+            x.group_create_from_indices("G", np.arange(16, n - 8))
+        c = s.group_get_center("G")
+        nf_c = s.fallback_frames()
+        m = s.group_get_com("G")
+        r = s.calc_rmsd(ref, "G")
+        nf_r = s.fallback_frames()
+        c2, r2 = s.group_center_and_rmsd(ref, "G")
+        res[name] = (c, m, r, c2, r2)
+        if name != "exact":
+            assert nf_c == F and nf_r == F
+    for name in ("device", "host"):
+        for a, b in zip(res[name], res["exact"]):
+            assert np.array_equal(bits(a), bits(b)), name
