@@ -194,6 +194,8 @@ def run_gpu_arm(args):
     idx = np.arange(N_ATOMS, dtype=np.uint32)
     s.group_create_from_indices("G", idx)
     ref.group_create_from_indices("G", idx)
+    if os.environ.get("GROAN_BENCH_FLAGS"):  # tuning experiments only (include/groan_gpu.h GROAN_FLAG_*)
+        s.set_flags(int(os.environ["GROAN_BENCH_FLAGS"]))
     # a non-default torch stream: torch.cuda.Event then times exactly the stream the kernels are launched on
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)

@@ -230,74 +230,72 @@ int blocks_per_frame_fast(size_t g, size_t F, int occ) {
 // TMA-fed kernels need a contiguous group (one byte range per frame), enough atoms to fill the ring, and a
 // 16-byte aligned coordinate buffer (cudaMalloc'ed slots always are; attached buffers are checked)
 bool tma_ok(const groan_gpu_ctx *ctx, const Group &g, int occ) {
-    return occ > 0 && g.contiguous && g.n >= 4 * (size_t)kChunk && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
+    return occ > 0 && g.contiguous && g.n >= 4096 && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
            !(ctx->flags & GROAN_FLAG_NO_TMA);
 }
 
 int blocks_per_frame_tma(size_t g, size_t F, int occ) {
-    size_t nb = (g + kChunk - 1) / kChunk;  // at least one chunk per CTA
+    size_t nb = (g + 1023) / 1024;  // at least one chunk per CTA
     nb = std::max<size_t>(nb, 1);
     nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
     nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
     return (int)nb;
 }
 
-// Cluster size along the frame axis for the reference multicast: the CTAs of a cluster must walk identical chunk
-// sequences, i.e. every frame must put the group at the same offset modulo 4 atoms (n_atoms % 4 == 0), and the
-// cluster size must divide the number of frames.
-int multicast_cluster_size(const groan_gpu_ctx *ctx) {
-    // Opt-in: measured on B200 (profiles/r1_multicast_experiment.md) the cluster version halves the reference's L2 traffic
-    // but runs 1.6-1.8x slower than the plain ring (warps wait on the shared stage), so it is off by default.
-    if (!(ctx->flags & GROAN_FLAG_MULTICAST)) return 1;
-    if (ctx->n_atoms % 4 != 0) return 1;
-    int cap = 8;
-    if (const char *e = std::getenv("GROAN_MULTICAST_MAX")) cap = std::max(1, std::atoi(e));  // tuning knob
-    for (int cs = std::min(8, cap); cs > 1; cs >>= 1)
-        if (ctx->n_frames % (size_t)cs == 0) return cs;
-    return 1;
+// frames served by one CTA of the TMA-fed RMSD kernels.  Opt-in (GROAN_FLAG_FRAME_SHARING): 4 frames share one copy of
+// each reference chunk when the batch has a multiple of 4 frames and every frame puts the group at the same offset modulo
+// 4 atoms (n_atoms % 4 == 0).  It cuts the reference's L2 -> SM traffic 4x, but measured on B200 it is SLOWER than one
+// frame per CTA (0.200 vs 0.127 ms per 8 x 4M-atom batch, profiles/r1_summary.md): the per-frame constants stop being
+// CTA-uniform, which costs registers (spills in the fused variant) and issue slots.
+int frames_per_cta(const groan_gpu_ctx *ctx) {
+    if (!(ctx->flags & GROAN_FLAG_FRAME_SHARING)) return 1;
+    return (ctx->n_atoms % 4 == 0 && ctx->n_frames % 4 == 0) ? 4 : 1;
 }
 
-// launch a TMA-fed RMSD-type kernel on grid (nb, F) with clusters (1, cs, 1); nb is capped by the number of
-// co-resident clusters so that the launch stays a single wave
-template <typename... KArgs, typename... Args>
-int launch_rmsd_tma(groan_gpu_ctx *ctx, void (*kernel)(KArgs...), const Group &g, int cs, Args... args) {
-    const size_t smem = TmaSmem<true, kRmsdStages>::kBytes;
-    int nb = blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_rmsd_tma);
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(kTmaThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx->compute;
-    if (cs > 1) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1;
-        attr[0].val.clusterDim.y = (unsigned)cs;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cfg.gridDim = dim3((unsigned)nb, (unsigned)ctx->n_frames);
-        int max_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters <= 0) {
-            cudaGetLastError();
-            cs = 1;
-            cfg.attrs = nullptr;
-            cfg.numAttrs = 0;
-        } else {
-            const int per_x = (int)(ctx->n_frames / (size_t)cs);  // clusters per grid column
-            nb = std::max(1, std::min(nb, max_clusters / std::max(per_x, 1)));
-        }
+template <bool SAME_MASS, int CENTER, int FPC>
+int launch_rmsd_tma_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, float *d_center, float *d_rmsd, float *d_rot,
+                      const FallbackPlan &fp) {
+    typedef TmaCfg<true, kRmsdStages, FPC> C;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_rmsd_tma<SAME_MASS, CENTER, FPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes));
+        attr_set = true;
     }
-    cfg.gridDim = dim3((unsigned)nb, (unsigned)ctx->n_frames);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args..., cs);
-    ctx->launches++;
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cluster launch");
+    const size_t groups = ctx->n_frames / FPC;
+    size_t nb = (g.n + C::CH - 1) / C::CH;  // at least one chunk per CTA
+    nb = std::max<size_t>(1, std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * 2) / groups)));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
+    dim3 grid((unsigned)nb, (unsigned)groups);
+    k_rmsd_tma<SAME_MASS, CENTER, FPC><<<grid, kTmaThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, ctx->d_partials,
+                                                                                       ctx->d_tickets, d_center, d_rmsd, d_rot,
+                                                                                       ctx->d_cen, ctx->d_flags, fp);
+    LAUNCHED();
     return GROAN_OK;
+}
+
+// center_mode: 0 = RMSD only, 1 = + geometric centre, 2 = + centre of mass
+int launch_rmsd_tma(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, bool same_mass, int center_mode, float *d_center,
+                    float *d_rmsd, float *d_rot, const FallbackPlan &fp) {
+    const int fpc = frames_per_cta(ctx);
+#define GO(SM, CM)                                                                                      \
+    return fpc == 4 ? launch_rmsd_tma_t<SM, CM, 4>(ctx, g, rv, d_center, d_rmsd, d_rot, fp)              \
+                    : launch_rmsd_tma_t<SM, CM, 1>(ctx, g, rv, d_center, d_rmsd, d_rot, fp)
+    if (same_mass) {
+        if (center_mode == 0) GO(true, 0);
+        if (center_mode == 1) GO(true, 1);
+        GO(true, 2);
+    }
+    if (center_mode == 0) GO(false, 0);
+    if (center_mode == 1) GO(false, 1);
+    GO(false, 2);
+#undef GO
 }
 
 FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
                            float *rmsd_out, float *rot_out) {
     FallbackPlan fp;
     fp.enabled = (ctx->flags & GROAN_FLAG_HOST_FALLBACK) ? 0 : 1;
+    fp.n_frames = (int)ctx->n_frames;
     fp.nb_exact = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
     fp.nb_cov = blocks_per_frame_fast(g.n, ctx->n_frames, 2);
     fp.frames_done = ctx->d_frames_done;
@@ -413,7 +411,7 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
     const int *flags = nullptr;
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
         dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaSmem<false, kCenterStages>::kBytes;
+        const size_t smem = TmaCfg<false, kCenterStages, 1>::kBytes;
         const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
         if (weighted)
             k_center_tma<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
@@ -685,29 +683,17 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     bool center_done = false, device_fallback = false;
     if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
-        const int cs = multicast_cluster_size(ctx);
         const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
         device_fallback = fp.enabled != 0;
-#define FUSED_LAUNCH(SM, WC)                                                                                                  \
-    rc = launch_rmsd_tma(ctx, k_center_rmsd_tma<SM, WC>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, \
-                         d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags, fp)
-        if (R.same_mass) { if (center_weighted) FUSED_LAUNCH(true, true); else FUSED_LAUNCH(true, false); }
-        else { if (center_weighted) FUSED_LAUNCH(false, true); else FUSED_LAUNCH(false, false); }
-#undef FUSED_LAUNCH
+        rc = launch_rmsd_tma(ctx, *g, rv, R.same_mass, center_weighted ? 2 : 1, d_center, d_rmsd, d_rot, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
         center_done = true;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // single pass, TMA-fed (kernels_tma.cuh)
-        const int cs = multicast_cluster_size(ctx);
         const FallbackPlan fp = fallback_plan(ctx, *g, false, false, nullptr, true, d_rmsd, d_rot);
         device_fallback = fp.enabled != 0;
-        if (R.same_mass)
-            rc = launch_rmsd_tma(ctx, k_rmsd_tma<true>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                 d_rot, ctx->d_cen, ctx->d_flags, fp);
-        else
-            rc = launch_rmsd_tma(ctx, k_rmsd_tma<false>, *g, cs, frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets, d_rmsd,
-                                 d_rot, ctx->d_cen, ctx->d_flags, fp);
+        rc = launch_rmsd_tma(ctx, *g, rv, R.same_mass, 0, nullptr, d_rmsd, d_rot, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
@@ -807,24 +793,17 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
         ctx->occ_rmsd = std::max(1, std::min(ctx->occ_rmsd, 8));
-        // TMA-fed versions: dynamic shared memory ring (48 KB centre, 112 KB RMSD)
-        const int sc = (int)TmaSmem<false, kCenterStages>::kBytes, sr = (int)TmaSmem<true, kRmsdStages>::kBytes;
+        // TMA-fed versions: dynamic shared memory ring (48 KB centre, ~100 KB RMSD: set per instantiation at first launch)
+        const int sc = (int)TmaCfg<false, kCenterStages, 1>::kBytes;
         CK(cudaFuncSetAttribute(k_center_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
         CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
-        CK(cudaFuncSetAttribute(k_rmsd_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
-        CK(cudaFuncSetAttribute(k_rmsd_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
-        CK(cudaFuncSetAttribute(k_center_rmsd_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
-        CK(cudaFuncSetAttribute(k_center_rmsd_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
-        CK(cudaFuncSetAttribute(k_center_rmsd_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
-        CK(cudaFuncSetAttribute(k_center_rmsd_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sr));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd_tma, k_rmsd_tma<true>, kTmaThreads, sr));
+        ctx->occ_rmsd_tma = 2;
         if (const char *e = std::getenv("GROAN_DEBUG_SKIP_REF")) {
             const int v = std::atoi(e);
             CK(cudaMemcpyToSymbol(g_debug_skip_ref, &v, sizeof(int)));
         }
         ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
-        ctx->occ_rmsd_tma = std::min(ctx->occ_rmsd_tma, 2);
         return GROAN_OK;
     }();
     if (rc) {

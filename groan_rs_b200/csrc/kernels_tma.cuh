@@ -7,11 +7,16 @@
 // kernels (profiles/r1_v2_*.md) showed exactly that limit: 75 % of the warp stalls were long-scoreboard
 // waits with 16 resident warps per SM.
 //
-//   CTA = 8 warps, all consumers.  Ring of 3-4 stages; a stage holds one chunk of kChunk atoms: 12 KB of
-//   coordinates (+ 16 KB of the RMSD reference, float4 per atom).  full[s] (count 1 + tx bytes) is armed by
-//   whoever issues the copies and completed by the TMA; the last warp to finish reading a stage (an atomic
-//   counter in shared memory) re-arms it and issues the copies for the chunk one ring ahead, so no warp is
-//   spent polling for free stages.
+//   CTA = 8 warps, all consumers.  Ring of 3-4 stages.  full[s] (count 1 + tx bytes) is armed by whoever issues the
+//   copies and completed by the TMA; the last warp to finish reading a stage (an atomic counter in shared memory)
+//   re-arms it and issues the copies for the chunk one ring ahead, so no warp is spent polling for free stages.
+//
+//   A CTA serves FPC frames at once (FPC = 4 when the batch allows it, else 1): its warps are split into FPC
+//   groups, group q streams frame q's chunk, and ALL groups share one copy of the RMSD reference chunk of the
+//   stage.  For a 4M-atom group the prepared reference (64 MB) lives in L2 and every frame needs all of it:
+//   sharing it between 4 frames cuts the reference's L2 -> SM traffic from 16 to 4 B per atom per frame
+//   (profiles/r1_summary.md; the cluster-multicast alternative was measured slower, r1_multicast_experiment.md).
+//   Stage = reference blocks (12 KB for 512 atoms / 20 KB for 1024) + FPC x chunk x 12 B.
 //   Coordinates are read from shared memory with stride-3 LDS.32 (3 is coprime to 32: conflict-free), the
 //   reference with LDS.128.  Frame bytes carry an L2 evict-first policy, reference bytes evict-last, so the
 //   64 MB reference of the 4M-atom workload stays in the 126 MB L2 while 48 MB frames stream through.
@@ -25,7 +30,6 @@
 
 namespace groan {
 
-constexpr int kChunk = 1024;          // atoms per stage
 constexpr int kTmaThreads = kThreads; // 8 warps, all consumers; the last warp to leave a stage refills it
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,57 +77,29 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// ---- thread-block cluster helpers: the CTAs that process the same chunks of DIFFERENT frames form a cluster along y,
-// and the reference chunk they all need is fetched from L2 once and multicast into every CTA's ring.
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// atomic add on the counter at the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory);
-// acq_rel at cluster scope: every CTA's reads of a stage happen-before the copies issued by the CTA that arrives last
-__device__ __forceinline__ uint32_t atomic_add_remote(unsigned int *ctr, uint32_t rank, uint32_t v) {
-    uint32_t raddr, old;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(ctr)), "r"(rank));
-    asm volatile("atom.acq_rel.cluster.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(raddr), "r"(v) : "memory");
-    return old;
-}
-// bulk copy delivered to the same offset of every CTA in `mask`, completing on each CTA's own mbarrier at that offset
-__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask,
-                                                   uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask), "l"(policy)
-        : "memory");
-}
-
-template <bool WITH_REF, int STAGES>
-struct TmaSmem {
-    static constexpr size_t kFrameBytes = (size_t)kChunk * 12;
-    // reference: whole blocks of kRefBlock atoms; a chunk that does not start on a block boundary touches one more
-    static constexpr size_t kRefBytes = WITH_REF ? (size_t)(kChunk / kRefBlock + 1) * kRefBlock * 16 : 0;
-    static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
+// ring geometry: FPC frames per CTA, CH atoms per chunk and frame
+template <bool WITH_REF, int STAGES, int FPC>
+struct TmaCfg {
+    static constexpr int CH = (FPC == 1) ? 1024 : 512;         // atoms per chunk (per frame)
+    static constexpr int GT = kThreads / FPC;                  // threads serving one frame
+    static constexpr size_t kRefBytes = WITH_REF ? (size_t)(CH / kRefBlock + 1) * kRefBlock * 16 : 0; // whole blocks, +1 if unaligned
+    static constexpr size_t kFrameBytes = (size_t)CH * 12;
+    static constexpr size_t kStageBytes = kRefBytes + FPC * kFrameBytes;
     static constexpr size_t kBytes = STAGES * kStageBytes + 128;
 };
 constexpr int kCenterStages = 4; // 48 KB of ring: 4 CTAs per SM
-constexpr int kRmsdStages = 3;   // 96 KB of ring: 2 CTAs per SM
+constexpr int kRmsdStages = 3;   // 96 KB (FPC = 1) / 108 KB (FPC = 4) of ring: 2 CTAs per SM
 
 template <int STAGES>
 struct TmaCtl {
     uint64_t full[STAGES];     // count 1 + tx bytes: armed by whoever issues the copies, completed by the TMA
-    unsigned int done[STAGES];  // consumer warps that have finished reading the stage
-    unsigned int cdone[STAGES]; // cluster rank 0's copy only: CTAs of the cluster that have finished reading the stage
+    unsigned int done[STAGES]; // consumer warps that have finished reading the stage
 };
 
 // Geometry of a contiguous group inside frame f: `head` atoms before the first 16-byte boundary, a body whose
 // length is a multiple of 4 atoms (so every chunk and its byte count are 16-byte multiples), then `tail` atoms.
 struct BodyGeom {
-    uint32_t head, body, tail, chunks;
+    uint32_t head, body, tail;
 };
 __device__ __forceinline__ BodyGeom body_geom(const FrameView &fv, const GroupView &g, int f) {
     BodyGeom b;
@@ -132,21 +108,9 @@ __device__ __forceinline__ BodyGeom body_geom(const FrameView &fv, const GroupVi
     if (b.head > g.n) b.head = g.n;
     b.body = (g.n - b.head) & ~3u;
     b.tail = g.n - b.head - b.body;
-    b.chunks = (b.body + kChunk - 1) / kChunk;
     return b;
 }
 
-// Stream the body of the group in frame f through the ring, two atoms per call:
-//   fn(i0, i1, X, Y, Z, ref)   with X = (x of atom i0, x of atom i1) etc. and ref the reference (pc.xyz, w) of the
-// two atoms, component-wise paired (zero when !WITH_REF).  Pairs feed the packed f32x2 arithmetic of sm_100 (FADD2 / FMUL2 / FFMA2: one
-// issue slot for two lanes of work), which is what lifts these kernels from issue-bound to HBM-bound
-// (profiles/r1_v4_*).  The two atoms of a pair sit half a chunk apart, so every LDS.32 of a warp walks
-// consecutive atoms (stride 3 words, conflict-free) and lands in a register pair the packed ops can use.
-// The up-to-3 atoms before and after the 16-byte aligned body are NOT visited; the finishing thread adds them.
-//
-// There is no producer warp and nobody polls for a free stage: a warp that has read its share of a stage bumps
-// done[s]; the warp that brings it to 8 is the last reader, so it re-arms full[s] and issues the copies of the
-// chunk STAGES ahead into the stage it has just emptied.  Consumers only ever wait on full[s].
 // profiling experiment only (GROAN_DEBUG_SKIP_REF=1): do not copy the reference into the ring, to measure how much
 // of the RMSD kernel's time is its L2 -> SM traffic.  Results are garbage with it set; never set in tests or bench.
 __device__ int g_debug_skip_ref = 0;
@@ -155,71 +119,55 @@ struct RefPair {
     float2 x, y, z, w; // (atom i0, atom i1) per component
 };
 
-template <bool WITH_REF, int STAGES, typename F>
-__device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg,
-                                                 const float *ref_pc, unsigned char *smem, TmaCtl<STAGES> &ctl, int cs, F &&fn) {
-    // cs = cluster size along y (frames).  cs > 1: all CTAs of the cluster walk the same chunk sequence (same blockIdx.x,
-    // same body geometry -- the host guarantees it) and share one L2 read of each reference chunk: the CTA that is the
-    // LAST of the cluster to finish a stage (a counter in rank 0's shared memory) multicasts the next chunk into it.
-    typedef TmaSmem<WITH_REF, STAGES> S;
+// Stream the body of the group through the ring, two atoms per call, for the frame this thread's warp group serves
+// (frame f0 + threadIdx.x / GT):
+//   fn(i0, i1, X, Y, Z, ref)   with X = (x of atom i0, x of atom i1) etc. and ref the reference (pc.xyz, w) of the
+// two atoms, component-wise paired (zero when !WITH_REF).  Pairs feed the packed f32x2 arithmetic of sm_100 (FADD2 /
+// FMUL2 / FFMA2: one issue slot for two lanes of work).  The two atoms of a pair sit half a chunk apart, so every
+// LDS.32 of a warp walks consecutive atoms (stride 3 words for coordinates, stride 1 inside a reference block:
+// conflict-free) and lands in a register pair the packed ops can use.
+// The up-to-3 atoms before and after the 16-byte aligned body are NOT visited; the finishing thread adds them.
+// All FPC frames of a CTA must share the body geometry (the host guarantees it: FPC > 1 only if n_atoms % 4 == 0).
+template <bool WITH_REF, int STAGES, int FPC, typename F>
+__device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const GroupView &g, int f0, const BodyGeom &bg, const float *ref_pc,
+                                                 unsigned char *smem, TmaCtl<STAGES> &ctl, F &&fn) {
+    typedef TmaCfg<WITH_REF, STAGES, FPC> C;
+    constexpr int CH = C::CH, GT = C::GT;
     const int lane = threadIdx.x & 31;
-    const bool mc = WITH_REF && cs > 1;
-    const uint32_t rank = mc ? cluster_rank() : 0u;
-    const float *fr = fv.frame(f);
-    const char *src = reinterpret_cast<const char *>(fr + ((size_t)g.first + bg.head) * 3);
-    const uint32_t my_chunks = bg.chunks > blockIdx.x ? (bg.chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int q = threadIdx.x / GT, tg = threadIdx.x % GT; // frame slot of this thread, index inside its group
+    const uint32_t chunks = (bg.body + CH - 1) / CH;
+    const uint32_t my_chunks = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
-    // byte counts of this CTA's chunk `it`
-    auto geom = [&](uint32_t it, uint32_t &c, uint32_t &atoms, uint32_t &b0, uint32_t &ref_bytes) {
-        c = blockIdx.x + it * gridDim.x;
-        atoms = min((uint32_t)kChunk, bg.body - c * kChunk);
-        const uint32_t i0 = bg.head + c * kChunk;
-        b0 = i0 >> 8; // reference blocks covering group atoms [i0, i0 + atoms)
-        ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (((i0 + atoms - 1) >> 8) - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
-    };
-    // arm full[s] for everything that will land in the stage and copy this CTA's own frame chunk (+ reference if not multicast)
-    auto issue_own = [&](uint32_t it) {
-        uint32_t c, atoms, b0, ref_bytes;
-        geom(it, c, atoms, b0, ref_bytes);
-        const uint32_t s = it % STAGES;
-        mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
-        unsigned char *dst = smem + s * S::kStageBytes;
-        bulk_g2s(dst, src + (size_t)c * kChunk * 12, atoms * 12u, ctl.full + s, pol_frame);
-        if (WITH_REF && !mc && ref_bytes)
-            bulk_g2s(dst + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);
-    };
-    // one L2 read of the reference chunk, delivered to every CTA of the cluster
-    auto issue_multicast = [&](uint32_t it) {
-        uint32_t c, atoms, b0, ref_bytes;
-        geom(it, c, atoms, b0, ref_bytes);
-        const uint32_t s = it % STAGES;
-        if (ref_bytes)
-            bulk_g2s_multicast(smem + s * S::kStageBytes + S::kFrameBytes, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes,
-                               ctl.full + s, (uint16_t)((1u << cs) - 1u), pol_ref);
+    auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` (reference once, FPC frames) into stage it % STAGES
+        const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
+        const uint32_t atoms = min((uint32_t)CH, bg.body - c * CH);
+        const uint32_t i0 = bg.head + c * CH, b0 = i0 >> 8; // reference blocks covering group atoms [i0, i0 + atoms)
+        const uint32_t ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (((i0 + atoms - 1) >> 8) - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
+        mbar_expect_tx(ctl.full + s, atoms * 12u * FPC + ref_bytes);
+        unsigned char *dst = smem + s * C::kStageBytes;
+        if (WITH_REF && ref_bytes) bulk_g2s(dst, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);
+#pragma unroll
+        for (int k = 0; k < FPC; k++) {
+            const char *src = reinterpret_cast<const char *>(fv.frame(f0 + k) + ((size_t)g.first + bg.head) * 3);
+            bulk_g2s(dst + C::kRefBytes + k * C::kFrameBytes, src + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, pol_frame);
+        }
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(ctl.full + s, 1);
             ctl.done[s] = 0;
-            ctl.cdone[s] = 0;
         }
         fence_mbar_init();
+        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
     }
-    if (mc) cluster_sync_all(); // every CTA's barriers exist before any multicast can signal them
-    else __syncthreads();
-    if (threadIdx.x == 0) {
-        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) {
-            issue_own(it);
-            if (mc && rank == 0) issue_multicast(it);
-        }
-    }
+    __syncthreads();
     for (uint32_t it = 0; it < my_chunks; it++) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         const uint32_t c = blockIdx.x + it * gridDim.x;
-        const uint32_t atoms = min((uint32_t)kChunk, bg.body - c * kChunk); // a multiple of 4
-        const float *sf = reinterpret_cast<const float *>(smem + s * S::kStageBytes);
-        const float *sr = reinterpret_cast<const float *>(smem + s * S::kStageBytes + S::kFrameBytes);
-        const uint32_t i0 = bg.head + c * kChunk;
+        const uint32_t atoms = min((uint32_t)CH, bg.body - c * CH); // a multiple of 4
+        const float *sr = reinterpret_cast<const float *>(smem + s * C::kStageBytes);
+        const float *sf = reinterpret_cast<const float *>(smem + s * C::kStageBytes + C::kRefBytes + q * C::kFrameBytes);
+        const uint32_t i0 = bg.head + c * CH;
         const uint32_t lo = i0 & (kRefBlock - 1); // position of the chunk's first atom inside its reference block
         mbar_wait(ctl.full + s, ph);
         auto pair = [&](uint32_t j0, uint32_t j1) {
@@ -237,12 +185,12 @@ __device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const Grou
             }
             fn(i0 + j0, i0 + j1, X, Y, Z, r);
         };
-        if (atoms == kChunk) {
+        if (atoms == CH) {
 #pragma unroll
-            for (int u = 0; u < kChunk / 2 / kThreads; u++) pair(threadIdx.x + u * kThreads, threadIdx.x + u * kThreads + kChunk / 2);
+            for (int u = 0; u < CH / 2 / GT; u++) pair(tg + u * GT, tg + u * GT + CH / 2);
         } else {
             const uint32_t half = atoms >> 1;
-            for (uint32_t j = threadIdx.x; j < half; j += kThreads) pair(j, j + half);
+            for (uint32_t j = tg; j < half; j += GT) pair(j, j + half);
         }
         __syncwarp();
         if (lane == 0) {
@@ -250,15 +198,10 @@ __device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const Grou
             if (atomicAdd(&ctl.done[s], 1u) == (unsigned)(kWarps - 1)) { // last reader of the stage: refill it
                 ctl.done[s] = 0;
                 __threadfence_block();
-                if (it + STAGES < my_chunks) {
-                    issue_own(it + STAGES);
-                    // this CTA no longer reads the stage's reference and has armed full[s]; the last CTA to say so multicasts
-                    if (mc && atomic_add_remote(&ctl.cdone[s], 0, 1u) % (uint32_t)cs == (uint32_t)(cs - 1)) issue_multicast(it + STAGES);
-                }
+                if (it + STAGES < my_chunks) issue(it + STAGES);
             }
         }
     }
-    if (mc) cluster_sync_all(); // no CTA may exit while a peer can still signal its barriers
 }
 
 // packed helpers (sm_100 f32x2 pipe)
@@ -270,6 +213,41 @@ __device__ __forceinline__ float2 pilot_delta2(float2 x, float negp, float L, fl
     return __ffma2_rn(splat(-L), k, d);
 }
 
+// Per-frame reduction for a CTA that serves FPC frames: one frame_reduce per frame slot, in which the threads of the other
+// slots contribute neutral values.  Returns, for the calling thread's own slot, whether this CTA drew the frame's last
+// ticket; the totals of the thread's own frame are left in tot / tmn / tmx.
+template <int KS, int FPC>
+__device__ __forceinline__ bool multi_frame_reduce(const float (&a)[KS], const float (&mn)[3], const float (&mx)[3], int f0, int nb,
+                                                   double *partials, unsigned int *tickets, FrameReduceSmem<KS, 3> &sm,
+                                                   double (&tot)[KS], float (&tmn)[3], float (&tmx)[3]) {
+    constexpr int GT = kThreads / FPC;
+    const int q = threadIdx.x / GT;
+    bool mine_last = false;
+#pragma unroll 1
+    for (int k = 0; k < FPC; k++) {
+        float b[KS], bmn[3], bmx[3];
+#pragma unroll
+        for (int i = 0; i < KS; i++) b[i] = (FPC == 1 || q == k) ? a[i] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            bmn[i] = (FPC == 1 || q == k) ? mn[i] : 3.0e38f;
+            bmx[i] = (FPC == 1 || q == k) ? mx[i] : -3.0e38f;
+        }
+        double t[KS];
+        float t0[3], t1[3];
+        const bool last = frame_reduce<KS, 3>(b, bmn, bmx, partials + (size_t)(f0 + k) * nb * (KS + 6), tickets + f0 + k, nb, sm, t, t0, t1);
+        if (last && q == k) {
+            mine_last = true;
+#pragma unroll
+            for (int i = 0; i < KS; i++) tot[i] = t[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { tmn[i] = t0[i]; tmx[i] = t1[i]; }
+        }
+        __syncthreads(); // sm is reused by the next slot
+    }
+    return mine_last;
+}
+
 // ---------------------------------------------------------------- device-side launch of the fallback passes
 // The reference-order passes are needed only for frames the single pass could not certify -- usually none.  Launching
 // them from the host every time costs four grids of early-exiting CTAs per call (~17 us of a 145 us step,
@@ -278,6 +256,7 @@ __device__ __forceinline__ float2 pilot_delta2(float2 x, float negp, float L, fl
 // run in order after this grid, before anything the host enqueues next on the stream).
 struct FallbackPlan {
     int enabled;              // 0: the host launches the fallback passes itself
+    int n_frames;             // frames of the batch
     int nb_exact, nb_cov;     // CTAs per frame of k_trig / k_unwrap and of k_cov
     unsigned int *frames_done;
     float *c0;                // Bai-Breen estimates of the flagged frames
@@ -291,13 +270,13 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
     if (!fp.enabled) return;
     __threadfence();
     const unsigned int done = atomicAdd(fp.frames_done, 1u);
-    if (done != gridDim.y - 1) return;
+    if (done != (unsigned)fp.n_frames - 1) return;
     *fp.frames_done = 0u; // re-arm
     __threadfence();
     int any = 0;
-    for (unsigned int f = 0; f < gridDim.y; f++) any |= ((const volatile int *)flags)[f];
+    for (int f = 0; f < fp.n_frames; f++) any |= ((const volatile int *)flags)[f];
     if (!any) return;
-    const dim3 ge(fp.nb_exact, gridDim.y), gc(fp.nb_cov, gridDim.y);
+    const dim3 ge(fp.nb_exact, fp.n_frames), gc(fp.nb_cov, fp.n_frames);
     k_trig<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.c0, flags);
     if (fp.want_rmsd) {
         k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.com, flags);
@@ -330,8 +309,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
 #pragma unroll
     for (int k = 0; k < 10; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<false, kCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl, 1,
-                                            [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &) {
+    stream_pairs_tma<false, kCenterStages, 1>(fv, g, f, bg, nullptr, dyn_smem, ctl,
+                                               [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &) {
         const float2 dx = pilot_delta2(X, -px, L[0], ix), dy = pilot_delta2(Y, -py, L[1], iy), dz = pilot_delta2(Z, -pz, L[2], iz);
         if (WEIGHTED) {
             const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
@@ -368,9 +347,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
             for (int k = 0; k < 3; k++) {
                 const float d = pilot_delta(__ldg(q + k), pp[k], L[k], 1.0f / L[k]);
                 tot[k] += m * (double)d;
-                const double th = (double)d * 6.283185307179586 / (double)L[k];
-                tot[4 + k] += cos(th);
-                tot[7 + k] += sin(th);
+                float sn, cs;
+                sincosf(d * (6.2831853f / L[k]), &sn, &cs);
+                tot[4 + k] += (double)cs;
+                tot[7 + k] += (double)sn;
                 tmn[k] = fminf(tmn[k], d);
                 tmx[k] = fmaxf(tmx[k], d);
             }
@@ -380,29 +360,38 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
     }
 }
 
-// ---------------------------------------------------------------- calc_rmsd, single pass
-// per-thread sums as float2 (one partial per atom of the pair), same meaning as kFastSums of kernels_rmsd.cuh
-template <bool SAME_MASS>
+// ---------------------------------------------------------------- calc_rmsd (+ optionally the centre), single pass
+// CENTER: 0 = RMSD only, 1 = also group_get_center (geometric), 2 = also group_get_com (mass-weighted = the COM the RMSD
+// needs anyway).  A trajectory analysis usually wants several per-frame quantities of the same group; each extra pass
+// costs another 12 B/atom of HBM, so the fused variants take them from one read of the frame.
+// per-thread sums as float2 (one partial per atom of the pair): [0..25] as kFastSums of kernels_rmsd.cuh,
+// then (CENTER != 0) [26..28] sum d (geometric centre), [29..31] sum cos, [32..34] sum sin
+constexpr int kFusedSums = kFastSums + 9;
+
+template <bool SAME_MASS, int CENTER, int FPC>
 __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
-                                                              unsigned int *tickets, float *rmsd_out, float *rot_out, float *com_out,
-                                                              int *flags, FallbackPlan fp, int cs) {
+                                                              unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
+                                                              float *com_out, int *flags, FallbackPlan fp) {
+    constexpr int KS = CENTER ? kFusedSums : kFastSums;
+    constexpr int GT = kThreads / FPC;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<kFastSums, 3> sm;
+    __shared__ FrameReduceSmem<KS, 3> sm;
     __shared__ TmaCtl<kRmsdStages> ctl;
-    const int f = blockIdx.y, nb = gridDim.x;
+    const int f0 = blockIdx.y * FPC, f = f0 + threadIdx.x / GT, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
     const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
     const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
-    const BodyGeom bg = body_geom(fv, g, f);
-    float2 a2[kFastSums];
+    const float sc[3] = {pi_x2() * ix, pi_x2() * iy, pi_x2() * iz};
+    const BodyGeom bg = body_geom(fv, g, f0);
+    float2 a2[KS];
 #pragma unroll
-    for (int k = 0; k < kFastSums; k++) a2[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k < KS; k++) a2[k] = make_float2(0.f, 0.f);
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl, cs,
-                                         [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
+    stream_pairs_tma<true, kRmsdStages, FPC>(fv, g, f0, bg, ref.pc, dyn_smem, ctl,
+                                              [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
         const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
         const float2 pc[3] = {r.x, r.y, r.z};
         const float2 w = r.w;
@@ -422,6 +411,15 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
             a2[21] = __ffma2_rn(wd, d[v], a2[21]);
             mn[v] = fminf(mn[v], fminf(d[v].x, d[v].y));
             mx[v] = fmaxf(mx[v], fmaxf(d[v].x, d[v].y));
+            if (CENTER) {
+                if (CENTER == 1) a2[KS - 9 + v] = __fadd2_rn(a2[KS - 9 + v], d[v]);
+                const float2 th = __fmul2_rn(d[v], splat(sc[v]));
+                float2 s, c;
+                __sincosf(th.x, &s.x, &c.x);
+                __sincosf(th.y, &s.y, &c.y);
+                a2[KS - 6 + v] = __fadd2_rn(a2[KS - 6 + v], c);
+                a2[KS - 3 + v] = __fadd2_rn(a2[KS - 3 + v], s);
+            }
         }
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
@@ -430,13 +428,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
             a2[25] = __fadd2_rn(a2[25], m);
         }
     });
-    float a[kFastSums];
+    float a[KS];
 #pragma unroll
-    for (int k = 0; k < kFastSums; k++) a[k] = a2[k].x + a2[k].y;
-    double tot[kFastSums];
+    for (int k = 0; k < KS; k++) a[k] = a2[k].x + a2[k].y;
+    double tot[KS];
     float tmn[3], tmx[3];
-    if (frame_reduce<kFastSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFastSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
-        threadIdx.x == 0) {
+    const bool last = multi_frame_reduce<KS, FPC>(a, mn, mx, f0, nb, partials, tickets, sm, tot, tmn, tmx);
+    if (last && threadIdx.x % GT == 0) {
         // the up-to-6 atoms outside the 16-byte aligned body, in f64 with the same definitions
         for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
             const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
@@ -450,113 +448,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
                 d[k] = (double)dk;
                 tmn[k] = fminf(tmn[k], dk);
                 tmx[k] = fmaxf(tmx[k], dk);
-            }
-            for (int u = 0; u < 3; u++)
-                for (int v = 0; v < 3; v++) {
-                    tot[u * 3 + v] += pcd[u] * d[v];
-                    tot[9 + u * 3 + v] += w * pcd[u] * d[v];
+                if (CENTER) {
+                    float sn, cs;
+                    sincosf(dk * (6.2831853f / L[k]), &sn, &cs);
+                    if (CENTER == 1) tot[KS - 9 + k] += d[k];
+                    tot[KS - 6 + k] += (double)cs;
+                    tot[KS - 3 + k] += (double)sn;
                 }
-            for (int v = 0; v < 3; v++) {
-                tot[18 + v] += w * d[v];
-                tot[21] += w * d[v] * d[v];
-            }
-            if (!SAME_MASS) {
-                const double m = (double)__ldg(g.mass + i);
-                for (int v = 0; v < 3; v++) tot[22 + v] += m * d[v];
-                tot[25] += m;
-            }
-        }
-        finish_rmsd<SAME_MASS>(tot, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, flags + f);
-        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
-    }
-}
-
-// ---------------------------------------------------------------- group_get_center (or group_get_com) + calc_rmsd in ONE pass
-// A trajectory analysis usually wants several per-frame quantities of the same group; each extra pass costs
-// another 12 B/atom of HBM.  This kernel produces the refined centre (geometric, or mass-weighted = the COM the
-// RMSD needs anyway) and the Kabsch RMSD from a single read of the frame.
-// sums: [0..25] as k_rmsd_tma, [26..28] sum d (geometric centre), [29..31] sum cos, [32..34] sum sin
-constexpr int kFusedSums = kFastSums + 9;
-
-template <bool SAME_MASS, bool WEIGHTED_CENTER>
-__global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv, GroupView g, RefView ref, double *partials,
-                                                                     unsigned int *tickets, float *center_out, float *rmsd_out,
-                                                                     float *rot_out, float *com_out, int *flags, FallbackPlan fp, int cs) {
-    extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<kFusedSums, 3> sm;
-    __shared__ TmaCtl<kRmsdStages> ctl;
-    const int f = blockIdx.y, nb = gridDim.x;
-    float L[3];
-    fv.lengths(f, L[0], L[1], L[2]);
-    const float *fr = fv.frame(f);
-    const float *p0 = fr + (size_t)g.first * 3;
-    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
-    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
-    const float sc[3] = {pi_x2() * ix, pi_x2() * iy, pi_x2() * iz};
-    const BodyGeom bg = body_geom(fv, g, f);
-    float2 a2[kFusedSums];
-#pragma unroll
-    for (int k = 0; k < kFusedSums; k++) a2[k] = make_float2(0.f, 0.f);
-    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    stream_pairs_tma<true, kRmsdStages>(fv, g, f, bg, ref.pc, dyn_smem, ctl, cs,
-                                         [&](uint32_t i0, uint32_t i1, float2 X, float2 Y, float2 Z, const RefPair &r) {
-        const float2 d[3] = {pilot_delta2(X, -px, L[0], ix), pilot_delta2(Y, -py, L[1], iy), pilot_delta2(Z, -pz, L[2], iz)};
-        const float2 pc[3] = {r.x, r.y, r.z};
-        const float2 w = r.w;
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const float2 wp = __fmul2_rn(w, pc[u]);
-#pragma unroll
-            for (int v = 0; v < 3; v++) {
-                a2[u * 3 + v] = __ffma2_rn(pc[u], d[v], a2[u * 3 + v]);
-                a2[9 + u * 3 + v] = __ffma2_rn(wp, d[v], a2[9 + u * 3 + v]);
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-            const float2 wd = __fmul2_rn(w, d[v]);
-            a2[18 + v] = __fadd2_rn(a2[18 + v], wd);
-            a2[21] = __ffma2_rn(wd, d[v], a2[21]);
-            mn[v] = fminf(mn[v], fminf(d[v].x, d[v].y));
-            mx[v] = fmaxf(mx[v], fmaxf(d[v].x, d[v].y));
-            if (!WEIGHTED_CENTER) a2[26 + v] = __fadd2_rn(a2[26 + v], d[v]);
-            const float2 th = __fmul2_rn(d[v], splat(sc[v]));
-            float2 s, c;
-            __sincosf(th.x, &s.x, &c.x);
-            __sincosf(th.y, &s.y, &c.y);
-            a2[29 + v] = __fadd2_rn(a2[29 + v], c);
-            a2[32 + v] = __fadd2_rn(a2[32 + v], s);
-        }
-        if (!SAME_MASS) {
-            const float2 m = make_float2(__ldg(g.mass + i0), __ldg(g.mass + i1));
-#pragma unroll
-            for (int v = 0; v < 3; v++) a2[22 + v] = __ffma2_rn(m, d[v], a2[22 + v]);
-            a2[25] = __fadd2_rn(a2[25], m);
-        }
-    });
-    float a[kFusedSums];
-#pragma unroll
-    for (int k = 0; k < kFusedSums; k++) a[k] = a2[k].x + a2[k].y;
-    double tot[kFusedSums];
-    float tmn[3], tmx[3];
-    if (frame_reduce<kFusedSums, 3>(a, mn, mx, partials + (size_t)f * nb * (kFusedSums + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
-        threadIdx.x == 0) {
-        for (uint32_t t = 0; t < bg.head + bg.tail; t++) { // atoms outside the 16-byte aligned body, in f64
-            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
-            const float *q = fr + ((size_t)g.first + i) * 3;
-            const float4 r = ref_at(ref.pc, i);
-            const float pp[3] = {px, py, pz};
-            const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
-            double d[3];
-            for (int k = 0; k < 3; k++) {
-                const float dk = pilot_delta(__ldg(q + k), pp[k], L[k], 1.0f / L[k]);
-                d[k] = (double)dk;
-                tmn[k] = fminf(tmn[k], dk);
-                tmx[k] = fmaxf(tmx[k], dk);
-                const double th = d[k] * 6.283185307179586 / (double)L[k];
-                if (!WEIGHTED_CENTER) tot[26 + k] += d[k];
-                tot[29 + k] += cos(th);
-                tot[32 + k] += sin(th);
             }
             for (int u = 0; u < 3; u++)
                 for (int v = 0; v < 3; v++) {
@@ -577,15 +475,18 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_center_rmsd_tma(FrameView fv
         for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
         int flag_r = 0, flag_c = 0;
         finish_rmsd<SAME_MASS>(rt, tmn, tmx, px, py, pz, L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, &flag_r);
-        // centre: geometric (sum d / n) or mass-weighted with the target group's masses (= the COM of the RMSD)
-        double ct[10];
-        for (int k = 0; k < 3; k++) {
-            ct[k] = WEIGHTED_CENTER ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[26 + k];
-            ct[4 + k] = tot[29 + k];
-            ct[7 + k] = tot[32 + k];
+        if (CENTER) {
+            // centre: geometric (sum d / n) or mass-weighted with the target group's masses (= the COM of the RMSD)
+            double ct[10];
+            for (int k = 0; k < 3; k++) {
+                ct[k] = CENTER == 2 ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[KS - 9 + k];
+                ct[4 + k] = tot[KS - 6 + k];
+                ct[7 + k] = tot[KS - 3 + k];
+            }
+            ct[3] = SAME_MASS ? ref.sum_w : tot[25];
+            if (CENTER == 2) finish_center<true>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
+            else finish_center<false>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
         }
-        ct[3] = SAME_MASS ? ref.sum_w : tot[25];
-        finish_center<WEIGHTED_CENTER>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
         flags[f] = flag_r | (flag_c << 1);
         maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
     }

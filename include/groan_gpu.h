@@ -62,8 +62,8 @@ enum groan_dim {
 #define GROAN_FLAG_TRICLINIC 1u  /* enable the triclinic EXTENSION (wrap, min-image distances); without it a
                                     non-orthogonal box returns GROAN_ENOTORTHO exactly like the reference */
 #define GROAN_FLAG_EXACT_ONLY 2u /* disable the single-pass fast paths; always run the reference-order passes */
-#define GROAN_FLAG_MULTICAST 8u  /* opt in: thread-block clusters along the frame axis share one multicast copy of each reference
-                                    chunk (halves the L2 traffic of the RMSD kernels, but measured slower on B200; see profiles/) */
+#define GROAN_FLAG_FRAME_SHARING 8u /* opt in: RMSD kernels serve four frames per CTA, sharing each reference chunk (less L2
+                                       traffic, but measured slower than one frame per CTA on B200; see profiles/) */
 #define GROAN_FLAG_HOST_FALLBACK 16u /* launch the reference-order fallback passes from the host after every single-pass kernel
                                         instead of letting the kernel tail-launch them from the device when a frame needs them */
 #define GROAN_FLAG_NO_TMA 4u     /* single-pass kernels with register-staged 256-bit loads instead of the TMA-fed ring */
