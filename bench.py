@@ -393,6 +393,32 @@ def run_extras(torch, g, local, peak):
     out["atoms_wrap"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "gbs": 24 * N_ATOMS * F * 1e-9 / (t * 1e-3),
                          "frac_of_hbm_peak": 24 * N_ATOMS * F * 1e-9 / (t * 1e-3) / peak}
     w.close()
+    # calc_rmsd_and_fit (all 4M atoms rewritten per frame: 12 B read + 24 B fit traffic per atom) and a scattered group
+    # (every 5th atom through an index list: the gather path), both on the blob workload
+    m = masses(N_ATOMS)
+    b = g.System(N_ATOMS, masses=m, device=local, max_frames=F)
+    r = g.System(N_ATOMS, masses=m, device=local, max_frames=1)
+    b.set_stream(torch.cuda.current_stream().cuda_stream)
+    every5 = np.arange(0, N_ATOMS, 5, dtype=np.uint32)
+    for sysm in (b, r):
+        sysm.group_create_from_indices("G", np.arange(N_ATOMS, dtype=np.uint32))
+        sysm.group_create_from_indices("S", every5)
+    r.set_frames(b.synth_blob_ref(SEED, BLOB_SCALE, [BOX / 2] * 3), [BOX] * 3)
+    rot, cen = frame_params(0, F)
+    b.synth_blob(SEED, 0, F, BLOB_SCALE, NOISE_SCALE, rot, cen, [BOX] * 3, wrap=True)
+    d_r = torch.empty((F,), dtype=torch.float32, device=dev)
+    d_c = torch.empty((F, 3), dtype=torch.float32, device=dev)
+    t = time_op(lambda: b.group_center_and_rmsd(r, "S", center_out=d_c, rmsd_out=d_r))
+    nS = len(every5)
+    out["scattered_group_center_and_rmsd"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "group_atoms": nS,
+                                              "fallback_frames": b.fallback_frames(),
+                                              "alg_gbs": (16 * F + 16) * nS * 1e-9 / (t * 1e-3)}
+    t = time_op(lambda: b.calc_rmsd_and_fit(r, "G", out=d_r), reps=3)  # each call fits the already fitted frames again
+    out["calc_rmsd_and_fit"] = {"ms": t, "frames_per_s": F / (t * 1e-3),
+                                "gbs": ((12 + 24) * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3),
+                                "frac_of_hbm_peak": ((12 + 24) * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
+    b.close()
+    r.close()
     # configs[3]: 1M atoms, box 21.5, 2 000 x 200 000 all-pairs
     n1, n2, N = 2000, 200000, 1_000_000
     p = g.System(N, device=local, max_frames=2)
