@@ -98,6 +98,7 @@ struct groan_gpu_ctx {
     unsigned int *d_frames_done = nullptr;  // device-side fallback launch: frames finished by the running single-pass kernel
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
     int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
+    bool rmsd_attr_set[2][3][2] = {};           // k_rmsd_tma<SAME_MASS, CENTER, FPC>: shared-memory attribute set on this device
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
 
@@ -256,7 +257,8 @@ template <bool SAME_MASS, int CENTER, int FPC>
 int launch_rmsd_tma_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, float *d_center, float *d_rmsd, float *d_rot,
                       const FallbackPlan &fp) {
     typedef TmaCfg<true, kRmsdStages, FPC> C;
-    static bool attr_set = false;
+    // the dynamic shared memory limit is a per-device function attribute: remember it per ctx, not per process
+    bool &attr_set = ctx->rmsd_attr_set[SAME_MASS ? 1 : 0][CENTER][FPC == 4 ? 1 : 0];
     if (!attr_set) {
         CK(cudaFuncSetAttribute(k_rmsd_tma<SAME_MASS, CENTER, FPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes));
         attr_set = true;
