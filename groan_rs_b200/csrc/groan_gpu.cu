@@ -25,6 +25,7 @@
 #include "kernels_rmsd.cuh"
 #include "kernels_synth.cuh"
 #include "kernels_tma.cuh"
+#include "kernels_quad.cuh"
 
 using namespace groan;
 
@@ -98,6 +99,7 @@ struct groan_gpu_ctx {
     unsigned int *d_frames_done = nullptr;  // device-side fallback launch: frames finished by the running single-pass kernel
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
     int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
+    int occ_center_quad = 0;                   // quad kernels (kernels_quad.cuh)
     bool rmsd_attr_set[2][3][2] = {};           // k_rmsd_tma<SAME_MASS, CENTER, FPC>: shared-memory attribute set on this device
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -107,6 +109,8 @@ struct groan_gpu_ctx {
         bool set = false;
         size_t n = 0;
         float *d_pc = nullptr;  // block-SoA prepared reference (kernels_rmsd.cuh)
+        float *d_pq = nullptr;  // quad-permuted copy of the aligned body (kernels_quad.cuh), built on first use
+        int pq_head = -1;       // head (atoms before the first 16-byte boundary) d_pq was built for
         double sums[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
         bool same_mass = true;  // reference masses == the target group's masses
         float com[3] = {0, 0, 0};
@@ -293,6 +297,72 @@ int launch_rmsd_tma(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, bool 
 #undef GO
 }
 
+// ---- quad kernels (kernels_quad.cuh) -----------------------------------------------------------------
+// They need what the TMA-fed kernels need, plus the same 16-byte phase of the group in every frame of the batch
+// (n_atoms % 4 == 0, or a single frame): the permuted reference is laid out relative to the aligned body.
+bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) {
+    return tma_ok(ctx, g, 2) && !(ctx->flags & GROAN_FLAG_NO_QUAD) && (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1);
+}
+
+uint32_t quad_head(const Group &g) { return (uint32_t)((4 - (g.first & 3)) & 3); }
+
+int blocks_per_frame_quad(size_t g, size_t F, int occ) {
+    size_t nb = (g + kQuadAtoms - 1) / kQuadAtoms;  // at least one chunk per CTA
+    nb = std::max<size_t>(nb, 1);
+    nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
+    return (int)nb;
+}
+
+int ensure_quad_ref(groan_gpu_ctx *ctx, groan_gpu_ctx::Ref &R, const Group &g) {
+    const uint32_t head = quad_head(g);
+    if (R.d_pq && R.pq_head == (int)head) return GROAN_OK;
+    const uint32_t body = ((uint32_t)g.n - head) & ~3u;
+    if (!R.d_pq) {
+        const size_t bytes = quad_ref_floats(g.n) * sizeof(float);
+        CK(cudaMalloc(&R.d_pq, bytes));
+        CK(cudaMemsetAsync(R.d_pq, 0, bytes, ctx->compute));
+    }
+    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((body / 4 + kThreads - 1) / kThreads, (size_t)kSMs * 8));
+    k_ref_permute<<<nb, kThreads, 0, ctx->compute>>>(R.d_pc, R.d_pq, head, body);
+    LAUNCHED();
+    R.pq_head = (int)head;
+    return GROAN_OK;
+}
+
+template <bool SAME_MASS, int CENTER>
+int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const float *d_pq, float *d_center, float *d_rmsd,
+                       float *d_rot, const FallbackPlan &fp) {
+    typedef QuadCfg<true, kQuadRmsdStages> C;
+    dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2), (unsigned)ctx->n_frames);
+    k_rmsd_quad<SAME_MASS, CENTER><<<grid, kTmaThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+                                                                                   ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
+                                                                                   ctx->d_flags, fp);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const float *d_pq, bool same_mass, int center_mode,
+                     float *d_center, float *d_rmsd, float *d_rot, const FallbackPlan &fp) {
+#define GO(SM, CM) return launch_rmsd_quad_t<SM, CM>(ctx, g, rv, d_pq, d_center, d_rmsd, d_rot, fp)
+    if (same_mass) {
+        if (center_mode == 0) GO(true, 0);
+        if (center_mode == 1) GO(true, 1);
+        GO(true, 2);
+    }
+    if (center_mode == 0) GO(false, 0);
+    if (center_mode == 1) GO(false, 1);
+    GO(false, 2);
+#undef GO
+}
+
+template <bool SAME_MASS, int CENTER>
+int set_quad_attr(groan_gpu_ctx *ctx) {
+    CK(cudaFuncSetAttribute(k_rmsd_quad<SAME_MASS, CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)QuadCfg<true, kQuadRmsdStages>::kBytes));
+    return GROAN_OK;
+}
+
 FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
                            float *rmsd_out, float *rot_out) {
     FallbackPlan fp;
@@ -411,7 +481,20 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
 // (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && ctx->occ_center_quad > 0 && quad_ok(ctx, g)) {
+        dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad), (unsigned)ctx->n_frames);
+        const size_t smem = QuadCfg<false, kQuadCenterStages>::kBytes;
+        const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
+        if (weighted)
+            k_center_quad<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+                                                                           out, ctx->d_flags, fp);
+        else
+            k_center_quad<false><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+                                                                            out, ctx->d_flags, fp);
+        LAUNCHED();
+        if (fp.enabled) return GROAN_OK;
+        flags = ctx->d_flags;
+    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
         dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
         const size_t smem = TmaCfg<false, kCenterStages, 1>::kBytes;
         const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
@@ -663,7 +746,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     if (rc) return rc;
     rc = check_masses(ctx, *g);
     if (rc) return rc;
-    const groan_gpu_ctx::Ref &R = ctx->refs[gid];
+    groan_gpu_ctx::Ref &R = ctx->refs[gid];
     if (R.n != g->n) {  // number_of_positions_consistent, rmsd.rs:405-422
         ctx->err_a = R.n;
         ctx->err_b = g->n;
@@ -683,7 +766,17 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
     bool center_done = false, device_fallback = false;
-    if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && quad_ok(ctx, *g)) {
+        // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
+        rc = ensure_quad_ref(ctx, R, *g);
+        if (rc) return rc;
+        const FallbackPlan fp = fallback_plan(ctx, *g, center != nullptr, center_weighted != 0, d_center, true, d_rmsd, d_rot);
+        device_fallback = fp.enabled != 0;
+        rc = launch_rmsd_quad(ctx, *g, rv, R.d_pq, R.same_mass, center ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
+        if (rc) return rc;
+        flags = ctx->d_flags;
+        center_done = center != nullptr;
+    } else if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
         const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
         device_fallback = fp.enabled != 0;
@@ -806,6 +899,18 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
             CK(cudaMemcpyToSymbol(g_debug_skip_ref, &v, sizeof(int)));
         }
         ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
+        const int sq = (int)QuadCfg<false, kQuadCenterStages>::kBytes;
+        CK(cudaFuncSetAttribute(k_center_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaFuncSetAttribute(k_center_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_quad, k_center_quad<false>, kTmaThreads, sq));
+        ctx->occ_center_quad = std::min(ctx->occ_center_quad, 4);
+        int qrc = set_quad_attr<true, 0>(ctx);
+        if (!qrc) qrc = set_quad_attr<true, 1>(ctx);
+        if (!qrc) qrc = set_quad_attr<true, 2>(ctx);
+        if (!qrc) qrc = set_quad_attr<false, 0>(ctx);
+        if (!qrc) qrc = set_quad_attr<false, 1>(ctx);
+        if (!qrc) qrc = set_quad_attr<false, 2>(ctx);
+        if (qrc) return qrc;
         return GROAN_OK;
     }();
     if (rc) {
@@ -835,8 +940,10 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         if (g.d_idx) cudaFree(g.d_idx);
         if (g.d_mass) cudaFree(g.d_mass);
     }
-    for (auto &r : ctx->refs)
+    for (auto &r : ctx->refs) {
         if (r.d_pc) cudaFree(r.d_pc);
+        if (r.d_pq) cudaFree(r.d_pq);
+    }
     void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -1167,6 +1274,8 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
     groan_gpu_ctx::Ref &R = ctx->refs[gid];
     CK(cudaStreamSynchronize(ctx->compute));
     if (R.d_pc) { cudaFree(R.d_pc); R.d_pc = nullptr; }
+    if (R.d_pq) { cudaFree(R.d_pq); R.d_pq = nullptr; }
+    R.pq_head = -1;
     R.set = false;
     float *d_ref = nullptr, *d_refbox = nullptr, *d_small = nullptr, *d_rmass = nullptr;
     uint32_t *d_ridx = nullptr;

@@ -1,0 +1,487 @@
+// kernels_quad.cuh -- the single-pass centre / RMSD kernels, third generation: one QUAD of four consecutive atoms per
+// thread and iteration, 128-bit shared-memory reads, mixed-component f32x2 arithmetic, one trigonometric sum per axis.
+//
+// What limits kernels_tma.cuh (profiles/r1_summary.md): it is ISSUE bound, 72 warp instructions per atom at 54 % issue
+// utilisation, while the frame bytes already arrive by TMA.  Per atom it spends 7 LDS.32 (stride-3 coordinates plus the
+// block-SoA reference), 6 MUFU + 3 FMUL.RZ for sin AND cos, and ~18 instructions of loop control and epilogue.
+// This version removes most of that:
+//
+//  * Four consecutive atoms are 48 contiguous bytes of the AoS frame: three LDS.128 per quad (thread stride 48 B:
+//    conflict-free).  The twelve floats land in six register pairs of MIXED components,
+//        A = (x0,y0)  B = (z0,x1)  C = (y1,z1)     A' = (x2,y2)  B' = (z2,x3)  C' = (y3,z3),
+//    and all per-coordinate work (pilot displacement, minimum image, angle) is component-agnostic: it runs packed with
+//    per-frame constants held in the same three patterns (x,y) (z,x) (y,z).
+//  * The outer products pc (x) d run on those pairs as well.  For the atom pair (a, b) = (0,1) or (2,3):
+//        acc1[u] += pc_u(a) * A      -> (H_ux, H_uy)      scalar-broadcast operand (SASS: R.F32)
+//        acc2[u] += (pc_u(a), pc_u(b)) * B -> (H_uz of a, H_ux of b)
+//        acc3[u] += pc_u(b) * C      -> (H_uy, H_uz)
+//    three FFMA2 per row u and atom pair, nothing wasted; the accumulators are folded to H at the end.  The prepared
+//    reference is stored so that (pc_u(a), pc_u(b)) IS a register pair after one LDS.128: per quad four LDS.128
+//    [pcx_a pcx_b pcy_a pcy_b] [pcz_a pcz_b w_a w_b] x 2, laid out in planes so that consecutive lanes read consecutive
+//    16-byte units (k_ref_permute).  7 LDS per quad instead of 28.
+//  * Only the SINE sum per axis.  The Bai-Breen estimate c0 (iterators.rs:1152-1191) is needed for one thing: the
+//    integer m = floor(c~ / L) that places the unwrapped mean in the reference's periodic image,
+//    c~ being the circular mean unwrapped next to the group.  With the group certified compact (extent < L/2), c~ lies
+//    inside [lo, hi] = [p + min d, p + max d].  If floor(lo / L) == floor(hi / L) no trigonometry is needed at all;
+//    otherwise exactly one box boundary b = floor(hi / L) * L lies in (lo, hi], all angles 2 pi (u_i - b) / L lie in an
+//    arc shorter than pi around 0, and c~ >= b  <=>  sum_i sin(2 pi u_i / L) >= 0.  |sum sin| / n bounds the angle of the
+//    mean from below, so a fixed threshold on it (kSinGuard) replaces the edge-band test; frames below it are flagged
+//    and re-done by the reference-order passes like before.
+//  * Loop control: stage/phase counters instead of divisions, full chunks only in the hot loop.
+#pragma once
+#include "kernels_tma.cuh"
+
+namespace groan {
+
+constexpr int kQuadAtoms = 1024;                   // atoms per chunk: one quad per thread
+constexpr int kQuadRefBlock = 128;                 // atoms per permuted reference block (32 quads = one warp)
+constexpr double kSinGuard = 2.0e-4;               // |sum sin| / n below this: side of the boundary not certain
+constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23: (x + kMagic) - kMagic = rint(x) for |x| < 2^22
+
+__host__ __device__ inline size_t quad_ref_floats(size_t body) {
+    return ((body + kQuadRefBlock - 1) / kQuadRefBlock) * (size_t)(4 * kQuadRefBlock);
+}
+
+// block-SoA reference (group order, kernels_rmsd.cuh) -> quad-permuted reference (body order: group index - head).
+// Block of 32 quads = 2 KB = 4 planes of 32 x 16 B; plane k of quad q holds
+//   k = 0: pcx(0) pcx(1) pcy(0) pcy(1)   k = 1: pcz(0) pcz(1) w(0) w(1)   k = 2, 3: the same for atoms 2, 3 of the quad.
+__global__ void __launch_bounds__(kThreads) k_ref_permute(const float *pc, float *pq, uint32_t head, uint32_t body) {
+    const uint32_t quads = body / 4;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+        float4 r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = ref_at(pc, head + q * 4 + k);
+        float4 *o = reinterpret_cast<float4 *>(pq) + (size_t)(q >> 5) * 128 + (q & 31);
+        o[0] = make_float4(r[0].x, r[1].x, r[0].y, r[1].y);
+        o[32] = make_float4(r[0].z, r[1].z, r[0].w, r[1].w);
+        o[64] = make_float4(r[2].x, r[3].x, r[2].y, r[3].y);
+        o[96] = make_float4(r[2].z, r[3].z, r[2].w, r[3].w);
+    }
+}
+
+// a 3-vector sum held as three register pairs in the patterns of the quad: a = (x,y), b = (z,x), c = (y,z)
+struct V3 {
+    float2 a, b, c;
+};
+__device__ __forceinline__ V3 v3_zero() {
+    V3 v;
+    v.a = v.b = v.c = make_float2(0.f, 0.f);
+    return v;
+}
+__device__ __forceinline__ void v3_add(V3 &s, const V3 &d) {
+    s.a = __fadd2_rn(s.a, d.a);
+    s.b = __fadd2_rn(s.b, d.b);
+    s.c = __fadd2_rn(s.c, d.c);
+}
+// s += P.x * d(atom a) + P.y * d(atom b), d = the three pairs of an atom pair: a = d(a).xy, b = (d(a).z, d(b).x), c = d(b).yz
+__device__ __forceinline__ void v3_fma(V3 &s, float2 P, const V3 &d) {
+    s.a = __ffma2_rn(splat(P.x), d.a, s.a);
+    s.b = __ffma2_rn(P, d.b, s.b);
+    s.c = __ffma2_rn(splat(P.y), d.c, s.c);
+}
+__device__ __forceinline__ V3 v3_mul(float2 P, const V3 &d) {
+    V3 r;
+    r.a = __fmul2_rn(splat(P.x), d.a);
+    r.b = __fmul2_rn(P, d.b);
+    r.c = __fmul2_rn(splat(P.y), d.c);
+    return r;
+}
+__device__ __forceinline__ float v3_x(const V3 &s) { return s.a.x + s.b.y; }
+__device__ __forceinline__ float v3_y(const V3 &s) { return s.a.y + s.c.x; }
+__device__ __forceinline__ float v3_z(const V3 &s) { return s.b.x + s.c.y; }
+
+// per-frame constants in the three patterns
+struct QuadConst {
+    V3 negp; // -pilot
+    V3 inv;  // 1 / L
+    V3 negl; // -L
+    float sc[3], ph[3]; // 2 pi / L, 2 pi frac(pilot / L)
+};
+__device__ __forceinline__ V3 v3_pattern(float x, float y, float z) {
+    V3 v;
+    v.a = make_float2(x, y);
+    v.b = make_float2(z, x);
+    v.c = make_float2(y, z);
+    return v;
+}
+
+// min-image displacement from the pilot, pattern-wise; same arithmetic as pilot_delta (kernels_center.cuh)
+__device__ __forceinline__ float2 quad_delta(float2 x, float2 negp, float2 inv, float2 negl) {
+    const float2 d = __fadd2_rn(x, negp);
+    const float2 k = __fadd2_rn(__ffma2_rn(d, inv, splat(kMagic)), splat(-kMagic));
+    return __ffma2_rn(negl, k, d);
+}
+// sin(2 pi (d / L + frac(p / L))) on the SFU for both halves.  The angle is formed by scalar FFMAs from scalar per-axis
+// constants (sc = 2 pi / L, ph = 2 pi frac(p / L)): as many issue slots as the packed form plus its 2 pi multiply, and no
+// pattern registers.
+__device__ __forceinline__ float2 quad_sin(float2 d, float sc0, float ph0, float sc1, float ph1) {
+    return make_float2(__sinf(__fmaf_rn(d.x, sc0, ph0)), __sinf(__fmaf_rn(d.y, sc1, ph1)));
+}
+
+struct QuadMinMax {
+    float mn[3], mx[3];
+};
+// the three pairs of an atom pair -> per-axis min / max (FMNMX3)
+__device__ __forceinline__ void quad_minmax(QuadMinMax &m, const V3 &d) {
+    m.mn[0] = fminf(m.mn[0], fminf(d.a.x, d.b.y)); m.mx[0] = fmaxf(m.mx[0], fmaxf(d.a.x, d.b.y));
+    m.mn[1] = fminf(m.mn[1], fminf(d.a.y, d.c.x)); m.mx[1] = fmaxf(m.mx[1], fmaxf(d.a.y, d.c.x));
+    m.mn[2] = fminf(m.mn[2], fminf(d.b.x, d.c.y)); m.mx[2] = fmaxf(m.mx[2], fmaxf(d.b.x, d.c.y));
+}
+
+template <bool WITH_REF, int STAGES>
+struct QuadCfg {
+    static constexpr size_t kFrameBytes = (size_t)kQuadAtoms * 12;
+    static constexpr size_t kRefBytes = WITH_REF ? (size_t)kQuadAtoms * 16 : 0;
+    static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
+    static constexpr size_t kBytes = STAGES * kStageBytes + 128;
+};
+constexpr int kQuadCenterStages = 4; // 48 KB ring: 4 CTAs per SM
+constexpr int kQuadRmsdStages = 3;   // 84 KB ring: 2 CTAs per SM
+
+// control block of the quad ring: full[s] (count 1 + tx bytes) is armed by whoever issues the copies and completed by
+// the TMA; empty[s] (count = warps) collects one arrival per warp that has finished reading stage s.  mbarrier.arrive
+// returns the state BEFORE the arrival, so exactly one warp sees "pending == 1": it is the last reader, and it refills
+// the stage (no polling, no separate counter to reset: the phase completes and re-arms itself).
+template <int STAGES>
+struct QuadCtl {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+};
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(20000u)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (++spins > (1u << 24)) __trap(); // a protocol bug fails the launch instead of hanging the GPU
+    }
+}
+// arrive (release) and return the pending count before this arrival
+__device__ __forceinline__ uint32_t mbar_arrive_pending(uint32_t bar) {
+    uint32_t cnt;
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%1];\n\tmbarrier.pending_count.b64 %0, st;\n\t}"
+                 : "=r"(cnt)
+                 : "r"(bar)
+                 : "memory");
+    return cnt;
+}
+
+// Stream the 16-byte aligned body of the group through the ring; fn(j, c0, c1, c2, r) per quad with j the body index of
+// the quad's first atom, c0..c2 the twelve coordinates and r the four reference units (undefined when !WITH_REF).
+// Chunk c of the frame goes to CTA c % gridDim.x.  Only the last chunk of a frame can be ragged (a multiple of 4 atoms).
+template <bool WITH_REF, int STAGES, typename F>
+__device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *ref_pq,
+                                             unsigned char *smem, QuadCtl<STAGES> &ctl, F &&fn) {
+    typedef QuadCfg<WITH_REF, STAGES> C;
+    constexpr uint32_t CH = kQuadAtoms;
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    const uint32_t chunks = (bg.body + CH - 1) / CH;
+    const uint32_t my_chunks = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // the frame's last chunk, if ragged, belongs to CTA (chunks - 1) % gridDim.x as its last iteration
+    const uint32_t rag_atoms = bg.body % CH;
+    const bool mine_ragged = rag_atoms != 0 && my_chunks != 0 && (chunks - 1) % gridDim.x == blockIdx.x;
+    const uint32_t rag_it = mine_ragged ? my_chunks - 1 : 0xffffffffu, rag_quads = rag_atoms >> 2;
+    const char *src0 = reinterpret_cast<const char *>(fv.frame(f) + ((size_t)g.first + bg.head) * 3);
+    const uint32_t ring = smem_u32(smem), full0 = smem_u32(ctl.full), empty0 = smem_u32(ctl.empty);
+    auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES (one thread)
+        const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
+        const uint32_t atoms = min(CH, bg.body - c * CH);
+        const uint32_t ref_bytes = WITH_REF ? ((atoms + kQuadRefBlock - 1) / kQuadRefBlock) * (uint32_t)(kQuadRefBlock * 16) : 0u;
+        mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
+        unsigned char *dst = smem + s * C::kStageBytes;
+        bulk_g2s(dst, src0 + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, l2_policy_evict_first());
+        if (WITH_REF) bulk_g2s(dst + C::kFrameBytes, ref_pq + (size_t)c * CH * 4, ref_bytes, ctl.full + s, l2_policy_evict_last());
+    };
+    if (t == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(ctl.full + s, 1);
+            mbar_init(ctl.empty + s, kWarps);
+        }
+        fence_mbar_init();
+        for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
+    }
+    __syncthreads();
+    // this thread's quad inside a stage: coordinates at t * 48 B, reference unit k at (warp * 128 + k * 32 + lane) * 16 B
+    const uint32_t off_f = ring + t * 48u, off_r = ring + (uint32_t)C::kFrameBytes + ((t >> 5) * 128u + lane) * 16u;
+    // unrolled over the ring so that stage addresses are immediates and the phase flips once per trip
+    uint32_t ph = 0, it = 0;
+    uint32_t j = blockIdx.x * CH + t * 4;
+    const uint32_t jstep = gridDim.x * CH;
+    while (it < my_chunks) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            if (it >= my_chunks) break;
+            constexpr uint32_t kSt = (uint32_t)C::kStageBytes;
+            mbar_wait_a(full0 + s * 8u, ph);
+            if (it != rag_it || t < rag_quads) {
+                const float4 c0 = lds128(off_f + s * kSt), c1 = lds128(off_f + s * kSt + 16u), c2 = lds128(off_f + s * kSt + 32u);
+                float4 r[4];
+                if (WITH_REF) {
+                    r[0] = lds128(off_r + s * kSt);
+                    r[1] = lds128(off_r + s * kSt + 512u);
+                    r[2] = lds128(off_r + s * kSt + 1024u);
+                    r[3] = lds128(off_r + s * kSt + 1536u);
+                }
+                fn(j, c0, c1, c2, r);
+            }
+            __syncwarp();
+            if (lane == 0 && mbar_arrive_pending(empty0 + s * 8u) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
+            it++;
+            j += jstep;
+        }
+        ph ^= 1;
+    }
+}
+
+// finishing thread of the single-pass centre, sine-only version (see the header): certify and place the mean.
+// tot_md = sum m d (or sum d), M = sum m (or n), S = sum sin(2 pi u / L) (unweighted, geometric estimate: iterators.rs:1407)
+__device__ inline void finish_center_sin(const double tot_md[3], double M, const double S[3], const float *tmn, const float *tmx,
+                                         const float p[3], const float *L, uint32_t n, float *out3, int *flag) {
+    int redo = 0;
+    for (int k = 0; k < 3; k++) {
+        const double Lk = (double)L[k];
+        if (!((double)tmx[k] - (double)tmn[k] < 0.5 * Lk * kExtentSlack)) redo = 1; // not compact: images may differ
+        if (!(fabs((double)p[k]) < 64.0 * Lk)) redo = 1;                            // f32 frac(p / L) no longer good enough
+        const double lo = (double)p[k] + (double)tmn[k], hi = (double)p[k] + (double)tmx[k];
+        const double mlo = floor(lo / Lk), mhi = floor(hi / Lk);
+        double m = mlo;
+        if (mlo != mhi) { // the group straddles the boundary mhi * L: which side is the circular mean on?
+            if (!(fabs(S[k]) >= kSinGuard * (double)n)) redo = 1;
+            m = S[k] > 0.0 ? mhi : mlo;
+        }
+        const double um = (double)p[k] + tot_md[k] / M; // mean of the unwrapped group
+        out3[k] = (float)(um - m * Lk);                 // c0 = c~ - m L lies in [0, L): the image within L/2 of c0
+    }
+    *flag = redo;
+}
+
+__device__ __forceinline__ QuadConst quad_constants(const float p[3], const float L[3]) {
+    QuadConst q;
+    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
+    q.negp = v3_pattern(-p[0], -p[1], -p[2]);
+    q.inv = v3_pattern(ix, iy, iz);
+    q.negl = v3_pattern(-L[0], -L[1], -L[2]);
+    const float inv[3] = {ix, iy, iz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float t = p[k] * inv[k];
+        q.sc[k] = 6.283185307179586f * inv[k];
+        q.ph[k] = 6.283185307179586f * (t - floorf(t));
+    }
+    return q;
+}
+
+// the six pairs of a quad -> min-image displacements of atom pair (0,1) in d01 and (2,3) in d23
+__device__ __forceinline__ void quad_deltas(const QuadConst &q, const float4 &c0, const float4 &c1, const float4 &c2, V3 &d01, V3 &d23) {
+    d01.a = quad_delta(make_float2(c0.x, c0.y), q.negp.a, q.inv.a, q.negl.a);
+    d01.b = quad_delta(make_float2(c0.z, c0.w), q.negp.b, q.inv.b, q.negl.b);
+    d01.c = quad_delta(make_float2(c1.x, c1.y), q.negp.c, q.inv.c, q.negl.c);
+    d23.a = quad_delta(make_float2(c1.z, c1.w), q.negp.a, q.inv.a, q.negl.a);
+    d23.b = quad_delta(make_float2(c2.x, c2.y), q.negp.b, q.inv.b, q.negl.b);
+    d23.c = quad_delta(make_float2(c2.z, c2.w), q.negp.c, q.inv.c, q.negl.c);
+}
+__device__ __forceinline__ void quad_sines(const QuadConst &q, const V3 &d, V3 &ssin) {
+    ssin.a = __fadd2_rn(ssin.a, quad_sin(d.a, q.sc[0], q.ph[0], q.sc[1], q.ph[1]));
+    ssin.b = __fadd2_rn(ssin.b, quad_sin(d.b, q.sc[2], q.ph[2], q.sc[0], q.ph[0]));
+    ssin.c = __fadd2_rn(ssin.c, quad_sin(d.c, q.sc[1], q.ph[1], q.sc[2], q.ph[2]));
+}
+
+// sine of one atom's axis for the finishing thread's head / tail atoms, same definition as quad_sin
+__device__ __forceinline__ double edge_sin(float d, float p, float L) {
+    const float inv = 1.0f / L, t = p * inv;
+    return (double)__sinf(__fmaf_rn(d, 6.283185307179586f * inv, 6.283185307179586f * (t - floorf(t))));
+}
+
+// ---------------------------------------------------------------- group_get_center / group_get_com
+// sums: [0..2] sum m d, [3] sum m, [4..6] sum sin
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
+                                                                 float *out, int *flags, FallbackPlan fp) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ FrameReduceSmem<7, 3> sm;
+    __shared__ QuadCtl<kQuadCenterStages> ctl;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *fr = fv.frame(f);
+    const float *p0 = fr + (size_t)g.first * 3;
+    const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    const QuadConst qc = quad_constants(p, L);
+    const BodyGeom bg = body_geom(fv, g, f);
+    V3 smd = v3_zero(), ssin = v3_zero();
+    float2 sm2 = make_float2(0.f, 0.f);
+    QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
+    stream_quads<false, kQuadCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl,
+                                           [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&)[4]) {
+        V3 d01, d23;
+        quad_deltas(qc, c0, c1, c2, d01, d23);
+        if (WEIGHTED) {
+            const float *mp = g.mass + bg.head + j;
+            const float2 m01 = make_float2(__ldg(mp), __ldg(mp + 1)), m23 = make_float2(__ldg(mp + 2), __ldg(mp + 3));
+            v3_fma(smd, m01, d01);
+            v3_fma(smd, m23, d23);
+            sm2 = __fadd2_rn(sm2, __fadd2_rn(m01, m23));
+        } else {
+            v3_add(smd, d01);
+            v3_add(smd, d23);
+        }
+        quad_sines(qc, d01, ssin);
+        quad_sines(qc, d23, ssin);
+        quad_minmax(mm, d01);
+        quad_minmax(mm, d23);
+    });
+    const float a[7] = {v3_x(smd), v3_y(smd), v3_z(smd), sm2.x + sm2.y, v3_x(ssin), v3_y(ssin), v3_z(ssin)};
+    double tot[7];
+    float tmn[3], tmx[3];
+    if (frame_reduce<7, 3>(a, mm.mn, mm.mx, partials + (size_t)f * nb * 13, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
+        // the up-to-6 atoms outside the 16-byte aligned body, in f64 with the same definitions
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const double m = WEIGHTED ? (double)__ldg(g.mass + i) : 1.0;
+            if (WEIGHTED) tot[3] += m;
+            for (int k = 0; k < 3; k++) {
+                const float d = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+                tot[k] += m * (double)d;
+                tot[4 + k] += edge_sin(d, p[k], L[k]);
+                tmn[k] = fminf(tmn[k], d);
+                tmx[k] = fmaxf(tmx[k], d);
+            }
+        }
+        finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, flags + f);
+        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags);
+    }
+}
+
+// ---------------------------------------------------------------- calc_rmsd (+ optionally the centre)
+// CENTER: 0 = RMSD only, 1 = also group_get_center, 2 = also group_get_com.
+// canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum sin
+constexpr int kQuadSums = kFastSums + 6;
+
+template <bool SAME_MASS, int CENTER>
+__global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, const float *ref_pq, double *partials,
+                                                               unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
+                                                               float *com_out, int *flags, FallbackPlan fp) {
+    constexpr int KS = CENTER ? kQuadSums : kFastSums;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ FrameReduceSmem<KS, 3> sm;
+    __shared__ QuadCtl<kQuadRmsdStages> ctl;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *fr = fv.frame(f);
+    const float *p0 = fr + (size_t)g.first * 3;
+    const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    const QuadConst qc = quad_constants(p, L);
+    const BodyGeom bg = body_geom(fv, g, f);
+    V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero(), sd = v3_zero(), ssin = v3_zero();
+#pragma unroll
+    for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
+    float2 sq = make_float2(0.f, 0.f), sm2 = make_float2(0.f, 0.f);
+    QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
+    auto atom_pair = [&](const V3 &d, const float4 &r0, const float4 &r1, uint32_t i) {
+        const float2 pc[3] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y)};
+        const float2 w = make_float2(r1.z, r1.w);
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            v3_fma(h[u], pc[u], d);
+            v3_fma(hw[u], __fmul2_rn(w, pc[u]), d);
+        }
+        const V3 wd = v3_mul(w, d);
+        v3_add(swd, wd);
+        sq = __ffma2_rn(wd.a, d.a, sq);
+        sq = __ffma2_rn(wd.b, d.b, sq);
+        sq = __ffma2_rn(wd.c, d.c, sq);
+        if (CENTER == 1) v3_add(sd, d);
+        if (CENTER) quad_sines(qc, d, ssin);
+        quad_minmax(mm, d);
+        if (!SAME_MASS) {
+            const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
+            v3_fma(smd, m, d);
+            sm2 = __fadd2_rn(sm2, m);
+        }
+    };
+    stream_quads<true, kQuadRmsdStages>(fv, g, f, bg, ref_pq, dyn_smem, ctl,
+                                        [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+        V3 d01, d23;
+        quad_deltas(qc, c0, c1, c2, d01, d23);
+        atom_pair(d01, r[0], r[1], bg.head + j);
+        atom_pair(d23, r[2], r[3], bg.head + j + 2);
+    });
+    float a[KS];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        a[u * 3 + 0] = v3_x(h[u]); a[u * 3 + 1] = v3_y(h[u]); a[u * 3 + 2] = v3_z(h[u]);
+        a[9 + u * 3 + 0] = v3_x(hw[u]); a[9 + u * 3 + 1] = v3_y(hw[u]); a[9 + u * 3 + 2] = v3_z(hw[u]);
+    }
+    a[18] = v3_x(swd); a[19] = v3_y(swd); a[20] = v3_z(swd);
+    a[21] = sq.x + sq.y;
+    a[22] = v3_x(smd); a[23] = v3_y(smd); a[24] = v3_z(smd);
+    a[25] = sm2.x + sm2.y;
+    if (CENTER) {
+        a[KS - 6] = v3_x(sd); a[KS - 5] = v3_y(sd); a[KS - 4] = v3_z(sd);
+        a[KS - 3] = v3_x(ssin); a[KS - 2] = v3_y(ssin); a[KS - 1] = v3_z(ssin);
+    }
+    double tot[KS];
+    float tmn[3], tmx[3];
+    if (frame_reduce<KS, 3>(a, mm.mn, mm.mx, partials + (size_t)f * nb * (KS + 6), tickets + f, nb, sm, tot, tmn, tmx) &&
+        threadIdx.x == 0) {
+        // the up-to-6 atoms outside the 16-byte aligned body, in f64 with the same definitions
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const float4 r = ref_at(ref.pc, i);
+            const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
+            double d[3];
+            for (int k = 0; k < 3; k++) {
+                const float dk = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+                d[k] = (double)dk;
+                tmn[k] = fminf(tmn[k], dk);
+                tmx[k] = fmaxf(tmx[k], dk);
+                if (CENTER) {
+                    tot[KS - 6 + k] += d[k];
+                    tot[KS - 3 + k] += edge_sin(dk, p[k], L[k]);
+                }
+            }
+            for (int u = 0; u < 3; u++)
+                for (int v = 0; v < 3; v++) {
+                    tot[u * 3 + v] += pcd[u] * d[v];
+                    tot[9 + u * 3 + v] += w * pcd[u] * d[v];
+                }
+            for (int v = 0; v < 3; v++) {
+                tot[18 + v] += w * d[v];
+                tot[21] += w * d[v] * d[v];
+            }
+            if (!SAME_MASS) {
+                const double m = (double)__ldg(g.mass + i);
+                for (int v = 0; v < 3; v++) tot[22 + v] += m * d[v];
+                tot[25] += m;
+            }
+        }
+        double rt[kFastSums];
+        for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
+        int flag_r = 0, flag_c = 0;
+        finish_rmsd<SAME_MASS>(rt, tmn, tmx, p[0], p[1], p[2], L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, &flag_r);
+        if (CENTER) {
+            // centre: geometric (sum d / n) or mass-weighted with the target group's masses (= the COM of the RMSD)
+            double md[3];
+            for (int k = 0; k < 3; k++) md[k] = CENTER == 2 ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[KS - 6 + k];
+            const double M = CENTER == 2 ? (SAME_MASS ? ref.sum_w : tot[25]) : (double)g.n;
+            finish_center_sin(md, M, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
+        }
+        flags[f] = flag_r | (flag_c << 1);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
+    }
+}
+
+} // namespace groan

@@ -67,6 +67,8 @@ enum groan_dim {
 #define GROAN_FLAG_HOST_FALLBACK 16u /* launch the reference-order fallback passes from the host after every single-pass kernel
                                         instead of letting the kernel tail-launch them from the device when a frame needs them */
 #define GROAN_FLAG_NO_TMA 4u     /* single-pass kernels with register-staged 256-bit loads instead of the TMA-fed ring */
+#define GROAN_FLAG_NO_QUAD 32u   /* single-pass kernels of kernels_tma.cuh (pairs of atoms, sin + cos sums) instead of the quad
+                                    kernels of kernels_quad.cuh; for A/B measurements and tests */
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
 int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out);
