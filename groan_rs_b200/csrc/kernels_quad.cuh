@@ -133,10 +133,10 @@ struct QuadCfg {
     static constexpr size_t kFrameBytes = (size_t)kQuadAtoms * 12;
     static constexpr size_t kRefBytes = WITH_REF ? (size_t)kQuadAtoms * 16 : 0;
     static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
-    static constexpr size_t kBytes = STAGES * kStageBytes + 128;
+    static constexpr size_t kBytes = STAGES * kStageBytes + 128; // ring + QuadCtl
 };
 constexpr int kQuadCenterStages = 4; // 48 KB ring: 4 CTAs per SM
-constexpr int kQuadRmsdStages = 3;   // 84 KB ring: 2 CTAs per SM
+constexpr int kQuadRmsdStages = 4;   // 112 KB ring: 2 CTAs per SM (no static shared memory: the reduction scratch aliases the ring)
 
 // control block of the quad ring: full[s] (count 1 + tx bytes) is armed by whoever issues the copies and completed by
 // the TMA; empty[s] (count = warps) collects one arrival per warp that has finished reading stage s.  mbarrier.arrive
@@ -178,21 +178,21 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint32_t bar) {
 
 // Stream the 16-byte aligned body of the group through the ring; fn(j, c0, c1, c2, r) per quad with j the body index of
 // the quad's first atom, c0..c2 the twelve coordinates and r the four reference units (undefined when !WITH_REF).
-// Chunk c of the frame goes to CTA c % gridDim.x.  Only the last chunk of a frame can be ragged (a multiple of 4 atoms).
+// Chunk c of the frame goes to CTA c % gridDim.x.  Only the last chunk of a frame can be ragged (a multiple of 4 atoms),
+// so every chunk of a CTA but its last runs the unchecked, stage-unrolled loop.
+// Dynamic shared memory: [ring: STAGES x (frame chunk | reference chunk)] [QuadCtl].  After the call the ring is free
+// (every copy issued has been consumed) and the caller may reuse it once the CTA has synchronised.
 template <bool WITH_REF, int STAGES, typename F>
 __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *ref_pq,
-                                             unsigned char *smem, QuadCtl<STAGES> &ctl, F &&fn) {
+                                             unsigned char *smem, F &&fn) {
     typedef QuadCfg<WITH_REF, STAGES> C;
-    constexpr uint32_t CH = kQuadAtoms;
+    constexpr uint32_t CH = kQuadAtoms, kSt = (uint32_t)C::kStageBytes;
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t chunks = (bg.body + CH - 1) / CH;
     const uint32_t my_chunks = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    // the frame's last chunk, if ragged, belongs to CTA (chunks - 1) % gridDim.x as its last iteration
-    const uint32_t rag_atoms = bg.body % CH;
-    const bool mine_ragged = rag_atoms != 0 && my_chunks != 0 && (chunks - 1) % gridDim.x == blockIdx.x;
-    const uint32_t rag_it = mine_ragged ? my_chunks - 1 : 0xffffffffu, rag_quads = rag_atoms >> 2;
     const char *src0 = reinterpret_cast<const char *>(fv.frame(f) + ((size_t)g.first + bg.head) * 3);
-    const uint32_t ring = smem_u32(smem), full0 = smem_u32(ctl.full), empty0 = smem_u32(ctl.empty);
+    QuadCtl<STAGES> &ctl = *reinterpret_cast<QuadCtl<STAGES> *>(smem + STAGES * C::kStageBytes);
+    const uint32_t ring = smem_u32(smem), full0 = ring + STAGES * kSt, empty0 = full0 + STAGES * 8u;
     auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES (one thread)
         const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
         const uint32_t atoms = min(CH, bg.body - c * CH);
@@ -211,35 +211,48 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
         for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
     }
     __syncthreads();
+    if (my_chunks == 0) return;
     // this thread's quad inside a stage: coordinates at t * 48 B, reference unit k at (warp * 128 + k * 32 + lane) * 16 B
     const uint32_t off_f = ring + t * 48u, off_r = ring + (uint32_t)C::kFrameBytes + ((t >> 5) * 128u + lane) * 16u;
-    // unrolled over the ring so that stage addresses are immediates and the phase flips once per trip
-    uint32_t ph = 0, it = 0;
     uint32_t j = blockIdx.x * CH + t * 4;
     const uint32_t jstep = gridDim.x * CH;
-    while (it < my_chunks) {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++) {
-            if (it >= my_chunks) break;
-            constexpr uint32_t kSt = (uint32_t)C::kStageBytes;
-            mbar_wait_a(full0 + s * 8u, ph);
-            if (it != rag_it || t < rag_quads) {
-                const float4 c0 = lds128(off_f + s * kSt), c1 = lds128(off_f + s * kSt + 16u), c2 = lds128(off_f + s * kSt + 32u);
-                float4 r[4];
-                if (WITH_REF) {
-                    r[0] = lds128(off_r + s * kSt);
-                    r[1] = lds128(off_r + s * kSt + 512u);
-                    r[2] = lds128(off_r + s * kSt + 1024u);
-                    r[3] = lds128(off_r + s * kSt + 1536u);
-                }
-                fn(j, c0, c1, c2, r);
-            }
-            __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(empty0 + s * 8u) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
-            it++;
-            j += jstep;
+    auto quad = [&](uint32_t st) { // st = byte offset of the stage
+        const float4 c0 = lds128(off_f + st), c1 = lds128(off_f + st + 16u), c2 = lds128(off_f + st + 32u);
+        float4 r[4];
+        if (WITH_REF) {
+            r[0] = lds128(off_r + st);
+            r[1] = lds128(off_r + st + 512u);
+            r[2] = lds128(off_r + st + 1024u);
+            r[3] = lds128(off_r + st + 1536u);
         }
-        ph ^= 1;
+        fn(j, c0, c1, c2, r);
+    };
+    static_assert(STAGES == 4, "the loop below walks the ring in pairs of stages");
+    const uint32_t hot = (my_chunks - 1) & ~1u; // chunks of this CTA that are certainly full, in pairs
+    uint32_t ph = 0, it = 0, st = 0;            // st = byte offset of the pair's first stage: 0 or 2 stages
+    // Two chunks per trip (stages s, s + 1 with s = 0 or 2): loop control and address arithmetic are paid once per
+    // eight atoms of a thread, while each stage keeps its own barriers and is refilled as soon as its last reader leaves.
+    for (; it < hot; it += 2) {
+        const uint32_t fb = full0 + (st ? 16u : 0u), eb = empty0 + (st ? 16u : 0u);
+        mbar_wait_a(fb, ph);
+        quad(st);
+        __syncwarp();
+        if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
+        j += jstep;
+        mbar_wait_a(fb + 8u, ph);
+        quad(st + kSt);
+        __syncwarp();
+        if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
+        j += jstep;
+        ph ^= (st != 0);
+        st ^= 2u * kSt;
+    }
+    // the remaining one or two chunks; the very last one may be ragged.  Nothing is left to refill.
+    for (; it < my_chunks; it++, j += jstep) {
+        const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
+        const uint32_t quads = min(CH, bg.body - c * CH) >> 2;
+        mbar_wait_a(full0 + s * 8u, (it / STAGES) & 1u);
+        if (t < quads) quad(s * kSt);
     }
 }
 
@@ -308,8 +321,7 @@ template <bool WEIGHTED>
 __global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
                                                                  float *out, int *flags, FallbackPlan fp) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<7, 3> sm;
-    __shared__ QuadCtl<kQuadCenterStages> ctl;
+    FrameReduceSmem<7, 3> &sm = *reinterpret_cast<FrameReduceSmem<7, 3> *>(dyn_smem); // reuses the ring once it has drained
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, Gr
     V3 smd = v3_zero(), ssin = v3_zero();
     float2 sm2 = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
-    stream_quads<false, kQuadCenterStages>(fv, g, f, bg, nullptr, dyn_smem, ctl,
+    stream_quads<false, kQuadCenterStages>(fv, g, f, bg, nullptr, dyn_smem,
                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
@@ -340,6 +352,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, Gr
         quad_minmax(mm, d01);
         quad_minmax(mm, d23);
     });
+    __syncthreads(); // every warp has left the ring: its memory becomes the reduction scratch
     const float a[7] = {v3_x(smd), v3_y(smd), v3_z(smd), sm2.x + sm2.y, v3_x(ssin), v3_y(ssin), v3_z(ssin)};
     double tot[7];
     float tmn[3], tmx[3];
@@ -374,8 +387,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_quad(FrameView fv, Grou
                                                                float *com_out, int *flags, FallbackPlan fp) {
     constexpr int KS = CENTER ? kQuadSums : kFastSums;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ FrameReduceSmem<KS, 3> sm;
-    __shared__ QuadCtl<kQuadRmsdStages> ctl;
+    FrameReduceSmem<KS, 3> &sm = *reinterpret_cast<FrameReduceSmem<KS, 3> *>(dyn_smem); // reuses the ring once it has drained
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
@@ -411,13 +423,14 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_quad(FrameView fv, Grou
             sm2 = __fadd2_rn(sm2, m);
         }
     };
-    stream_quads<true, kQuadRmsdStages>(fv, g, f, bg, ref_pq, dyn_smem, ctl,
+    stream_quads<true, kQuadRmsdStages>(fv, g, f, bg, ref_pq, dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
         atom_pair(d01, r[0], r[1], bg.head + j);
         atom_pair(d23, r[2], r[3], bg.head + j + 2);
     });
+    __syncthreads(); // every warp has left the ring: its memory becomes the reduction scratch
     float a[KS];
 #pragma unroll
     for (int u = 0; u < 3; u++) {
