@@ -306,8 +306,8 @@ bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) {
 
 uint32_t quad_head(const Group &g) { return (uint32_t)((4 - (g.first & 3)) & 3); }
 
-int blocks_per_frame_quad(size_t g, size_t F, int occ) {
-    size_t nb = (g + kQuadAtoms - 1) / kQuadAtoms;  // at least one chunk per CTA
+int blocks_per_frame_quad(size_t g, size_t F, int occ, size_t chunk) {
+    size_t nb = (g + chunk - 1) / chunk;  // at least one chunk per CTA
     nb = std::max<size_t>(nb, 1);
     nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
     nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
@@ -333,9 +333,9 @@ int ensure_quad_ref(groan_gpu_ctx *ctx, groan_gpu_ctx::Ref &R, const Group &g) {
 template <bool SAME_MASS, int CENTER>
 int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const float *d_pq, float *d_center, float *d_rmsd,
                        float *d_rot, const FallbackPlan &fp) {
-    typedef QuadCfg<true, kQuadRmsdStages> C;
-    dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2), (unsigned)ctx->n_frames);
-    k_rmsd_quad<SAME_MASS, CENTER><<<grid, kTmaThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+    typedef QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads> C;
+    dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2, C::kAtoms), (unsigned)ctx->n_frames);
+    k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
                                                                                    ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
                                                                                    ctx->d_flags, fp);
     LAUNCHED();
@@ -359,7 +359,7 @@ int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, cons
 template <bool SAME_MASS, int CENTER>
 int set_quad_attr(groan_gpu_ctx *ctx) {
     CK(cudaFuncSetAttribute(k_rmsd_quad<SAME_MASS, CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)QuadCfg<true, kQuadRmsdStages>::kBytes));
+                            (int)QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kBytes));
     return GROAN_OK;
 }
 
@@ -482,14 +482,15 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && ctx->occ_center_quad > 0 && quad_ok(ctx, g)) {
-        dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad), (unsigned)ctx->n_frames);
-        const size_t smem = QuadCfg<false, kQuadCenterStages>::kBytes;
+        typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
+        dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad, C::kAtoms), (unsigned)ctx->n_frames);
+        const size_t smem = C::kBytes;
         const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
         if (weighted)
-            k_center_quad<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+            k_center_quad<true><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
                                                                            out, ctx->d_flags, fp);
         else
-            k_center_quad<false><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+            k_center_quad<false><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
                                                                             out, ctx->d_flags, fp);
         LAUNCHED();
         if (fp.enabled) return GROAN_OK;
@@ -899,10 +900,10 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
             CK(cudaMemcpyToSymbol(g_debug_skip_ref, &v, sizeof(int)));
         }
         ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
-        const int sq = (int)QuadCfg<false, kQuadCenterStages>::kBytes;
+        const int sq = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
         CK(cudaFuncSetAttribute(k_center_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
         CK(cudaFuncSetAttribute(k_center_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_quad, k_center_quad<false>, kTmaThreads, sq));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_quad, k_center_quad<false>, kQuadCenterThreads, sq));
         ctx->occ_center_quad = std::min(ctx->occ_center_quad, 4);
         int qrc = set_quad_attr<true, 0>(ctx);
         if (!qrc) qrc = set_quad_attr<true, 1>(ctx);

@@ -33,7 +33,8 @@
 
 namespace groan {
 
-constexpr int kQuadAtoms = 1024;                   // atoms per chunk: one quad per thread
+constexpr int kQuadCenterThreads = 256;            // CTA size of k_center_quad; a chunk is one quad per thread
+constexpr int kQuadRmsdThreads = 256;              // CTA size of k_rmsd_quad
 constexpr int kQuadRefBlock = 128;                 // atoms per permuted reference block (32 quads = one warp)
 constexpr double kSinGuard = 2.0e-4;               // |sum sin| / n below this: side of the boundary not certain
 constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23: (x + kMagic) - kMagic = rint(x) for |x| < 2^22
@@ -128,12 +129,14 @@ __device__ __forceinline__ void quad_minmax(QuadMinMax &m, const V3 &d) {
     m.mn[2] = fminf(m.mn[2], fminf(d.b.x, d.c.y)); m.mx[2] = fmaxf(m.mx[2], fmaxf(d.b.x, d.c.y));
 }
 
-template <bool WITH_REF, int STAGES>
+template <bool WITH_REF, int STAGES, int NT>
 struct QuadCfg {
-    static constexpr size_t kFrameBytes = (size_t)kQuadAtoms * 12;
-    static constexpr size_t kRefBytes = WITH_REF ? (size_t)kQuadAtoms * 16 : 0;
+    static constexpr int kAtoms = NT * 4; // atoms per chunk
+    static constexpr size_t kFrameBytes = (size_t)kAtoms * 12;
+    static constexpr size_t kRefBytes = WITH_REF ? (size_t)kAtoms * 16 : 0;
     static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
-    static constexpr size_t kBytes = STAGES * kStageBytes + 128; // ring + QuadCtl
+    static constexpr size_t kConstOff = STAGES * kStageBytes + 128; // ring, QuadCtl, then 24 floats of per-frame constants
+    static constexpr size_t kBytes = kConstOff + 128;
 };
 constexpr int kQuadCenterStages = 4; // 48 KB ring: 4 CTAs per SM
 constexpr int kQuadRmsdStages = 4;   // 112 KB ring: 2 CTAs per SM (no static shared memory: the reduction scratch aliases the ring)
@@ -182,11 +185,11 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint32_t bar) {
 // so every chunk of a CTA but its last runs the unchecked, stage-unrolled loop.
 // Dynamic shared memory: [ring: STAGES x (frame chunk | reference chunk)] [QuadCtl].  After the call the ring is free
 // (every copy issued has been consumed) and the caller may reuse it once the CTA has synchronised.
-template <bool WITH_REF, int STAGES, typename F>
+template <bool WITH_REF, int STAGES, int NT, typename F>
 __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *ref_pq,
                                              unsigned char *smem, F &&fn) {
-    typedef QuadCfg<WITH_REF, STAGES> C;
-    constexpr uint32_t CH = kQuadAtoms, kSt = (uint32_t)C::kStageBytes;
+    typedef QuadCfg<WITH_REF, STAGES, NT> C;
+    constexpr uint32_t CH = C::kAtoms, kSt = (uint32_t)C::kStageBytes;
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t chunks = (bg.body + CH - 1) / CH;
     const uint32_t my_chunks = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -205,7 +208,7 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     if (t == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(ctl.full + s, 1);
-            mbar_init(ctl.empty + s, kWarps);
+            mbar_init(ctl.empty + s, NT / 32);
         }
         fence_mbar_init();
         for (uint32_t it = 0; it < (uint32_t)STAGES && it < my_chunks; it++) issue(it);
@@ -278,18 +281,48 @@ __device__ inline void finish_center_sin(const double tot_md[3], double M, const
     *flag = redo;
 }
 
-__device__ __forceinline__ QuadConst quad_constants(const float p[3], const float L[3]) {
+// Per-frame constants, computed by one thread, parked in shared memory and read back by everybody with volatile loads.
+// The detour is deliberate: if the compiler can see that the two x (y, z) of a pattern are the same value it keeps ONE
+// copy and rebuilds the register pairs with MOVs in front of every packed instruction (~25 MOV per quad in SASS; a
+// mov-through-asm is not enough, ptxas propagates copies through it).  Values loaded from different addresses stay
+// in their own registers.  `scratch` = 24 floats of shared memory; contains a __syncthreads().
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ QuadConst quad_constants(const float p[3], const float L[3], float *scratch) {
+    if (threadIdx.x == 0) {
+        const float inv[3] = {1.0f / L[0], 1.0f / L[1], 1.0f / L[2]};
+        const int pat[6] = {0, 1, 2, 0, 1, 2};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            scratch[k] = -p[pat[k]];
+            scratch[6 + k] = inv[pat[k]];
+            scratch[12 + k] = -L[pat[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float t = p[k] * inv[k];
+            scratch[18 + k] = 6.283185307179586f * inv[k];
+            scratch[21 + k] = 6.283185307179586f * (t - floorf(t));
+        }
+    }
+    __syncthreads();
+    const uint32_t a = smem_u32(scratch);
     QuadConst q;
-    const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
-    q.negp = v3_pattern(-p[0], -p[1], -p[2]);
-    q.inv = v3_pattern(ix, iy, iz);
-    q.negl = v3_pattern(-L[0], -L[1], -L[2]);
-    const float inv[3] = {ix, iy, iz};
+    q.negp.a = lds64(a); q.negp.b = lds64(a + 8); q.negp.c = lds64(a + 16);
+    q.inv.a = lds64(a + 24); q.inv.b = lds64(a + 32); q.inv.c = lds64(a + 40);
+    q.negl.a = lds64(a + 48); q.negl.b = lds64(a + 56); q.negl.c = lds64(a + 64);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float t = p[k] * inv[k];
-        q.sc[k] = 6.283185307179586f * inv[k];
-        q.ph[k] = 6.283185307179586f * (t - floorf(t));
+        q.sc[k] = lds32(a + 72 + 4 * k);
+        q.ph[k] = lds32(a + 84 + 4 * k);
     }
     return q;
 }
@@ -318,22 +351,22 @@ __device__ __forceinline__ double edge_sin(float d, float p, float L) {
 // ---------------------------------------------------------------- group_get_center / group_get_com
 // sums: [0..2] sum m d, [3] sum m, [4..6] sum sin
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
+__global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
                                                                  float *out, int *flags, FallbackPlan fp) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    FrameReduceSmem<7, 3> &sm = *reinterpret_cast<FrameReduceSmem<7, 3> *>(dyn_smem); // reuses the ring once it has drained
+    FrameReduceSmem<7, 3, kQuadCenterThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<7, 3, kQuadCenterThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
-    const QuadConst qc = quad_constants(p, L);
+    const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 smd = v3_zero(), ssin = v3_zero();
     float2 sm2 = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
-    stream_quads<false, kQuadCenterStages>(fv, g, f, bg, nullptr, dyn_smem,
+    stream_quads<false, kQuadCenterStages, kQuadCenterThreads>(fv, g, f, bg, nullptr, dyn_smem,
                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
@@ -382,19 +415,19 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_quad(FrameView fv, Gr
 constexpr int kQuadSums = kFastSums + 6;
 
 template <bool SAME_MASS, int CENTER>
-__global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, const float *ref_pq, double *partials,
+__global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, const float *ref_pq, double *partials,
                                                                unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
                                                                float *com_out, int *flags, FallbackPlan fp) {
     constexpr int KS = CENTER ? kQuadSums : kFastSums;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    FrameReduceSmem<KS, 3> &sm = *reinterpret_cast<FrameReduceSmem<KS, 3> *>(dyn_smem); // reuses the ring once it has drained
+    FrameReduceSmem<KS, 3, kQuadRmsdThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<KS, 3, kQuadRmsdThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
-    const QuadConst qc = quad_constants(p, L);
+    const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero(), sd = v3_zero(), ssin = v3_zero();
 #pragma unroll
@@ -423,7 +456,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_quad(FrameView fv, Grou
             sm2 = __fadd2_rn(sm2, m);
         }
     };
-    stream_quads<true, kQuadRmsdStages>(fv, g, f, bg, ref_pq, dyn_smem,
+    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq, dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
