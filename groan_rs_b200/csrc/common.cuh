@@ -255,46 +255,86 @@ __device__ inline void svd3(const double A[9], double U[9], double S[3], double 
     }
 }
 
+// f64 reciprocal / square root for the serial per-frame finish.  The library versions are ABI calls of ~100 dependent
+// instructions each under -rdc, and the finish runs in ONE thread per frame while the rest of the GPU waits:
+// an SFU seed in f32 plus two Newton steps in f64 FMAs gives the same result to ~1e-16 relative.
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double ax = fabs(x);
+    if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+    double y = (double)__frcp_rn((float)x);
+    y = fma(fma(-x, y, 1.0), y, y);
+    y = fma(fma(-x, y, 1.0), y, y);
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return sqrt(x);
+    double y = (double)rsqrtf((float)x);
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+// floor(x / L) for L > 0 with the quotient formed by a reciprocal: corrected with the exact remainder
+__device__ __forceinline__ double floor_div(double x, double L, double invL) {
+    double q = floor(x * invL);
+    const double r = fma(-q, L, x);
+    if (r < 0.0) q -= 1.0;
+    else if (r >= L) q += 1.0;
+    return q;
+}
+
 // r = U * diag(1, 1, sign det(U Vt)) * Vt, rmsd.rs:573-583 (row-major).
 //
 // For det(H) > 0 (every non-degenerate, non-reflected case) that matrix is the orthogonal polar factor of H, which a
-// scaled Newton iteration X <- (g X + X^-T / g) / 2 reaches in ~8 steps of plain f64 multiply-adds -- about 10x
-// fewer dependent operations than the one-sided Jacobi SVD, and this code runs in ONE thread at the very end of a
-// frame while the rest of the GPU waits (profiles/r1_summary.md: the serial finish was ~25 % of the kernel).
+// scaled Newton iteration X <- (g X + X^-T / g) / 2 reaches in ~8 steps -- about 10x fewer dependent operations than
+// the one-sided Jacobi SVD, and this code runs in ONE thread at the very end of a frame while the rest of the GPU
+// waits.  The iteration is self-correcting, so it runs in f32 (4-cycle FMAs, SFU reciprocal / square roots) until it
+// stalls at f32 precision, and two unscaled f64 steps X <- (X + X^-T) / 2 (quadratic: 1e-6 -> 1e-12 -> 1e-24) finish it.
 // Reflections (det < 0) and near-singular H (planar / collinear groups) keep the SVD path.
 __device__ inline void kabsch_rotation(const double H[9], double r[9]) {
     double n2 = 0.0;
     for (int i = 0; i < 9; i++) n2 += H[i] * H[i];
     const double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
-    const double n = sqrt(n2);
+    const double n = fast_sqrt(n2);
     if (n2 > 0.0 && det > 1e-7 * n2 * n) {
-        double X[9];
-        const double inv_n = 1.0 / n;
-        for (int i = 0; i < 9; i++) X[i] = H[i] * inv_n;
+        float X[9];
+        const double inv_n = fast_rcp(n);
+        for (int i = 0; i < 9; i++) X[i] = (float)(H[i] * inv_n);
         bool ok = false;
-        for (int it = 0; it < 40; it++) {
+        for (int it = 0; it < 30; it++) {
             // Y = X^-T = cofactor(X) / det(X)
-            double C[9];
+            float C[9];
             C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
             C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
             C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
-            const double dx = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
-            if (!(dx > 0.0)) break;
-            const double idx = 1.0 / dx;
-            double nx = 0.0, ny = 0.0;
+            const float dx = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+            if (!(dx > 0.0f)) break;
+            const float idx = __frcp_rn(dx);
+            float nx = 0.0f, ny = 0.0f;
             for (int i = 0; i < 9; i++) { C[i] *= idx; nx += X[i] * X[i]; ny += C[i] * C[i]; }
-            const double g = sqrt(sqrt(ny / nx)); // Frobenius-norm scaling
-            const double a = 0.5 * g, b = 0.5 / g;
-            double diff = 0.0;
+            const float g = __fsqrt_rn(__fsqrt_rn(ny * __frcp_rn(nx))); // Frobenius-norm scaling
+            const float a = 0.5f * g, b = 0.5f * __frcp_rn(g);
+            float diff = 0.0f;
             for (int i = 0; i < 9; i++) {
-                const double v = a * X[i] + b * C[i];
+                const float v = a * X[i] + b * C[i];
                 diff += (v - X[i]) * (v - X[i]);
                 X[i] = v;
             }
-            if (diff < 1e-30) { ok = true; break; }
+            if (diff < 1e-11f) { ok = true; break; }
         }
         if (ok) {
-            for (int i = 0; i < 9; i++) r[i] = X[i];
+            double Y[9];
+            for (int i = 0; i < 9; i++) Y[i] = (double)X[i];
+            for (int it = 0; it < 2; it++) {
+                double C[9];
+                C[0] = Y[4] * Y[8] - Y[5] * Y[7]; C[1] = Y[5] * Y[6] - Y[3] * Y[8]; C[2] = Y[3] * Y[7] - Y[4] * Y[6];
+                C[3] = Y[2] * Y[7] - Y[1] * Y[8]; C[4] = Y[0] * Y[8] - Y[2] * Y[6]; C[5] = Y[1] * Y[6] - Y[0] * Y[7];
+                C[6] = Y[1] * Y[5] - Y[2] * Y[4]; C[7] = Y[2] * Y[3] - Y[0] * Y[5]; C[8] = Y[0] * Y[4] - Y[1] * Y[3];
+                const double hd = 0.5 * fast_rcp(Y[0] * C[0] + Y[1] * C[1] + Y[2] * C[2]);
+                for (int i = 0; i < 9; i++) Y[i] = fma(hd, C[i], 0.5 * Y[i]);
+            }
+            for (int i = 0; i < 9; i++) r[i] = Y[i];
             return;
         }
     }

@@ -264,18 +264,19 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
 __device__ inline void finish_center_sin(const double tot_md[3], double M, const double S[3], const float *tmn, const float *tmx,
                                          const float p[3], const float *L, uint32_t n, float *out3, int *flag) {
     int redo = 0;
+    const double inv_m = fast_rcp(M);
     for (int k = 0; k < 3; k++) {
-        const double Lk = (double)L[k];
+        const double Lk = (double)L[k], inv_l = fast_rcp(Lk);
         if (!((double)tmx[k] - (double)tmn[k] < 0.5 * Lk * kExtentSlack)) redo = 1; // not compact: images may differ
         if (!(fabs((double)p[k]) < 64.0 * Lk)) redo = 1;                            // f32 frac(p / L) no longer good enough
         const double lo = (double)p[k] + (double)tmn[k], hi = (double)p[k] + (double)tmx[k];
-        const double mlo = floor(lo / Lk), mhi = floor(hi / Lk);
+        const double mlo = floor_div(lo, Lk, inv_l), mhi = floor_div(hi, Lk, inv_l);
         double m = mlo;
         if (mlo != mhi) { // the group straddles the boundary mhi * L: which side is the circular mean on?
             if (!(fabs(S[k]) >= kSinGuard * (double)n)) redo = 1;
             m = S[k] > 0.0 ? mhi : mlo;
         }
-        const double um = (double)p[k] + tot_md[k] / M; // mean of the unwrapped group
+        const double um = (double)p[k] + tot_md[k] * inv_m; // mean of the unwrapped group
         out3[k] = (float)(um - m * Lk);                 // c0 = c~ - m L lies in [0, L): the image within L/2 of c0
     }
     *flag = redo;

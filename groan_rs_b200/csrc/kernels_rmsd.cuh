@@ -73,9 +73,9 @@ __device__ inline double finish_kabsch(const double H[9], const double Hw[9], do
     for (int k = 0; k < 9; k++) cross += r[k] * Hw[k];
     const double T = ref.sum_wpp + sum_wqq;
     double R = T - 2.0 * cross;
-    if (ratio) *ratio = (T > 0.0) ? R / T : 1.0;
+    if (ratio) *ratio = (T > 0.0) ? R * fast_rcp(T) : 1.0;
     if (R < 0.0) R = 0.0;
-    return sqrt(R / ref.sum_w);
+    return fast_sqrt(R * fast_rcp(ref.sum_w));
 }
 
 constexpr int kCovSums = 19; // H[9], Hw[9], sum w|qc|^2
@@ -170,9 +170,10 @@ __device__ inline void finish_rmsd(const double (&tot)[kFastSums], const float *
                                    const float *L, const RefView &ref, float *rmsd_out, float *rot9, float *com3, int *flag) {
     int redo = 0;
     double delta[3];
+    const double inv_m = fast_rcp(SAME_MASS ? ref.sum_w : tot[25]);
     for (int k = 0; k < 3; k++) {
         if (!((double)tmx[k] - (double)tmn[k] < 0.5 * (double)L[k] * kExtentSlack)) redo = 1;
-        delta[k] = SAME_MASS ? tot[18 + k] / ref.sum_w : tot[22 + k] / tot[25];
+        delta[k] = (SAME_MASS ? tot[18 + k] : tot[22 + k]) * inv_m;
     }
     double H[9], Hw[9];
     for (int u = 0; u < 3; u++)
