@@ -760,3 +760,99 @@ def test_device_side_fallback_matches_exact_only():
     for name in ("device", "host"):
         for a, b in zip(res[name], res["exact"]):
             assert np.array_equal(bits(a), bits(b)), name
+
+
+# ------------------------------------------------------------------ quad kernels (kernels_quad.cuh)
+def test_quad_kernels_match_pair_kernels_and_x64():
+    """kernels_quad.cuh (quads of atoms, permuted reference, sine-only image decision) against kernels_tma.cuh
+    (GROAN_FLAG_NO_QUAD) and the exact64 oracle: heads of 0..3 atoms, ragged tails, a group smaller than one chunk per
+    CTA, blobs straddling box faces (frame 0 of _blob_system sits on two of them), non-cubic box."""
+    import groan_rs_b200 as g
+    n, F, L = 300_000, 6, np.array([20.0, 23.0, 17.5], np.float32)
+    masses = np.random.default_rng(4).uniform(1.0, 100.0, n).astype(np.float32)
+    scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
+    quad = _blob_system(n, F, L, 11, scale, nscale, masses)
+    pair = _blob_system(n, F, L, 11, scale, nscale, masses, flags=g.FLAG_NO_QUAD)
+    ref = g.System(n, masses=masses)
+    ref_xyz = quad.synth_blob_ref(11, scale, L / 2)
+    ref.set_frames(ref_xyz, L)
+    other = np.random.default_rng(5).uniform(1.0, 100.0, n).astype(np.float32)  # reference masses != target masses
+    ref2 = g.System(n, masses=other)
+    ref2.set_frames(ref_xyz, L)
+    frames = quad.get_frames()
+    groups = {"h0": np.arange(0, n), "h3": np.arange(1, n - 2), "h2": np.arange(2, n - 5), "h1": np.arange(3, 9000),
+              "small": np.arange(40_000, 45_001)}
+    for name, idx in groups.items():
+        for s in (quad, pair, ref, ref2):
+            s.group_create_from_indices(name, idx)
+        cq, cp = quad.group_get_center(name), pair.group_get_center(name)
+        assert quad.fallback_frames() == 0 and pair.fallback_frames() == 0
+        mq, mp = quad.group_get_com(name), pair.group_get_com(name)
+        rq, rp = quad.calc_rmsd(ref, name), pair.calc_rmsd(ref, name)
+        assert quad.fallback_frames() == 0
+        assert np.abs(cq - cp).max() <= 4e-6 and np.abs(mq - mp).max() <= 4e-6 and np.abs(rq - rp).max() <= 2e-6
+        for weighted, sep in ((False, cq), (True, mq)):
+            c2, r2 = quad.group_center_and_rmsd(ref, name, weighted=weighted)
+            assert quad.fallback_frames() == 0
+            assert np.abs(c2 - sep).max() <= 4e-6 and np.abs(r2 - rq).max() <= 2e-6
+        # SAME_MASS = false instantiations (weights from the reference system, COM of the target from its own masses:
+        # rmsd.rs:154,192); the x64 oracle takes one mass array, so these are pinned to the pair kernels only
+        c3, r3 = quad.group_center_and_rmsd(ref2, name, weighted=True)
+        c4, r4 = pair.group_center_and_rmsd(ref2, name, weighted=True)
+        assert np.abs(c3 - c4).max() <= 4e-6 and np.abs(r3 - r4).max() <= 2e-6
+        for f in (0, F - 1):
+            c64 = orc.get_center_x64(frames[f], idx, L)
+            m64 = orc.get_center_x64(frames[f], idx, L, mass=masses[idx])
+            r64, _ = orc.calc_rmsd_x64(ref_xyz, idx, L, masses[idx], frames[f], idx, L)
+            assert np.abs(cq[f] - c64).max() <= TOL_CENTER and np.abs(mq[f] - m64).max() <= TOL_CENTER, (name, f, cq[f], c64)
+            assert abs(rq[f] - r64) <= 2e-5, (name, f, rq[f], r64)
+
+
+def test_back_to_back_calls_keep_stream_order():
+    """Back-to-back calls that write the SAME result buffers -- one on a group every frame of which needs the device-launched
+    fallback passes (tail-launched grids), one on a compact group -- must leave the results of the call issued last, and
+    repeated calls must be bit-identical (fixed-order reductions, static chunk assignment)."""
+    import groan_rs_b200 as g
+    import torch
+    n, F = 200_000, 4
+    L = np.array([12.0, 12.0, 12.0], np.float32)
+    masses = np.random.default_rng(3).uniform(1.0, 50.0, n).astype(np.float32)
+    out = {}
+    for name, flags in (("device", 0), ("host", g.FLAG_HOST_FALLBACK)):
+        s = g.System(n, masses=masses, max_frames=F)
+        s.set_flags(flags)
+        s.synth_uniform(5, 0, F, [0, 0, 0], L, L)
+        ref = g.System(n, masses=masses)
+        ref.set_frames(s.get_frames()[0], L)
+        for x in (s, ref):
+            x.group_create_from_indices("wide", np.arange(0, n))            # uniform in the box: every frame is flagged
+            x.group_create_from_indices("narrow", np.arange(1000, 1000 + 8192))
+        # make the narrow group compact: its atoms are uniform in the box too, so move them into a small cube
+        fr = s.get_frames().copy()
+        fr[:, 1000:1000 + 8192] = 5.0 + 0.1 * fr[:, 1000:1000 + 8192]
+        s.set_frames(fr, np.tile(L, (F, 1)))
+        rf = fr[0].copy()  # reference = frame 0 plus a ripple, so that no RMSD is ~0 (that would be flagged, by design)
+        rf[1000:1000 + 8192] += (0.02 * np.sin(np.arange(8192 * 3, dtype=np.float32))).reshape(8192, 3)
+        ref.set_frames(rf, L)
+        dev = torch.device("cuda", 0)
+        d_c = torch.empty((F, 3), dtype=torch.float32, device=dev)
+        d_r = torch.empty((F,), dtype=torch.float32, device=dev)
+        want_wide = tuple(np.array(a, copy=True) for a in s.group_center_and_rmsd(ref, "wide"))
+        want_narrow = tuple(np.array(a, copy=True) for a in s.group_center_and_rmsd(ref, "narrow"))
+        assert s.fallback_frames() == 0
+        for rep in range(60):
+            s.group_center_and_rmsd(ref, "wide", center_out=d_c, rmsd_out=d_r)
+            s.group_center_and_rmsd(ref, "narrow", center_out=d_c, rmsd_out=d_r)
+            if rep % 20 == 19:
+                s.sync()
+                assert np.array_equal(bits(d_c.cpu().numpy()), bits(want_narrow[0])), (name, rep)
+                assert np.array_equal(bits(d_r.cpu().numpy()), bits(want_narrow[1])), (name, rep)
+        for rep in range(20):
+            s.group_get_center("narrow", out=d_c)
+            s.group_center_and_rmsd(ref, "wide", center_out=d_c, rmsd_out=d_r)
+        s.sync()
+        assert np.array_equal(bits(d_c.cpu().numpy()), bits(want_wide[0])), name
+        assert np.array_equal(bits(d_r.cpu().numpy()), bits(want_wide[1])), name
+        out[name] = (want_wide, want_narrow)
+    for a, b in zip(out["device"][0] + out["device"][1], out["host"][0] + out["host"][1]):
+        assert np.array_equal(bits(a), bits(b))
