@@ -405,8 +405,10 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
                 tmx[k] = fmaxf(tmx[k], d);
             }
         }
-        finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, flags + f);
-        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags);
+        int flag = 0;
+        finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, &flag);
+        flags[f] = flag;
+        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag);
     }
 }
 
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             finish_center_sin(md, M, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
         }
         flags[f] = flag_r | (flag_c << 1);
-        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags, flag_r | flag_c);
     }
 }
 

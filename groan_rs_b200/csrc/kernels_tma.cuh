@@ -265,17 +265,18 @@ struct FallbackPlan {
     float *com, *rmsd_out, *rot_out; // want_rmsd
 };
 
+// frames_done counts finished frames in its low 16 bits and flagged ones above, so that the thread that finishes the last
+// frame learns from its own atomic whether any frame needs the passes: no read-back of the flags (8 dependent L2 round
+// trips at the very end of the kernel, ~3 us, in the first version).  Batches are far below 65535 frames (kPartialSlots).
 __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, const FrameView &fv, const GroupView &g, const RefView &ref,
-                                                      double *partials, unsigned int *tickets, const int *flags) {
+                                                      double *partials, unsigned int *tickets, const int *flags, int my_flag) {
     if (!fp.enabled) return;
     __threadfence();
-    const unsigned int done = atomicAdd(fp.frames_done, 1u);
-    if (done != (unsigned)fp.n_frames - 1) return;
+    const unsigned int done = atomicAdd(fp.frames_done, my_flag ? 0x10001u : 1u);
+    if ((done & 0xffffu) != (unsigned)fp.n_frames - 1) return;
     *fp.frames_done = 0u; // re-arm
+    if (!my_flag && (done >> 16) == 0u) return;
     __threadfence();
-    int any = 0;
-    for (int f = 0; f < fp.n_frames; f++) any |= ((const volatile int *)flags)[f];
-    if (!any) return;
     const dim3 ge(fp.nb_exact, fp.n_frames), gc(fp.nb_cov, fp.n_frames);
     k_trig<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.c0, flags);
     if (fp.want_rmsd) {
@@ -355,8 +356,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4) k_center_tma(FrameView fv, Gro
                 tmx[k] = fmaxf(tmx[k], d);
             }
         }
-        finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, flags + f);
-        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags);
+        int flag = 0;
+        finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, &flag);
+        flags[f] = flag;
+        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag);
     }
 }
 
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_rmsd_tma(FrameView fv, Group
             else finish_center<false>(ct, tmn, tmx, px, py, pz, L, g.n, center_out + f * 3, &flag_c);
         }
         flags[f] = flag_r | (flag_c << 1);
-        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags, flag_r | flag_c);
     }
 }
 
