@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "groan_gpu.cu")]
+    extra = os.environ.get("GROAN_NVCC_EXTRA", "").split()  # experiments only (e.g. -DGROAN_EXP_NOMATH, profiles/exp/README.md)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "groan_gpu.cu")]
     subprocess.check_call(cmd)
     return LIB
 

@@ -315,15 +315,17 @@ __device__ __forceinline__ QuadConst quad_constants(const float p[3], const floa
         }
     }
     __syncthreads();
-    const uint32_t a = smem_u32(scratch);
+    // plain loads from warp-uniform addresses: the compiler may keep the values in uniform registers (FFMA2 / FADD2 take
+    // uniform register pairs as operands), which leaves the vector registers to the accumulators and the scheduler
+    const float2 *c2 = reinterpret_cast<const float2 *>(scratch);
     QuadConst q;
-    q.negp.a = lds64(a); q.negp.b = lds64(a + 8); q.negp.c = lds64(a + 16);
-    q.inv.a = lds64(a + 24); q.inv.b = lds64(a + 32); q.inv.c = lds64(a + 40);
-    q.negl.a = lds64(a + 48); q.negl.b = lds64(a + 56); q.negl.c = lds64(a + 64);
+    q.negp.a = c2[0]; q.negp.b = c2[1]; q.negp.c = c2[2];
+    q.inv.a = c2[3]; q.inv.b = c2[4]; q.inv.c = c2[5];
+    q.negl.a = c2[6]; q.negl.b = c2[7]; q.negl.c = c2[8];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        q.sc[k] = lds32(a + 72 + 4 * k);
-        q.ph[k] = lds32(a + 84 + 4 * k);
+        q.sc[k] = scratch[18 + k];
+        q.ph[k] = scratch[21 + k];
     }
     return q;
 }
@@ -440,12 +442,12 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     auto atom_pair = [&](const V3 &d, const float4 &r0, const float4 &r1, uint32_t i) {
         const float2 pc[3] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y)};
         const float2 w = make_float2(r1.z, r1.w);
+        const V3 wd = v3_mul(w, d); // w d also serves Hw = sum pc (w d)^T: no separate w pc products
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             v3_fma(h[u], pc[u], d);
-            v3_fma(hw[u], __fmul2_rn(w, pc[u]), d);
+            v3_fma(hw[u], pc[u], wd);
         }
-        const V3 wd = v3_mul(w, d);
         v3_add(swd, wd);
         sq = __ffma2_rn(wd.a, d.a, sq);
         sq = __ffma2_rn(wd.b, d.b, sq);
@@ -461,6 +463,11 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     };
     stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq, dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+#ifdef GROAN_EXP_NOMATH
+        // experiment (profiles/exp/README.md): how fast does the ring alone stream?  Results are garbage.
+        sq = __fadd2_rn(sq, make_float2(c0.x + c1.y + c2.z, r[0].x + r[1].y + r[2].z + r[3].w));
+        return;
+#endif
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
         atom_pair(d01, r[0], r[1], bg.head + j);
