@@ -109,8 +109,8 @@ struct groan_gpu_ctx {
         bool set = false;
         size_t n = 0;
         float *d_pc = nullptr;  // block-SoA prepared reference (kernels_rmsd.cuh)
-        float *d_pq = nullptr;  // quad-permuted copy of the aligned body (kernels_quad.cuh), built on first use
-        int pq_head = -1;       // head (atoms before the first 16-byte boundary) d_pq was built for
+        float *d_pq[4] = {nullptr, nullptr, nullptr, nullptr};  // quad-permuted copies of the aligned body (kernels_quad.cuh), one per
+                                                                 // head (atoms before the first 16-byte boundary), built on first use
         double sums[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
         bool same_mass = true;  // reference masses == the target group's masses
         float com[3] = {0, 0, 0};
@@ -300,11 +300,18 @@ int launch_rmsd_tma(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, bool 
 // ---- quad kernels (kernels_quad.cuh) -----------------------------------------------------------------
 // They need what the TMA-fed kernels need, plus the same 16-byte phase of the group in every frame of the batch
 // (n_atoms % 4 == 0, or a single frame): the permuted reference is laid out relative to the aligned body.
+// They need what the TMA-fed kernels need.  The centre kernels take any frame size (the 16-byte phase of the group is worked
+// out per frame).  The RMSD kernels read a reference laid out relative to the aligned body, one copy per phase: a single
+// copy when every frame puts the group at the same phase (n_atoms % 4 == 0, or one frame), otherwise up to four -- which is
+// only worth it while they all stay in L2 (<= 64 MB); larger groups with odd frame sizes keep the pair kernels.
+bool quad_center_ok(const groan_gpu_ctx *ctx, const Group &g) {
+    return tma_ok(ctx, g, 2) && !(ctx->flags & GROAN_FLAG_NO_QUAD);
+}
 bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) {
-    return tma_ok(ctx, g, 2) && !(ctx->flags & GROAN_FLAG_NO_QUAD) && (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1);
+    return quad_center_ok(ctx, g) && (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1 || g.n <= (1u << 20));
 }
 
-uint32_t quad_head(const Group &g) { return (uint32_t)((4 - (g.first & 3)) & 3); }
+uint32_t quad_head(const groan_gpu_ctx *ctx, const Group &g, size_t f) { return (uint32_t)((4 - ((f * ctx->n_atoms + g.first) & 3)) & 3); }
 
 int blocks_per_frame_quad(size_t g, size_t F, int occ, size_t chunk) {
     size_t nb = (g + chunk - 1) / chunk;  // at least one chunk per CTA
@@ -314,24 +321,25 @@ int blocks_per_frame_quad(size_t g, size_t F, int occ, size_t chunk) {
     return (int)nb;
 }
 
-int ensure_quad_ref(groan_gpu_ctx *ctx, groan_gpu_ctx::Ref &R, const Group &g) {
-    const uint32_t head = quad_head(g);
-    if (R.d_pq && R.pq_head == (int)head) return GROAN_OK;
-    const uint32_t body = ((uint32_t)g.n - head) & ~3u;
-    if (!R.d_pq) {
+// build the permuted reference for every phase the frames of the batch put the group at
+int ensure_quad_ref(groan_gpu_ctx *ctx, groan_gpu_ctx::Ref &R, const Group &g, QuadRef *out) {
+    for (size_t f = 0; f < std::min<size_t>(ctx->n_frames, 4); f++) {
+        const uint32_t head = quad_head(ctx, g, f);
+        if (R.d_pq[head]) continue;
+        const uint32_t body = ((uint32_t)g.n - head) & ~3u;
         const size_t bytes = quad_ref_floats(g.n) * sizeof(float);
-        CK(cudaMalloc(&R.d_pq, bytes));
-        CK(cudaMemsetAsync(R.d_pq, 0, bytes, ctx->compute));
+        CK(cudaMalloc(&R.d_pq[head], bytes));
+        CK(cudaMemsetAsync(R.d_pq[head], 0, bytes, ctx->compute));
+        const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((body / 4 + kThreads - 1) / kThreads, (size_t)kSMs * 8));
+        k_ref_permute<<<nb, kThreads, 0, ctx->compute>>>(R.d_pc, R.d_pq[head], head, body);
+        LAUNCHED();
     }
-    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((body / 4 + kThreads - 1) / kThreads, (size_t)kSMs * 8));
-    k_ref_permute<<<nb, kThreads, 0, ctx->compute>>>(R.d_pc, R.d_pq, head, body);
-    LAUNCHED();
-    R.pq_head = (int)head;
+    for (int h = 0; h < 4; h++) out->v[h] = R.d_pq[h];
     return GROAN_OK;
 }
 
 template <bool SAME_MASS, int CENTER>
-int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const float *d_pq, float *d_center, float *d_rmsd,
+int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, float *d_center, float *d_rmsd,
                        float *d_rot, const FallbackPlan &fp) {
     typedef QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads> C;
     dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2, C::kAtoms), (unsigned)ctx->n_frames);
@@ -342,7 +350,7 @@ int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, co
     return GROAN_OK;
 }
 
-int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const float *d_pq, bool same_mass, int center_mode,
+int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, bool same_mass, int center_mode,
                      float *d_center, float *d_rmsd, float *d_rot, const FallbackPlan &fp) {
 #define GO(SM, CM) return launch_rmsd_quad_t<SM, CM>(ctx, g, rv, d_pq, d_center, d_rmsd, d_rot, fp)
     if (same_mass) {
@@ -481,7 +489,7 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
 // (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && ctx->occ_center_quad > 0 && quad_ok(ctx, g)) {
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
         typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
         dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad, C::kAtoms), (unsigned)ctx->n_frames);
         const size_t smem = C::kBytes;
@@ -769,11 +777,12 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     bool center_done = false, device_fallback = false;
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && quad_ok(ctx, *g)) {
         // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
-        rc = ensure_quad_ref(ctx, R, *g);
+        QuadRef qr;
+        rc = ensure_quad_ref(ctx, R, *g, &qr);
         if (rc) return rc;
         const FallbackPlan fp = fallback_plan(ctx, *g, center != nullptr, center_weighted != 0, d_center, true, d_rmsd, d_rot);
         device_fallback = fp.enabled != 0;
-        rc = launch_rmsd_quad(ctx, *g, rv, R.d_pq, R.same_mass, center ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
+        rc = launch_rmsd_quad(ctx, *g, rv, qr, R.same_mass, center ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
         center_done = center != nullptr;
@@ -943,7 +952,8 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
     }
     for (auto &r : ctx->refs) {
         if (r.d_pc) cudaFree(r.d_pc);
-        if (r.d_pq) cudaFree(r.d_pq);
+        for (float *q : r.d_pq)
+            if (q) cudaFree(q);
     }
     void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done};
     for (void *b : bufs)
@@ -1275,8 +1285,8 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
     groan_gpu_ctx::Ref &R = ctx->refs[gid];
     CK(cudaStreamSynchronize(ctx->compute));
     if (R.d_pc) { cudaFree(R.d_pc); R.d_pc = nullptr; }
-    if (R.d_pq) { cudaFree(R.d_pq); R.d_pq = nullptr; }
-    R.pq_head = -1;
+    for (float *&q : R.d_pq)
+        if (q) { cudaFree(q); q = nullptr; }
     R.set = false;
     float *d_ref = nullptr, *d_refbox = nullptr, *d_small = nullptr, *d_rmass = nullptr;
     uint32_t *d_ridx = nullptr;

@@ -60,6 +60,11 @@ __global__ void __launch_bounds__(kThreads) k_ref_permute(const float *pc, float
     }
 }
 
+// the permuted reference, one copy per head (0..3 atoms before the first 16-byte boundary of the group in a frame)
+struct QuadRef {
+    const float *v[4];
+};
+
 // a 3-vector sum held as three register pairs in the patterns of the quad: a = (x,y), b = (z,x), c = (y,z)
 struct V3 {
     float2 a, b, c;
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
 constexpr int kQuadSums = kFastSums + 6;
 
 template <bool SAME_MASS, int CENTER>
-__global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, const float *ref_pq, double *partials,
+__global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, double *partials,
                                                                unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
                                                                float *com_out, int *flags, FallbackPlan fp) {
     constexpr int KS = CENTER ? kQuadSums : kFastSums;
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             sm2 = __fadd2_rn(sm2, m);
         }
     };
-    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq, dyn_smem,
+    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
 #ifdef GROAN_EXP_NOMATH
         // experiment (profiles/exp/README.md): how fast does the ring alone stream?  Results are garbage.

@@ -763,12 +763,15 @@ def test_device_side_fallback_matches_exact_only():
 
 
 # ------------------------------------------------------------------ quad kernels (kernels_quad.cuh)
-def test_quad_kernels_match_pair_kernels_and_x64():
+@pytest.mark.parametrize("n", [300_000, 300_001, 300_002])
+def test_quad_kernels_match_pair_kernels_and_x64(n):
     """kernels_quad.cuh (quads of atoms, permuted reference, sine-only image decision) against kernels_tma.cuh
     (GROAN_FLAG_NO_QUAD) and the exact64 oracle: heads of 0..3 atoms, ragged tails, a group smaller than one chunk per
-    CTA, blobs straddling box faces (frame 0 of _blob_system sits on two of them), non-cubic box."""
+    CTA, blobs straddling box faces (frame 0 of _blob_system sits on two of them), non-cubic box, and frame sizes that
+    are not multiples of four atoms (the group's 16-byte phase then changes from frame to frame: one permuted reference
+    per phase)."""
     import groan_rs_b200 as g
-    n, F, L = 300_000, 6, np.array([20.0, 23.0, 17.5], np.float32)
+    F, L = 6, np.array([20.0, 23.0, 17.5], np.float32)
     masses = np.random.default_rng(4).uniform(1.0, 100.0, n).astype(np.float32)
     scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
     quad = _blob_system(n, F, L, 11, scale, nscale, masses)
