@@ -306,7 +306,7 @@ def run_gpu_arm(args):
         "group_center_and_rmsd": {"ms": t_fused, "alg_bytes": (12 * F + 16) * N_ATOMS,
                                   "gbs": (12 * F + 16) * N_ATOMS * gb / (t_fused * 1e-3)},
     }
-    dom = "group_center_and_rmsd"  # the kernel the timed step runs (k_center_rmsd_tma)
+    dom = "group_center_and_rmsd"  # the kernel the timed step runs (k_rmsd_quad<SAME_MASS, CENTER = 1>, kernels_quad.cuh)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": ops[dom]["gbs"] / peak, "traffic": ncu_traffic(F), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ops[dom]["alg_bytes"], "ops": ops,
