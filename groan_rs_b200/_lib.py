@@ -52,6 +52,10 @@ SIGNATURES = {
     "groan_gpu_all_distances_reduce": (_int, [_vp, _int, _int, _int, _f, _vp, _vp, _vp, _vp, _vp]),
     "groan_gpu_wrap": (_int, [_vp, _int, _vp]),
     "groan_gpu_translate": (_int, [_vp, _int, C.POINTER(_f), _vp]),
+    "groan_gpu_make_group_whole": (_int, [_vp, _int]),
+    "groan_gpu_set_molecules": (_int, [_vp, _vp]),
+    "groan_gpu_make_molecules_whole": (_int, [_vp]),
+    "groan_gpu_atoms_center": (_int, [_vp, _int, _int, _int]),
     "groan_gpu_rmsd_set_reference": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
     "groan_gpu_rmsd": (_int, [_vp, _int, _vp, _vp]),
     "groan_gpu_center_rmsd": (_int, [_vp, _int, _int, _vp, _vp, _vp]),

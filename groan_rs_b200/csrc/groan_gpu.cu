@@ -103,6 +103,8 @@ struct groan_gpu_ctx {
     bool rmsd_attr_set[2][3][2] = {};           // k_rmsd_tma<SAME_MASS, CENTER, FPC>: shared-memory attribute set on this device
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    uint32_t *d_mol_ref = nullptr;      // make_molecules_whole: reference atom of every atom's molecule (groan_gpu_set_molecules)
+    std::vector<uint32_t> mol_ref;      // host copy (position checks)
 
     // RMSD reference (per group id)
     struct Ref {
@@ -955,7 +957,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         for (float *q : r.d_pq)
             if (q) cudaFree(q);
     }
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done};
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done, ctx->d_mol_ref};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
@@ -1246,6 +1248,79 @@ int groan_gpu_translate(groan_gpu_ctx *ctx, int gid, const float t[3], int8_t *s
     if (rc) return rc;
     if (g->n == 0) return GROAN_OK;
     return run_wrap(ctx, *g, true, t, shifts, tric);
+}
+
+// ---- whole groups / molecules, centering ---------------------------------------
+int groan_gpu_make_group_whole(groan_gpu_ctx *ctx, int gid) {
+    // group_estimate_center(group)? comes first (modifying.rs:439), with all of its checks
+    const Group *g = nullptr;
+    int rc = check_center_args(ctx, gid, false, &g);
+    if (rc) return rc;
+    rc = run_trig(ctx, *g, false, ctx->d_c0, nullptr);
+    if (rc) return rc;
+    size_t nb = (g->n + kThreads - 1) / kThreads;
+    nb = std::max<size_t>(1, std::min<size_t>(nb, (size_t)kMaxBlocksPerFrame * 4));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    k_make_whole<<<grid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->d_box[ctx->slot], ctx->n_atoms, view_of(*g), ctx->d_c0);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+int groan_gpu_set_molecules(groan_gpu_ctx *ctx, const uint32_t *mol_ref) {
+    if (!ctx || !mol_ref) return GROAN_EINVAL;
+    for (size_t i = 0; i < ctx->n_atoms; i++) {
+        const uint32_t r = mol_ref[i];
+        if (r == kNoMolecule) continue;
+        // the reference atom of a molecule is its lowest index (modifying.rs:258-283) and refers to itself
+        if (r > i || mol_ref[r] != r) return GROAN_EINVAL;
+    }
+    CK(cudaStreamSynchronize(ctx->compute));
+    if (!ctx->d_mol_ref) CK(cudaMalloc(&ctx->d_mol_ref, ctx->n_atoms * sizeof(uint32_t)));
+    ctx->mol_ref.assign(mol_ref, mol_ref + ctx->n_atoms);
+    CK(cudaMemcpy(ctx->d_mol_ref, mol_ref, ctx->n_atoms * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return GROAN_OK;
+}
+
+int groan_gpu_make_molecules_whole(groan_gpu_ctx *ctx) {
+    if (!ctx) return GROAN_EINVAL;
+    if (!ctx->d_mol_ref) return GROAN_EINVAL;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    int rc = check_box(ctx, false, nullptr);  // simbox_check first (modifying.rs:350)
+    if (rc) return rc;
+    if (!ctx->valid.empty()) {  // first atom of a polyatomic molecule without a position (modifying.rs:362-380)
+        for (size_t f = 0; f < ctx->n_frames; f++)
+            for (size_t i = 0; i < ctx->n_atoms; i++)
+                if (ctx->mol_ref[i] != kNoMolecule && !ctx->valid[f * ctx->n_atoms + i]) {
+                    ctx->err_a = f;
+                    ctx->err_b = i;
+                    return GROAN_ENOPOS;
+                }
+    }
+    size_t nb = (ctx->n_atoms + kThreads - 1) / kThreads;
+    nb = std::max<size_t>(1, std::min<size_t>(nb, (size_t)kMaxBlocksPerFrame * 4));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    k_mol_whole<<<grid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->d_box[ctx->slot], ctx->n_atoms, ctx->d_mol_ref);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+int groan_gpu_atoms_center(groan_gpu_ctx *ctx, int gid, int weighted, int dim) {
+    if (dim < 0 || dim > 7) return GROAN_EINVAL;
+    // group_estimate_center / group_estimate_com of the reference group first (utility.rs:114,173) ...
+    const Group *g = nullptr;
+    int rc = check_center_args(ctx, gid, weighted != 0, &g);
+    if (rc) return rc;
+    // ... then atoms_translate: every atom of the system needs a position (utility.rs:120-125)
+    rc = check_positions(ctx, ctx->all);
+    if (rc) return rc;
+    rc = run_trig(ctx, *g, weighted != 0, ctx->d_c0, nullptr);
+    if (rc) return rc;
+    size_t nb = (ctx->n_atoms + kThreads - 1) / kThreads;
+    nb = std::max<size_t>(1, std::min<size_t>(nb, (size_t)kMaxBlocksPerFrame * 4));
+    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
+    k_center_atoms<<<grid, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, ctx->d_box[ctx->slot], ctx->n_atoms, ctx->d_c0, dim);
+    LAUNCHED();
+    return GROAN_OK;
 }
 
 // ---- RMSD -----------------------------------------------------------------------------------------

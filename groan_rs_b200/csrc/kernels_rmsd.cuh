@@ -272,6 +272,66 @@ __global__ void __launch_bounds__(kThreads) k_wrap(float *xyz, const float *box,
     }
 }
 
+// ---------------------------------------------------------------- whole groups / molecules, centering (in place)
+// System::make_group_whole, modifying.rs:437-465: pos = c + vector_to(c, pos) with c = group_estimate_center of the frame
+__global__ void __launch_bounds__(kThreads) k_make_whole(float *xyz, const float *box, size_t n_atoms, GroupView g, const float *c0) {
+    const int f = blockIdx.y;
+    const float lx = __ldg(box + f * 9), ly = __ldg(box + f * 9 + 4), lz = __ldg(box + f * 9 + 8);
+    const float cx = c0[f * 3 + 0], cy = c0[f * 3 + 1], cz = c0[f * 3 + 2];
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
+        float *p = fr + (size_t)g.atom(i) * 3;
+        const float x = p[0], y = p[1], z = p[2];
+        p[0] = cx + vector_to_1(cx, x, lx);
+        p[1] = cy + vector_to_1(cy, y, ly);
+        p[2] = cz + vector_to_1(cz, z, lz);
+    }
+}
+
+// System::make_molecules_whole, modifying.rs:338-391.  mol_ref[i] = reference atom (lowest index) of atom i's molecule,
+// kNoMolecule for atoms of monoatomic molecules (untouched).  The reference atom is wrapped into the box; every other atom
+// goes to ref + vector_to(ref, pos).  A thread reads its reference atom while that atom's own thread may be storing the
+// wrapped value: wrap is idempotent per component (the result lies in [0, L]), so wrapping whatever is read gives the same.
+constexpr uint32_t kNoMolecule = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(kThreads) k_mol_whole(float *xyz, const float *box, size_t n_atoms, const uint32_t *mol_ref) {
+    const int f = blockIdx.y;
+    const float lx = __ldg(box + f * 9), ly = __ldg(box + f * 9 + 4), lz = __ldg(box + f * 9 + 8);
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_atoms; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = __ldg(mol_ref + i);
+        if (r == kNoMolecule) continue;
+        const volatile float *q = fr + (size_t)r * 3;
+        const float rx = wrap_coordinate(q[0], lx), ry = wrap_coordinate(q[1], ly), rz = wrap_coordinate(q[2], lz);
+        float *p = fr + i * 3;
+        if (r == (uint32_t)i) {
+            p[0] = rx; p[1] = ry; p[2] = rz;
+        } else {
+            const float x = p[0], y = p[1], z = p[2];
+            p[0] = rx + vector_to_1(rx, x, lx);
+            p[1] = ry + vector_to_1(ry, y, ly);
+            p[2] = rz + vector_to_1(rz, z, lz);
+        }
+    }
+}
+
+// System::atoms_center / atoms_center_mass, utility.rs:109-130,168-189: shift = box_centre - estimate (f32), components
+// outside `dim` zeroed (Vector3D::filter), then atoms_translate: pos += shift; wrap (atom.rs:498-511)
+__global__ void __launch_bounds__(kThreads) k_center_atoms(float *xyz, const float *box, size_t n_atoms, const float *c0, int dim) {
+    const int f = blockIdx.y;
+    const float lx = __ldg(box + f * 9), ly = __ldg(box + f * 9 + 4), lz = __ldg(box + f * 9 + 8);
+    const bool kx = dim == 1 || dim == 4 || dim == 5 || dim == 7, ky = dim == 2 || dim == 4 || dim == 6 || dim == 7,
+               kz = dim == 3 || dim == 5 || dim == 6 || dim == 7;
+    const float sx = kx ? lx / 2.0f - c0[f * 3 + 0] : 0.0f, sy = ky ? ly / 2.0f - c0[f * 3 + 1] : 0.0f,
+                sz = kz ? lz / 2.0f - c0[f * 3 + 2] : 0.0f;
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_atoms; i += (size_t)gridDim.x * blockDim.x) {
+        float *p = fr + i * 3;
+        p[0] = wrap_coordinate(p[0] + sx, lx);
+        p[1] = wrap_coordinate(p[1] + sy, ly);
+        p[2] = wrap_coordinate(p[2] + sz, lz);
+    }
+}
+
 // triclinic EXTENSION (no reference counterpart; definition in DESIGN.md, oracle orc_tric_wrap1):
 // z, then y, then x, removing whole box vectors with the reference's strict loop comparisons.
 template <bool TRANSLATE, bool SHIFTS>

@@ -478,6 +478,55 @@ class System:
         self._host_frames = None
         return sh
 
+    # ------------------------------------------------------------------ whole molecules / groups, centering
+    def add_bonds(self, pairs):
+        """Bonds as (i, j) index pairs, e.g. from CONECT records (System::add_bonds_from_pdb, pdb_io.rs:129-200).  The
+        topology stays on the host: molecules = connected components, reference atom = lowest index of a polyatomic
+        molecule (System::create_mol_references, modifying.rs:258-283); the device only gets mol_ref[i]."""
+        parent = np.arange(self.n_atoms, dtype=np.int64)
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        bonded = np.zeros(self.n_atoms, bool)
+        for a, b in np.asarray(pairs, dtype=np.int64).reshape(-1, 2):
+            bonded[a] = bonded[b] = True
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+        mol_ref = np.full(self.n_atoms, 0xFFFFFFFF, np.uint32)
+        for i in np.nonzero(bonded)[0]:
+            mol_ref[i] = find(i)
+        self._mol_ref = mol_ref
+        self._check(self._lib.groan_gpu_set_molecules(self._h, _ptr(mol_ref)), "add_bonds")
+
+    def make_molecules_whole(self):
+        """System::make_molecules_whole (modifying.rs:338-391)"""
+        if getattr(self, "_mol_ref", None) is None:  # no bonds: no polyatomic molecule, nothing moves
+            self._mol_ref = np.full(self.n_atoms, 0xFFFFFFFF, np.uint32)
+            self._check(self._lib.groan_gpu_set_molecules(self._h, _ptr(self._mol_ref)), "make_molecules_whole")
+        self._check(self._lib.groan_gpu_make_molecules_whole(self._h), "make_molecules_whole")
+        self._host_frames = None
+
+    def make_group_whole(self, name):
+        """System::make_group_whole (modifying.rs:437-465)"""
+        self._check(self._lib.groan_gpu_make_group_whole(self._h, self._gid(name)), "make_group_whole", name)
+        self._host_frames = None
+
+    def atoms_center(self, reference, dimension=Dimension.XYZ):
+        """System::atoms_center (utility.rs:109-130)"""
+        self._check(self._lib.groan_gpu_atoms_center(self._h, self._gid(reference), 0, int(dimension)), "atoms_center", reference)
+        self._host_frames = None
+
+    def atoms_center_mass(self, reference, dimension=Dimension.XYZ):
+        """System::atoms_center_mass (utility.rs:168-189)"""
+        self._check(self._lib.groan_gpu_atoms_center(self._h, self._gid(reference), 1, int(dimension)), "atoms_center_mass",
+                    reference)
+        self._host_frames = None
+
     # ------------------------------------------------------------------ RMSD (src/system/rmsd.rs)
     def _frame0(self):
         if self._host_frames is not None:

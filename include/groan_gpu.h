@@ -133,6 +133,22 @@ int groan_gpu_wrap(groan_gpu_ctx *ctx, int gid, int8_t *shifts);
 /* System::atoms_translate / group_translate (modifying.rs:73; atom.rs:498-511) */
 int groan_gpu_translate(groan_gpu_ctx *ctx, int gid, const float t[3], int8_t *shifts);
 
+/* ---- whole groups / molecules, centering (in place on the current batch) ---- */
+/* System::make_group_whole (modifying.rs:437-465): every atom of the group goes to c + vector_to(c, pos) with
+ * c = group_estimate_center of the frame.  Errors as group_estimate_center. */
+int groan_gpu_make_group_whole(groan_gpu_ctx *ctx, int gid);
+/* The molecule topology lives on the host (bonds, System::mol_references: modifying.rs:258-283).  mol_ref[i], i < n_atoms:
+ * index of the reference atom of atom i's molecule = the molecule's lowest atom index (mol_ref[r] == r for a reference atom),
+ * GROAN_NO_MOLECULE for atoms of monoatomic molecules, which make_molecules_whole leaves untouched. */
+#define GROAN_NO_MOLECULE 0xFFFFFFFFu
+int groan_gpu_set_molecules(groan_gpu_ctx *ctx, const uint32_t *mol_ref);
+/* System::make_molecules_whole (modifying.rs:338-391): reference atoms are wrapped into the box, every other atom of a
+ * polyatomic molecule goes to ref + vector_to(ref, pos).  GROAN_EINVAL before groan_gpu_set_molecules. */
+int groan_gpu_make_molecules_whole(groan_gpu_ctx *ctx);
+/* System::atoms_center (weighted = 0) / atoms_center_mass (1) (utility.rs:109-130,168-189): all atoms are translated by
+ * box_centre - group_estimate_center/com(gid), restricted to the axes of dim (GROAN_DIM_*), and wrapped. */
+int groan_gpu_atoms_center(groan_gpu_ctx *ctx, int gid, int weighted, int dim);
+
 /* ---- RMSD / Kabsch ----------------------------------------------------------------------------- */
 /* RMSDConverterAnalyzer::new (rmsd.rs:186-203): the reference may be a different System (own atom count,
  * own index list for the same group name, rmsd.rs:823-841).  ref_mass: the n_ref masses of the REFERENCE

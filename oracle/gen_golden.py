@@ -100,6 +100,35 @@ def quantise(frames, prec):
     return q.astype(np.int16)
 
 
+def read_pdb(path):
+    """ATOM/HETATM coordinates in nm (f32 parse, then / 10.0 in f32: pdb_io.rs:348-400), CRYST1 lengths (pdb_io.rs:412-430),
+    CONECT bonds as index pairs (atom numbers -> indices, pdb_io.rs:129-200,463-520)"""
+    xyz, numbers, box, conect = [], [], None, []
+    with open(path) as fh:
+        for ln in fh:
+            ln = ln.rstrip("\n")
+            if ln[:4] == "ATOM" or ln[:6] == "HETATM":
+                numbers.append(int(ln[6:11]))
+                xyz.append([np.float32(ln[30 + 8 * k:38 + 8 * k]) / np.float32(10.0) for k in range(3)])
+            elif ln[:6] == "CRYST1":
+                box = [np.float32(ln[6 + 9 * k:15 + 9 * k]) / np.float32(10.0) for k in range(3)]
+            elif ln[:6] == "CONECT":
+                conect.append(ln)
+    num2idx = {a: i for i, a in enumerate(numbers)}
+    bonds = set()
+    for ln in conect:
+        a = num2idx[int(ln[6:11])]
+        it = 11
+        while it + 4 < len(ln):
+            t = ln[it:it + 5].strip()
+            if t:
+                b = num2idx[int(t)]
+                if a != b:
+                    bonds.add((min(a, b), max(a, b)))
+            it += 5
+    return np.array(xyz, np.float32), np.array(box, np.float32), np.array(sorted(bonds), np.uint32)
+
+
 PROTEIN_RES = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLU", "GLN", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE",
                "PRO", "SER", "THR", "TRP", "TYR", "VAL"}
 
@@ -150,6 +179,14 @@ def main():
         assert f.shape == (11, 50, 3)
         tri[name + "_gro_xyz"], tri[name + "_gro_box"], tri[name + "_frames"], tri[name + "_boxes"] = gx, gb, f, b
     np.savez_compressed(os.path.join(OUT, "triclinic.npz"), **tri)
+
+    # ---- make_group_whole / make_molecules_whole goldens (modifying.rs:1108-1153)
+    cxyz, cbox, cbonds = read_pdb(os.path.join(TF, "conect.pdb"))
+    wg, wgbox, _, _ = read_gro(os.path.join(TF, "whole_group_expected.gro"))
+    wm, wmbox, _, _ = read_gro(os.path.join(TF, "whole_molecules_expected.gro"))
+    assert cxyz.shape == wg.shape == wm.shape == (50, 3), (cxyz.shape, wg.shape, wm.shape)
+    np.savez_compressed(os.path.join(OUT, "conect.npz"), xyz=cxyz, box=cbox, bonds=cbonds,
+                        translate=np.array([3.5, 4.5, -3.0], np.float32), whole_group=wg, whole_molecules=wm)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

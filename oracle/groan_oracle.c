@@ -250,6 +250,71 @@ int orc_translate(float *xyz, size_t stride, const uint32_t *idx, size_t g, cons
     return ORC_OK;
 }
 
+/* ------------------------------------------------------------------ whole molecules / groups, centering */
+
+/* Vector3D::filter (vector3d.rs): keep the components of `dim`, zero the others.
+ * dim: 0 None, 1 X, 2 Y, 3 Z, 4 XY, 5 XZ, 6 YZ, 7 XYZ (Dimension, dimension.rs:15-25) */
+static void filter_dim(float v[3], int dim) {
+    const int keep_x = (dim == 1 || dim == 4 || dim == 5 || dim == 7);
+    const int keep_y = (dim == 2 || dim == 4 || dim == 6 || dim == 7);
+    const int keep_z = (dim == 3 || dim == 5 || dim == 6 || dim == 7);
+    if (!keep_x) v[0] = 0.0f;
+    if (!keep_y) v[1] = 0.0f;
+    if (!keep_z) v[2] = 0.0f;
+}
+
+/* System::make_group_whole, modifying.rs:437-465: c = group_estimate_center; pos = c + vector_to(c, pos) */
+int orc_make_group_whole(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float L[3]) {
+    float c[3];
+    int st = orc_estimate_center(xyz, stride, idx, g, NULL, L, c);
+    if (st) return st;
+    for (size_t i = 0; i < g; i++) {
+        float *p = POS(xyz, stride, idx[i]);
+        float v[3];
+        orc_vector_to(c, p, L, v);
+        for (int k = 0; k < 3; k++) p[k] = c[k] + v[k];
+    }
+    return ORC_OK;
+}
+
+/* System::make_molecules_whole, modifying.rs:338-391.  mol_ref[i] = index of the reference atom of atom i's molecule (the
+ * lowest index of the molecule, modifying.rs:258-283); ORC_NO_MOL for atoms of monoatomic molecules (left untouched).
+ * The reference atom is wrapped into the box, every other atom goes to ref + vector_to(ref, pos). */
+int orc_make_molecules_whole(float *xyz, size_t stride, size_t n, const uint32_t *mol_ref, const float L[3]) {
+    if (L[0] == 0.0f || L[1] == 0.0f || L[2] == 0.0f) return ORC_EZEROBOX;
+    for (size_t i = 0; i < n; i++) /* references first: they are the lowest indices of their molecules in the reference, too */
+        if (mol_ref[i] == (uint32_t)i) {
+            float *p = POS(xyz, stride, i);
+            for (int k = 0; k < 3; k++) p[k] = orc_wrap1(p[k], L[k]);
+        }
+    for (size_t i = 0; i < n; i++) {
+        if (mol_ref[i] == ORC_NO_MOL || mol_ref[i] == (uint32_t)i) continue;
+        const float *r = POS(xyz, stride, mol_ref[i]);
+        float *p = POS(xyz, stride, i);
+        float v[3];
+        orc_vector_to(r, p, L, v);
+        for (int k = 0; k < 3; k++) p[k] = r[k] + v[k];
+    }
+    return ORC_OK;
+}
+
+/* System::atoms_center / atoms_center_mass, utility.rs:109-130,168-189: shift = box_centre - estimate(reference group),
+ * filtered by the dimension, then atoms_translate (all n atoms: pos += shift; wrap) */
+int orc_atoms_center(float *xyz, size_t stride, size_t n, const uint32_t *idx, size_t g, const float *mass, int dim,
+                     const float L[3]) {
+    float c[3];
+    int st = orc_estimate_center(xyz, stride, idx, g, mass, L, c);
+    if (st) return st;
+    float shift[3];
+    for (int k = 0; k < 3; k++) shift[k] = L[k] / 2.0f - c[k]; /* get_box_center, mod.rs:298-308 */
+    filter_dim(shift, dim);
+    for (size_t i = 0; i < n; i++) {
+        float *p = POS(xyz, stride, i);
+        for (int k = 0; k < 3; k++) p[k] = orc_wrap1(p[k] + shift[k], L[k]);
+    }
+    return ORC_OK;
+}
+
 /* ------------------------------------------------------------------ 3x3 SVD (f64 one-sided Jacobi) */
 /* nalgebra's Matrix3::svd (rmsd.rs:573) is un-vendored; the optimal rotation is unique for
  * rank >= 2 H, pinned by rmsd.rs:618-780 to 1e-6.  Singular values sorted descending like nalgebra. */

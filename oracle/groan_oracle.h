@@ -72,6 +72,11 @@ int orc_all_distances_minmax(const float *xyz, size_t stride, const uint32_t *id
                              size_t g2, int dim, const float L[3], float *dmin, uint32_t *imin /*[2] = (i,j)*/,
                              float *dmax, uint32_t *imax, float cutoff, uint64_t *count_below);
 int orc_wrap(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float L[3], int8_t *shifts /* g*3 or NULL */); /* iterators.rs:1548, vector3d.rs:380 */
+#define ORC_NO_MOL 0xFFFFFFFFu
+int orc_make_group_whole(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float L[3]);   /* modifying.rs:437-465 */
+int orc_make_molecules_whole(float *xyz, size_t stride, size_t n, const uint32_t *mol_ref, const float L[3]); /* modifying.rs:338-391 */
+int orc_atoms_center(float *xyz, size_t stride, size_t n, const uint32_t *idx, size_t g, const float *mass /* nullable */, int dim,
+                     const float L[3]);                                                                /* utility.rs:109-189 */
 int orc_translate(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float t[3], const float L[3],
                   int8_t *shifts);                                                                                /* atom.rs:498-511 */
 

@@ -217,6 +217,41 @@ def translate(xyz, idx, t, box):
     return x, sh
 
 
+NO_MOL = 0xFFFFFFFF
+
+
+def make_group_whole(xyz, idx, box):
+    """System::make_group_whole (modifying.rs:437-465); returns the modified copy"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    i = _idx(idx)
+    _chk(lib().orc_make_group_whole(_fp(x), _sz(3), i.ctypes.data_as(_u), _sz(i.size), _fp(L)))
+    return x
+
+
+def make_molecules_whole(xyz, mol_ref, box):
+    """System::make_molecules_whole (modifying.rs:338-391); mol_ref[i] = reference atom of i's molecule or NO_MOL"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    r = np.ascontiguousarray(mol_ref, dtype=np.uint32)
+    _chk(lib().orc_make_molecules_whole(_fp(x), _sz(3), _sz(x.shape[0]), r.ctypes.data_as(_u), _fp(L)))
+    return x
+
+
+def atoms_center(xyz, idx, dim, box, mass=None):
+    """System::atoms_center / atoms_center_mass (utility.rs:109-189); dim as in distance(); returns the modified copy"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3).copy()
+    i = _idx(idx)
+    m = _f32(mass) if mass is not None else None
+    _chk(lib().orc_atoms_center(_fp(x), _sz(3), _sz(x.shape[0]), i.ctypes.data_as(_u), _sz(i.size),
+                                _fp(m) if m is not None else None, C.c_int(DIM[dim]), _fp(L)))
+    return x
+
+
 def kabsch(p, q, w, cp, cq, sum_w):
     p, q, w = _f32(p).reshape(-1, 3), _f32(q).reshape(-1, 3), _f32(w)
     r, t = np.zeros(9, np.float32), np.zeros(3, np.float32)

@@ -66,3 +66,28 @@ def aa_pep():
 @pytest.fixture(scope="session")
 def tric():
     return load_golden("triclinic")
+
+
+@pytest.fixture(scope="session")
+def conect():
+    """conect.pdb (50 atoms, one CONECT-bonded molecule + one free atom) with the reference's make-whole goldens"""
+    return load_golden("conect")
+
+
+def mol_refs(n, bonds):
+    """System::create_mol_references (modifying.rs:258-283): lowest index of every polyatomic molecule, per atom"""
+    parent = list(range(n))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    bonded = np.zeros(n, bool)
+    for a, b in np.asarray(bonds, dtype=np.int64).reshape(-1, 2):
+        bonded[a] = bonded[b] = True
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    return np.array([find(i) if bonded[i] else 0xFFFFFFFF for i in range(n)], np.uint32)

@@ -859,3 +859,94 @@ def test_back_to_back_calls_keep_stream_order():
         out[name] = (want_wide, want_narrow)
     for a, b in zip(out["device"][0] + out["device"][1], out["host"][0] + out["host"][1]):
         assert np.array_equal(bits(a), bits(b))
+
+
+# ------------------------------------------------------------------ whole groups / molecules, centering
+def test_make_whole_goldens_gpu(conect):
+    """modifying.rs:1108-1153: conect.pdb translated by (3.5, 4.5, -3.0), then make_group_whole("all") /
+    make_molecules_whole(): the reference's expected .gro files (3 decimals) and the ref32 oracle"""
+    from conftest import mol_refs
+    xyz, box, n = conect["xyz"], conect["box"], conect["xyz"].shape[0]
+    s = _sys(n)
+    s.set_frames(xyz, box)
+    s.atoms_translate(conect["translate"])
+    moved = s.get_frames()[0].copy()
+    assert np.array_equal(bits(moved), bits(orc.translate(xyz, np.arange(n), conect["translate"], box)[0]))
+    s.make_group_whole("all")
+    got = s.get_frames()[0]
+    assert np.abs(got - conect["whole_group"]).max() < 5.1e-4
+    assert np.abs(got - orc.make_group_whole(moved, np.arange(n), box)).max() <= TOL_CENTER
+    s.set_frames(moved, box)
+    s.add_bonds(conect["bonds"])
+    s.make_molecules_whole()
+    got = s.get_frames()[0]
+    assert np.abs(got - conect["whole_molecules"]).max() < 5.1e-4
+    # per-atom arithmetic is the reference's, f32: bit-identical to the oracle
+    assert np.array_equal(bits(got), bits(orc.make_molecules_whole(moved, mol_refs(n, conect["bonds"]), box)))
+
+
+@pytest.mark.parametrize("dim", ["None", "X", "Y", "Z", "XY", "XZ", "YZ", "XYZ"])
+def test_atoms_center_gpu(example, dim):
+    """utility.rs:336-520 through the oracle (pinned to those numbers by tests/test_oracle_kat.py): centre and COM variants"""
+    xyz, box = example["xyz"], example["box"]
+    n = xyz.shape[0]
+    m = np.random.default_rng(6).uniform(1.0, 80.0, n).astype(np.float32)
+    s = _sys(n, masses=m, max_frames=2)
+    s.group_create_from_indices("Protein", example["Protein"])
+    for weighted in (False, True):
+        s.set_frames(np.stack([xyz, xyz + np.float32(0.37)]), np.stack([box, box]))
+        (s.atoms_center_mass if weighted else s.atoms_center)("Protein", _dim(dim))
+        got = s.get_frames()
+        for f, src in enumerate((xyz, xyz + np.float32(0.37))):
+            exp = orc.atoms_center(src, example["Protein"], dim, box, mass=m[example["Protein"]] if weighted else None)
+            L = box.diagonal()
+            d = np.abs(got[f] - exp)
+            d = np.minimum(d, np.abs(d - L))  # an atom within 1e-6 of a box face may land on either side of it
+            assert d.max() <= TOL_CENTER, (dim, weighted, f, d.max())
+
+
+def test_make_whole_synthetic_molecules():
+    """many small molecules scattered over the box, several frames, atoms shifted by random whole box vectors: every molecule
+    comes out whole (bit-identical to the oracle), free atoms are untouched, and the group version agrees with the oracle"""
+    rng = np.random.default_rng(12)
+    n_mol, per = 20_000, 5
+    n = n_mol * per + 777  # + free atoms
+    L = np.array([11.0, 12.5, 9.75], np.float32)
+    F = 3
+    frames = np.empty((F, n, 3), np.float32)
+    for f in range(F):
+        start = rng.uniform(0, L, size=(n_mol, 1, 3))
+        mol = start + np.cumsum(rng.normal(0, 0.12, size=(n_mol, per, 3)), axis=1)
+        free = rng.uniform(-0.2 * L, 1.2 * L, size=(777, 3))
+        x = np.concatenate([mol.reshape(-1, 3), free]).astype(np.float32)
+        x[: n_mol * per] += (rng.integers(-2, 3, size=(n_mol * per, 3)) * L).astype(np.float32)
+        frames[f] = x
+    bonds = np.stack([np.arange(n_mol * per - 1), np.arange(1, n_mol * per)], axis=1)
+    bonds = bonds[(bonds[:, 1] % per) != 0]
+    from conftest import mol_refs
+    ref = mol_refs(n, bonds)
+    s = _sys(n, max_frames=F)
+    s.add_bonds(bonds)
+    s.set_frames(frames, np.tile(L, (F, 1)))
+    s.make_molecules_whole()
+    got = s.get_frames()
+    for f in range(F):
+        exp = orc.make_molecules_whole(frames[f], ref, L)
+        assert np.array_equal(bits(got[f]), bits(exp)), f
+        m = got[f, : n_mol * per].reshape(n_mol, per, 3)
+        assert np.abs(m - m[:, :1]).max() < 2.0  # whole: every atom within a few bond lengths of its reference atom
+        assert np.all((m[:, 0] >= 0) & (m[:, 0] <= L))  # reference atoms inside the box
+    idx = np.arange(40, 40 + per * 300)
+    s.group_create_from_indices("blob", idx)
+    small = frames.copy()
+    small[:, idx] = (np.float32(3.0) + 0.2 * frames[:, idx] / L).astype(np.float32) + \
+        (rng.integers(-1, 2, size=(F, len(idx), 3)) * L).astype(np.float32)
+    s.set_frames(small, np.tile(L, (F, 1)))
+    s.make_group_whole("blob")
+    got = s.get_frames()
+    for f in range(F):
+        exp = orc.make_group_whole(small[f], idx, L)
+        assert np.abs(got[f] - exp).max() <= TOL_CENTER
+        assert np.ptp(got[f, idx], axis=0).max() < 1.2  # the blob spans ~1 nm; before, its atoms were up to a box apart
+        other = np.setdiff1d(np.arange(n), idx)
+        assert np.array_equal(bits(got[f, other]), bits(small[f, other]))

@@ -189,6 +189,49 @@ def test_atoms_wrap_restores(example):
     assert not sh[untouched].any()
 
 
+# ---- make_group_whole / make_molecules_whole (modifying.rs:1079-1153), atoms_center (utility.rs:336-520)
+def test_make_whole_goldens(conect):
+    from conftest import mol_refs
+    xyz, box, n = conect["xyz"], conect["box"], conect["xyz"].shape[0]
+    moved, _ = orc.translate(xyz, np.arange(n), conect["translate"], box)
+    # whole_group_expected.gro / whole_molecules_expected.gro are written with 3 decimals: half a quantum + f32 noise
+    assert np.abs(orc.make_group_whole(moved, np.arange(n), box) - conect["whole_group"]).max() < 5.1e-4
+    ref = mol_refs(n, conect["bonds"])
+    assert (ref == 0).sum() == n - 1 and ref[-1] == orc.NO_MOL  # one bonded molecule, the last atom is free
+    whole = orc.make_molecules_whole(moved, ref, box)
+    assert np.abs(whole - conect["whole_molecules"]).max() < 5.1e-4
+    assert np.array_equal(whole[-1].view(np.uint32), moved[-1].view(np.uint32))  # monoatomic: untouched
+
+
+def test_make_group_whole_artificial():
+    # modifying.rs:1079-1106: box 5^3... three atoms around the corner end up on the same side
+    xyz = np.array([[1.0, 4.0, 2.0], [4.0, 1.0, 2.0], [1.0, 1.0, 2.0]], np.float32)
+    w = orc.make_group_whole(xyz, [0, 1, 2], [5.0, 5.0, 5.0])
+    d = w[:, None, :] - w[None, :, :]
+    assert np.abs(d).max() <= 2.5 + 1e-5  # nobody is further than half a box from anybody else
+    assert np.abs(((w - xyz) / 5.0) - np.rint((w - xyz) / 5.0)).max() < 1e-6  # only whole box vectors were added
+
+
+@pytest.mark.parametrize("dim,a1,a2", [
+    ("None", (9.497, 1.989, 7.498), (8.829, 11.186, 2.075)),
+    ("X", (6.1465545, 1.989, 7.498), (5.478555, 11.186, 2.075)),
+    ("Y", (9.497, 6.033055, 7.498), (8.829, 2.2167444, 2.075)),
+    ("Z", (9.497, 1.989, 7.6634398), (8.829, 11.186, 2.2404397)),
+    ("XY", (6.1465545, 6.033055, 7.498), (5.478555, 2.2167444, 2.075)),
+])
+def test_atoms_center_kats(example, dim, a1, a2):
+    # utility.rs:336-450: first and last atom of example.gro after centering Protein
+    c = orc.atoms_center(example["xyz"], example["Protein"], dim, example["box"])
+    assert np.abs(c[0] - np.array(a1, np.float32)).max() < 2e-6, c[0]
+    assert np.abs(c[-1] - np.array(a2, np.float32)).max() < 2e-6, c[-1]
+    if dim != "None":
+        e = orc.estimate_center(c, example["Protein"], example["box"])
+        bc = example["box"].diagonal() / 2
+        for k, ax in enumerate("XYZ"):
+            if ax in dim:
+                assert abs(e[k] - bc[k]) < 1e-4  # the group's estimate now sits at the box centre (utility.rs:362-366)
+
+
 # ---- rmsd.rs:618-780 (Kabsch, synthetic).  nalgebra Matrix3::from([[..]]) lists COLUMNS.
 def _cols(m):
     return np.array(m, np.float32).T
