@@ -1,0 +1,384 @@
+// groan_gpu.hpp -- C++17 host-side mirror of the reference's System / Group / SimBox / Dimension interface for the
+// per-frame PBC geometry path, header-only, on top of the C ABI of groan_gpu.h (libgroan_gpu.so).
+//
+// groan_rs is Rust and this image has no Rust toolchain, so the host side above the C ABI is written in C++ with the
+// reference's names, argument meaning and error behaviour (INTEGRATION.md shows the Rust binding a maintainer would add
+// for the same entry points).  Every method evaluates the reference function it is named after for EVERY frame of the
+// current batch and returns one result per frame.  There is no CPU implementation behind any of them.
+//
+//   reference                                            here
+//   System::group_get_center (analysis.rs:105)           System::group_get_center(name)  -> std::vector<Vector3D>, one per frame
+//   System::calc_rmsd (rmsd.rs:75)                       System::calc_rmsd(reference, name) -> std::vector<float>
+//   GroupError::NotFound / EmptyGroup / InvalidSimBox    exceptions GroupError{variant = "NotFound" / ...}
+//   traj_iter_map_reduce body (parallel.rs:208-269)      FrameBatcher: buffers frames, flushes a batch to the GPU every B frames
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "groan_gpu.h"
+
+namespace groan {
+
+// src/structures/dimension.rs:15-25
+enum class Dimension : int { None = 0, X = 1, Y = 2, Z = 3, XY = 4, XZ = 5, YZ = 6, XYZ = 7 };
+
+// src/structures/vector3d.rs (only as a value type: all arithmetic happens on the device)
+using Vector3D = std::array<float, 3>;
+
+// src/structures/simbox.rs:13-26.  Stored as the row-major 3x3 matrix the xtc reader emits (io/xdrfile.rs:170-187).
+struct SimBox {
+    float m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static SimBox orthogonal(float x, float y, float z) {
+        SimBox b;
+        b.m[0] = x; b.m[4] = y; b.m[8] = z;
+        return b;
+    }
+    // From<[f32; 9]>, simbox.rs:28-52: v1x v2y v3z v1y v1z v2x v2z v3x v3y (the order of a .gro box line)
+    static SimBox from_gro(const std::array<float, 9> &g) {
+        SimBox b;
+        b.m[0] = g[0]; b.m[1] = g[3]; b.m[2] = g[4];
+        b.m[3] = g[5]; b.m[4] = g[1]; b.m[5] = g[6];
+        b.m[6] = g[7]; b.m[7] = g[8]; b.m[8] = g[2];
+        return b;
+    }
+    bool is_orthogonal() const { return m[1] == 0 && m[2] == 0 && m[3] == 0 && m[5] == 0 && m[6] == 0 && m[7] == 0; } // simbox.rs:185
+};
+
+// ---- errors (src/errors.rs): one exception type per reference enum, `variant` = the enum variant ----------------
+struct GroanError : std::runtime_error {
+    int status;
+    std::string variant;
+    size_t a = 0, b = 0; // PositionError / MassError: (frame, atom); RMSDError::InconsistentGroup: (n_ref, n_target)
+    GroanError(const std::string &v, const std::string &msg, int st) : std::runtime_error(v + ": " + msg), status(st), variant(v) {}
+};
+struct SimBoxError : GroanError { using GroanError::GroanError; };   // errors.rs:556-582
+struct GroupError : GroanError { using GroanError::GroanError; };    // errors.rs:624-650
+struct RMSDError : GroanError { using GroanError::GroanError; };     // rmsd.rs errors
+struct GpuError : GroanError { using GroanError::GroanError; };      // CUDA failure / misuse of the batch interface
+
+class System {
+  public:
+    // n_atoms atoms; up to max_frames frames per batch; one System = one GPU context = one host thread
+    explicit System(size_t n_atoms, size_t max_frames = 1, int device = 0) : n_atoms_(n_atoms), max_frames_(max_frames) {
+        const int st = groan_gpu_create(device, n_atoms, max_frames, &ctx_);
+        if (st != GROAN_OK) throw GpuError("Create", groan_gpu_strerror(st), st);
+        groups_["all"] = Group{GROAN_GROUP_ALL, {}};
+    }
+    ~System() {
+        if (ctx_) groan_gpu_destroy(ctx_);
+    }
+    System(const System &) = delete;
+    System &operator=(const System &) = delete;
+
+    size_t get_n_atoms() const { return n_atoms_; }
+    size_t n_frames() const { return n_frames_; }
+
+    // masses per atom (Atom::mass is Option<f32>: a negative value = "no mass"); apply before creating groups
+    void set_masses(std::vector<float> masses) {
+        if (masses.size() != n_atoms_) throw GpuError("InvalidArgument", "one mass per atom expected", GROAN_EINVAL);
+        masses_ = std::move(masses);
+        for (auto &kv : groups_)
+            if (kv.second.gid >= 0) upload_group(kv.second);
+    }
+
+    // System::group_create_from_indices (groups.rs) -> Group::from_indices (container.rs:51-115): sorted, de-duplicated
+    void group_create_from_indices(const std::string &name, std::vector<uint32_t> indices) {
+        std::sort(indices.begin(), indices.end());
+        indices.erase(std::unique(indices.begin(), indices.end()), indices.end());
+        if (!indices.empty() && indices.back() >= n_atoms_) throw GroupError("InvalidIndex", name, GROAN_EINVAL);
+        auto it = groups_.find(name);
+        Group g;
+        if (it != groups_.end() && it->second.gid >= 0) g.gid = it->second.gid; // overwrite, like the reference (with a warning there)
+        else if (next_gid_ >= GROAN_MAX_GROUPS) throw GpuError("Capacity", "too many groups", GROAN_ECAPACITY);
+        else g.gid = next_gid_++;
+        g.indices = std::move(indices);
+        upload_group(g);
+        groups_[name] = std::move(g);
+    }
+    void group_create_from_range(const std::string &name, uint32_t first, uint32_t last_inclusive) {
+        std::vector<uint32_t> idx;
+        for (uint32_t i = first; i <= last_inclusive; i++) idx.push_back(i);
+        group_create_from_indices(name, std::move(idx));
+    }
+    bool group_exists(const std::string &name) const { return groups_.count(name) != 0; }
+    size_t group_get_n_atoms(const std::string &name) const {
+        const Group &g = group(name, false);
+        return g.gid == GROAN_GROUP_ALL ? n_atoms_ : g.indices.size();
+    }
+
+    // ---- frames: what FrameData::update_system would copy into Vec<Atom> (traj_read.rs:50-63), for a whole batch
+    // xyz: n_frames x n_atoms x 3; boxes: n_frames entries or nullptr (= the system has no box)
+    void set_frames(const float *xyz, const SimBox *boxes, size_t n_frames) {
+        std::vector<float> b;
+        if (boxes) {
+            b.resize(n_frames * 9);
+            for (size_t f = 0; f < n_frames; f++) std::memcpy(&b[f * 9], boxes[f].m, sizeof(boxes[f].m));
+        }
+        check(groan_gpu_push_frames(ctx_, xyz, boxes ? b.data() : nullptr, n_frames), "set_frames");
+        n_frames_ = n_frames;
+        frame0_.assign(xyz, xyz + n_atoms_ * 3); // a System used as an RMSD reference is read on the host (rmsd.rs:186-203)
+        has_box0_ = boxes != nullptr;
+        if (boxes) box0_ = boxes[0];
+        version_++;
+    }
+    void set_frame(const std::vector<Vector3D> &positions, const SimBox &box) {
+        if (positions.size() != n_atoms_) throw GpuError("InvalidArgument", "one position per atom expected", GROAN_EINVAL);
+        set_frames(&positions[0][0], &box, 1);
+    }
+    std::vector<float> get_frames() {
+        std::vector<float> out(n_frames_ * n_atoms_ * 3);
+        check(groan_gpu_get_frames(ctx_, out.data()), "get_frames");
+        return out;
+    }
+    void sync() { check(groan_gpu_sync(ctx_), "sync"); }
+
+    // ---- centres (src/system/analysis.rs:52,105,258; iterators.rs)
+    std::vector<Vector3D> group_estimate_center(const std::string &name) { return centre(name, 0, 0); }
+    std::vector<Vector3D> group_estimate_com(const std::string &name) { return centre(name, 0, 1); }
+    std::vector<Vector3D> group_get_center(const std::string &name) { return centre(name, 1, 0); }
+    std::vector<Vector3D> group_get_com(const std::string &name) { return centre(name, 1, 1); }
+    std::vector<Vector3D> group_get_center_naive(const std::string &name) { return centre(name, 2, 0); }
+
+    // ---- distances (analysis.rs:348-427)
+    std::vector<float> group_distance(const std::string &g1, const std::string &g2, Dimension dim) {
+        std::vector<float> out(n_frames_);
+        check(groan_gpu_group_distance(ctx_, group(g1).gid, group(g2).gid, (int)dim, out.data()), "group_distance", g1);
+        return out;
+    }
+    // n_frames x n1 x n2, row-major like ndarray::Array2 per frame
+    std::vector<float> group_all_distances(const std::string &g1, const std::string &g2, Dimension dim) {
+        std::vector<float> out(n_frames_ * group_get_n_atoms(g1) * group_get_n_atoms(g2));
+        check(groan_gpu_all_distances(ctx_, group(g1).gid, group(g2).gid, (int)dim, out.data()), "group_all_distances", g1);
+        return out;
+    }
+
+    // ---- modifying (src/system/modifying.rs, utility.rs): in place on every frame of the batch
+    void atoms_wrap() { check(groan_gpu_wrap(ctx_, GROAN_GROUP_ALL, nullptr), "atoms_wrap"); }
+    void group_wrap(const std::string &name) { check(groan_gpu_wrap(ctx_, group(name).gid, nullptr), "group_wrap", name); }
+    void atoms_translate(const Vector3D &t) { check(groan_gpu_translate(ctx_, GROAN_GROUP_ALL, t.data(), nullptr), "atoms_translate"); }
+    void group_translate(const std::string &name, const Vector3D &t) {
+        check(groan_gpu_translate(ctx_, group(name).gid, t.data(), nullptr), "group_translate", name);
+    }
+    void make_group_whole(const std::string &name) { check(groan_gpu_make_group_whole(ctx_, group(name).gid), "make_group_whole", name); }
+    // bonds as index pairs (System::add_bonds_from_pdb); molecules and their reference atoms are worked out here, on the host
+    void add_bonds(const std::vector<std::pair<uint32_t, uint32_t>> &bonds) {
+        std::vector<uint32_t> parent(n_atoms_);
+        for (size_t i = 0; i < n_atoms_; i++) parent[i] = (uint32_t)i;
+        std::function<uint32_t(uint32_t)> find = [&](uint32_t a) {
+            while (parent[a] != a) a = parent[a] = parent[parent[a]];
+            return a;
+        };
+        std::vector<char> bonded(n_atoms_, 0);
+        for (const auto &bd : bonds) {
+            if (bd.first >= n_atoms_ || bd.second >= n_atoms_) throw GpuError("InvalidArgument", "bond index out of range", GROAN_EINVAL);
+            bonded[bd.first] = bonded[bd.second] = 1;
+            const uint32_t ra = find(bd.first), rb = find(bd.second);
+            if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb);
+        }
+        mol_ref_.assign(n_atoms_, GROAN_NO_MOLECULE);
+        for (size_t i = 0; i < n_atoms_; i++)
+            if (bonded[i]) mol_ref_[i] = find((uint32_t)i); // System::create_mol_references, modifying.rs:258-283
+        check(groan_gpu_set_molecules(ctx_, mol_ref_.data()), "add_bonds");
+    }
+    void make_molecules_whole() {
+        if (mol_ref_.empty()) {
+            mol_ref_.assign(n_atoms_, GROAN_NO_MOLECULE);
+            check(groan_gpu_set_molecules(ctx_, mol_ref_.data()), "make_molecules_whole");
+        }
+        check(groan_gpu_make_molecules_whole(ctx_), "make_molecules_whole");
+    }
+    void atoms_center(const std::string &reference, Dimension dim) {
+        check(groan_gpu_atoms_center(ctx_, group(reference).gid, 0, (int)dim), "atoms_center", reference);
+    }
+    void atoms_center_mass(const std::string &reference, Dimension dim) {
+        check(groan_gpu_atoms_center(ctx_, group(reference).gid, 1, (int)dim), "atoms_center_mass", reference);
+    }
+
+    // ---- RMSD (src/system/rmsd.rs:75,129).  `reference` may be another System with its own atom count; the group is looked
+    // up by name in both (rmsd.rs:823-841); masses come from the reference system (rmsd.rs:154,192)
+    std::vector<float> calc_rmsd(const System &reference, const std::string &name) {
+        set_reference(reference, name);
+        std::vector<float> out(n_frames_);
+        check(groan_gpu_rmsd(ctx_, group(name, true).gid, out.data(), nullptr), "calc_rmsd", name, true);
+        return out;
+    }
+    std::vector<float> calc_rmsd_and_fit(const System &reference, const std::string &name) {
+        set_reference(reference, name);
+        std::vector<float> out(n_frames_);
+        check(groan_gpu_rmsd_fit(ctx_, group(name, true).gid, out.data()), "calc_rmsd_and_fit", name, true);
+        return out;
+    }
+    // group_get_center (or group_get_com) AND calc_rmsd from one read of every frame
+    std::pair<std::vector<Vector3D>, std::vector<float>> group_center_and_rmsd(const System &reference, const std::string &name,
+                                                                              bool weighted = false) {
+        set_reference(reference, name);
+        std::vector<Vector3D> c(n_frames_);
+        std::vector<float> r(n_frames_);
+        check(groan_gpu_center_rmsd(ctx_, group(name, true).gid, weighted ? 1 : 0, &c[0][0], r.data(), nullptr), "group_center_and_rmsd",
+              name, true);
+        return {std::move(c), std::move(r)};
+    }
+
+    groan_gpu_ctx *raw() { return ctx_; }
+
+  private:
+    struct Group {
+        int gid = -2;
+        std::vector<uint32_t> indices;
+    };
+
+    const Group &group(const std::string &name, bool rmsd = false) const {
+        auto it = groups_.find(name);
+        if (it == groups_.end()) {
+            if (rmsd) throw RMSDError("NonexistentGroup", name, GROAN_ENOGROUP);
+            throw GroupError("NotFound", name, GROAN_ENOGROUP);
+        }
+        return it->second;
+    }
+    void upload_group(const Group &g) {
+        std::vector<float> m;
+        if (!masses_.empty()) {
+            m.reserve(g.indices.size());
+            for (uint32_t i : g.indices) m.push_back(masses_[i]);
+        }
+        check(groan_gpu_set_group(ctx_, g.gid, g.indices.data(), g.indices.size(), masses_.empty() ? nullptr : m.data()), "group_create");
+    }
+    std::vector<Vector3D> centre(const std::string &name, int kind, int weighted) {
+        std::vector<Vector3D> out(n_frames_);
+        const int gid = group(name).gid;
+        int st;
+        if (kind == 0) st = groan_gpu_estimate_center(ctx_, gid, weighted, &out[0][0]);
+        else if (kind == 1) st = groan_gpu_get_center(ctx_, gid, weighted, &out[0][0]);
+        else st = groan_gpu_get_center_naive(ctx_, gid, &out[0][0]);
+        check(st, "group_center", name);
+        return out;
+    }
+    void set_reference(const System &ref, const std::string &name) {
+        const Group &mine = group(name, true);
+        const Group &theirs = ref.group(name, true);
+        if (mine.gid < 0) throw RMSDError("NonexistentGroup", name + " (use a named group, not 'all')", GROAN_ENOGROUP);
+        const auto key = std::make_pair(&ref, ref.version_);
+        auto it = ref_keys_.find(name);
+        if (it != ref_keys_.end() && it->second == key) return;
+        if (ref.frame0_.empty()) throw GpuError("NoFrames", "the reference system has no frame", GROAN_ENOFRAMES);
+        std::vector<float> m;
+        if (!ref.masses_.empty())
+            for (uint32_t i : theirs.indices) m.push_back(ref.masses_[i]);
+        check(groan_gpu_rmsd_set_reference(ctx_, mine.gid, ref.frame0_.data(), ref.n_atoms_, theirs.indices.data(), theirs.indices.size(),
+                                           ref.has_box0_ ? ref.box0_.m : nullptr, m.empty() ? nullptr : m.data()),
+              "calc_rmsd", name, true);
+        ref_keys_[name] = key;
+    }
+
+    // status -> the reference's error enums (same mapping as INTEGRATION.md section 3)
+    void check(int st, const char *what, const std::string &grp = std::string(), bool rmsd = false) const {
+        if (st == GROAN_OK) return;
+        const std::string msg = std::string(groan_gpu_strerror(st)) + " in " + what + (grp.empty() ? "" : " (" + grp + ")");
+        size_t a = 0, b = 0;
+        groan_gpu_error_detail(ctx_, &a, &b);
+        switch (st) {
+        case GROAN_ENOBOX:
+        case GROAN_ENOTORTHO:
+        case GROAN_EZEROBOX: {
+            const std::string v = st == GROAN_ENOBOX ? "SimBoxError::DoesNotExist"
+                                  : st == GROAN_ENOTORTHO ? "SimBoxError::NotOrthogonal" : "panic: Box len should not be zero";
+            if (rmsd) throw RMSDError("InvalidSimBox(" + v + ")", msg, st);
+            if (!grp.empty()) throw GroupError("InvalidSimBox(" + v + ")", msg, st);
+            throw SimBoxError(v, msg, st);
+        }
+        case GROAN_EEMPTY:
+            if (rmsd) throw RMSDError("EmptyGroup", msg, st);
+            throw GroupError("EmptyGroup", msg, st);
+        case GROAN_ENOGROUP:
+            if (rmsd) throw RMSDError("NonexistentGroup", msg, st);
+            throw GroupError("NotFound", msg, st);
+        case GROAN_ENOPOS: {
+            const std::string v = "InvalidPosition(PositionError::NoPosition(" + std::to_string(b) + "))";
+            if (rmsd) {
+                RMSDError r(v, msg, st);
+                r.a = a;
+                r.b = b;
+                throw r;
+            }
+            GroupError ge(v, msg, st);
+            ge.a = a;
+            ge.b = b;
+            throw ge;
+        }
+        case GROAN_ENOMASS: {
+            const std::string v = "InvalidMass(MassError::NoMass(" + std::to_string(b) + "))";
+            if (rmsd) throw RMSDError(v, msg, st);
+            throw GroupError(v, msg, st);
+        }
+        case GROAN_EGROUPSIZE: {
+            RMSDError e("InconsistentGroup", msg + ": " + std::to_string(a) + " atoms in the reference, " + std::to_string(b) + " in the target", st);
+            e.a = a;
+            e.b = b;
+            throw e;
+        }
+        case GROAN_ECUDA: throw GpuError("CudaError", groan_gpu_last_cuda_error(ctx_), st);
+        default:
+            throw GpuError(st == GROAN_EINVAL ? "InvalidArgument" : st == GROAN_ENOFRAMES ? "NoFrames" : st == GROAN_ENOREF ? "NoReference"
+                           : st == GROAN_ECAPACITY ? "Capacity" : "Unknown", msg, st);
+        }
+    }
+
+    groan_gpu_ctx *ctx_ = nullptr;
+    size_t n_atoms_, max_frames_, n_frames_ = 0;
+    int next_gid_ = 0;
+    std::map<std::string, Group> groups_;
+    std::vector<float> masses_;
+    std::vector<uint32_t> mol_ref_;
+    std::vector<float> frame0_;
+    SimBox box0_;
+    bool has_box0_ = false;
+    unsigned long version_ = 0;
+    std::map<std::string, std::pair<const System *, unsigned long>> ref_keys_;
+};
+
+// The seam the reference offers to per-frame code is `body: Fn(&System, &mut Data)` of traj_iter_map_reduce
+// (parallel.rs:208-269) / FrameAnalyze::analyze (traj_convert.rs:76-83): one frame at a time.  A GPU operator wants batches:
+// FrameBatcher collects the frames handed to it one by one and, every `batch` frames (and at finish(), the reducer's
+// place), stages them with one set_frames and calls `flush(system, first_frame_index, n)`.
+class FrameBatcher {
+  public:
+    using Flush = std::function<void(System &, size_t first_frame, size_t n_frames)>;
+    FrameBatcher(System &system, size_t batch, Flush flush) : sys_(system), batch_(batch), flush_(std::move(flush)) {
+        xyz_.reserve(batch * system.get_n_atoms() * 3);
+        boxes_.reserve(batch);
+    }
+    // what the body closure does with the frame the reader has just produced
+    void push(const float *xyz, const SimBox &box) {
+        xyz_.insert(xyz_.end(), xyz, xyz + sys_.get_n_atoms() * 3);
+        boxes_.push_back(box);
+        if (boxes_.size() == batch_) flush();
+    }
+    void finish() {
+        if (!boxes_.empty()) flush();
+    }
+    size_t frames_seen() const { return seen_; }
+
+  private:
+    void flush() {
+        sys_.set_frames(xyz_.data(), boxes_.data(), boxes_.size());
+        flush_(sys_, seen_, boxes_.size());
+        seen_ += boxes_.size();
+        xyz_.clear();
+        boxes_.clear();
+    }
+    System &sys_;
+    size_t batch_, seen_ = 0;
+    Flush flush_;
+    std::vector<float> xyz_;
+    std::vector<SimBox> boxes_;
+};
+
+} // namespace groan

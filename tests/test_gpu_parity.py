@@ -950,3 +950,55 @@ def test_make_whole_synthetic_molecules():
         assert np.ptp(got[f, idx], axis=0).max() < 1.2  # the blob spans ~1 nm; before, its atoms were up to a box apart
         other = np.setdiff1d(np.arange(n), idx)
         assert np.array_equal(bits(got[f, other]), bits(small[f, other]))
+
+
+def test_whole_and_center_error_paths(protein):
+    """error order of the 8f rank-1 functions: modifying.rs:1155-1250 (make_*_whole_fail_*), utility.rs:452-520"""
+    import groan_rs_b200 as g
+    s = _sys(61, max_frames=2)
+    s.group_create_from_indices("Protein", range(61))
+    s.group_create_from_indices("Empty", [])
+    s.set_frames(protein["frames"][:2], None)  # no box
+    for call in (lambda: s.make_group_whole("Protein"), lambda: s.make_molecules_whole(),
+                 lambda: s.atoms_center("Protein", g.Dimension.XYZ)):
+        with pytest.raises(g.GroanError) as ei:
+            call()
+        assert "DoesNotExist" in ei.value.variant
+    s.set_frames(protein["frames"][:2], protein["boxes"][:2])
+    with pytest.raises(g.GroupError) as ei:
+        s.make_group_whole("Nope")
+    assert ei.value.variant == "NotFound"
+    with pytest.raises(g.GroupError) as ei:
+        s.atoms_center("Empty")
+    assert ei.value.variant == "EmptyGroup"
+    with pytest.raises(g.GroupError) as ei:  # no masses
+        s.atoms_center_mass("Protein")
+    assert "NoMass" in ei.value.variant
+    valid = np.ones((2, 61), np.uint8)
+    valid[1, 5] = 0
+    s.set_valid(valid)
+    with pytest.raises(g.GroupError) as ei:
+        s.make_group_whole("Protein")
+    assert "NoPosition(5)" in ei.value.variant
+    s.add_bonds([(4, 5), (5, 6)])
+    with pytest.raises(g.GroanError) as ei:
+        s.make_molecules_whole()
+    assert "NoPosition(5)" in ei.value.variant
+    s.group_create_from_indices("Head", range(5))
+    with pytest.raises(g.GroupError) as ei:  # the reference group is fine, but atoms_translate needs every atom
+        s.atoms_center("Head")
+    assert "NoPosition(5)" in ei.value.variant
+    s.add_bonds([(0, 1)])  # atom 5 is now a free atom: make_molecules_whole does not look at it (modifying.rs:267-270)
+    s.make_molecules_whole()
+    with pytest.raises(g.GpuError):  # a reference atom must be the lowest index of its molecule
+        s._check(s._lib.groan_gpu_set_molecules(s._h, np.array([1, 1] + [0xFFFFFFFF] * 59, np.uint32).ctypes.data_as(
+            __import__("ctypes").c_void_p)), "set_molecules")
+    # triclinic boxes are rejected like everywhere else in the reference (simbox.rs:230-236)
+    tb = protein["boxes"][:2].copy()
+    tb[:, 1, 0] = 1.0
+    s.set_valid(None)
+    s.set_frames(protein["frames"][:2], tb)
+    for call in (lambda: s.make_group_whole("Protein"), lambda: s.make_molecules_whole(), lambda: s.atoms_center("Protein")):
+        with pytest.raises(g.GroanError) as ei:
+            call()
+        assert "NotOrthogonal" in ei.value.variant
