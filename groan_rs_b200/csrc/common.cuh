@@ -425,6 +425,40 @@ __device__ __forceinline__ void for_each_group_atom(const FrameView &fv, const G
     }
 }
 
+// In-place update of the contiguous atoms [first, first + n) of frame f: fn(i, x, y, z) with i the position inside the
+// range and x, y, z by reference.  The 16-byte aligned body goes in quads -- three 128-bit loads and stores per four
+// atoms, the same register picture as the quad kernels -- the up-to-3 atoms before and after it one by one.
+template <typename F>
+__device__ __forceinline__ void for_each_atom_inplace(float *xyz, size_t n_atoms, int f, uint32_t first, uint32_t n, F &&fn) {
+    float *fr = xyz + (size_t)f * n_atoms * 3;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const size_t a0 = (size_t)f * n_atoms + first;
+    const bool base_ok = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0);
+    uint32_t head = base_ok ? (uint32_t)((4 - (a0 & 3)) & 3) : n;
+    if (head > n) head = n;
+    const uint32_t quads = (n - head) >> 2;
+    float4 *body = reinterpret_cast<float4 *>(fr + ((size_t)first + head) * 3);
+    for (uint32_t q = tid; q < quads; q += nth) {
+        float4 v0 = body[q * 3], v1 = body[q * 3 + 1], v2 = body[q * 3 + 2];
+        const uint32_t i = head + q * 4;
+        fn(i, v0.x, v0.y, v0.z);
+        fn(i + 1, v0.w, v1.x, v1.y);
+        fn(i + 2, v1.z, v1.w, v2.x);
+        fn(i + 3, v2.y, v2.z, v2.w);
+        body[q * 3] = v0;
+        body[q * 3 + 1] = v1;
+        body[q * 3 + 2] = v2;
+    }
+    const uint32_t tail0 = head + quads * 4, ntail = n - tail0;
+    if (tid < head + ntail) {
+        const uint32_t i = tid < head ? tid : tail0 + (tid - head);
+        float *p = fr + ((size_t)first + i) * 3;
+        float x = p[0], y = p[1], z = p[2];
+        fn(i, x, y, z);
+        p[0] = x; p[1] = y; p[2] = z;
+    }
+}
+
 // counter-based generator shared with oracle/groan_oracle.c (orc_splitmix64 / orc_hash)
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;

@@ -233,19 +233,17 @@ __global__ void __launch_bounds__(kThreads) k_fit(float *xyz, const float *box, 
     float r[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) r[k] = rot[f * 9 + k];
-    float *fr = xyz + (size_t)f * n_atoms * 3;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_atoms; i += (size_t)gridDim.x * blockDim.x) {
-        float *p = fr + i * 3;
-        const float vx = wrap_coordinate(p[0] + shx, lx) + nbx;
-        const float vy = wrap_coordinate(p[1] + shy, ly) + nby;
-        const float vz = wrap_coordinate(p[2] + shz, lz) + nbz;
+    for_each_atom_inplace(xyz, n_atoms, f, 0u, (uint32_t)n_atoms, [&](uint32_t, float &x, float &y, float &z) {
+        const float vx = wrap_coordinate(x + shx, lx) + nbx;
+        const float vy = wrap_coordinate(y + shy, ly) + nby;
+        const float vz = wrap_coordinate(z + shz, lz) + nbz;
         const float ox = (r[0] * vx + r[1] * vy) + r[2] * vz;
         const float oy = (r[3] * vx + r[4] * vy) + r[5] * vz;
         const float oz = (r[6] * vx + r[7] * vy) + r[8] * vz;
-        p[0] = ox + rcx;
-        p[1] = oy + rcy;
-        p[2] = oz + rcz;
-    }
+        x = ox + rcx;
+        y = oy + rcy;
+        z = oz + rcz;
+    });
 }
 
 // ---------------------------------------------------------------- wrap / translate (in place)
@@ -256,6 +254,15 @@ __global__ void __launch_bounds__(kThreads) k_wrap(float *xyz, const float *box,
     const int f = blockIdx.y;
     const float lx = __ldg(box + f * 9), ly = __ldg(box + f * 9 + 4), lz = __ldg(box + f * 9 + 8);
     float *fr = xyz + (size_t)f * n_atoms * 3;
+    if (!SHIFTS && !g.idx) { // contiguous range, positions only: quads of atoms, 128-bit loads and stores
+        for_each_atom_inplace(xyz, n_atoms, f, g.first, g.n, [&](uint32_t, float &x, float &y, float &z) {
+            if (TRANSLATE) { x += tx; y += ty; z += tz; }
+            x = wrap_coordinate(x, lx);
+            y = wrap_coordinate(y, ly);
+            z = wrap_coordinate(z, lz);
+        });
+        return;
+    }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
         float *p = fr + (size_t)g.atom(i) * 3;
         float x = p[0], y = p[1], z = p[2];
@@ -279,6 +286,14 @@ __global__ void __launch_bounds__(kThreads) k_make_whole(float *xyz, const float
     const float lx = __ldg(box + f * 9), ly = __ldg(box + f * 9 + 4), lz = __ldg(box + f * 9 + 8);
     const float cx = c0[f * 3 + 0], cy = c0[f * 3 + 1], cz = c0[f * 3 + 2];
     float *fr = xyz + (size_t)f * n_atoms * 3;
+    if (!g.idx) {
+        for_each_atom_inplace(xyz, n_atoms, f, g.first, g.n, [&](uint32_t, float &x, float &y, float &z) {
+            x = cx + vector_to_1(cx, x, lx);
+            y = cy + vector_to_1(cy, y, ly);
+            z = cz + vector_to_1(cz, z, lz);
+        });
+        return;
+    }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
         float *p = fr + (size_t)g.atom(i) * 3;
         const float x = p[0], y = p[1], z = p[2];
@@ -323,13 +338,11 @@ __global__ void __launch_bounds__(kThreads) k_center_atoms(float *xyz, const flo
                kz = dim == 3 || dim == 5 || dim == 6 || dim == 7;
     const float sx = kx ? lx / 2.0f - c0[f * 3 + 0] : 0.0f, sy = ky ? ly / 2.0f - c0[f * 3 + 1] : 0.0f,
                 sz = kz ? lz / 2.0f - c0[f * 3 + 2] : 0.0f;
-    float *fr = xyz + (size_t)f * n_atoms * 3;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_atoms; i += (size_t)gridDim.x * blockDim.x) {
-        float *p = fr + i * 3;
-        p[0] = wrap_coordinate(p[0] + sx, lx);
-        p[1] = wrap_coordinate(p[1] + sy, ly);
-        p[2] = wrap_coordinate(p[2] + sz, lz);
-    }
+    for_each_atom_inplace(xyz, n_atoms, f, 0u, (uint32_t)n_atoms, [&](uint32_t, float &x, float &y, float &z) {
+        x = wrap_coordinate(x + sx, lx);
+        y = wrap_coordinate(y + sy, ly);
+        z = wrap_coordinate(z + sz, lz);
+    });
 }
 
 // triclinic EXTENSION (no reference counterpart; definition in DESIGN.md, oracle orc_tric_wrap1):
