@@ -353,6 +353,44 @@ def run_gpu_arm(args):
                "d2h_bytes_per_step": F * 16, "ms_per_step": dt * 1e3 / Ke, "steps": Ke,
                "timing": "host wall clock around the steps, sync both sides"}
 
+        # the same steps fed with the xtc decoder's integers (int16 lattice points at precision 1000 + a per-frame origin,
+        # groan_gpu_push_frames_quantized): the frames are those of h_in rounded to the xtc grid, half the PCIe bytes
+        h_q = []
+        prec = 1000.0
+        x = h_in[0].numpy()
+        lat = np.rint(x.astype(np.float64) * prec).astype(np.int32)
+        origin = ((lat.reshape(F, -1, 3).min(axis=1).astype(np.int64) + lat.reshape(F, -1, 3).max(axis=1)) // 2).astype(np.int32)
+        rel = lat - origin[:, None, :]
+        assert np.abs(rel).max() < 32768
+        for _ in range(2):
+            h_q.append(torch.from_numpy(rel.astype(np.int16)).pin_memory())
+        del lat, rel
+
+        def e2e_q_step(k):
+            s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin)
+            s.group_center_and_rmsd(ref, "G", center_out=h_cen, rmsd_out=h_rmsd)
+
+        for k in range(2):
+            e2e_q_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            e2e_q_step(k)
+        s.sync()
+        torch.cuda.synchronize()
+        dtq = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtq], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtq = float(t.item())
+        assert np.all(np.abs(h_rmsd.numpy() - 0.0866) < 2e-3)
+        e2e["quantized_int16"] = {"value": world * F * Ke / dtq, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48,
+                                  "ms_per_step": dtq * 1e3 / Ke,
+                                  "note": "frames rounded to the xtc grid (precision 1000) and uploaded as the decoder's int16 lattice "
+                                          "points; floats rebuilt on the device with the reader's expression"}
+        s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
+        del h_q
+
     extras = None
     if rank == 0 and not args.no_extras:
         extras = run_extras(torch, g, local, peak)

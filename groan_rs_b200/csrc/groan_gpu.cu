@@ -84,6 +84,9 @@ struct groan_gpu_ctx {
     std::vector<uint8_t> valid; // F x N, empty = all valid
     cudaEvent_t ev_h2d = nullptr, ev_done[2] = {nullptr, nullptr};
     bool done_recorded[2] = {false, false};
+    void *d_quant[2] = {nullptr, nullptr};       // quantised frames as uploaded (groan_gpu_push_frames_quantized), one per slot
+    size_t quant_bytes = 0;
+    int32_t *d_origin[2] = {nullptr, nullptr};   // their per-frame integer origins (F x 3)
     float *h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 
@@ -945,6 +948,8 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         if (ctx->d_slot[s]) cudaFree(ctx->d_slot[s]);
         if (ctx->d_box[s]) cudaFree(ctx->d_box[s]);
         if (ctx->h_stage[s]) cudaFreeHost(ctx->h_stage[s]);
+        if (ctx->d_quant[s]) cudaFree(ctx->d_quant[s]);
+        if (ctx->d_origin[s]) cudaFree(ctx->d_origin[s]);
         if (ctx->ev_done[s]) cudaEventDestroy(ctx->ev_done[s]);
         if (ctx->ev_stage[s]) cudaEventDestroy(ctx->ev_stage[s]);
     }
@@ -1068,6 +1073,35 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
 }
 
 // ---- frames ---------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+// host -> device on the copy stream; a pageable source bounces through two pinned chunks so that the host memcpy of
+// chunk i + 1 overlaps the DMA of chunk i
+int h2d_on_copy_stream(groan_gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (classify(src) != PK_PAGEABLE) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->copy));
+        return GROAN_OK;
+    }
+    for (int s = 0; s < 2; s++)
+        if (!ctx->h_stage[s]) CK(cudaMallocHost(&ctx->h_stage[s], kStageBytes));
+    size_t off = 0;
+    int s = 0;
+    while (off < bytes) {
+        const size_t chunk = std::min(kStageBytes, bytes - off);
+        CK(cudaEventSynchronize(ctx->ev_stage[s]));
+        std::memcpy(ctx->h_stage[s], reinterpret_cast<const char *>(src) + off, chunk);
+        CK(cudaMemcpyAsync(reinterpret_cast<char *>(dst) + off, ctx->h_stage[s], chunk, cudaMemcpyHostToDevice, ctx->copy));
+        CK(cudaEventRecord(ctx->ev_stage[s], ctx->copy));
+        off += chunk;
+        s ^= 1;
+    }
+    return GROAN_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box, size_t n_frames) {
     if (!ctx || !xyz) return GROAN_EINVAL;
     int rc = begin_batch(ctx, n_frames, box, true);
@@ -1075,25 +1109,44 @@ int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box
     ctx->attached = false;
     float *dst = ctx->d_slot[ctx->slot];
     ctx->cur_xyz = dst;
-    const size_t bytes = n_frames * ctx->n_atoms * 3 * sizeof(float);
-    if (classify(xyz) != PK_PAGEABLE) {
-        CK(cudaMemcpyAsync(dst, xyz, bytes, cudaMemcpyDefault, ctx->copy));
-    } else {
-        // pageable source: bounce through two pinned chunks so that the host memcpy of chunk i+1 overlaps the DMA of chunk i
-        for (int s = 0; s < 2; s++)
-            if (!ctx->h_stage[s]) CK(cudaMallocHost(&ctx->h_stage[s], kStageBytes));
-        size_t off = 0;
-        int s = 0;
-        while (off < bytes) {
-            const size_t chunk = std::min(kStageBytes, bytes - off);
-            CK(cudaEventSynchronize(ctx->ev_stage[s]));
-            std::memcpy(ctx->h_stage[s], reinterpret_cast<const char *>(xyz) + off, chunk);
-            CK(cudaMemcpyAsync(reinterpret_cast<char *>(dst) + off, ctx->h_stage[s], chunk, cudaMemcpyHostToDevice, ctx->copy));
-            CK(cudaEventRecord(ctx->ev_stage[s], ctx->copy));
-            off += chunk;
-            s ^= 1;
+    rc = h2d_on_copy_stream(ctx, dst, xyz, n_frames * ctx->n_atoms * 3 * sizeof(float));
+    if (rc) return rc;
+    return end_batch(ctx);
+}
+
+int groan_gpu_push_frames_quantized(groan_gpu_ctx *ctx, const void *q, int elem_bytes, const int32_t *origin, float precision,
+                                    const float *box, size_t n_frames) {
+    if (!ctx || !q || (elem_bytes != 2 && elem_bytes != 4) || !(precision > 0.0f)) return GROAN_EINVAL;
+    int rc = begin_batch(ctx, n_frames, box, true);
+    if (rc) return rc;
+    ctx->attached = false;
+    const int slot = ctx->slot;
+    float *dst = ctx->d_slot[slot];
+    ctx->cur_xyz = dst;
+    const size_t cap = ctx->max_frames * ctx->n_atoms * 3 * sizeof(int32_t);
+    if (!ctx->d_quant[0]) {
+        for (int s = 0; s < 2; s++) {
+            CK(cudaMalloc(&ctx->d_quant[s], cap));
+            CK(cudaMalloc(&ctx->d_origin[s], ctx->max_frames * 3 * sizeof(int32_t)));
         }
+        ctx->quant_bytes = cap;
     }
+    const size_t count = n_frames * ctx->n_atoms * 3;
+    rc = h2d_on_copy_stream(ctx, ctx->d_quant[slot], q, count * (size_t)elem_bytes);
+    if (rc) return rc;
+    if (origin) CK(cudaMemcpyAsync(ctx->d_origin[slot], origin, n_frames * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy));
+    // xdrfile.c:844: inv_precision = 1.0 / *precision (double quotient stored in a float); :915 coordinate = int * inv_precision
+    const float inv = (float)(1.0 / (double)precision);
+    const unsigned nb = (unsigned)std::min<size_t>((ctx->n_atoms * 3 + kThreads * 4 - 1) / (kThreads * 4), (size_t)kMaxBlocksPerFrame * 4);
+    dim3 grid(std::max(1u, nb), (unsigned)n_frames);
+    // on the COPY stream: ordered behind its own upload, overlapping the kernels still running on the previous batch
+    if (elem_bytes == 2)
+        k_dequantize<int16_t><<<grid, kThreads, 0, ctx->copy>>>((const int16_t *)ctx->d_quant[slot], origin ? ctx->d_origin[slot] : nullptr,
+                                                                 inv, dst, ctx->n_atoms);
+    else
+        k_dequantize<int32_t><<<grid, kThreads, 0, ctx->copy>>>((const int32_t *)ctx->d_quant[slot], origin ? ctx->d_origin[slot] : nullptr,
+                                                                 inv, dst, ctx->n_atoms);
+    LAUNCHED();
     return end_batch(ctx);
 }
 

@@ -84,4 +84,21 @@ __global__ void __launch_bounds__(kThreads) k_synth_blob(float *xyz, size_t n_at
     }
 }
 
+// Frames as the xtc decoder's integer stage holds them: coordinate = (float)(q + origin) * inv_precision, the expression of
+// external/xdrfile/xdrfile.c:915-917 (int -> float conversion, then one f32 multiply), so the floats are the reader's, bit
+// for bit.  T = int16_t (relative to a per-frame, per-axis origin) or int32_t.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_dequantize(const T *q, const int32_t *origin, float inv_precision, float *out, size_t n_atoms) {
+    const int f = blockIdx.y;
+    const size_t n3 = n_atoms * 3;
+    const T *src = q + (size_t)f * n3;
+    float *dst = out + (size_t)f * n3;
+    int32_t o[3] = {0, 0, 0};
+    if (origin) { o[0] = origin[f * 3]; o[1] = origin[f * 3 + 1]; o[2] = origin[f * 3 + 2]; }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % 3);
+        dst[i] = (float)((int32_t)src[i] + (k == 0 ? o[0] : k == 1 ? o[1] : o[2])) * inv_precision;
+    }
+}
+
 } // namespace groan

@@ -97,6 +97,14 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
  * copy stream into the slot NOT used by the previous batch, so the copy overlaps kernels still running
  * on the previous batch.  box: F x 9 row-major matrices, NULL = system has no box. */
 int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box, size_t n_frames);
+/* The same batch in the form the xtc decoder holds it one step before it emits floats: every xtc coordinate is an integer
+ * lattice point, and the float the reader hands out is (float)int * (1 / precision) (external/xdrfile/xdrfile.c:844,915-917;
+ * molly does the same).  Uploading the integers halves the bytes over PCIe, the bound of the host-fed path, when the span of
+ * a frame fits 16 bits (65 nm at the usual precision of 1000); the floats are rebuilt on the device with the reader's own
+ * expression, bit for bit (tests/test_gpu_parity.py::test_quantized_frames_are_the_readers_floats).
+ * q: F x N x 3 integers of elem_bytes (2 = int16, 4 = int32); origin: F x 3 int32 added to every q of the frame (NULL = 0). */
+int groan_gpu_push_frames_quantized(groan_gpu_ctx *ctx, const void *q, int elem_bytes, const int32_t *origin, float precision,
+                                    const float *box, size_t n_frames);
 /* zero-copy: operate in place on a caller-owned DEVICE buffer of F x N x 3 floats (16-byte aligned) */
 int groan_gpu_attach_frames(groan_gpu_ctx *ctx, float *d_xyz, const float *box, size_t n_frames);
 /* Option<Vector3D> positions: valid[f*N + i] == 0 marks "atom i has no position in frame f" (host array,

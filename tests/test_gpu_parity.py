@@ -1002,3 +1002,39 @@ def test_whole_and_center_error_paths(protein):
         with pytest.raises(g.GroanError) as ei:
             call()
         assert "NotOrthogonal" in ei.value.variant
+
+
+# ------------------------------------------------------------------ frames uploaded as the xtc decoder's integers
+def test_quantized_frames_are_the_readers_floats(example, short_traj):
+    """groan_gpu_push_frames_quantized: short_trajectory.xtc as int16 lattice points (tests/golden, proved by
+    oracle/gen_golden.py to reproduce read_xtc's floats bit for bit) against the same frames pushed as f32: the frames on
+    the device and every result are bit-identical; int32 and a per-frame origin give the same again."""
+    from conftest import load_golden
+    g0 = load_golden("short_trajectory")
+    q, prec = g0["q"], float(g0["prec"])
+    frames, boxes = short_traj["frames"], short_traj["boxes"]
+    F, n = q.shape[0], q.shape[1]
+    m = np.ones(n, np.float32)
+    m[:61] = short_traj["protein_mass"]
+    ref = _sys(n, masses=m)
+    ref.group_create_from_indices("Protein", example["Protein"])
+    ref.set_frames(example["xyz"], example["box"].reshape(1, 9))
+    res = []
+    org = q.reshape(F, -1, 3).min(axis=1).astype(np.int32)
+    variants = (("f32", None), ("i16", (q, None)), ("i32", (q.astype(np.int32), None)),
+                ("i16+origin", ((q.astype(np.int32) - org[:, None, :]).astype(np.int16), org)))
+    for name, v in variants:
+        s = _sys(n, masses=m, max_frames=F)
+        s.group_create_from_indices("Protein", example["Protein"])
+        if v is None:
+            s.set_frames(frames, boxes)
+        else:
+            s.set_frames_quantized(v[0], prec, boxes, origin=v[1])
+        got = s.get_frames()
+        assert np.array_equal(bits(got), bits(frames)), name
+        res.append((s.group_get_center("Protein"), s.calc_rmsd(ref, "Protein")))
+    for c, r in res[1:]:
+        assert np.array_equal(bits(c), bits(res[0][0])) and np.array_equal(bits(r), bits(res[0][1]))
+    kat = [0.23669721, 0.2634763, 0.26021627, 0.21364464, 0.22166993, 0.19383307, 0.26422343, 0.27013618, 0.26398134,
+           0.23475659, 0.24208021]  # rmsd.rs:811-814
+    assert np.abs(res[1][1] - np.array(kat, np.float32)).max() < TOL_RMSD
