@@ -391,7 +391,20 @@ __device__ __forceinline__ void for_each_group_atom(const FrameView &fv, const G
     const float *fr = fv.frame(f);
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (g.idx) {
-        for (uint32_t i = tid; i < g.n; i += nth) {
+        // index list: four atoms per thread and trip, all twelve coordinate loads in flight before the first use
+        // (one atom per trip left the gather latency bound: 3 dependent-on-index loads at a time per thread)
+        uint32_t i = tid;
+        for (; i + 3 * nth < g.n; i += 4 * nth) {
+            const uint32_t a0 = __ldg(g.idx + i), a1 = __ldg(g.idx + i + nth), a2 = __ldg(g.idx + i + 2 * nth), a3 = __ldg(g.idx + i + 3 * nth);
+            const float *p0 = fr + (size_t)a0 * 3, *p1 = fr + (size_t)a1 * 3, *p2 = fr + (size_t)a2 * 3, *p3 = fr + (size_t)a3 * 3;
+            const float x0 = __ldg(p0), y0 = __ldg(p0 + 1), z0 = __ldg(p0 + 2), x1 = __ldg(p1), y1 = __ldg(p1 + 1), z1 = __ldg(p1 + 2);
+            const float x2 = __ldg(p2), y2 = __ldg(p2 + 1), z2 = __ldg(p2 + 2), x3 = __ldg(p3), y3 = __ldg(p3 + 1), z3 = __ldg(p3 + 2);
+            fn(i, x0, y0, z0);
+            fn(i + nth, x1, y1, z1);
+            fn(i + 2 * nth, x2, y2, z2);
+            fn(i + 3 * nth, x3, y3, z3);
+        }
+        for (; i < g.n; i += nth) {
             const float *p = fr + (size_t)__ldg(g.idx + i) * 3;
             fn(i, __ldg(p), __ldg(p + 1), __ldg(p + 2));
         }
