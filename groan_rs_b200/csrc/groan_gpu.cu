@@ -26,6 +26,7 @@
 #include "kernels_synth.cuh"
 #include "kernels_tma.cuh"
 #include "kernels_quad.cuh"
+#include "kernels_cells.cuh"
 
 using namespace groan;
 
@@ -1281,6 +1282,85 @@ int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, 
     if ((rc = deliver(ctx, imin, o.imin, F * 2 * sizeof(uint32_t)))) return rc;
     if ((rc = deliver(ctx, imax, o.imax, F * 2 * sizeof(uint32_t)))) return rc;
     return deliver(ctx, count, o.count, F * sizeof(uint64_t));
+}
+
+// ---- cutoff pair search through a cell grid ---------------------------------------
+int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uint64_t *count, uint32_t *pairs, float *dist,
+                           size_t capacity) {
+    if (!ctx || !count || !(cutoff > 0.0f) || (dist && !pairs)) return GROAN_EINVAL;
+    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
+    if (!a || !b) return GROAN_ENOGROUP;
+    // CellGrid::new: the box must exist and be orthogonal (cellgrid.rs:308-312), then the positions of the group
+    int rc = check_box(ctx, false, nullptr);
+    if (rc) return rc;
+    rc = check_pair_positions(ctx, *a, *b);
+    if (rc) return rc;
+    const size_t F = ctx->n_frames, nb_atoms = b->n;
+    if (!pairs) capacity = 0;
+    // one grid geometry for the batch, from the smallest box: cells at least cutoff * (1 + 1e-4) wide in every frame
+    float lmin[3] = {3.0e38f, 3.0e38f, 3.0e38f};
+    for (size_t f = 0; f < F; f++)
+        for (int k = 0; k < 3; k++) lmin[k] = std::min(lmin[k], ctx->h_box[f * 9 + 4 * k]);
+    long nc[3];
+    for (int k = 0; k < 3; k++) nc[k] = std::max<long>(1, std::min<long>(1024, (long)std::floor((double)lmin[k] / ((double)cutoff * 1.0001))));
+    const size_t cell_cap = std::max<size_t>(4096, std::min<size_t>((size_t)8 << 20, 4 * nb_atoms + 4096));
+    while ((size_t)nc[0] * nc[1] * nc[2] > cell_cap) {  // wider cells are always correct, only slower
+        const int k = nc[0] >= nc[1] && nc[0] >= nc[2] ? 0 : (nc[1] >= nc[2] ? 1 : 2);
+        nc[k] = (nc[k] + 1) / 2;
+    }
+    CellGeom cg = {(int)nc[0], (int)nc[1], (int)nc[2]};
+    const size_t cells = (size_t)nc[0] * nc[1] * nc[2];
+    // scratch layout (one allocation): results first, then per-frame grid storage for as many frames as fit ~1.5 GB
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t per_frame = up(nb_atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(nb_atoms * 16);
+    const size_t fb = std::max<size_t>(1, std::min<size_t>(F, ((size_t)3 << 29) / std::max<size_t>(per_frame, 1)));
+    const bool stage_pairs = pairs && classify(pairs) != PK_DEVICE, stage_dist = dist && classify(dist) != PK_DEVICE;
+    const size_t o_count = 0, o_cursor = up(F * 8), o_pairs = o_cursor + up(F * 8),
+                 o_dist = o_pairs + (stage_pairs ? up(F * capacity * 8) : 0), o_grid = o_dist + (stage_dist ? up(F * capacity * 4) : 0);
+    rc = ensure_tmp(ctx, o_grid + fb * per_frame);
+    if (rc) return rc;
+    char *base = (char *)ctx->d_tmp;
+    unsigned long long *d_count = (unsigned long long *)(base + o_count), *d_cursor = (unsigned long long *)(base + o_cursor);
+    uint32_t *d_pairs = pairs ? (stage_pairs ? (uint32_t *)(base + o_pairs) : pairs) : nullptr;
+    float *d_dist = dist ? (stage_dist ? (float *)(base + o_dist) : dist) : nullptr;
+    CK(cudaMemsetAsync(base, 0, o_pairs, ctx->compute));
+    char *grid0 = base + o_grid;
+    uint32_t *d_cell_of = (uint32_t *)grid0;
+    uint32_t *d_counts = (uint32_t *)(grid0 + fb * up(nb_atoms * 4));
+    uint32_t *d_fill = (uint32_t *)((char *)d_counts + fb * up(cells * 4));
+    uint32_t *d_offsets = (uint32_t *)((char *)d_fill + fb * up(cells * 4));
+    float4 *d_sorted = (float4 *)((char *)d_offsets + fb * up((cells + 1) * 4));
+    const GroupView ga = view_of(*a), gb = view_of(*b);
+    for (size_t f0 = 0; f0 < F; f0 += fb) {
+        const size_t nf = std::min(fb, F - f0);
+        FrameView fv = frames_of(ctx);
+        fv.xyz += f0 * ctx->n_atoms * 3;
+        fv.box += f0 * 9;
+        CK(cudaMemsetAsync(d_counts, 0, nf * cells * 4, ctx->compute));
+        const unsigned nbb = (unsigned)std::max<size_t>(1, std::min<size_t>((nb_atoms + kThreads - 1) / kThreads, (size_t)kSMs * 8));
+        if (nb_atoms) {
+            k_cell_count<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, cg, d_cell_of, d_counts, cells);
+            LAUNCHED();
+        }
+        k_cell_scan<<<(unsigned)nf, 1024, 0, ctx->compute>>>(d_counts, d_offsets, d_fill, cells);
+        LAUNCHED();
+        if (nb_atoms) {
+            k_cell_fill<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, d_cell_of, d_fill, d_sorted, cells);
+            LAUNCHED();
+        }
+        if (a->n) {
+            const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((a->n + 7) / 8, (size_t)kSMs * 16));
+            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, d_offsets, d_sorted, cells, cutoff,
+                                                                               d_count + f0, d_pairs ? d_pairs + f0 * capacity * 2 : nullptr,
+                                                                               d_dist ? d_dist + f0 * capacity : nullptr,
+                                                                               (unsigned long long)capacity, d_cursor + f0);
+            LAUNCHED();
+        }
+    }
+    if ((rc = deliver(ctx, count, d_count, F * sizeof(uint64_t)))) return rc;
+    if (stage_pairs && (rc = deliver(ctx, pairs, d_pairs, F * capacity * 8))) return rc;
+    if (stage_dist && (rc = deliver(ctx, dist, d_dist, F * capacity * 4))) return rc;
+    return GROAN_OK;
 }
 
 // ---- wrap / translate -----------------------------------------------------------------------------

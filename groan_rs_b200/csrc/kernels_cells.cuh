@@ -1,0 +1,162 @@
+// kernels_cells.cuh -- cutoff pair search through a cell grid: the sparse counterpart of the all-pairs kernels.
+//
+// Reference: CellGrid::new (cellgrid.rs:301-381) bins the atoms of a group into cells, CellGrid::neighbors_iter (:383-420)
+// walks the cells around a reference point, and the users keep the atoms within a cutoff (guess.rs:362-470 bond guessing,
+// hbonds.rs:240-335 donor/acceptor search).  Here, per frame:
+//
+//   k_cell_count   cell of every atom of group B (from its wrapped position) + histogram
+//   k_cell_scan    exclusive prefix sum of the histogram (one CTA per frame)
+//   k_cell_fill    counting sort: (x, y, z, position in B) of every atom, cell by cell
+//   k_cell_query   one warp per atom of group A: the 27 cells around it (fewer when the grid is narrower than 3 cells, so
+//                  that no cell is visited twice: NeighborsRange::convert, cellgrid.rs:207-231), lanes over the atoms of a
+//                  cell, Vector3D::distance with the reference's arithmetic on the ORIGINAL coordinates (bit-identical to
+//                  the all-pairs matrix), pairs below the cutoff counted and, if asked for, appended to the frame's list
+//
+// Cells are at least cutoff * (1 + 1e-4) wide: two atoms closer than the cutoff then sit in the same or in adjacent cells
+// even if the f32 cell assignment of either is off by a rounding error at a cell boundary.
+// The order of the emitted pairs is undefined, as is the order of neighbors_iter (cellgrid.rs:141-144).
+#pragma once
+#include "common.cuh"
+#include "kernels_pairs.cuh"
+
+namespace groan {
+
+struct CellGeom {
+    int nx, ny, nz; // cells per axis
+};
+
+__device__ __forceinline__ int cell_coord(float x, float L, int n) {
+    const float w = wrap_coordinate(x, L); // in [0, L]
+    int c = (int)(w * ((float)n / L));
+    return c < 0 ? 0 : (c >= n ? n - 1 : c); // w == L (wrap keeps x == L) and rounding at the upper face
+}
+__device__ __forceinline__ uint32_t cell_index(float x, float y, float z, const BoxOrtho &B, const CellGeom &cg) {
+    const int cx = cell_coord(x, B.lx, cg.nx), cy = cell_coord(y, B.ly, cg.ny), cz = cell_coord(z, B.lz, cg.nz);
+    return ((uint32_t)cz * cg.ny + cy) * cg.nx + cx;
+}
+
+// cells per axis for a frame: the grid differs from frame to frame only through the box, and all frames share one
+// geometry chosen on the host from the SMALLEST box of the batch (cells can only get wider for the other frames)
+__global__ void __launch_bounds__(kThreads) k_cell_count(FrameView fv, GroupView gb, CellGeom cg, uint32_t *cell_of, uint32_t *counts,
+                                                          size_t cells) {
+    const int f = blockIdx.y;
+    BoxOrtho B;
+    load_box(fv.box, f, B);
+    const float *fr = fv.frame(f);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < gb.n; j += gridDim.x * blockDim.x) {
+        const float *p = fr + (size_t)gb.atom(j) * 3;
+        const uint32_t c = cell_index(__ldg(p), __ldg(p + 1), __ldg(p + 2), B, cg);
+        cell_of[(size_t)f * gb.n + j] = c;
+        atomicAdd(counts + (size_t)f * cells + c, 1u);
+    }
+}
+
+// offsets[c] = number of atoms in cells < c; cursor[c] = the same (k_cell_fill advances it).  One CTA per frame.
+__global__ void __launch_bounds__(1024) k_cell_scan(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor, size_t cells) {
+    __shared__ uint32_t part[1024];
+    const int f = blockIdx.x;
+    const uint32_t *cn = counts + (size_t)f * cells;
+    uint32_t *of = offsets + (size_t)f * (cells + 1), *cu = cursor + (size_t)f * cells;
+    const size_t per = (cells + 1023) / 1024, lo = threadIdx.x * per, hi = lo + per < cells ? lo + per : cells;
+    uint32_t sum = 0;
+    for (size_t c = lo; c < hi; c++) sum += cn[c];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (size_t c = lo; c < hi; c++) {
+        of[c] = run;
+        cu[c] = run;
+        run += cn[c];
+    }
+    if (threadIdx.x == 1023) of[cells] = part[1023];
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_fill(FrameView fv, GroupView gb, const uint32_t *cell_of, uint32_t *cursor, float4 *sorted,
+                                                         size_t cells) {
+    const int f = blockIdx.y;
+    const float *fr = fv.frame(f);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < gb.n; j += gridDim.x * blockDim.x) {
+        const float *p = fr + (size_t)gb.atom(j) * 3;
+        const uint32_t c = cell_of[(size_t)f * gb.n + j];
+        const uint32_t pos = atomicAdd(cursor + (size_t)f * cells + c, 1u);
+        sorted[(size_t)f * gb.n + pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __uint_as_float(j));
+    }
+}
+
+// neighbour offsets along one axis of n cells around cell c without visiting a cell twice (cellgrid.rs:207-231)
+__device__ __forceinline__ void axis_cells(int c, int n, int (&out)[3], int &m) {
+    if (n >= 3) {
+        out[0] = c == 0 ? n - 1 : c - 1;
+        out[1] = c;
+        out[2] = c == n - 1 ? 0 : c + 1;
+        m = 3;
+    } else {
+        for (int k = 0; k < n; k++) out[k] = k;
+        m = n;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView ga, uint32_t nb_atoms, CellGeom cg, const uint32_t *offsets,
+                                                          const float4 *sorted, size_t cells, float cutoff, unsigned long long *count,
+                                                          uint32_t *pairs, float *dist, unsigned long long capacity,
+                                                          unsigned long long *cursor) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    BoxOrtho B;
+    load_box(fv.box, f, B);
+    const float *fr = fv.frame(f);
+    const uint32_t *of = offsets + (size_t)f * (cells + 1);
+    const float4 *sb = sorted + (size_t)f * nb_atoms;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    unsigned long long mine = 0;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < ga.n; i += warps) {
+        const float *p = fr + (size_t)ga.atom(i) * 3;
+        const float ax = __ldg(p), ay = __ldg(p + 1), az = __ldg(p + 2);
+        int xs[3], ys[3], zs[3], mx, my, mz;
+        axis_cells(cell_coord(ax, B.lx, cg.nx), cg.nx, xs, mx);
+        axis_cells(cell_coord(ay, B.ly, cg.ny), cg.ny, ys, my);
+        axis_cells(cell_coord(az, B.lz, cg.nz), cg.nz, zs, mz);
+        for (int kz = 0; kz < mz; kz++)
+            for (int ky = 0; ky < my; ky++)
+                for (int kx = 0; kx < mx; kx++) {
+                    const uint32_t c = ((uint32_t)zs[kz] * cg.ny + ys[ky]) * cg.nx + xs[kx];
+                    const uint32_t lo = of[c], hi = of[c + 1];
+                    for (uint32_t s0 = lo; s0 < hi; s0 += 32) {
+                        const uint32_t s = s0 + lane;
+                        bool hit = false;
+                        float d = 0.0f;
+                        uint32_t j = 0;
+                        if (s < hi) {
+                            const float4 b = sb[s];
+                            d = pair_distance_loop<7>(ax, ay, az, b.x, b.y, b.z, B); // Vector3D::distance, XYZ (vector3d.rs:458-486)
+                            j = __float_as_uint(b.w);
+                            hit = d < cutoff;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m == 0u) continue;
+                        const int n_hit = __popc(m);
+                        if (lane == 0) mine += n_hit;
+                        if (pairs) { // one atomic per warp and step; pairs beyond the capacity are counted but not stored
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)n_hit);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+                            if (hit && at < capacity) {
+                                uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
+                                o[0] = i;
+                                o[1] = j;
+                                if (dist) dist[(size_t)f * capacity + at] = d;
+                            }
+                        }
+                    }
+                }
+    }
+    if (lane == 0 && mine) atomicAdd(count + f, mine);
+}
+
+} // namespace groan

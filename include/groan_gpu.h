@@ -134,6 +134,16 @@ int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, 
                                    uint32_t *imin /* F x 2 */, float *dmax /* F */, uint32_t *imax /* F x 2 */,
                                    uint64_t *count /* F */);
 
+/* ---- cutoff pair search through a cell grid -------------------------------- */
+/* CellGrid::new over group g2 + CellGrid::neighbors_iter around every atom of g1 + the distance filter its users apply
+ * (cellgrid.rs:301-420; guess.rs:362-470, hbonds.rs:240-335): every pair (i in g1, j in g2) with
+ * Vector3D::distance(pos_i, pos_j, XYZ) < cutoff, per frame.  Distances are bit-identical to groan_gpu_all_distances.
+ * count: F; pairs (nullable): F x capacity x 2 positions inside (g1, g2); dist (nullable, needs pairs): F x capacity.
+ * A frame with more than `capacity` pairs keeps the first `capacity` it found and still reports the full count.
+ * The order of the pairs is undefined (as the order of neighbors_iter is, cellgrid.rs:141-144).  Orthogonal boxes only. */
+int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uint64_t *count, uint32_t *pairs, float *dist,
+                           size_t capacity);
+
 /* ---- wrap / translate (in place on the current batch) ------------------------------------------ */
 /* System::atoms_wrap / group_wrap (modifying.rs:201,215; vector3d.rs:380-417).  shifts (nullable):
  * F x G x 3 int8, net number of +L steps per axis (for the triclinic extension: multiples of box vectors) */

@@ -160,6 +160,25 @@ class System {
         return out;
     }
 
+    // ---- cutoff pair search: CellGrid::new(g2) + neighbors_iter around every atom of g1 + distance filter (cellgrid.rs:301-420)
+    struct PairList {
+        std::vector<uint64_t> count;                        // per frame, always complete
+        std::vector<std::array<uint32_t, 2>> pairs;         // n_frames x capacity (positions inside g1, g2), order undefined
+        std::vector<float> dist;                            // n_frames x capacity
+        size_t capacity = 0;
+    };
+    PairList group_pairs_within(const std::string &g1, const std::string &g2, float cutoff, size_t capacity = 0) {
+        PairList out;
+        out.capacity = capacity;
+        out.count.assign(n_frames_, 0);
+        out.pairs.resize(n_frames_ * capacity);
+        out.dist.resize(n_frames_ * capacity);
+        check(groan_gpu_pairs_within(ctx_, group(g1).gid, group(g2).gid, cutoff, out.count.data(),
+                                     capacity ? &out.pairs[0][0] : nullptr, capacity ? out.dist.data() : nullptr, capacity),
+              "group_pairs_within", g1);
+        return out;
+    }
+
     // ---- modifying (src/system/modifying.rs, utility.rs): in place on every frame of the batch
     void atoms_wrap() { check(groan_gpu_wrap(ctx_, GROAN_GROUP_ALL, nullptr), "atoms_wrap"); }
     void group_wrap(const std::string &name) { check(groan_gpu_wrap(ctx_, group(name).gid, nullptr), "group_wrap", name); }

@@ -250,6 +250,31 @@ int orc_translate(float *xyz, size_t stride, const uint32_t *idx, size_t g, cons
     return ORC_OK;
 }
 
+/* ------------------------------------------------------------------ cutoff pair search */
+/* What CellGrid::neighbors_iter + a distance filter returns for every atom of group 1 over a grid of group 2
+ * (cellgrid.rs:301-420; guess.rs:362-470): the pairs with Vector3D::distance(XYZ) < cutoff -- restated as the plain double
+ * loop, which a cell grid with cells >= cutoff must reproduce as a SET (its order is undefined, cellgrid.rs:141-144).
+ * pairs / dist may be NULL; at most `capacity` pairs are stored, in row-major order; the count is always complete. */
+int orc_pairs_within(const float *xyz, size_t stride, const uint32_t *idx1, size_t g1, const uint32_t *idx2, size_t g2,
+                     float cutoff, const float L[3], uint64_t *count, uint32_t *pairs, float *dist, size_t capacity) {
+    if (L[0] == 0.0f || L[1] == 0.0f || L[2] == 0.0f) return ORC_EZEROBOX;
+    uint64_t n = 0;
+    for (size_t i = 0; i < g1; i++)
+        for (size_t j = 0; j < g2; j++) {
+            const float d = orc_distance(POS(xyz, stride, idx1[i]), POS(xyz, stride, idx2[j]), 7, L);
+            if (d < cutoff) {
+                if (pairs && n < capacity) {
+                    pairs[n * 2] = (uint32_t)i;
+                    pairs[n * 2 + 1] = (uint32_t)j;
+                    if (dist) dist[n] = d;
+                }
+                n++;
+            }
+        }
+    *count = n;
+    return ORC_OK;
+}
+
 /* ------------------------------------------------------------------ whole molecules / groups, centering */
 
 /* Vector3D::filter (vector3d.rs): keep the components of `dim`, zero the others.

@@ -72,6 +72,8 @@ int orc_all_distances_minmax(const float *xyz, size_t stride, const uint32_t *id
                              size_t g2, int dim, const float L[3], float *dmin, uint32_t *imin /*[2] = (i,j)*/,
                              float *dmax, uint32_t *imax, float cutoff, uint64_t *count_below);
 int orc_wrap(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float L[3], int8_t *shifts /* g*3 or NULL */); /* iterators.rs:1548, vector3d.rs:380 */
+int orc_pairs_within(const float *xyz, size_t stride, const uint32_t *idx1, size_t g1, const uint32_t *idx2, size_t g2, float cutoff,
+                     const float L[3], uint64_t *count, uint32_t *pairs, float *dist, size_t capacity); /* cellgrid.rs:301-420 */
 #define ORC_NO_MOL 0xFFFFFFFFu
 int orc_make_group_whole(float *xyz, size_t stride, const uint32_t *idx, size_t g, const float L[3]);   /* modifying.rs:437-465 */
 int orc_make_molecules_whole(float *xyz, size_t stride, size_t n, const uint32_t *mol_ref, const float L[3]); /* modifying.rs:338-391 */

@@ -217,6 +217,22 @@ def translate(xyz, idx, t, box):
     return x, sh
 
 
+def pairs_within(xyz, idx1, idx2, cutoff, box, capacity=0):
+    """brute-force restatement of CellGrid::neighbors_iter + distance filter: (count, pairs [n,2], dist [n]) row-major"""
+    st, L = _L(box)
+    _chk(st)
+    x, i1 = _grp(xyz, idx1)
+    i2 = _idx(idx2)
+    cnt = C.c_uint64(0)
+    pairs = np.zeros((max(capacity, 1), 2), np.uint32)
+    dist = np.zeros(max(capacity, 1), np.float32)
+    _chk(lib().orc_pairs_within(_fp(x), _sz(3), i1.ctypes.data_as(_u), _sz(i1.size), i2.ctypes.data_as(_u), _sz(i2.size),
+                                C.c_float(cutoff), _fp(L), C.byref(cnt), pairs.ctypes.data_as(_u) if capacity else None,
+                                _fp(dist) if capacity else None, _sz(capacity)))
+    n = min(int(cnt.value), capacity)
+    return int(cnt.value), pairs[:n], dist[:n]
+
+
 NO_MOL = 0xFFFFFFFF
 
 

@@ -144,6 +144,30 @@ int main() {
             CHECK(e.variant.find("DoesNotExist") != std::string::npos);
         }
     }
+    // ---- cellgrid.rs: neighbours within a cutoff == the pairs of the all-pairs matrix below it
+    {
+        const size_t n = 3000;
+        System s(n);
+        std::vector<Vector3D> x(n);
+        unsigned long long st = 12345;
+        auto rnd = [&]() {
+            st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+            return float((st >> 33) & 0xFFFFFF) / float(0x1000000);
+        };
+        for (auto &v : x) v = {rnd() * 6.0f, rnd() * 5.0f, rnd() * 7.0f};
+        s.set_frame(x, SimBox::orthogonal(6, 5, 7));
+        s.group_create_from_range("A", 0, 99);
+        s.group_create_from_range("B", 50, 2999);
+        const float cutoff = 0.8f;
+        const std::vector<float> D = s.group_all_distances("A", "B", Dimension::XYZ);
+        size_t expect = 0;
+        for (float d : D) expect += d < cutoff;
+        const auto pl = s.group_pairs_within("A", "B", cutoff, expect + 8);
+        CHECK(pl.count[0] == expect);
+        bool ok = true;
+        for (size_t k = 0; k < expect; k++) ok = ok && D[pl.pairs[k][0] * 2950 + pl.pairs[k][1]] == pl.dist[k] && pl.dist[k] < cutoff;
+        CHECK(ok);
+    }
     // ---- FrameBatcher: frames arrive one by one (traj_iter_map_reduce body), results come back per batch, in order
     {
         const size_t n = 5000, total = 11, batch = 4;

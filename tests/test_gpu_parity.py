@@ -1038,3 +1038,71 @@ def test_quantized_frames_are_the_readers_floats(example, short_traj):
     kat = [0.23669721, 0.2634763, 0.26021627, 0.21364464, 0.22166993, 0.19383307, 0.26422343, 0.27013618, 0.26398134,
            0.23475659, 0.24208021]  # rmsd.rs:811-814
     assert np.abs(res[1][1] - np.array(kat, np.float32)).max() < TOL_RMSD
+
+
+# ------------------------------------------------------------------ cutoff pair search through a cell grid
+@pytest.mark.parametrize("cutoff", [0.35, 1.1, 4.0, 30.0])
+def test_pairs_within_matches_brute_force(cutoff):
+    """CellGrid + neighbors_iter + distance filter (cellgrid.rs:301-420) against the plain double loop: the same SET of pairs
+    per frame, distances bit-identical to the all-pairs matrix; cutoffs from a fraction of a cell to larger than the box
+    (grids of 1 and 2 cells per axis), atoms outside the box, boxes that change from frame to frame."""
+    rng = np.random.default_rng(21)
+    n, F = 6000, 3
+    L = np.array([[7.5, 8.25, 6.75], [7.4, 8.3, 6.9], [7.6, 8.2, 6.7]], np.float32)
+    frames = np.stack([rng.uniform(-0.15 * L[f], 1.15 * L[f], size=(n, 3)) for f in range(F)]).astype(np.float32)
+    frames[:, 10] = frames[:, 11]            # coincident atoms: distance 0
+    frames[0, 12] = [0.0, L[0, 1], 3.0]      # on the box faces
+    s = _sys(n, max_frames=F)
+    a_idx, b_idx = np.arange(0, 300), np.arange(200, 5200)
+    s.group_create_from_indices("A", a_idx)
+    s.group_create_from_indices("B", b_idx)
+    s.set_frames(frames, L)
+    exp = [orc.pairs_within(frames[f], a_idx, b_idx, cutoff, L[f], capacity=300 * 5000) for f in range(F)]
+    cap = max(e[0] for e in exp) + 5
+    count, pairs, dist = s.group_pairs_within("A", "B", cutoff, capacity=cap, with_distances=True)
+    for f in range(F):
+        ec, ep, ed = exp[f]
+        assert int(count[f]) == ec, (cutoff, f, int(count[f]), ec)
+        got = {(int(i), int(j)): d for (i, j), d in zip(pairs[f, :ec], dist[f, :ec])}
+        assert len(got) == ec  # no pair twice
+        want = {(int(i), int(j)): d for (i, j), d in zip(ep, ed)}
+        assert got.keys() == want.keys()
+        assert all(np.float32(got[k]).view(np.uint32) == np.float32(want[k]).view(np.uint32) for k in want)
+    # count only, and a capacity smaller than the number of pairs: the count stays complete
+    c2, _, _ = s.group_pairs_within("A", "B", cutoff)
+    assert np.array_equal(c2, count)
+    c3, p3, _ = s.group_pairs_within("A", "B", cutoff, capacity=7)
+    assert np.array_equal(c3, count)
+    for f in range(F):
+        want = {(int(i), int(j)) for i, j in exp[f][1]}
+        assert all((int(i), int(j)) in want for i, j in p3[f, :min(7, exp[f][0])])
+
+
+def test_pairs_within_self_search_and_errors(protein):
+    """a group against itself (both (i, j) and (j, i), and the diagonal, like the all-pairs matrix) == count of the fused
+    all-pairs reduction; error order of CellGrid::new (cellgrid.rs:308-330)"""
+    import groan_rs_b200 as g
+    rng = np.random.default_rng(5)
+    n = 20_000
+    L = np.array([9.0, 9.0, 9.0], np.float32)
+    x = rng.uniform(0, L, size=(n, 3)).astype(np.float32)
+    s = _sys(n)
+    s.group_create_from_indices("G", np.arange(n))
+    s.set_frames(x, L)
+    count, _, _ = s.group_pairs_within("G", "G", 0.6)
+    red = s.group_all_distances_reduce("G", "G", g.Dimension.XYZ, cutoff=0.6)
+    assert int(count[0]) == int(red["count"][0]) and int(count[0]) > n
+    e = _sys(61, max_frames=1)
+    e.group_create_from_indices("P", range(61))
+    e.group_create_from_indices("Empty", [])
+    e.set_frames(protein["frames"][:1], None)
+    with pytest.raises(g.GroanError) as ei:
+        e.group_pairs_within("P", "P", 1.0)
+    assert "DoesNotExist" in ei.value.variant
+    e.set_frames(protein["frames"][:1], protein["boxes"][:1])
+    with pytest.raises(g.GroupError):
+        e.group_pairs_within("P", "Nope", 1.0)
+    c, _, _ = e.group_pairs_within("P", "Empty", 1.0)
+    assert int(c[0]) == 0
+    with pytest.raises(g.GpuError):
+        e.group_pairs_within("P", "P", -1.0)
