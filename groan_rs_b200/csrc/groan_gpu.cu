@@ -1309,6 +1309,7 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
         nc[k] = (nc[k] + 1) / 2;
     }
     CellGeom cg = {(int)nc[0], (int)nc[1], (int)nc[2]};
+    const float cutoff2 = cutoff_squared_threshold(cutoff);
     const size_t cells = (size_t)nc[0] * nc[1] * nc[2];
     // scratch layout (one allocation): results first, then per-frame grid storage for as many frames as fit ~1.5 GB
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1350,7 +1351,7 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
         }
         if (a->n) {
             const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((a->n + 7) / 8, (size_t)kSMs * 16));
-            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, d_offsets, d_sorted, cells, cutoff,
+            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, d_offsets, d_sorted, cells, cutoff2,
                                                                                d_count + f0, d_pairs ? d_pairs + f0 * capacity * 2 : nullptr,
                                                                                d_dist ? d_dist + f0 * capacity : nullptr,
                                                                                (unsigned long long)capacity, d_cursor + f0);

@@ -103,7 +103,7 @@ __device__ __forceinline__ void axis_cells(int c, int n, int (&out)[3], int &m) 
 }
 
 __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView ga, uint32_t nb_atoms, CellGeom cg, const uint32_t *offsets,
-                                                          const float4 *sorted, size_t cells, float cutoff, unsigned long long *count,
+                                                          const float4 *sorted, size_t cells, float cutoff2, unsigned long long *count,
                                                           uint32_t *pairs, float *dist, unsigned long long capacity,
                                                           unsigned long long *cursor) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -129,13 +129,16 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
                     for (uint32_t s0 = lo; s0 < hi; s0 += 32) {
                         const uint32_t s = s0 + lane;
                         bool hit = false;
-                        float d = 0.0f;
+                        float d2 = 0.0f;
                         uint32_t j = 0;
                         if (s < hi) {
+                            // Vector3D::distance, XYZ (vector3d.rs:458-486), compared before the square root: cutoff2 is the
+                            // smallest float whose sqrtf reaches the cutoff (host: cutoff_squared_threshold), sqrtf is monotone
                             const float4 b = sb[s];
-                            d = pair_distance_loop<7>(ax, ay, az, b.x, b.y, b.z, B); // Vector3D::distance, XYZ (vector3d.rs:458-486)
+                            const float dx = min_image(ax - b.x, B.lx), dy = min_image(ay - b.y, B.ly), dz = min_image(az - b.z, B.lz);
+                            d2 = (dx * dx + dy * dy) + dz * dz;
                             j = __float_as_uint(b.w);
-                            hit = d < cutoff;
+                            hit = d2 < cutoff2;
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, hit);
                         if (m == 0u) continue;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
                                 uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
                                 o[0] = i;
                                 o[1] = j;
-                                if (dist) dist[(size_t)f * capacity + at] = d;
+                                if (dist) dist[(size_t)f * capacity + at] = sqrt1_rn(d2);
                             }
                         }
                     }
