@@ -729,6 +729,17 @@ def test_full_size_properties_cfg4_cfg5():
     fr = p.get_frames()[0]
     sub = orc.all_distances(fr, np.arange(64), np.arange(500_000, 500_000 + 4096), "XYZ", [21.5] * 3)
     assert np.array_equal(bits(mat[0, :64, :4096].cpu().numpy()), bits(sub))
+    # the cell-grid search finds exactly the pairs of the matrix below the cutoff (2 000 x 200 000, cutoff 1.0 and 0.3 nm):
+    # the same count, every stored pair below the cutoff with the matrix's own distance, no pair twice
+    for cutoff in (1.0, 0.3):
+        want = int((flat < cutoff).sum())
+        count, pairs, dist = p.group_pairs_within("A", "B", cutoff, capacity=want + 16, with_distances=True)
+        assert int(count[0]) == want
+        pi = torch.from_numpy(pairs[0, :want].astype(np.int64)).cuda()
+        lin = pi[:, 0] * n2 + pi[:, 1]
+        assert int(torch.unique(lin).numel()) == want
+        assert torch.equal(flat[lin].cpu(), torch.from_numpy(dist[0, :want]))
+        assert float(dist[0, :want].max()) < cutoff
 
 
 def test_device_side_fallback_matches_exact_only():
