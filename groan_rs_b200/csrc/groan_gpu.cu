@@ -364,9 +364,10 @@ int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, cons
         if (center_mode == 1) GO(true, 1);
         GO(true, 2);
     }
+    // target masses != reference masses: only the RMSD-only kernel exists.  The fused variants would need 70 accumulator
+    // registers and spill inside the loop (which costs ~40 %, profiles/exp/README.md); rmsd_common runs the centre separately.
     if (center_mode == 0) GO(false, 0);
-    if (center_mode == 1) GO(false, 1);
-    GO(false, 2);
+    return GROAN_EINVAL;
 #undef GO
 }
 
@@ -778,6 +779,8 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         rv.sum_wpc[k] = R.sums[5 + k];
         rv.com[k] = R.com[k];
     }
+    rv.sum_m_target = 0.0;
+    for (float m : g->mass) rv.sum_m_target += (double)m;
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
     bool center_done = false, device_fallback = false;
@@ -786,12 +789,13 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         QuadRef qr;
         rc = ensure_quad_ref(ctx, R, *g, &qr);
         if (rc) return rc;
-        const FallbackPlan fp = fallback_plan(ctx, *g, center != nullptr, center_weighted != 0, d_center, true, d_rmsd, d_rot);
+        const bool fused = center != nullptr && R.same_mass;  // see launch_rmsd_quad
+        const FallbackPlan fp = fallback_plan(ctx, *g, fused, center_weighted != 0, d_center, true, d_rmsd, d_rot);
         device_fallback = fp.enabled != 0;
-        rc = launch_rmsd_quad(ctx, *g, rv, qr, R.same_mass, center ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
+        rc = launch_rmsd_quad(ctx, *g, rv, qr, R.same_mass, fused ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
-        center_done = center != nullptr;
+        center_done = fused;
     } else if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
         const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
@@ -924,8 +928,6 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         if (!qrc) qrc = set_quad_attr<true, 1>(ctx);
         if (!qrc) qrc = set_quad_attr<true, 2>(ctx);
         if (!qrc) qrc = set_quad_attr<false, 0>(ctx);
-        if (!qrc) qrc = set_quad_attr<false, 1>(ctx);
-        if (!qrc) qrc = set_quad_attr<false, 2>(ctx);
         if (qrc) return qrc;
         return GROAN_OK;
     }();

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero(), sd = v3_zero(), ssin = v3_zero();
 #pragma unroll
     for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
-    float2 sq = make_float2(0.f, 0.f), sm2 = make_float2(0.f, 0.f);
+    float2 sq = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
     auto atom_pair = [&](const V3 &d, const float4 &r0, const float4 &r1, uint32_t i) {
         const float2 pc[3] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y)};
@@ -462,8 +462,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         quad_minmax(mm, d);
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
-            v3_fma(smd, m, d);
-            sm2 = __fadd2_rn(sm2, m);
+            v3_fma(smd, m, d); // sum m is a constant of the group: ref.sum_m_target, no accumulator
         }
     };
     stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
@@ -488,7 +487,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     a[18] = v3_x(swd); a[19] = v3_y(swd); a[20] = v3_z(swd);
     a[21] = sq.x + sq.y;
     a[22] = v3_x(smd); a[23] = v3_y(smd); a[24] = v3_z(smd);
-    a[25] = sm2.x + sm2.y;
+    a[25] = 0.0f;
     if (CENTER) {
         a[KS - 6] = v3_x(sd); a[KS - 5] = v3_y(sd); a[KS - 4] = v3_z(sd);
         a[KS - 3] = v3_x(ssin); a[KS - 2] = v3_y(ssin); a[KS - 1] = v3_z(ssin);
@@ -526,9 +525,9 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             if (!SAME_MASS) {
                 const double m = (double)__ldg(g.mass + i);
                 for (int v = 0; v < 3; v++) tot[22 + v] += m * d[v];
-                tot[25] += m;
             }
         }
+        tot[25] = ref.sum_m_target;
         double rt[kFastSums];
         for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
         int flag_r = 0, flag_c = 0;

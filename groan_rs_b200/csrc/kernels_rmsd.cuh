@@ -33,6 +33,7 @@ struct RefView {
     double sum_w;      // sum w
     double sum_pc[3];  // sum pc
     double sum_wpc[3]; // sum w pc
+    double sum_m_target; // sum of the TARGET group's own masses (constant over the frames; used by the quad kernels)
     float com[3];      // reference.group_get_com(group) (rmsd.rs:133,198)
 };
 
