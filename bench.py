@@ -355,15 +355,17 @@ def run_gpu_arm(args):
 
         # the same steps fed with the xtc decoder's integers (int16 lattice points at precision 1000 + a per-frame origin,
         # groan_gpu_push_frames_quantized): the frames are those of h_in rounded to the xtc grid, half the PCIe bytes
-        h_q = []
         prec = 1000.0
         x = h_in[0].numpy()
-        lat = np.rint(x.astype(np.float64) * prec).astype(np.int32)
-        origin = ((lat.reshape(F, -1, 3).min(axis=1).astype(np.int64) + lat.reshape(F, -1, 3).max(axis=1)) // 2).astype(np.int32)
-        rel = lat - origin[:, None, :]
-        assert np.abs(rel).max() < 32768
-        for _ in range(2):
-            h_q.append(torch.from_numpy(rel.astype(np.int16)).pin_memory())
+        h_q = [torch.empty((F, N_ATOMS, 3), dtype=torch.int16).pin_memory() for _ in range(2)]
+        origin = np.zeros((F, 3), np.int32)
+        for f in range(F):  # frame by frame: no multi-GB temporaries
+            lat = np.rint(x[f].astype(np.float64) * prec).astype(np.int32)
+            origin[f] = ((lat.min(axis=0).astype(np.int64) + lat.max(axis=0)) // 2).astype(np.int32)
+            rel = lat - origin[f]
+            assert np.abs(rel).max() < 32768
+            h_q[0][f] = torch.from_numpy(rel.astype(np.int16))
+        h_q[1].copy_(h_q[0])
         del lat, rel
 
         def e2e_q_step(k):

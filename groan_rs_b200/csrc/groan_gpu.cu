@@ -1318,12 +1318,13 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
     const size_t per_frame = up(nb_atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(nb_atoms * 16);
     const size_t fb = std::max<size_t>(1, std::min<size_t>(F, ((size_t)3 << 29) / std::max<size_t>(per_frame, 1)));
     const bool stage_pairs = pairs && classify(pairs) != PK_DEVICE, stage_dist = dist && classify(dist) != PK_DEVICE;
-    const size_t o_count = 0, o_cursor = up(F * 8), o_pairs = o_cursor + up(F * 8),
+    const size_t o_count = 0, o_cursor = up(F * 8), o_far = o_cursor + up(F * 8), o_pairs = o_far + up(F * 4),
                  o_dist = o_pairs + (stage_pairs ? up(F * capacity * 8) : 0), o_grid = o_dist + (stage_dist ? up(F * capacity * 4) : 0);
     rc = ensure_tmp(ctx, o_grid + fb * per_frame);
     if (rc) return rc;
     char *base = (char *)ctx->d_tmp;
     unsigned long long *d_count = (unsigned long long *)(base + o_count), *d_cursor = (unsigned long long *)(base + o_cursor);
+    unsigned int *d_far = (unsigned int *)(base + o_far);
     uint32_t *d_pairs = pairs ? (stage_pairs ? (uint32_t *)(base + o_pairs) : pairs) : nullptr;
     float *d_dist = dist ? (stage_dist ? (float *)(base + o_dist) : dist) : nullptr;
     CK(cudaMemsetAsync(base, 0, o_pairs, ctx->compute));
@@ -1342,7 +1343,7 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
         CK(cudaMemsetAsync(d_counts, 0, nf * cells * 4, ctx->compute));
         const unsigned nbb = (unsigned)std::max<size_t>(1, std::min<size_t>((nb_atoms + kThreads - 1) / kThreads, (size_t)kSMs * 8));
         if (nb_atoms) {
-            k_cell_count<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, cg, d_cell_of, d_counts, cells);
+            k_cell_count<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, cg, d_cell_of, d_counts, cells, d_far + f0);
             LAUNCHED();
         }
         k_cell_scan<<<(unsigned)nf, 1024, 0, ctx->compute>>>(d_counts, d_offsets, d_fill, cells);
@@ -1356,7 +1357,7 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
             k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, d_offsets, d_sorted, cells, cutoff2,
                                                                                d_count + f0, d_pairs ? d_pairs + f0 * capacity * 2 : nullptr,
                                                                                d_dist ? d_dist + f0 * capacity : nullptr,
-                                                                               (unsigned long long)capacity, d_cursor + f0);
+                                                                               (unsigned long long)capacity, d_cursor + f0, d_far + f0);
             LAUNCHED();
         }
     }

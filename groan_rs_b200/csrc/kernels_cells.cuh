@@ -37,18 +37,24 @@ __device__ __forceinline__ uint32_t cell_index(float x, float y, float z, const 
 
 // cells per axis for a frame: the grid differs from frame to frame only through the box, and all frames share one
 // geometry chosen on the host from the SMALLEST box of the batch (cells can only get wider for the other frames)
+// far[f] is set when an atom of group B lies more than L/4 outside the box: the query then uses the reference's loop
+// form of the minimum image instead of the branch-free one-step fold (kernels_pairs.cuh)
 __global__ void __launch_bounds__(kThreads) k_cell_count(FrameView fv, GroupView gb, CellGeom cg, uint32_t *cell_of, uint32_t *counts,
-                                                          size_t cells) {
+                                                          size_t cells, unsigned int *far) {
     const int f = blockIdx.y;
     BoxOrtho B;
     load_box(fv.box, f, B);
     const float *fr = fv.frame(f);
+    bool ok = true;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < gb.n; j += gridDim.x * blockDim.x) {
         const float *p = fr + (size_t)gb.atom(j) * 3;
-        const uint32_t c = cell_index(__ldg(p), __ldg(p + 1), __ldg(p + 2), B, cg);
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        const uint32_t c = cell_index(x, y, z, B, cg);
+        ok = ok && atom_in_fold_range<7>(x, y, z, B);
         cell_of[(size_t)f * gb.n + j] = c;
         atomicAdd(counts + (size_t)f * cells + c, 1u);
     }
+    if (!ok) atomicOr(far + f, 1u);
 }
 
 // offsets[c] = number of atoms in cells < c; cursor[c] = the same (k_cell_fill advances it).  One CTA per frame.
@@ -105,7 +111,7 @@ __device__ __forceinline__ void axis_cells(int c, int n, int (&out)[3], int &m) 
 __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView ga, uint32_t nb_atoms, CellGeom cg, const uint32_t *offsets,
                                                           const float4 *sorted, size_t cells, float cutoff2, unsigned long long *count,
                                                           uint32_t *pairs, float *dist, unsigned long long capacity,
-                                                          unsigned long long *cursor) {
+                                                          unsigned long long *cursor, const unsigned int *far) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     BoxOrtho B;
     load_box(fv.box, f, B);
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
     const uint32_t *of = offsets + (size_t)f * (cells + 1);
     const float4 *sb = sorted + (size_t)f * nb_atoms;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const bool b_near = far[f] == 0u;
     unsigned long long mine = 0;
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < ga.n; i += warps) {
         const float *p = fr + (size_t)ga.atom(i) * 3;
@@ -121,43 +128,66 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
         axis_cells(cell_coord(ax, B.lx, cg.nx), cg.nx, xs, mx);
         axis_cells(cell_coord(ay, B.ly, cg.ny), cg.ny, ys, my);
         axis_cells(cell_coord(az, B.lz, cg.nz), cg.nz, zs, mz);
-        for (int kz = 0; kz < mz; kz++)
-            for (int ky = 0; ky < my; ky++)
-                for (int kx = 0; kx < mx; kx++) {
-                    const uint32_t c = ((uint32_t)zs[kz] * cg.ny + ys[ky]) * cg.nx + xs[kx];
-                    const uint32_t lo = of[c], hi = of[c + 1];
-                    for (uint32_t s0 = lo; s0 < hi; s0 += 32) {
-                        const uint32_t s = s0 + lane;
-                        bool hit = false;
-                        float d2 = 0.0f;
-                        uint32_t j = 0;
-                        if (s < hi) {
-                            // Vector3D::distance, XYZ (vector3d.rs:458-486), compared before the square root: cutoff2 is the
-                            // smallest float whose sqrtf reaches the cutoff (host: cutoff_squared_threshold), sqrtf is monotone
-                            const float4 b = sb[s];
-                            const float dx = min_image(ax - b.x, B.lx), dy = min_image(ay - b.y, B.ly), dz = min_image(az - b.z, B.lz);
-                            d2 = (dx * dx + dy * dy) + dz * dz;
-                            j = __float_as_uint(b.w);
-                            hit = d2 < cutoff2;
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        if (m == 0u) continue;
-                        const int n_hit = __popc(m);
-                        if (lane == 0) mine += n_hit;
-                        if (pairs) { // one atomic per warp and step; pairs beyond the capacity are counted but not stored
-                            unsigned long long base = 0;
-                            if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)n_hit);
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-                            if (hit && at < capacity) {
-                                uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
-                                o[0] = i;
-                                o[1] = j;
-                                if (dist) dist[(size_t)f * capacity + at] = sqrt1_rn(d2);
-                            }
+        // the (up to 27) cell ranges are fetched by 27 lanes at once and handed round by shuffles: one L2 round trip per
+        // atom instead of one per cell
+        const int ncell = mx * my * mz;
+        const bool fold = b_near && atom_in_fold_range<7>(ax, ay, az, B); // warp-uniform
+        uint32_t my_lo = 0, my_hi = 0;
+        if (lane < ncell) {
+            const int kx = lane % mx, ky = (lane / mx) % my, kz = lane / (mx * my);
+            const uint32_t c = ((uint32_t)zs[kz] * cg.ny + ys[ky]) * cg.nx + xs[kx];
+            my_lo = of[c];
+            my_hi = of[c + 1];
+        }
+        for (int k = 0; k < ncell; k++) {
+            const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
+            // four candidates per lane and trip, their loads issued before the first use
+            for (uint32_t s0 = lo; s0 < hi; s0 += 128) {
+                float4 b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t s = s0 + u * 32 + lane;
+                    b[u] = s < hi ? sb[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t s = s0 + u * 32 + lane;
+                    // Vector3D::distance, XYZ (vector3d.rs:458-486), compared before the square root: cutoff2 is the
+                    // smallest float whose sqrtf reaches the cutoff (host: cutoff_squared_threshold), sqrtf is monotone.
+                    // With both atoms within L/4 of the box |min_image(d)| = min(|d|, ||d| - L|) exactly:
+                    // no loops, no divergence bookkeeping; otherwise the reference's loops.
+                    float dx, dy, dz;
+                    if (fold) {
+                        const float rx = fabsf(ax - b[u].x), ry = fabsf(ay - b[u].y), rz = fabsf(az - b[u].z);
+                        dx = fminf(rx, fabsf(rx - B.lx));
+                        dy = fminf(ry, fabsf(ry - B.ly));
+                        dz = fminf(rz, fabsf(rz - B.lz));
+                    } else {
+                        dx = min_image(ax - b[u].x, B.lx);
+                        dy = min_image(ay - b[u].y, B.ly);
+                        dz = min_image(az - b[u].z, B.lz);
+                    }
+                    const float d2 = (dx * dx + dy * dy) + dz * dz;
+                    const bool hit = s < hi && d2 < cutoff2;
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m == 0u) continue;
+                    const int n_hit = __popc(m);
+                    if (lane == 0) mine += n_hit;
+                    if (pairs) { // one atomic per warp and step; pairs beyond the capacity are counted but not stored
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)n_hit);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+                        if (hit && at < capacity) {
+                            uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
+                            o[0] = i;
+                            o[1] = __float_as_uint(b[u].w);
+                            if (dist) dist[(size_t)f * capacity + at] = sqrt1_rn(d2);
                         }
                     }
                 }
+            }
+        }
     }
     if (lane == 0 && mine) atomicAdd(count + f, mine);
 }

@@ -1063,6 +1063,7 @@ def test_pairs_within_matches_brute_force(cutoff):
     frames = np.stack([rng.uniform(-0.15 * L[f], 1.15 * L[f], size=(n, 3)) for f in range(F)]).astype(np.float32)
     frames[:, 10] = frames[:, 11]            # coincident atoms: distance 0
     frames[0, 12] = [0.0, L[0, 1], 3.0]      # on the box faces
+    frames[1, 213] = [40.0, -30.0, 100.0]   # many box lengths away: this frame takes the reference's loop form of min_image
     s = _sys(n, max_frames=F)
     a_idx, b_idx = np.arange(0, 300), np.arange(200, 5200)
     s.group_create_from_indices("A", a_idx)
