@@ -42,6 +42,7 @@ SIGNATURES = {
     "groan_gpu_set_group": (_int, [_vp, _int, _vp, _sz, _vp]),
     "groan_gpu_push_frames": (_int, [_vp, _vp, _vp, _sz]),
     "groan_gpu_push_frames_quantized": (_int, [_vp, _vp, _int, _vp, _f, _vp, _sz]),
+    "groan_gpu_get_frames_quantized": (_int, [_vp, _vp, _f]),
     "groan_gpu_attach_frames": (_int, [_vp, _vp, _vp, _sz]),
     "groan_gpu_set_valid": (_int, [_vp, _vp]),
     "groan_gpu_get_frames": (_int, [_vp, _vp]),

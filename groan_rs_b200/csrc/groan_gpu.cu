@@ -1176,6 +1176,22 @@ int groan_gpu_get_frames(groan_gpu_ctx *ctx, float *xyz_out) {
     return deliver(ctx, xyz_out, ctx->cur_xyz, ctx->n_frames * ctx->n_atoms * 3 * sizeof(float));
 }
 
+int groan_gpu_get_frames_quantized(groan_gpu_ctx *ctx, int32_t *q_out, float precision) {
+    if (!ctx || !q_out || !(precision > 0.0f)) return GROAN_EINVAL;
+    if (!ctx->have_frames) return GROAN_ENOFRAMES;
+    const size_t count = ctx->n_frames * ctx->n_atoms * 3;
+    int32_t *d_q = q_out;
+    if (classify(q_out) != PK_DEVICE) {
+        int rc = ensure_tmp(ctx, count * sizeof(int32_t));
+        if (rc) return rc;
+        d_q = (int32_t *)ctx->d_tmp;
+    }
+    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((count + kThreads * 4 - 1) / (kThreads * 4), (size_t)kSMs * 16));
+    k_quantize<<<nb, kThreads, 0, ctx->compute>>>(ctx->cur_xyz, precision, d_q, count);
+    LAUNCHED();
+    return deliver(ctx, q_out, d_q, count * sizeof(int32_t));
+}
+
 // ---- centres --------------------------------------------------------------------------------------
 int groan_gpu_estimate_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out) {
     const Group *g = nullptr;

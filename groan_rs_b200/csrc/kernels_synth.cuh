@@ -101,4 +101,15 @@ __global__ void __launch_bounds__(kThreads) k_dequantize(const T *q, const int32
     }
 }
 
+// The other direction, for writing a (fitted / wrapped / centred) batch as xtc: the integer lattice point xdrfile's encoder
+// derives from every coordinate before it compresses (external/xdrfile/xdrfile.c:1018-1031): lf = x * precision +- 0.5 in
+// f32 (sign of x), truncated to int.  No FMA contraction (-fmad=false), so the integers are the encoder's.
+__global__ void __launch_bounds__(kThreads) k_quantize(const float *xyz, float precision, int32_t *out, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = xyz[i];
+        const float lf = x >= 0.0f ? x * precision + 0.5f : x * precision - 0.5f;
+        out[i] = (int32_t)lf;
+    }
+}
+
 } // namespace groan

@@ -381,6 +381,13 @@ class System:
         self._check(self._lib.groan_gpu_get_frames(self._h, _ptr(out)), "get_frames")
         return out
 
+    def get_frames_quantized(self, precision, out=None):
+        """the batch as the xtc encoder's integer lattice points, (int)(x * precision +- 0.5) in f32 (xdrfile.c:1018-1031)"""
+        if out is None:
+            out = np.empty((self.n_frames, self.n_atoms, 3), np.int32)
+        self._check(self._lib.groan_gpu_get_frames_quantized(self._h, _ptr(out), C.c_float(precision)), "get_frames_quantized")
+        return out
+
     def synth_uniform(self, seed, frame0, n_frames, lo, span, boxes):
         bm = _boxes_to_matrices(boxes, n_frames)
         lo3 = (C.c_float * 3)(*[float(v) for v in lo])

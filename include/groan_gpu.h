@@ -105,6 +105,10 @@ int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box
  * q: F x N x 3 integers of elem_bytes (2 = int16, 4 = int32); origin: F x 3 int32 added to every q of the frame (NULL = 0). */
 int groan_gpu_push_frames_quantized(groan_gpu_ctx *ctx, const void *q, int elem_bytes, const int32_t *origin, float precision,
                                     const float *box, size_t n_frames);
+/* ... and the current batch in the form the xtc ENCODER starts from (writing fitted trajectories): the
+ * integer lattice point of every coordinate, (int)(x * precision +- 0.5) in f32 exactly as external/xdrfile/xdrfile.c:1018-1031
+ * computes it.  q_out: F x N x 3 int32, host or device. */
+int groan_gpu_get_frames_quantized(groan_gpu_ctx *ctx, int32_t *q_out, float precision);
 /* zero-copy: operate in place on a caller-owned DEVICE buffer of F x N x 3 floats (16-byte aligned) */
 int groan_gpu_attach_frames(groan_gpu_ctx *ctx, float *d_xyz, const float *box, size_t n_frames);
 /* Option<Vector3D> positions: valid[f*N + i] == 0 marks "atom i has no position in frame f" (host array,

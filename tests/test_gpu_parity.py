@@ -1049,6 +1049,14 @@ def test_quantized_frames_are_the_readers_floats(example, short_traj):
     kat = [0.23669721, 0.2634763, 0.26021627, 0.21364464, 0.22166993, 0.19383307, 0.26422343, 0.27013618, 0.26398134,
            0.23475659, 0.24208021]  # rmsd.rs:811-814
     assert np.abs(res[1][1] - np.array(kat, np.float32)).max() < TOL_RMSD
+    # the encoder's direction: what xtc writing would store for the frames it has just read is what was read
+    assert np.array_equal(s.get_frames_quantized(prec), q.astype(np.int32))
+    # ... and for the fitted trajectory (rmsd.rs:952-994, golden short_trajectory_fit.xtc): the same lattice points as the
+    # reference wrote, up to the fit's own 7e-5 nm pushing a coordinate across a rounding boundary
+    s.calc_rmsd_and_fit(ref, "Protein")
+    fq = s.get_frames_quantized(prec)
+    diff = np.abs(fq - g0["fit_q"].astype(np.int32))
+    assert diff.max() <= 1 and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())
 
 
 # ------------------------------------------------------------------ cutoff pair search through a cell grid
