@@ -476,6 +476,16 @@ class System:
                     "group_all_distances", "%s/%s" % (group1, group2))
         return out
 
+    def atoms_distance(self, index1, index2, dim):
+        """System::atoms_distance (analysis.rs:459-471) -> Atom::distance (atom.rs:780-790), per frame [F]; the first atom's
+        position is checked first, like the reference"""
+        for i in (index1, index2):
+            if not 0 <= int(i) < self.n_atoms:
+                raise IndexError("atom index %d out of range" % i)
+        self.group_create_from_indices("__atom1", [int(index1)])
+        self.group_create_from_indices("__atom2", [int(index2)])
+        return self.group_all_distances("__atom1", "__atom2", dim)[:, 0, 0]
+
     def group_all_distances_reduce(self, group1, group2, dim, cutoff=0.0):
         """The documented consumer of the matrix (analysis.rs:390-399) fused on the device:
         returns dict(min, argmin [F,2], max, argmax [F,2], count) without materialising the matrix."""

@@ -153,6 +153,12 @@ class System {
         check(groan_gpu_group_distance(ctx_, group(g1).gid, group(g2).gid, (int)dim, out.data()), "group_distance", g1);
         return out;
     }
+    // System::atoms_distance (analysis.rs:459-471), per frame
+    std::vector<float> atoms_distance(uint32_t index1, uint32_t index2, Dimension dim) {
+        group_create_from_indices("__atom1", {index1});
+        group_create_from_indices("__atom2", {index2});
+        return group_all_distances("__atom1", "__atom2", dim);
+    }
     // n_frames x n1 x n2, row-major like ndarray::Array2 per frame
     std::vector<float> group_all_distances(const std::string &g1, const std::string &g2, Dimension dim) {
         std::vector<float> out(n_frames_ * group_get_n_atoms(g1) * group_get_n_atoms(g2));

@@ -139,6 +139,19 @@ def test_group_distance_kats(example):
 
 
 # ------------------------------------------------------------------ all-pairs: analysis.rs:1420-1530
+def test_atoms_distance_kat(example):
+    """analysis.rs:1595-1619: System::atoms_distance on example.gro"""
+    xyz, box = example["xyz"], example["box"]
+    n = xyz.shape[0]
+    s = _sys(n)
+    s.set_frames(xyz, box.reshape(1, 9))
+    for (i, j), exp in (((0, 1), 0.31040135), ((n - 1, 0), 6.664787), ((n - 1, n - 2), 4.062491)):
+        d = s.atoms_distance(i, j, _dim("XYZ"))[0]
+        assert abs(d - exp) < 1e-5
+        assert bits(d) == bits(orc.distance(xyz[i], xyz[j], "XYZ", box.diagonal()))
+    assert s.atoms_distance(5, 5, _dim("XYZ"))[0] == 0.0
+
+
 def test_all_distances_example_bitexact(example):
     xyz, box = example["xyz"], example["box"]
     s = _sys(xyz.shape[0])
