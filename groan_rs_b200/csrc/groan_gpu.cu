@@ -1329,51 +1329,81 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
     CellGeom cg = {(int)nc[0], (int)nc[1], (int)nc[2]};
     const float cutoff2 = cutoff_squared_threshold(cutoff);
     const size_t cells = (size_t)nc[0] * nc[1] * nc[2];
-    // scratch layout (one allocation): results first, then per-frame grid storage for as many frames as fit ~1.5 GB
+    // scratch layout (one allocation): results first, then per-frame grid storage for as many frames as fit ~1.5 GB.
+    // Group A is binned as well when it has at least one atom per cell on average: one warp then serves a whole cell of A
+    // (k_cell_query_tiled); sparse query groups keep one warp per atom (k_cell_query).
+    const size_t na_atoms = a->n;
+    const bool tiled = na_atoms >= cells && !(ctx->flags & GROAN_FLAG_NO_QUAD);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t per_frame = up(nb_atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(nb_atoms * 16);
+    auto grid_bytes = [&](size_t atoms) { return up(atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(atoms * 16); };
+    const size_t per_frame = grid_bytes(nb_atoms) + (tiled ? grid_bytes(na_atoms) : 0);
     const size_t fb = std::max<size_t>(1, std::min<size_t>(F, ((size_t)3 << 29) / std::max<size_t>(per_frame, 1)));
     const bool stage_pairs = pairs && classify(pairs) != PK_DEVICE, stage_dist = dist && classify(dist) != PK_DEVICE;
-    const size_t o_count = 0, o_cursor = up(F * 8), o_far = o_cursor + up(F * 8), o_pairs = o_far + up(F * 4),
+    const size_t o_count = 0, o_cursor = up(F * 8), o_far = o_cursor + up(F * 8), o_pairs = o_far + up(2 * F * 4),
                  o_dist = o_pairs + (stage_pairs ? up(F * capacity * 8) : 0), o_grid = o_dist + (stage_dist ? up(F * capacity * 4) : 0);
     rc = ensure_tmp(ctx, o_grid + fb * per_frame);
     if (rc) return rc;
     char *base = (char *)ctx->d_tmp;
     unsigned long long *d_count = (unsigned long long *)(base + o_count), *d_cursor = (unsigned long long *)(base + o_cursor);
-    unsigned int *d_far = (unsigned int *)(base + o_far);
+    unsigned int *d_far_b = (unsigned int *)(base + o_far), *d_far_a = d_far_b + F;
     uint32_t *d_pairs = pairs ? (stage_pairs ? (uint32_t *)(base + o_pairs) : pairs) : nullptr;
     float *d_dist = dist ? (stage_dist ? (float *)(base + o_dist) : dist) : nullptr;
     CK(cudaMemsetAsync(base, 0, o_pairs, ctx->compute));
-    char *grid0 = base + o_grid;
-    uint32_t *d_cell_of = (uint32_t *)grid0;
-    uint32_t *d_counts = (uint32_t *)(grid0 + fb * up(nb_atoms * 4));
-    uint32_t *d_fill = (uint32_t *)((char *)d_counts + fb * up(cells * 4));
-    uint32_t *d_offsets = (uint32_t *)((char *)d_fill + fb * up(cells * 4));
-    float4 *d_sorted = (float4 *)((char *)d_offsets + fb * up((cells + 1) * 4));
+    struct CellLists {
+        uint32_t *cell_of, *counts, *fill, *offsets;
+        float4 *sorted;
+    };
+    auto carve = [&](char *p0, size_t atoms) {
+        CellLists c;
+        c.cell_of = (uint32_t *)p0;
+        c.counts = (uint32_t *)(p0 + fb * up(atoms * 4));
+        c.fill = (uint32_t *)((char *)c.counts + fb * up(cells * 4));
+        c.offsets = (uint32_t *)((char *)c.fill + fb * up(cells * 4));
+        c.sorted = (float4 *)((char *)c.offsets + fb * up((cells + 1) * 4));
+        return c;
+    };
+    const CellLists lb = carve(base + o_grid, nb_atoms);
+    const CellLists la = tiled ? carve(base + o_grid + fb * grid_bytes(nb_atoms), na_atoms) : CellLists();
     const GroupView ga = view_of(*a), gb = view_of(*b);
     for (size_t f0 = 0; f0 < F; f0 += fb) {
         const size_t nf = std::min(fb, F - f0);
         FrameView fv = frames_of(ctx);
         fv.xyz += f0 * ctx->n_atoms * 3;
         fv.box += f0 * 9;
-        CK(cudaMemsetAsync(d_counts, 0, nf * cells * 4, ctx->compute));
-        const unsigned nbb = (unsigned)std::max<size_t>(1, std::min<size_t>((nb_atoms + kThreads - 1) / kThreads, (size_t)kSMs * 8));
-        if (nb_atoms) {
-            k_cell_count<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, cg, d_cell_of, d_counts, cells, d_far + f0);
+        // counting sort of a group by cell: histogram, prefix sum, scatter
+        auto build = [&](const GroupView &gv, size_t atoms, const CellLists &cl, unsigned int *far) -> int {
+            CK(cudaMemsetAsync(cl.counts, 0, nf * cells * 4, ctx->compute));
+            const unsigned nbk = (unsigned)std::max<size_t>(1, std::min<size_t>((atoms + kThreads - 1) / kThreads, (size_t)kSMs * 8));
+            if (atoms) {
+                k_cell_count<<<dim3(nbk, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gv, cg, cl.cell_of, cl.counts, cells, far + f0);
+                LAUNCHED();
+            }
+            k_cell_scan<<<(unsigned)nf, 1024, 0, ctx->compute>>>(cl.counts, cl.offsets, cl.fill, cells);
             LAUNCHED();
-        }
-        k_cell_scan<<<(unsigned)nf, 1024, 0, ctx->compute>>>(d_counts, d_offsets, d_fill, cells);
-        LAUNCHED();
-        if (nb_atoms) {
-            k_cell_fill<<<dim3(nbb, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gb, d_cell_of, d_fill, d_sorted, cells);
+            if (atoms) {
+                k_cell_fill<<<dim3(nbk, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gv, cl.cell_of, cl.fill, cl.sorted, cells);
+                LAUNCHED();
+            }
+            return GROAN_OK;
+        };
+        rc = build(gb, nb_atoms, lb, d_far_b);
+        if (rc) return rc;
+        uint32_t *pp = d_pairs ? d_pairs + f0 * capacity * 2 : nullptr;
+        float *dp = d_dist ? d_dist + f0 * capacity : nullptr;
+        if (tiled) {
+            rc = build(ga, na_atoms, la, d_far_a);
+            if (rc) return rc;
+            const unsigned nq = (unsigned)std::max<size_t>(1, std::min<size_t>(cells, (size_t)kSMs * 64));
+            k_cell_query_tiled<<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets,
+                                                                                    la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
+                                                                                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0,
+                                                                                    d_far_b + f0);
             LAUNCHED();
-        }
-        if (a->n) {
-            const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((a->n + 7) / 8, (size_t)kSMs * 16));
-            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, d_offsets, d_sorted, cells, cutoff2,
-                                                                               d_count + f0, d_pairs ? d_pairs + f0 * capacity * 2 : nullptr,
-                                                                               d_dist ? d_dist + f0 * capacity : nullptr,
-                                                                               (unsigned long long)capacity, d_cursor + f0, d_far + f0);
+        } else if (na_atoms) {
+            const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((na_atoms + 7) / 8, (size_t)kSMs * 16));
+            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, lb.offsets, lb.sorted, cells, cutoff2,
+                                                                               d_count + f0, pp, dp, (unsigned long long)capacity, d_cursor + f0,
+                                                                               d_far_b + f0);
             LAUNCHED();
         }
     }

@@ -192,4 +192,104 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
     if (lane == 0 && mine) atomicAdd(count + f, mine);
 }
 
+// ---------------------------------------------------------------- query, group A sorted by cell as well
+// k_cell_query spends a 16-byte L2 load and the whole candidate bookkeeping on every single distance.  When group A is
+// binned too (the same three kernels), one CTA takes one cell of A: its atoms go through in tiles of four held in
+// registers (one tile per warp at a time), and every candidate a lane loads is compared with all four.
+constexpr int kCellTileA = 4;
+
+__global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uint32_t na_atoms, uint32_t nb_atoms, CellGeom cg,
+                                                                const uint32_t *offsets_a, const float4 *sorted_a, const uint32_t *offsets_b,
+                                                                const float4 *sorted_b, size_t cells, float cutoff2, unsigned long long *count,
+                                                                uint32_t *pairs, float *dist, unsigned long long capacity,
+                                                                unsigned long long *cursor, const unsigned int *far_a, const unsigned int *far_b) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    BoxOrtho B;
+    load_box(fv.box, f, B);
+    const uint32_t *ofa = offsets_a + (size_t)f * (cells + 1), *ofb = offsets_b + (size_t)f * (cells + 1);
+    const float4 *sa = sorted_a + (size_t)f * na_atoms, *sb = sorted_b + (size_t)f * nb_atoms;
+    const bool fold = far_a[f] == 0u && far_b[f] == 0u; // every atom of both groups within L/4 of the box: one-step fold
+    const uint32_t wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long mine = 0;
+    // one CTA per cell of A (grid-stride), its warps take the cell's tiles in turn: units of a few hundred distance
+    // evaluations keep the SMs evenly loaded (one warp per cell left 17 % of the warp slots busy: long, uneven tasks)
+    for (uint32_t ca = blockIdx.x; ca < cells; ca += gridDim.x) {
+        const uint32_t alo = ofa[ca], ahi = ofa[ca + 1];
+        if (alo == ahi) continue;
+        const int cx = (int)(ca % cg.nx), cy = (int)((ca / cg.nx) % cg.ny), cz = (int)(ca / ((uint32_t)cg.nx * cg.ny));
+        int xs[3], ys[3], zs[3], mx, my, mz;
+        axis_cells(cx, cg.nx, xs, mx);
+        axis_cells(cy, cg.ny, ys, my);
+        axis_cells(cz, cg.nz, zs, mz);
+        const int ncell = mx * my * mz;
+        uint32_t my_lo = 0, my_hi = 0;
+        if (lane < ncell) {
+            const int kx = lane % mx, ky = (lane / mx) % my, kz = lane / (mx * my);
+            const int vx = kx == 0 ? xs[0] : (kx == 1 ? xs[1] : xs[2]), vy = ky == 0 ? ys[0] : (ky == 1 ? ys[1] : ys[2]),
+                      vz = kz == 0 ? zs[0] : (kz == 1 ? zs[1] : zs[2]);
+            const uint32_t c = ((uint32_t)vz * cg.ny + vy) * cg.nx + vx;
+            my_lo = ofb[c];
+            my_hi = ofb[c + 1];
+        }
+        for (uint32_t a0 = alo + wid * kCellTileA; a0 < ahi; a0 += nw * kCellTileA) {
+            float ax[kCellTileA], ay[kCellTileA], az[kCellTileA];
+            uint32_t ai[kCellTileA];
+            const int na = (int)min((uint32_t)kCellTileA, ahi - a0);
+#pragma unroll
+            for (int t = 0; t < kCellTileA; t++) {
+                const float4 a = sa[min(a0 + t, ahi - 1)]; // warp-uniform address: one transaction, broadcast
+                ax[t] = a.x; ay[t] = a.y; az[t] = a.z; ai[t] = __float_as_uint(a.w);
+            }
+            for (int k = 0; k < ncell; k++) {
+                const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
+                for (uint32_t s0 = lo; s0 < hi; s0 += 64) {
+                    float4 b[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const uint32_t s = s0 + u * 32 + lane;
+                        b[u] = s < hi ? sb[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const bool in = s0 + u * 32 + lane < hi;
+#pragma unroll
+                        for (int t = 0; t < kCellTileA; t++) {
+                            float dx, dy, dz;
+                            if (fold) {
+                                const float rx = fabsf(ax[t] - b[u].x), ry = fabsf(ay[t] - b[u].y), rz = fabsf(az[t] - b[u].z);
+                                dx = fminf(rx, fabsf(rx - B.lx));
+                                dy = fminf(ry, fabsf(ry - B.ly));
+                                dz = fminf(rz, fabsf(rz - B.lz));
+                            } else {
+                                dx = min_image(ax[t] - b[u].x, B.lx);
+                                dy = min_image(ay[t] - b[u].y, B.ly);
+                                dz = min_image(az[t] - b[u].z, B.lz);
+                            }
+                            const float d2 = (dx * dx + dy * dy) + dz * dz;
+                            const bool hit = in && t < na && d2 < cutoff2;
+                            const unsigned m = __ballot_sync(0xffffffffu, hit);
+                            if (m == 0u) continue;
+                            const int n_hit = __popc(m);
+                            if (lane == 0) mine += n_hit;
+                            if (pairs) {
+                                unsigned long long base = 0;
+                                if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)n_hit);
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+                                if (hit && at < capacity) {
+                                    uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
+                                    o[0] = ai[t];
+                                    o[1] = __float_as_uint(b[u].w);
+                                    if (dist) dist[(size_t)f * capacity + at] = sqrt1_rn(d2);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(count + f, mine);
+}
+
 } // namespace groan
