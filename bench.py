@@ -210,34 +210,28 @@ def run_gpu_arm(args):
     frame0 = rank * F
     rot, cen = frame_params(frame0, F)
     s.synth_blob(SEED, frame0, F, BLOB_SCALE, NOISE_SCALE, rot, cen, [BOX] * 3, wrap=True)
-    # per-frame results, double-buffered so that the gather of batch k overlaps the kernels of batch k+1
-    d_cen = torch.empty((F, 3), dtype=torch.float32, device=dev)
-    d_rmsd = torch.empty((F,), dtype=torch.float32, device=dev)
-    bufs = [(torch.empty((F, 4), dtype=torch.float32, device=dev), torch.empty((world * F, 4), dtype=torch.float32, device=dev))
-            for _ in range(2)] if world > 1 else None
-    pending = [None, None]
+    # per-frame results of every step of the run stay on the device, in trajectory order; ONE exchange at the end of the
+    # timed region gathers them on all ranks (the only exchange of the path, 16 B per frame); the ranks never
+    # wait for each other inside the loop.
+    n_slots = max(K, W, 1)
+    cen_all = torch.empty((n_slots * F, 3), dtype=torch.float32, device=dev)
+    rmsd_all = torch.empty((n_slots * F,), dtype=torch.float32, device=dev)
+    d_cen, d_rmsd = cen_all[:F], rmsd_all[:F]  # slot 0, also used by the per-op timings below
+    g_cen = torch.empty((world * n_slots * F, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    g_rmsd = torch.empty((world * n_slots * F,), dtype=torch.float32, device=dev) if world > 1 else None
     step_no = [0]
 
     def step():
         # group_get_center + calc_rmsd of the same group: one read of every frame (groan_gpu_center_rmsd)
-        s.group_center_and_rmsd(ref, "G", center_out=d_cen, rmsd_out=d_rmsd)
-        if world > 1:
-            # the one exchange of the path: 16 B per frame, all ranks get the whole trajectory's results.
-            # Issued asynchronously on NCCL's stream; the slot is reused two steps later, after its gather has completed.
-            k = step_no[0] & 1
-            if pending[k] is not None:
-                pending[k].wait()
-            loc, glob = bufs[k]
-            loc[:, :3].copy_(d_cen)
-            loc[:, 3].copy_(d_rmsd)
-            pending[k] = dist.all_gather_into_tensor(glob, loc, async_op=True)
-            step_no[0] += 1
+        i = step_no[0] % n_slots
+        s.group_center_and_rmsd(ref, "G", center_out=cen_all[i * F:(i + 1) * F], rmsd_out=rmsd_all[i * F:(i + 1) * F])
+        step_no[0] += 1
 
     def drain():
-        for k in range(2):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
+        step_no[0] = 0
+        if world > 1:
+            dist.all_gather_into_tensor(g_cen, cen_all)
+            dist.all_gather_into_tensor(g_rmsd, rmsd_all)
 
     def barrier():
         if world > 1:
@@ -354,44 +348,46 @@ def run_gpu_arm(args):
                "timing": "host wall clock around the steps, sync both sides"}
 
         # the same steps fed with the xtc decoder's integers (int16 lattice points at precision 1000 + a per-frame origin,
-        # groan_gpu_push_frames_quantized): the frames are those of h_in rounded to the xtc grid, half the PCIe bytes
-        prec = 1000.0
-        x = h_in[0].numpy()
-        h_q = [torch.empty((F, N_ATOMS, 3), dtype=torch.int16).pin_memory() for _ in range(2)]
-        origin = np.zeros((F, 3), np.int32)
-        for f in range(F):  # frame by frame: no multi-GB temporaries
-            lat = np.rint(x[f].astype(np.float64) * prec).astype(np.int32)
-            origin[f] = ((lat.min(axis=0).astype(np.int64) + lat.max(axis=0)) // 2).astype(np.int32)
-            rel = lat - origin[f]
-            assert np.abs(rel).max() < 32768
-            h_q[0][f] = torch.from_numpy(rel.astype(np.int16))
-        h_q[1].copy_(h_q[0])
-        del lat, rel
+        # groan_gpu_push_frames_quantized): the frames are those of h_in rounded to the xtc grid, half the PCIe bytes.
+        # Single-GPU runs only: it is a property of the link, and N ranks would pin N x 1.8 GB more host memory for it.
+        if world == 1:
+            prec = 1000.0
+            x = h_in[0].numpy()
+            h_q = [torch.empty((F, N_ATOMS, 3), dtype=torch.int16).pin_memory() for _ in range(2)]
+            origin = np.zeros((F, 3), np.int32)
+            for f in range(F):  # frame by frame: no multi-GB temporaries
+                lat = np.rint(x[f].astype(np.float64) * prec).astype(np.int32)
+                origin[f] = ((lat.min(axis=0).astype(np.int64) + lat.max(axis=0)) // 2).astype(np.int32)
+                rel = lat - origin[f]
+                assert np.abs(rel).max() < 32768
+                h_q[0][f] = torch.from_numpy(rel.astype(np.int16))
+            h_q[1].copy_(h_q[0])
+            del lat, rel
 
-        def e2e_q_step(k):
-            s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin)
-            s.group_center_and_rmsd(ref, "G", center_out=h_cen, rmsd_out=h_rmsd)
+            def e2e_q_step(k):
+                s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin)
+                s.group_center_and_rmsd(ref, "G", center_out=h_cen, rmsd_out=h_rmsd)
 
-        for k in range(2):
-            e2e_q_step(k)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(Ke):
-            e2e_q_step(k)
-        s.sync()
-        torch.cuda.synchronize()
-        dtq = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dtq], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtq = float(t.item())
-        assert np.all(np.abs(h_rmsd.numpy() - 0.0866) < 2e-3)
-        e2e["quantized_int16"] = {"value": world * F * Ke / dtq, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48,
-                                  "ms_per_step": dtq * 1e3 / Ke,
-                                  "note": "frames rounded to the xtc grid (precision 1000) and uploaded as the decoder's int16 lattice "
-                                          "points; floats rebuilt on the device with the reader's expression"}
-        s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
-        del h_q
+            for k in range(2):
+                e2e_q_step(k)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(Ke):
+                e2e_q_step(k)
+            s.sync()
+            torch.cuda.synchronize()
+            dtq = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dtq], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtq = float(t.item())
+            assert np.all(np.abs(h_rmsd.numpy() - 0.0866) < 2e-3)
+            e2e["quantized_int16"] = {"value": world * F * Ke / dtq, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48,
+                                      "ms_per_step": dtq * 1e3 / Ke,
+                                      "note": "frames rounded to the xtc grid (precision 1000) and uploaded as the decoder's int16 lattice "
+                                              "points; floats rebuilt on the device with the reader's expression"}
+            s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
+            del h_q
 
     extras = None
     if rank == 0 and not args.no_extras:

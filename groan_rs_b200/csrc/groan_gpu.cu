@@ -47,6 +47,7 @@ struct Group {
     long no_mass_at = -1;  // position in the group of the first atom without mass
     float *d_mass = nullptr;
     std::vector<float> mass;  // host copy (compared with the RMSD reference's masses)
+    double mass_sum = 0.0;    // sum of `mass` in f64, ascending order (set once in groan_gpu_set_group, never per call)
 };
 
 enum PtrKind { PK_DEVICE, PK_PINNED, PK_PAGEABLE };
@@ -779,8 +780,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         rv.sum_wpc[k] = R.sums[5 + k];
         rv.com[k] = R.com[k];
     }
-    rv.sum_m_target = 0.0;
-    for (float m : g->mass) rv.sum_m_target += (double)m;
+    rv.sum_m_target = g->mass_sum;
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
     bool center_done = false, device_fallback = false;
@@ -1061,6 +1061,8 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
     g.no_mass_at = -1;
     g.mass.clear();
     if (mass) g.mass.assign(mass, mass + n);
+    g.mass_sum = 0.0;
+    for (float m : g.mass) g.mass_sum += (double)m;
     if (n) {
         CK(cudaMalloc(&g.d_idx, n * sizeof(uint32_t)));
         CK(cudaMemcpy(g.d_idx, idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
