@@ -100,8 +100,8 @@ __device__ __forceinline__ float v3_z(const V3 &s) { return s.b.x + s.c.y; }
 struct QuadConst {
     V3 negp; // -pilot
     V3 inv;  // 1 / L
-    V3 negl; // -L
-    float sc[3], ph[3]; // 2 pi / L, 2 pi frac(pilot / L)
+    float negl[3]; // -L (scalars: the last step of the min-image runs as two scalar FFMAs, see quad_delta)
+    float sc[3];   // 2 pi / L
 };
 __device__ __forceinline__ V3 v3_pattern(float x, float y, float z) {
     V3 v;
@@ -111,17 +111,20 @@ __device__ __forceinline__ V3 v3_pattern(float x, float y, float z) {
     return v;
 }
 
-// min-image displacement from the pilot, pattern-wise; same arithmetic as pilot_delta (kernels_center.cuh)
-__device__ __forceinline__ float2 quad_delta(float2 x, float2 negp, float2 inv, float2 negl) {
+// min-image displacement from the pilot, pattern-wise; same arithmetic as pilot_delta (kernels_center.cuh).
+// The last step has three different register operands: as an FFMA2 it would read six registers and hold the FMA pipe
+// for three cycles (profiles/exp/ffma2_rate.cu: 3.0 cycles per warp instruction against 2.06 with an immediate operand
+// and 1.03 for a scalar FFMA), so it is issued as two scalar FFMAs, and -L needs no register pairs.
+__device__ __forceinline__ float2 quad_delta(float2 x, float2 negp, float2 inv, float nl0, float nl1) {
     const float2 d = __fadd2_rn(x, negp);
     const float2 k = __fadd2_rn(__ffma2_rn(d, inv, splat(kMagic)), splat(-kMagic));
-    return __ffma2_rn(negl, k, d);
+    return make_float2(__fmaf_rn(nl0, k.x, d.x), __fmaf_rn(nl1, k.y, d.y));
 }
-// sin(2 pi (d / L + frac(p / L))) on the SFU for both halves.  The angle is formed by scalar FFMAs from scalar per-axis
-// constants (sc = 2 pi / L, ph = 2 pi frac(p / L)): as many issue slots as the packed form plus its 2 pi multiply, and no
-// pattern registers.
-__device__ __forceinline__ float2 quad_sin(float2 d, float sc0, float ph0, float sc1, float ph1) {
-    return make_float2(__sinf(__fmaf_rn(d.x, sc0, ph0)), __sinf(__fmaf_rn(d.y, sc1, ph1)));
+// sin(2 pi x / L) on the SFU for both halves, from the coordinate AS LOADED: the unwrapped coordinate u = p + d differs
+// from x by a whole number of box lengths, so sin(2 pi u / L) = sin(2 pi x / L); no phase constant, and the sines do not
+// wait for the min-image chain.  (|x| < 65 L is certified by the finishing thread, so the f32 angle is good to 3e-5.)
+__device__ __forceinline__ float2 quad_sin(float2 x, float sc0, float sc1) {
+    return make_float2(__sinf(__fmul_rn(x.x, sc0)), __sinf(__fmul_rn(x.y, sc1)));
 }
 
 struct QuadMinMax {
@@ -195,12 +198,20 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
                                              unsigned char *smem, F &&fn) {
     typedef QuadCfg<WITH_REF, STAGES, NT> C;
     constexpr uint32_t CH = C::kAtoms, kSt = (uint32_t)C::kStageBytes;
-    const uint32_t t = threadIdx.x, lane = t & 31;
+    // threadIdx.x through a volatile asm: the value then lives in a register.  Left to itself the allocator re-reads
+    // SR_TID.X (and re-derives the shared-memory window base from SR_CgaCtaId) in front of every quad, ~60 cycles of
+    // dependent latency before the first LDS of a quad can issue (ncu source view of the round-1 kernel).
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    const uint32_t lane = t & 31;
     const uint32_t chunks = (bg.body + CH - 1) / CH;
     const uint32_t my_chunks = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const char *src0 = reinterpret_cast<const char *>(fv.frame(f) + ((size_t)g.first + bg.head) * 3);
     QuadCtl<STAGES> &ctl = *reinterpret_cast<QuadCtl<STAGES> *>(smem + STAGES * C::kStageBytes);
-    const uint32_t ring = smem_u32(smem), full0 = ring + STAGES * kSt, empty0 = full0 + STAGES * 8u;
+    // the ring's shared-memory address, also through a volatile asm (see above)
+    uint32_t ring;
+    asm volatile("{\n\t.reg .u64 a;\n\tcvta.to.shared.u64 a, %1;\n\tcvt.u32.u64 %0, a;\n\t}" : "=r"(ring) : "l"(smem));
+    const uint32_t full0 = ring + STAGES * kSt, empty0 = full0 + STAGES * 8u;
     auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES (one thread)
         const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
         const uint32_t atoms = min(CH, bg.body - c * CH);
@@ -310,13 +321,11 @@ __device__ __forceinline__ QuadConst quad_constants(const float p[3], const floa
         for (int k = 0; k < 6; k++) {
             scratch[k] = -p[pat[k]];
             scratch[6 + k] = inv[pat[k]];
-            scratch[12 + k] = -L[pat[k]];
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float t = p[k] * inv[k];
+            scratch[12 + k] = -L[k];
             scratch[18 + k] = 6.283185307179586f * inv[k];
-            scratch[21 + k] = 6.283185307179586f * (t - floorf(t));
         }
     }
     __syncthreads();
@@ -326,34 +335,34 @@ __device__ __forceinline__ QuadConst quad_constants(const float p[3], const floa
     QuadConst q;
     q.negp.a = c2[0]; q.negp.b = c2[1]; q.negp.c = c2[2];
     q.inv.a = c2[3]; q.inv.b = c2[4]; q.inv.c = c2[5];
-    q.negl.a = c2[6]; q.negl.b = c2[7]; q.negl.c = c2[8];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
+        q.negl[k] = scratch[12 + k];
         q.sc[k] = scratch[18 + k];
-        q.ph[k] = scratch[21 + k];
     }
     return q;
 }
 
 // the six pairs of a quad -> min-image displacements of atom pair (0,1) in d01 and (2,3) in d23
 __device__ __forceinline__ void quad_deltas(const QuadConst &q, const float4 &c0, const float4 &c1, const float4 &c2, V3 &d01, V3 &d23) {
-    d01.a = quad_delta(make_float2(c0.x, c0.y), q.negp.a, q.inv.a, q.negl.a);
-    d01.b = quad_delta(make_float2(c0.z, c0.w), q.negp.b, q.inv.b, q.negl.b);
-    d01.c = quad_delta(make_float2(c1.x, c1.y), q.negp.c, q.inv.c, q.negl.c);
-    d23.a = quad_delta(make_float2(c1.z, c1.w), q.negp.a, q.inv.a, q.negl.a);
-    d23.b = quad_delta(make_float2(c2.x, c2.y), q.negp.b, q.inv.b, q.negl.b);
-    d23.c = quad_delta(make_float2(c2.z, c2.w), q.negp.c, q.inv.c, q.negl.c);
+    d01.a = quad_delta(make_float2(c0.x, c0.y), q.negp.a, q.inv.a, q.negl[0], q.negl[1]);
+    d01.b = quad_delta(make_float2(c0.z, c0.w), q.negp.b, q.inv.b, q.negl[2], q.negl[0]);
+    d01.c = quad_delta(make_float2(c1.x, c1.y), q.negp.c, q.inv.c, q.negl[1], q.negl[2]);
+    d23.a = quad_delta(make_float2(c1.z, c1.w), q.negp.a, q.inv.a, q.negl[0], q.negl[1]);
+    d23.b = quad_delta(make_float2(c2.x, c2.y), q.negp.b, q.inv.b, q.negl[2], q.negl[0]);
+    d23.c = quad_delta(make_float2(c2.z, c2.w), q.negp.c, q.inv.c, q.negl[1], q.negl[2]);
 }
-__device__ __forceinline__ void quad_sines(const QuadConst &q, const V3 &d, V3 &ssin) {
-    ssin.a = __fadd2_rn(ssin.a, quad_sin(d.a, q.sc[0], q.ph[0], q.sc[1], q.ph[1]));
-    ssin.b = __fadd2_rn(ssin.b, quad_sin(d.b, q.sc[2], q.ph[2], q.sc[0], q.ph[0]));
-    ssin.c = __fadd2_rn(ssin.c, quad_sin(d.c, q.sc[1], q.ph[1], q.sc[2], q.ph[2]));
+// xa, xb, xc = the three coordinate pairs of an atom pair as loaded: (x,y) (z,x') (y',z')
+__device__ __forceinline__ void quad_sines(const QuadConst &q, float2 xa, float2 xb, float2 xc, V3 &ssin) {
+    ssin.a = __fadd2_rn(ssin.a, quad_sin(xa, q.sc[0], q.sc[1]));
+    ssin.b = __fadd2_rn(ssin.b, quad_sin(xb, q.sc[2], q.sc[0]));
+    ssin.c = __fadd2_rn(ssin.c, quad_sin(xc, q.sc[1], q.sc[2]));
 }
 
 // sine of one atom's axis for the finishing thread's head / tail atoms, same definition as quad_sin
-__device__ __forceinline__ double edge_sin(float d, float p, float L) {
-    const float inv = 1.0f / L, t = p * inv;
-    return (double)__sinf(__fmaf_rn(d, 6.283185307179586f * inv, 6.283185307179586f * (t - floorf(t))));
+__device__ __forceinline__ double edge_sin(float x, float L) {
+    const float inv = 1.0f / L;
+    return (double)__sinf(__fmul_rn(x, 6.283185307179586f * inv));
 }
 
 // ---------------------------------------------------------------- group_get_center / group_get_com
@@ -388,8 +397,8 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
             v3_add(smd, d01);
             v3_add(smd, d23);
         }
-        quad_sines(qc, d01, ssin);
-        quad_sines(qc, d23, ssin);
+        quad_sines(qc, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), ssin);
+        quad_sines(qc, make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w), ssin);
         quad_minmax(mm, d01);
         quad_minmax(mm, d23);
     });
@@ -405,9 +414,9 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
             const double m = WEIGHTED ? (double)__ldg(g.mass + i) : 1.0;
             if (WEIGHTED) tot[3] += m;
             for (int k = 0; k < 3; k++) {
-                const float d = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+                const float xk = __ldg(q + k), d = pilot_delta(xk, p[k], L[k], 1.0f / L[k]);
                 tot[k] += m * (double)d;
-                tot[4 + k] += edge_sin(d, p[k], L[k]);
+                tot[4 + k] += edge_sin(xk, L[k]);
                 tmn[k] = fminf(tmn[k], d);
                 tmx[k] = fmaxf(tmx[k], d);
             }
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
     float2 sq = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
-    auto atom_pair = [&](const V3 &d, const float4 &r0, const float4 &r1, uint32_t i) {
+    auto atom_pair = [&](const V3 &d, float2 xa, float2 xb, float2 xc, const float4 &r0, const float4 &r1, uint32_t i) {
         const float2 pc[3] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y)};
         const float2 w = make_float2(r1.z, r1.w);
         const V3 wd = v3_mul(w, d); // w d also serves Hw = sum pc (w d)^T: no separate w pc products
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         sq = __ffma2_rn(wd.b, d.b, sq);
         sq = __ffma2_rn(wd.c, d.c, sq);
         if (CENTER == 1) v3_add(sd, d);
-        if (CENTER) quad_sines(qc, d, ssin);
+        if (CENTER) quad_sines(qc, xa, xb, xc, ssin);
         quad_minmax(mm, d);
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
@@ -474,8 +483,8 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
 #endif
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
-        atom_pair(d01, r[0], r[1], bg.head + j);
-        atom_pair(d23, r[2], r[3], bg.head + j + 2);
+        atom_pair(d01, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), r[0], r[1], bg.head + j);
+        atom_pair(d23, make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w), r[2], r[3], bg.head + j + 2);
     });
     __syncthreads(); // every warp has left the ring: its memory becomes the reduction scratch
     float a[KS];
@@ -504,13 +513,13 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
             double d[3];
             for (int k = 0; k < 3; k++) {
-                const float dk = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+                const float xk = __ldg(q + k), dk = pilot_delta(xk, p[k], L[k], 1.0f / L[k]);
                 d[k] = (double)dk;
                 tmn[k] = fminf(tmn[k], dk);
                 tmx[k] = fmaxf(tmx[k], dk);
                 if (CENTER) {
                     tot[KS - 6 + k] += d[k];
-                    tot[KS - 3 + k] += edge_sin(dk, p[k], L[k]);
+                    tot[KS - 3 + k] += edge_sin(xk, L[k]);
                 }
             }
             for (int u = 0; u < 3; u++)
