@@ -235,36 +235,50 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     const uint32_t off_f = ring + t * 48u, off_r = ring + (uint32_t)C::kFrameBytes + ((t >> 5) * 128u + lane) * 16u;
     uint32_t j = blockIdx.x * CH + t * 4;
     const uint32_t jstep = gridDim.x * CH;
-    auto quad = [&](uint32_t st) { // st = byte offset of the stage
-        const float4 c0 = lds128(off_f + st), c1 = lds128(off_f + st + 16u), c2 = lds128(off_f + st + 32u);
-        float4 r[4];
+    struct QuadRegs {
+        float4 c0, c1, c2, r[4];
+    };
+    auto load = [&](uint32_t st, QuadRegs &q) { // st = byte offset of the stage
+        q.c0 = lds128(off_f + st); q.c1 = lds128(off_f + st + 16u); q.c2 = lds128(off_f + st + 32u);
         if (WITH_REF) {
-            r[0] = lds128(off_r + st);
-            r[1] = lds128(off_r + st + 512u);
-            r[2] = lds128(off_r + st + 1024u);
-            r[3] = lds128(off_r + st + 1536u);
+            q.r[0] = lds128(off_r + st);
+            q.r[1] = lds128(off_r + st + 512u);
+            q.r[2] = lds128(off_r + st + 1024u);
+            q.r[3] = lds128(off_r + st + 1536u);
         }
-        fn(j, c0, c1, c2, r);
+    };
+    auto quad = [&](uint32_t st) {
+        QuadRegs q;
+        load(st, q);
+        fn(j, q.c0, q.c1, q.c2, q.r);
     };
     static_assert(STAGES == 4, "the loop below walks the ring in pairs of stages");
     const uint32_t hot = (my_chunks - 1) & ~1u; // chunks of this CTA that are certainly full, in pairs
     uint32_t ph = 0, it = 0, st = 0;            // st = byte offset of the pair's first stage: 0 or 2 stages
     // Two chunks per trip (stages s, s + 1 with s = 0 or 2): loop control and address arithmetic are paid once per
     // eight atoms of a thread, while each stage keeps its own barriers and is refilled as soon as its last reader leaves.
+    // The wait for a stage is issued one quad EARLY -- right after the loads of the quad before it, in front of that
+    // quad's ~170 instructions of arithmetic -- so the round trip of the barrier check is covered by arithmetic instead
+    // of standing between two quads (the ring is four stages deep: the stage is normally full long before).
+    if (hot) mbar_wait_a(full0, 0u);
     for (; it < hot; it += 2) {
         const uint32_t fb = full0 + (st ? 16u : 0u), eb = empty0 + (st ? 16u : 0u);
-        mbar_wait_a(fb, ph);
-        quad(st);
+        const uint32_t nst = st ^ (2u * kSt), nph = ph ^ (uint32_t)(st != 0);
+        QuadRegs q;
+        load(st, q);
+        mbar_wait_a(fb + 8u, ph);
+        fn(j, q.c0, q.c1, q.c2, q.r);
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
         j += jstep;
-        mbar_wait_a(fb + 8u, ph);
-        quad(st + kSt);
+        load(st + kSt, q);
+        if (it + 2 < my_chunks) mbar_wait_a(full0 + (nst ? 16u : 0u), nph);
+        fn(j, q.c0, q.c1, q.c2, q.r);
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
         j += jstep;
-        ph ^= (st != 0);
-        st ^= 2u * kSt;
+        ph = nph;
+        st = nst;
     }
     // the remaining one or two chunks; the very last one may be ragged.  Nothing is left to refill.
     for (; it < my_chunks; it++, j += jstep) {
