@@ -414,8 +414,8 @@ def run_extras(torch, g, local, peak):
     out = {}
     dev = torch.device("cuda", local)
 
-    def time_op(fn, reps=5):
-        for _ in range(2):
+    def time_op(fn, reps=5, warm=2):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -469,7 +469,12 @@ def run_extras(torch, g, local, peak):
     p.group_create_from_indices("A", np.arange(n1))
     p.group_create_from_indices("B", np.arange(500000, 500000 + n2))
     p.synth_uniform(SEED, 0, 2, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
-    t = time_op(lambda: p.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0), reps=3)
+    # 0.6 ms per call: enough launches for the clocks to settle after the allocations above (3 launches read 0.75 ms, 20 read 0.60 ms)
+    red = {"min": torch.empty(2, dtype=torch.float32, device=dev), "argmin": torch.empty((2, 2), dtype=torch.int32, device=dev),
+           "max": torch.empty(2, dtype=torch.float32, device=dev), "argmax": torch.empty((2, 2), dtype=torch.int32, device=dev),
+           "count": torch.empty(2, dtype=torch.int64, device=dev)}  # results stay on the device: the kernel, not five small D2H copies
+    t = time_op(lambda: p.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0, out=red), reps=20, warm=5)
+    assert int(red["count"][0].item()) > 0
     pairs = 2 * n1 * n2
     # FP32 roofline of SURVEY 8d: 18 reference FP32 ops per pair against 148 SM x 128 lanes x 1.965 GHz = 37.2 T op/s (non-FMA)
     out["all_pairs_fused_reduce"] = {"ms": t, "pairs_per_s": pairs / (t * 1e-3), "frames_per_s": 2 / (t * 1e-3),
@@ -477,7 +482,7 @@ def run_extras(torch, g, local, peak):
                                      "frac_of_fp32_peak": 18 * pairs / (t * 1e-3) / (148 * 128 * 1.965e9)}
     p.synth_uniform(SEED, 0, 1, [-0.1 * 21.5] * 3, [1.2 * 21.5] * 3, [21.5] * 3)
     mat = torch.empty((1, n1, n2), dtype=torch.float32, device=dev)
-    t = time_op(lambda: p.group_all_distances("A", "B", g.Dimension.XYZ, out=mat), reps=3)
+    t = time_op(lambda: p.group_all_distances("A", "B", g.Dimension.XYZ, out=mat), reps=10, warm=3)
     out["all_pairs_materialise"] = {"ms": t, "pairs_per_s": n1 * n2 / (t * 1e-3), "write_gbs": 4 * n1 * n2 * 1e-9 / (t * 1e-3),
                                     "frac_of_hbm_peak": 4 * n1 * n2 * 1e-9 / (t * 1e-3) / peak}
     del mat

@@ -486,13 +486,17 @@ class System:
         self.group_create_from_indices("__atom2", [int(index2)])
         return self.group_all_distances("__atom1", "__atom2", dim)[:, 0, 0]
 
-    def group_all_distances_reduce(self, group1, group2, dim, cutoff=0.0):
+    def group_all_distances_reduce(self, group1, group2, dim, cutoff=0.0, out=None):
         """The documented consumer of the matrix (analysis.rs:390-399) fused on the device:
-        returns dict(min, argmin [F,2], max, argmax [F,2], count) without materialising the matrix."""
+        returns dict(min, argmin [F,2], max, argmax [F,2], count) without materialising the matrix.
+        `out`: a dict with those five keys holding host arrays or device tensors (f32 / 2 x u32 / f32 / 2 x u32 / u64
+        per frame; torch has no unsigned 64-bit type, int32 pairs / int64 of the same size do) that receive the results;
+        with device tensors the call is asynchronous on the ctx's stream."""
         g1, g2 = self._gid(group1), self._gid(group2)
         F = self.n_frames
-        r = {"min": np.empty(F, np.float32), "argmin": np.empty((F, 2), np.uint32), "max": np.empty(F, np.float32),
-             "argmax": np.empty((F, 2), np.uint32), "count": np.empty(F, np.uint64)}
+        r = out if out is not None else {
+            "min": np.empty(F, np.float32), "argmin": np.empty((F, 2), np.uint32), "max": np.empty(F, np.float32),
+            "argmax": np.empty((F, 2), np.uint32), "count": np.empty(F, np.uint64)}
         self._check(self._lib.groan_gpu_all_distances_reduce(self._h, g1, g2, int(dim), float(cutoff), _ptr(r["min"]),
                                                              _ptr(r["argmin"]), _ptr(r["max"]), _ptr(r["argmax"]),
                                                              _ptr(r["count"])), "group_all_distances_reduce",
