@@ -663,6 +663,43 @@ def test_all_pairs_reduce_ties_and_many_chunks():
         assert int(red["count"][f]) == cnt
 
 
+def test_all_pairs_reduce_device_outputs_and_warp_shared_thresholds():
+    """results delivered into device tensors (no host copies) equal the host-delivered ones, on a case where the running
+    minimum / maximum of different lanes of a warp keep improving (sorted distances: every step is a record for some lane),
+    i.e. the thresholds the warp shares after an update are exercised all the time."""
+    import torch
+    n, F = 40_000, 3
+    L = np.array([30.0, 30.0, 30.0], np.float32)
+    s = _sys(n, max_frames=F)
+    frames = np.zeros((F, n, 3), np.float32)
+    rng = np.random.default_rng(11)
+    for f in range(F):
+        # group A near the origin, group B on a line of decreasing then increasing distance
+        frames[f, :16] = rng.uniform(0.0, 0.2, (16, 3))
+        x = np.linspace(14.9, 0.3, n - 16) if f != 1 else np.linspace(0.3, 14.9, n - 16)
+        frames[f, 16:, 0] = x
+        frames[f, 16:, 1] = rng.uniform(0.0, 0.05, n - 16)
+    s.set_frames(frames, L)
+    a, b = np.arange(0, 16), np.arange(16, n)
+    s.group_create_from_indices("A", a)
+    s.group_create_from_indices("B", b)
+    host = s.group_all_distances_reduce("A", "B", _dim("XYZ"), cutoff=1.0)
+    dev = torch.device("cuda", 0)
+    out = {"min": torch.empty(F, dtype=torch.float32, device=dev), "argmin": torch.empty((F, 2), dtype=torch.int32, device=dev),
+           "max": torch.empty(F, dtype=torch.float32, device=dev), "argmax": torch.empty((F, 2), dtype=torch.int32, device=dev),
+           "count": torch.empty(F, dtype=torch.int64, device=dev)}
+    s.group_all_distances_reduce("A", "B", _dim("XYZ"), cutoff=1.0, out=out)
+    s.sync()
+    for k in host:
+        assert np.array_equal(out[k].cpu().numpy().astype(np.int64 if k != "min" and k != "max" else np.float32),
+                              host[k].astype(np.int64 if k != "min" and k != "max" else np.float32)), k
+    for f in range(F):
+        mn, imn, mx, imx, cnt = orc.all_distances_minmax(frames[f], a, b, "XYZ", L, cutoff=1.0)
+        assert bits(host["min"][f]) == bits(mn) and tuple(host["argmin"][f]) == tuple(imn), (f, host["argmin"][f], imn)
+        assert bits(host["max"][f]) == bits(mx) and tuple(host["argmax"][f]) == tuple(imx), (f, host["argmax"][f], imx)
+        assert int(host["count"][f]) == cnt
+
+
 # ------------------------------------------------------------------ full-size, size-independent properties (BASELINE configs[3], [4])
 def test_full_size_properties_cfg4_cfg5():
     """At BASELINE.json's full sizes the oracle is too slow, so the CUDA path is checked through properties:
