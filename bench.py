@@ -67,6 +67,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin, self.t_end = None, None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -81,7 +88,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.perf_counter()])
 
     def stop(self):
         if not self.proc:
@@ -92,10 +99,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        # the sampler is started before the warm-up (so that nvidia-smi's start-up does not fall into the timed region);
+        # only the rows read between mark_begin() and mark_end() (+ one polling interval) count
+        rows = [r for r in self.rows if len(r) >= 8]
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [r for r in rows if self.t_begin <= r[-1] <= self.t_end + 0.03]
+            rows = inside or rows
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -238,6 +251,9 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step()
     drain()
@@ -254,18 +270,17 @@ def run_gpu_arm(args):
     s.group_center_and_rmsd(ref, "G", center_out=d_cen, rmsd_out=d_rmsd)
     fallback["group_center_and_rmsd"] = s.fallback_frames()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = s.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(K):
         step()
     drain()  # every batch's results have been gathered before the clock stops
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = s.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
