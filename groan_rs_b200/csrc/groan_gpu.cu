@@ -642,7 +642,7 @@ int launch_pairs_reduce(groan_gpu_ctx *ctx, const Group &a, const Group &b, floa
     return GROAN_OK;
 }
 
-template <int DIM>
+template <int DIM, typename BOX = BoxOrtho>
 int launch_pairs_reduce_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
     // persistent CTAs (4 per SM in total) striding over work units of (1024 B atoms) x (256 A atoms)
     const size_t units = ((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)) * ((a.n + kSliceA - 1) / kSliceA);
@@ -652,11 +652,11 @@ int launch_pairs_reduce_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b,
     dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
     const float c2 = cutoff_squared_threshold(cutoff);
     if (o.count)
-        k_pairs_reduce_fast<DIM, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
+        k_pairs_reduce_fast<DIM, true, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
                                                                             (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
                                                                             o.imin, o.dmax, o.imax, o.count);
     else
-        k_pairs_reduce_fast<DIM, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
+        k_pairs_reduce_fast<DIM, false, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
                                                                              (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
                                                                              o.imin, o.dmax, o.imax, o.count);
     LAUNCHED();
@@ -671,6 +671,15 @@ int dispatch_pairs_reduce(groan_gpu_ctx *ctx, int dim, const Group &a, const Gro
         case 5: return launch_pairs_reduce_fast<5>(ctx, a, b, cutoff, o);
         case 6: return launch_pairs_reduce_fast<6>(ctx, a, b, cutoff, o);
         case 7: return launch_pairs_reduce_fast<7>(ctx, a, b, cutoff, o);
+        default: break;
+        }
+    } else {
+        // triclinic extension, 2-D / 3-D: the same kernel with the 27-image d^2 (kernels_pairs.cuh pair_d2_tric)
+        switch (dim) {
+        case 4: return launch_pairs_reduce_fast<4, BoxTric>(ctx, a, b, cutoff, o);
+        case 5: return launch_pairs_reduce_fast<5, BoxTric>(ctx, a, b, cutoff, o);
+        case 6: return launch_pairs_reduce_fast<6, BoxTric>(ctx, a, b, cutoff, o);
+        case 7: return launch_pairs_reduce_fast<7, BoxTric>(ctx, a, b, cutoff, o);
         default: break;
         }
     }

@@ -331,6 +331,37 @@ def test_rmsd_identity_and_broken_reference(protein):
     assert np.all(np.abs(got) <= 1e-4), got
 
 
+def _check_reduce_against_matrix(s, ga, gb, dn, cutoff):
+    """group_all_distances_reduce == the reference's scan of the materialised matrix (analysis.rs:390-399), bit for bit"""
+    mat = s.group_all_distances(ga, gb, _dim(dn))
+    red = s.group_all_distances_reduce(ga, gb, _dim(dn), cutoff=cutoff)
+    F, n1, n2 = mat.shape
+    for f in range(F):
+        m = mat[f]
+        kmin = int(np.argmin(m))                      # first minimum in row-major order
+        kmax = m.size - 1 - int(np.argmax(m[::-1, ::-1]))  # last maximum in row-major order
+        assert bits(red["min"][f]) == bits(m.flat[kmin]) and tuple(red["argmin"][f]) == (kmin // n2, kmin % n2), (dn, f)
+        assert bits(red["max"][f]) == bits(m.flat[kmax]) and tuple(red["argmax"][f]) == (kmax // n2, kmax % n2), (dn, f)
+        assert int(red["count"][f]) == int(np.count_nonzero(m < np.float32(cutoff))), (dn, f)
+
+
+def test_triclinic_reduce_fast_path_synthetic():
+    """the 27-image d^2 of the fused reduction against the materialised triclinic matrix (itself bit-exact against the
+    oracle, test_triclinic_cfg3) on a dodecahedron-like box with atoms up to three box vectors outside the cell"""
+    n, F = 6000, 2
+    box = np.array([7.0, 0, 0, 0, 7.0, 0, 3.5, 3.5, 4.95], np.float32)
+    s = _sys(n, max_frames=F, triclinic=True)
+    rng = np.random.default_rng(21)
+    fr = rng.uniform(-14.0, 21.0, (F, n, 3)).astype(np.float32)
+    fr[:, 100] = fr[:, 3]  # a zero distance, and a tie with it
+    fr[:, 4000] = fr[:, 3]
+    s.set_frames(fr, box)
+    s.group_create_from_indices("A", range(0, 70))
+    s.group_create_from_indices("B", range(64, n))
+    for dn in ("XYZ", "XZ", "XY"):
+        _check_reduce_against_matrix(s, "A", "B", dn, cutoff=1.2)
+
+
 # ------------------------------------------------------------------ triclinic EXTENSION (config 3; unpinned by the reference)
 @pytest.mark.parametrize("name", ["triclinic", "dodecahedron", "octahedron"])
 def test_triclinic_cfg3(tric, name):
@@ -353,6 +384,13 @@ def test_triclinic_cfg3(tric, name):
         for f in range(fr.shape[0]):
             exp = orc.tric_all_distances(fr[f], range(n), range(n), dn, bx[f])
             assert np.array_equal(bits(got[f]), bits(exp)), (dn, f)
+    # the fused reduction (27-image d^2 on the fast path for 2-D / 3-D, reference loops for 1-D) = reduction of that matrix:
+    # first minimum, last maximum of the row-major scan, count below the cutoff
+    s.group_create_from_indices("A", range(0, 20))
+    s.group_create_from_indices("B", range(15, n))
+    for dn in ("XYZ", "XY", "YZ", "Z"):
+        _check_reduce_against_matrix(s, "A", "B", dn, cutoff=0.9)
+    _check_reduce_against_matrix(s, "all", "all", "XYZ", cutoff=0.5)
     # self-pin: f64 brute force over 5^3 images
     got = s.group_all_distances("all", "all", _dim("XYZ"))
     for f in (0, 5, 10):
