@@ -522,6 +522,11 @@ def run_extras(torch, g, local, peak):
     t = time_op(lambda: pt.group_all_distances_reduce("A", "B", g.Dimension.XYZ, cutoff=1.0, out=red1), reps=3, warm=1)
     out["all_pairs_triclinic_fused_reduce"] = {"ms": t, "pairs_per_s": n1 * n2 / (t * 1e-3),
                                                "note": "27-image search per pair (dodecahedron-safe), reference-order arithmetic"}
+    pt.group_create_from_indices("B2", np.arange(500000, 500000 + 20000))
+    mat = torch.empty((1, n1, 20000), dtype=torch.float32, device=dev)
+    t = time_op(lambda: pt.group_all_distances("A", "B2", g.Dimension.XYZ, out=mat), reps=3, warm=1)
+    out["all_pairs_triclinic_materialise"] = {"ms": t, "pairs_per_s": n1 * 20000 / (t * 1e-3)}
+    del mat
     pt.close()
     # cutoff pair search through a cell grid: 200 000 atoms against all 1M atoms, cutoff 1.0 nm
     # (~420 neighbours per atom at 100 atoms/nm^3); the brute-force equivalent is 2e11 pairs per frame

@@ -574,15 +574,15 @@ int launch_pairs(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_ou
 }
 
 // orthogonal box, 2-D / 3-D distance: packed one-step min-image (kernels_pairs.cuh "fast paths")
-template <int DIM>
+template <int DIM, typename BOX = BoxOrtho>
 int launch_pairs_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_out) {
     const bool vec = (b.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
     dim3 grid((unsigned)((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)),
               (unsigned)((a.n + kFastRows - 1) / kFastRows), (unsigned)ctx->n_frames);
     if (vec)
-        k_pairs_fast<DIM, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+        k_pairs_fast<DIM, true, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
     else
-        k_pairs_fast<DIM, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
+        k_pairs_fast<DIM, false, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
     LAUNCHED();
     return GROAN_OK;
 }
@@ -605,6 +605,15 @@ int dispatch_pairs(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, 
         case 5: return launch_pairs_fast<5>(ctx, a, b, d_out);
         case 6: return launch_pairs_fast<6>(ctx, a, b, d_out);
         case 7: return launch_pairs_fast<7>(ctx, a, b, d_out);
+        default: break;
+        }
+    } else {
+        // triclinic extension, 2-D / 3-D: the same kernel with the 27-image d^2 (kernels_pairs.cuh pair_d2_tric)
+        switch (dim) {
+        case 4: return launch_pairs_fast<4, BoxTric>(ctx, a, b, d_out);
+        case 5: return launch_pairs_fast<5, BoxTric>(ctx, a, b, d_out);
+        case 6: return launch_pairs_fast<6, BoxTric>(ctx, a, b, d_out);
+        case 7: return launch_pairs_fast<7, BoxTric>(ctx, a, b, d_out);
         default: break;
         }
     }
