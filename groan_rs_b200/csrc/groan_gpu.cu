@@ -833,7 +833,16 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
         const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
         dim3 fgrid(nbf, (unsigned)ctx->n_frames);
-        if (R.same_mass)
+        if (center && R.same_mass) {
+            // centre and RMSD from one gather of the group (kernels_quad.cuh k_rmsd_fast_center)
+            if (center_weighted)
+                k_rmsd_fast_center<2><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+                                                                             d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+            else
+                k_rmsd_fast_center<1><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+                                                                             d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
+            center_done = true;
+        } else if (R.same_mass)
             k_rmsd_fast<true><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
                                                                      d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
         else

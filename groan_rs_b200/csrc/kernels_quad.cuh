@@ -567,4 +567,53 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     }
 }
 
+// ---------------------------------------------------------------- centre + RMSD from ONE gather (index-list groups)
+// The quad kernels need a contiguous, 16-byte aligned range.  For index lists (and whatever else falls back to
+// k_rmsd_fast) the centre used to be a second gather of the same atoms; this is k_rmsd_fast with the three extra sums of
+// the sine-only centre, finished like k_rmsd_quad.  SAME_MASS only (see launch_rmsd_quad).  CENTER: 1 = geometry, 2 = COM.
+template <int CENTER>
+__global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast_center(FrameView fv, GroupView g, RefView ref, double *partials,
+                                                                   unsigned int *tickets, float *center_out, float *rmsd_out,
+                                                                   float *rot_out, float *com_out, int *flags) {
+    constexpr int KS = kQuadSums;
+    __shared__ FrameReduceSmem<KS, 3> sm;
+    const int f = blockIdx.y, nb = gridDim.x;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *p0 = fv.frame(f) + (size_t)g.atom(0) * 3;
+    const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    const float inv[3] = {1.0f / L[0], 1.0f / L[1], 1.0f / L[2]};
+    const float sc[3] = {6.283185307179586f * inv[0], 6.283185307179586f * inv[1], 6.283185307179586f * inv[2]};
+    float a[kFastSums], c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kFastSums; k++) a[k] = 0.0f;
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
+        const float4 r = ref_at(ref.pc, i);
+        const float d[3] = {pilot_delta(x, p[0], L[0], inv[0]), pilot_delta(y, p[1], L[1], inv[1]), pilot_delta(z, p[2], L[2], inv[2])};
+        rmsd_accumulate<true>(a, mn, mx, d, r, 0.0f);
+        if (CENTER == 1) { c[0] += d[0]; c[1] += d[1]; c[2] += d[2]; }
+        c[3] += __sinf(__fmul_rn(x, sc[0])); // same definition as quad_sin / edge_sin
+        c[4] += __sinf(__fmul_rn(y, sc[1]));
+        c[5] += __sinf(__fmul_rn(z, sc[2]));
+    });
+    float all[KS];
+#pragma unroll
+    for (int k = 0; k < kFastSums; k++) all[k] = a[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) all[kFastSums + k] = c[k];
+    double tot[KS];
+    float tmn[3], tmx[3];
+    if (frame_reduce<KS, 3>(all, mn, mx, partials + (size_t)f * nb * (KS + 6), tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
+        double rt[kFastSums];
+        for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
+        int flag_r = 0, flag_c = 0;
+        finish_rmsd<true>(rt, tmn, tmx, p[0], p[1], p[2], L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, &flag_r);
+        double md[3];
+        for (int k = 0; k < 3; k++) md[k] = CENTER == 2 ? tot[18 + k] : tot[KS - 6 + k];
+        finish_center_sin(md, CENTER == 2 ? ref.sum_w : (double)g.n, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
+        flags[f] = flag_r | (flag_c << 1);
+    }
+}
+
 } // namespace groan
