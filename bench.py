@@ -542,6 +542,16 @@ def run_extras(torch, g, local, peak):
     out["pairs_within_cell_grid"] = {"ms": t, "frames_per_s": 1 / (t * 1e-3), "pairs_found_per_frame": found,
                                      "pairs_found_per_s": found / (t * 1e-3),
                                      "brute_force_equivalent_pairs_per_s": 200000 * N / (t * 1e-3)}
+    # ... the same search with the pairs written out (device-resident lists, 8 B per pair; hits staged per warp in shared memory)
+    d_pairs = torch.empty((1, 120_000_000, 2), dtype=torch.int32, device=dev)
+
+    def search_store():
+        cnt[0] = p.group_pairs_within("Q", "all1M", 1.0, pairs_out=d_pairs)[0]
+
+    t = time_op(search_store, reps=3)
+    out["pairs_within_cell_grid_store"] = {"ms": t, "pairs_stored_per_s": int(cnt[0][0]) / (t * 1e-3),
+                                           "write_gbs": 8 * int(cnt[0][0]) * 1e-9 / (t * 1e-3)}
+    del d_pairs
     p.close()
     return out
 

@@ -1423,10 +1423,14 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
             rc = build(ga, na_atoms, la, d_far_a);
             if (rc) return rc;
             const unsigned nq = (unsigned)std::max<size_t>(1, std::min<size_t>(cells, (size_t)kSMs * 64));
-            k_cell_query_tiled<<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets,
-                                                                                    la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
-                                                                                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0,
-                                                                                    d_far_b + f0);
+            if (pp)
+                k_cell_query_tiled<true><<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(
+                    fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets, la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
+                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0, d_far_b + f0);
+            else
+                k_cell_query_tiled<false><<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(
+                    fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets, la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
+                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0, d_far_b + f0);
             LAUNCHED();
         } else if (na_atoms) {
             const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((na_atoms + 7) / 8, (size_t)kSMs * 16));

@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(kThreads) k_cell_query(FrameView fv, GroupView
 // binned too (the same three kernels), one CTA takes one cell of A: its atoms go through in tiles of four held in
 // registers (one tile per warp at a time), and every candidate a lane loads is compared with all four.
 constexpr int kCellTileA = 4;
+constexpr int kCellStage = 384; // staged hits per warp (flushed when fewer than 32 * kCellTileA slots are left)
 
+template <bool STORE>
 __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uint32_t na_atoms, uint32_t nb_atoms, CellGeom cg,
                                                                 const uint32_t *offsets_a, const float4 *sorted_a, const uint32_t *offsets_b,
                                                                 const float4 *sorted_b, size_t cells, float cutoff2, unsigned long long *count,
@@ -211,6 +213,28 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
     const bool fold = far_a[f] == 0u && far_b[f] == 0u; // every atom of both groups within L/4 of the box: one-step fold
     const uint32_t wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long mine = 0;
+    // Hits are staged per warp in shared memory and appended to the frame's list kCellStage / 2 or more at a time: one
+    // atomic on the list cursor and one coalesced burst of 8-byte stores per flush.  (One atomic per 32 candidates -- every
+    // step has hits at liquid density -- serialised the whole grid on a single L2 address: 9.9 ms against 2.0 ms counting only.)
+    __shared__ uint2 stage_p[STORE ? kThreads / 32 : 1][STORE ? kCellStage : 1];
+    __shared__ float stage_d[STORE ? kThreads / 32 : 1][STORE ? kCellStage : 1];
+    uint32_t fill = 0; // warp-uniform
+    auto flush = [&]() {
+        if (fill == 0u) return;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (uint32_t k = lane; k < fill; k += 32) {
+            const unsigned long long at = base + k;
+            if (at < capacity) { // pairs beyond the capacity are counted but not stored
+                reinterpret_cast<uint2 *>(pairs)[(size_t)f * capacity + at] = stage_p[wid][k];
+                if (dist) dist[(size_t)f * capacity + at] = stage_d[wid][k];
+            }
+        }
+        __syncwarp();
+        fill = 0u;
+    };
     // one CTA per cell of A (grid-stride), its warps take the cell's tiles in turn: units of a few hundred distance
     // evaluations keep the SMs evenly loaded (one warp per cell left 17 % of the warp slots busy: long, uneven tasks)
     for (uint32_t ca = blockIdx.x; ca < cells; ca += gridDim.x) {
@@ -252,6 +276,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const bool in = s0 + u * 32 + lane < hi;
+                        if (STORE && fill > (uint32_t)(kCellStage - 32 * kCellTileA)) flush(); // room for this batch's hits
 #pragma unroll
                         for (int t = 0; t < kCellTileA; t++) {
                             float dx, dy, dz;
@@ -271,17 +296,13 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
                             if (m == 0u) continue;
                             const int n_hit = __popc(m);
                             if (lane == 0) mine += n_hit;
-                            if (pairs) {
-                                unsigned long long base = 0;
-                                if (lane == 0) base = atomicAdd(cursor + f, (unsigned long long)n_hit);
-                                base = __shfl_sync(0xffffffffu, base, 0);
-                                const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-                                if (hit && at < capacity) {
-                                    uint32_t *o = pairs + ((size_t)f * capacity + at) * 2;
-                                    o[0] = ai[t];
-                                    o[1] = __float_as_uint(b[u].w);
-                                    if (dist) dist[(size_t)f * capacity + at] = sqrt1_rn(d2);
+                            if (STORE) {
+                                if (hit) {
+                                    const uint32_t k = fill + __popc(m & ((1u << lane) - 1u));
+                                    stage_p[wid][k] = make_uint2(ai[t], __float_as_uint(b[u].w));
+                                    if (dist) stage_d[wid][k] = sqrt1_rn(d2);
                                 }
+                                fill += (uint32_t)n_hit;
                             }
                         }
                     }
@@ -289,6 +310,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
             }
         }
     }
+    if (STORE) flush();
     if (lane == 0 && mine) atomicAdd(count + f, mine);
 }
 

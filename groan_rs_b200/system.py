@@ -529,14 +529,18 @@ class System:
         return sh
 
     # ------------------------------------------------------------------ cutoff pair search
-    def group_pairs_within(self, g1, g2, cutoff, capacity=0, with_distances=False):
+    def group_pairs_within(self, g1, g2, cutoff, capacity=0, with_distances=False, pairs_out=None, dist_out=None):
         """CellGrid::new(g2, cell >= cutoff) + neighbors_iter around every atom of g1 + distance filter (cellgrid.rs:301-420):
         per frame the number of pairs closer than `cutoff` and, if capacity > 0, up to `capacity` of them as positions inside
-        (g1, g2) -- in no particular order -- with their distances.  Returns (count [F], pairs [F, capacity, 2], dist)."""
+        (g1, g2) -- in no particular order -- with their distances.  Returns (count [F], pairs [F, capacity, 2], dist).
+        `pairs_out` / `dist_out`: device tensors ([F, capacity, 2] 32-bit integers, [F, capacity] f32) that receive the
+        pairs instead of freshly allocated host arrays (the lists stay on the device for whatever consumes them)."""
         F = self.n_frames
         count = np.zeros(F, np.uint64)
-        pairs = np.zeros((F, capacity, 2), np.uint32) if capacity else None
-        dist = np.zeros((F, capacity), np.float32) if (capacity and with_distances) else None
+        if pairs_out is not None:
+            capacity = int(pairs_out.shape[1])
+        pairs = pairs_out if pairs_out is not None else (np.zeros((F, capacity, 2), np.uint32) if capacity else None)
+        dist = dist_out if dist_out is not None else (np.zeros((F, capacity), np.float32) if (capacity and with_distances) else None)
         self._check(self._lib.groan_gpu_pairs_within(self._h, self._gid(g1), self._gid(g2), C.c_float(cutoff), _ptr(count), _ptr(pairs),
                                                      _ptr(dist), capacity), "group_pairs_within", g1)
         return count, pairs, dist
