@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
     __shared__ uint2 stage_p[STORE ? kThreads / 32 : 1][STORE ? kCellStage : 1];
     __shared__ float stage_d[STORE ? kThreads / 32 : 1][STORE ? kCellStage : 1];
     uint32_t fill = 0; // warp-uniform
+    uint32_t lane_hits = 0; // !STORE: far below 2^32 evaluations per lane
     auto flush = [&]() {
         if (fill == 0u) return;
         unsigned long long base = 0;
@@ -292,6 +293,10 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
                             }
                             const float d2 = (dx * dx + dy * dy) + dz * dz;
                             const bool hit = in && t < na && d2 < cutoff2;
+                            if (!STORE) { // counting only: a private counter per lane, no vote, no branch
+                                lane_hits += hit ? 1u : 0u;
+                                continue;
+                            }
                             const unsigned m = __ballot_sync(0xffffffffu, hit);
                             if (m == 0u) continue;
                             const int n_hit = __popc(m);
@@ -311,6 +316,10 @@ __global__ void __launch_bounds__(kThreads) k_cell_query_tiled(FrameView fv, uin
         }
     }
     if (STORE) flush();
+    if (!STORE) {
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, lane_hits);
+        if (lane == 0) mine += tot;
+    }
     if (lane == 0 && mine) atomicAdd(count + f, mine);
 }
 
