@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
-    V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero(), sd = v3_zero(), ssin = v3_zero();
+    V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero();
+    float sd[3] = {0.f, 0.f, 0.f}, ss[3] = {0.f, 0.f, 0.f}; // centre sums as scalars: six registers less than two pattern sums
 #pragma unroll
     for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
     float2 sq = make_float2(0.f, 0.f);
@@ -480,8 +481,17 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         sq = __ffma2_rn(wd.a, d.a, sq);
         sq = __ffma2_rn(wd.b, d.b, sq);
         sq = __ffma2_rn(wd.c, d.c, sq);
-        if (CENTER == 1) v3_add(sd, d);
-        if (CENTER) quad_sines(qc, xa, xb, xc, ssin);
+        if (CENTER == 1) {
+            sd[0] = (sd[0] + d.a.x) + d.b.y;
+            sd[1] = (sd[1] + d.a.y) + d.c.x;
+            sd[2] = (sd[2] + d.b.x) + d.c.y;
+        }
+        if (CENTER) {
+            const float2 sa = quad_sin(xa, qc.sc[0], qc.sc[1]), sb = quad_sin(xb, qc.sc[2], qc.sc[0]), sc = quad_sin(xc, qc.sc[1], qc.sc[2]);
+            ss[0] = (ss[0] + sa.x) + sb.y;
+            ss[1] = (ss[1] + sa.y) + sc.x;
+            ss[2] = (ss[2] + sb.x) + sc.y;
+        }
         quad_minmax(mm, d);
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
@@ -512,8 +522,8 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     a[22] = v3_x(smd); a[23] = v3_y(smd); a[24] = v3_z(smd);
     a[25] = 0.0f;
     if (CENTER) {
-        a[KS - 6] = v3_x(sd); a[KS - 5] = v3_y(sd); a[KS - 4] = v3_z(sd);
-        a[KS - 3] = v3_x(ssin); a[KS - 2] = v3_y(ssin); a[KS - 1] = v3_z(ssin);
+        a[KS - 6] = sd[0]; a[KS - 5] = sd[1]; a[KS - 4] = sd[2];
+        a[KS - 3] = ss[0]; a[KS - 2] = ss[1]; a[KS - 1] = ss[2];
     }
     double tot[KS];
     float tmn[3], tmx[3];
