@@ -99,6 +99,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        return self.summary()
+
+    def summary(self):
         # the sampler is started before the warm-up (so that nvidia-smi's start-up does not fall into the timed region);
         # only the rows read between mark_begin() and mark_end() (+ one polling interval) count
         rows = [r for r in self.rows if len(r) >= 8]
