@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GROAN_GPU_LIB") or os.path.join(HERE, "libgroan_gpu.so")  # override: tuning experiments only
+LIB_PATH = os.path.join(HERE, "libgroan_gpu.so")
 
 # status codes (include/groan_gpu.h, enum groan_status)
 OK, ENOBOX, ENOTORTHO, EEMPTY, ENOPOS, ENOMASS, EGROUPSIZE, EZEROBOX, ENOGROUP, EINVAL, ECUDA, ENOFRAMES, ENOREF, ECAPACITY = range(14)

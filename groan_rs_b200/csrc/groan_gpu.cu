@@ -7,217 +7,18 @@
 // geometry and delivers results.  There is no CPU fallback anywhere in this file.
 #include "../../include/groan_gpu.h"
 
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <string>
-#include <type_traits>
-#include <vector>
-
-#include "common.cuh"
+#include "ctx.cuh"
 #include "kernels_center.cuh"
-#include "kernels_pairs.cuh"
 #include "kernels_rmsd.cuh"
 #include "kernels_synth.cuh"
 #include "kernels_tma.cuh"
 #include "kernels_quad.cuh"
-#include "kernels_cells.cuh"
 
 using namespace groan;
+using namespace groan_host;
+static_assert(kRefSums == kRefSumsHost, "ctx.cuh: Ref::sums");
 
 namespace {
-
-constexpr size_t kStageBytes = 32u << 20;  // pinned staging chunk for pageable sources
-constexpr size_t kPartialSlots = 8192;     // (blocks per frame) x (frames) upper bound for reductions
-constexpr int kMaxSums = 48;               // widest per-CTA partial record, in doubles
-
-struct Group {
-    bool set = false;
-    std::vector<uint32_t> idx;  // host copy (validity / error reporting)
-    uint32_t *d_idx = nullptr;
-    bool contiguous = false;
-    uint32_t first = 0;
-    size_t n = 0;
-    bool has_mass = false;
-    long no_mass_at = -1;  // position in the group of the first atom without mass
-    float *d_mass = nullptr;
-    std::vector<float> mass;  // host copy (compared with the RMSD reference's masses)
-    double mass_sum = 0.0;    // sum of `mass` in f64, ascending order (set once in groan_gpu_set_group, never per call)
-};
-
-enum PtrKind { PK_DEVICE, PK_PINNED, PK_PAGEABLE };
-
-PtrKind classify(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return PK_PAGEABLE;
-    }
-    switch (a.type) {
-    case cudaMemoryTypeDevice:
-    case cudaMemoryTypeManaged: return PK_DEVICE;
-    case cudaMemoryTypeHost: return PK_PINNED;
-    default: return PK_PAGEABLE;
-    }
-}
-
-}  // namespace
-
-struct groan_gpu_ctx {
-    int device = 0;
-    size_t n_atoms = 0, max_frames = 0;
-    unsigned flags = 0;
-    cudaStream_t own_compute = nullptr, compute = nullptr, copy = nullptr;
-
-    // frames
-    float *d_slot[2] = {nullptr, nullptr};
-    float *d_box[2] = {nullptr, nullptr};
-    int slot = 1;               // slot of the current batch (first push goes to 0)
-    float *cur_xyz = nullptr;   // slot buffer or attached caller buffer
-    bool attached = false;
-    bool have_frames = false, have_box = false;
-    size_t n_frames = 0;
-    std::vector<float> h_box;   // F x 9 of the current batch
-    std::vector<uint8_t> valid; // F x N, empty = all valid
-    cudaEvent_t ev_h2d = nullptr, ev_done[2] = {nullptr, nullptr};
-    bool done_recorded[2] = {false, false};
-    void *d_quant[2] = {nullptr, nullptr};       // quantised frames as uploaded (groan_gpu_push_frames_quantized), one per slot
-    size_t quant_bytes = 0;
-    int32_t *d_origin[2] = {nullptr, nullptr};   // their per-frame integer origins (F x 3)
-    float *h_stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
-
-    Group groups[GROAN_MAX_GROUPS];
-    Group all;  // GROAN_GROUP_ALL
-
-    // scratch
-    double *d_partials = nullptr;
-    void *d_pair_partials = nullptr;
-    unsigned int *d_tickets = nullptr;
-    float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
-    int *d_flags = nullptr;  // per frame: 1 = the single-pass kernel could not certify its result, redo exactly
-    unsigned int *d_frames_done = nullptr;  // device-side fallback launch: frames finished by the running single-pass kernel
-    int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
-    int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
-    int occ_center_quad = 0;                   // quad kernels (kernels_quad.cuh)
-    bool rmsd_attr_set[2][3][2] = {};           // k_rmsd_tma<SAME_MASS, CENTER, FPC>: shared-memory attribute set on this device
-    void *d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    uint32_t *d_mol_ref = nullptr;      // make_molecules_whole: reference atom of every atom's molecule (groan_gpu_set_molecules)
-    std::vector<uint32_t> mol_ref;      // host copy (position checks)
-
-    // RMSD reference (per group id)
-    struct Ref {
-        bool set = false;
-        size_t n = 0;
-        float *d_pc = nullptr;  // block-SoA prepared reference (kernels_rmsd.cuh)
-        float *d_pq[4] = {nullptr, nullptr, nullptr, nullptr};  // quad-permuted copies of the aligned body (kernels_quad.cuh), one per
-                                                                 // head (atoms before the first 16-byte boundary), built on first use
-        double sums[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool same_mass = true;  // reference masses == the target group's masses
-        float com[3] = {0, 0, 0};
-    } refs[GROAN_MAX_GROUPS];
-
-    uint64_t launches = 0;
-    std::string cuda_err;
-    size_t err_a = 0, err_b = 0;
-};
-
-namespace {
-
-int cuda_fail(groan_gpu_ctx *c, cudaError_t e, const char *what) {
-    if (c) c->cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
-    cudaGetLastError();
-    return GROAN_ECUDA;
-}
-#define CK(call)                                                     \
-    do {                                                             \
-        cudaError_t e_ = (call);                                     \
-        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);     \
-    } while (0)
-#define LAUNCHED()                                                   \
-    do {                                                             \
-        ctx->launches++;                                             \
-        cudaError_t e_ = cudaGetLastError();                         \
-        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, "kernel launch"); \
-    } while (0)
-
-const Group *get_group(groan_gpu_ctx *ctx, int gid) {
-    if (gid == GROAN_GROUP_ALL) return &ctx->all;
-    if (gid < 0 || gid >= GROAN_MAX_GROUPS || !ctx->groups[gid].set) return nullptr;
-    return &ctx->groups[gid];
-}
-
-GroupView view_of(const Group &g) {
-    GroupView v;
-    v.idx = g.contiguous ? nullptr : g.d_idx;
-    v.first = g.first;
-    v.n = (uint32_t)g.n;
-    v.mass = g.d_mass;
-    return v;
-}
-
-FrameView frames_of(groan_gpu_ctx *ctx) {
-    FrameView fv;
-    fv.xyz = ctx->cur_xyz;
-    fv.box = ctx->d_box[ctx->slot];
-    fv.n_atoms = ctx->n_atoms;
-    return fv;
-}
-
-// simbox_check (simbox.rs:230-236) over every frame of the batch; zero box = the reference's panic
-int check_box(groan_gpu_ctx *ctx, bool allow_triclinic, bool *any_triclinic) {
-    if (any_triclinic) *any_triclinic = false;
-    if (!ctx->have_frames) return GROAN_ENOFRAMES;
-    if (!ctx->have_box) return GROAN_ENOBOX;
-    for (size_t f = 0; f < ctx->n_frames; f++) {
-        const float *b = &ctx->h_box[f * 9];
-        if (b[1] != 0.0f || b[2] != 0.0f || b[5] != 0.0f) return GROAN_EINVAL;  // matrix2simbox rejects (xdrfile.rs:171)
-        const bool tric = (b[3] != 0.0f || b[6] != 0.0f || b[7] != 0.0f);
-        if (tric) {
-            if (!allow_triclinic || !(ctx->flags & GROAN_FLAG_TRICLINIC)) return GROAN_ENOTORTHO;
-            if (any_triclinic) *any_triclinic = true;
-        }
-        if (b[0] == 0.0f || b[4] == 0.0f || b[8] == 0.0f) return GROAN_EZEROBOX;
-    }
-    return GROAN_OK;
-}
-
-// first atom of the group (group order) without a position, in the first frame that has one
-int check_positions(groan_gpu_ctx *ctx, const Group &g) {
-    if (ctx->valid.empty()) return GROAN_OK;
-    for (size_t f = 0; f < ctx->n_frames; f++) {
-        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
-        for (size_t i = 0; i < g.n; i++) {
-            const size_t a = g.contiguous ? g.first + i : g.idx[i];
-            if (!v[a]) {
-                ctx->err_a = f;
-                ctx->err_b = a;
-                return GROAN_ENOPOS;
-            }
-        }
-    }
-    return GROAN_OK;
-}
-
-int check_masses(groan_gpu_ctx *ctx, const Group &g) {
-    if (!g.has_mass) {
-        ctx->err_a = 0;
-        ctx->err_b = g.n ? (g.contiguous ? g.first : g.idx[0]) : 0;
-        return GROAN_ENOMASS;
-    }
-    if (g.no_mass_at >= 0) {
-        ctx->err_a = 0;
-        ctx->err_b = g.contiguous ? g.first + (size_t)g.no_mass_at : g.idx[(size_t)g.no_mass_at];
-        return GROAN_ENOMASS;
-    }
-    return GROAN_OK;
-}
 
 // blocks per frame for a streaming pass over g atoms of each of F frames
 int blocks_per_frame(size_t g, size_t F) {
@@ -398,33 +199,6 @@ FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center,
     return fp;
 }
 
-int ensure_tmp(groan_gpu_ctx *ctx, size_t bytes) {
-    if (bytes <= ctx->tmp_bytes) return GROAN_OK;
-    if (ctx->d_tmp) {
-        CK(cudaStreamSynchronize(ctx->compute));
-        CK(cudaFree(ctx->d_tmp));
-        ctx->d_tmp = nullptr;
-        ctx->tmp_bytes = 0;
-    }
-    CK(cudaMalloc(&ctx->d_tmp, bytes));
-    ctx->tmp_bytes = bytes;
-    return GROAN_OK;
-}
-
-// copy a device result to wherever the caller wants it (device / pinned: async; pageable: blocking)
-int deliver(groan_gpu_ctx *ctx, void *out, const void *d_src, size_t bytes) {
-    if (!out || out == d_src || bytes == 0) return GROAN_OK;
-    const PtrKind k = classify(out);
-    CK(cudaMemcpyAsync(out, d_src, bytes, cudaMemcpyDefault, ctx->compute));
-    if (k == PK_PAGEABLE) CK(cudaStreamSynchronize(ctx->compute));
-    return GROAN_OK;
-}
-
-template <typename T>
-T *target_of(void *out, T *scratch) {
-    return (out && classify(out) == PK_DEVICE) ? reinterpret_cast<T *>(out) : scratch;
-}
-
 int ensure_slots(groan_gpu_ctx *ctx) {
     if (ctx->d_slot[0]) return GROAN_OK;
     const size_t bytes = ctx->max_frames * ctx->n_atoms * 3 * sizeof(float) + 256;
@@ -432,6 +206,8 @@ int ensure_slots(groan_gpu_ctx *ctx) {
     return GROAN_OK;
 }
 
+}  // namespace
+namespace groan_host {
 // switch to the other slot; the copy stream may only overwrite it once every kernel that used it is done
 int begin_batch(groan_gpu_ctx *ctx, size_t F, const float *box, bool use_slot) {
     if (F == 0) return GROAN_EINVAL;
@@ -468,6 +244,8 @@ int end_batch(groan_gpu_ctx *ctx) {
     CK(cudaStreamWaitEvent(ctx->compute, ctx->ev_h2d, 0));
     return GROAN_OK;
 }
+}  // namespace groan_host
+namespace {
 
 // ---- centre passes -------------------------------------------------------------------------------
 int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out, const int *flags) {
@@ -559,167 +337,6 @@ int check_center_args(groan_gpu_ctx *ctx, int gid, bool weighted, const Group **
     *gp = g;
     return GROAN_OK;
 }
-
-template <int DIM, typename BOX>
-int launch_pairs(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_out) {
-    const bool vec = (b.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
-    dim3 grid((unsigned)((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)),
-              (unsigned)((a.n + kPairRows - 1) / kPairRows), (unsigned)ctx->n_frames);
-    if (vec)
-        k_pairs<DIM, BOX, true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
-    else
-        k_pairs<DIM, BOX, false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
-    LAUNCHED();
-    return GROAN_OK;
-}
-
-// orthogonal box, 2-D / 3-D distance: packed one-step min-image (kernels_pairs.cuh "fast paths")
-template <int DIM, typename BOX = BoxOrtho>
-int launch_pairs_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float *d_out) {
-    const bool vec = (b.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
-    dim3 grid((unsigned)((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)),
-              (unsigned)((a.n + kFastRows - 1) / kFastRows), (unsigned)ctx->n_frames);
-    if (vec)
-        k_pairs_fast<DIM, true, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
-    else
-        k_pairs_fast<DIM, false, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), d_out);
-    LAUNCHED();
-    return GROAN_OK;
-}
-
-// smallest float t with sqrtf(t) >= c: (d2 < t) <=> (sqrtf(d2) < c) for every float d2 >= 0
-float cutoff_squared_threshold(float c) {
-    if (!(c > 0.0f)) return 0.0f;
-    float t = c * c;
-    if (std::isinf(t)) return t;
-    while (std::sqrt(t) >= c && t > 0.0f) t = std::nextafter(t, 0.0f);
-    while (std::sqrt(t) < c) t = std::nextafter(t, INFINITY);
-    return t;
-}
-
-template <typename BOX>
-int dispatch_pairs(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float *d_out) {
-    if (std::is_same<BOX, BoxOrtho>::value) {
-        switch (dim) {
-        case 4: return launch_pairs_fast<4>(ctx, a, b, d_out);
-        case 5: return launch_pairs_fast<5>(ctx, a, b, d_out);
-        case 6: return launch_pairs_fast<6>(ctx, a, b, d_out);
-        case 7: return launch_pairs_fast<7>(ctx, a, b, d_out);
-        default: break;
-        }
-    } else {
-        // triclinic extension, 2-D / 3-D: the same kernel with the 27-image d^2 (kernels_pairs.cuh pair_d2_tric)
-        switch (dim) {
-        case 4: return launch_pairs_fast<4, BoxTric>(ctx, a, b, d_out);
-        case 5: return launch_pairs_fast<5, BoxTric>(ctx, a, b, d_out);
-        case 6: return launch_pairs_fast<6, BoxTric>(ctx, a, b, d_out);
-        case 7: return launch_pairs_fast<7, BoxTric>(ctx, a, b, d_out);
-        default: break;
-        }
-    }
-    switch (dim) {
-    case 0: return launch_pairs<0, BOX>(ctx, a, b, d_out);
-    case 1: return launch_pairs<1, BOX>(ctx, a, b, d_out);
-    case 2: return launch_pairs<2, BOX>(ctx, a, b, d_out);
-    case 3: return launch_pairs<3, BOX>(ctx, a, b, d_out);
-    case 4: return launch_pairs<4, BOX>(ctx, a, b, d_out);
-    case 5: return launch_pairs<5, BOX>(ctx, a, b, d_out);
-    case 6: return launch_pairs<6, BOX>(ctx, a, b, d_out);
-    case 7: return launch_pairs<7, BOX>(ctx, a, b, d_out);
-    default: return GROAN_EINVAL;
-    }
-}
-
-struct ReduceOut {
-    float *dmin;
-    uint32_t *imin;
-    float *dmax;
-    uint32_t *imax;
-    unsigned long long *count;
-};
-
-template <int DIM, typename BOX>
-int launch_pairs_reduce(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
-    size_t nb = (b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ);
-    nb = std::max<size_t>(1, std::min<size_t>(nb, kMaxBlocksPerFrame));
-    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
-    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
-    k_pairs_reduce<DIM, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff,
-                                                                  (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
-                                                                  o.imin, o.dmax, o.imax, o.count);
-    LAUNCHED();
-    return GROAN_OK;
-}
-
-template <int DIM, typename BOX = BoxOrtho>
-int launch_pairs_reduce_fast(groan_gpu_ctx *ctx, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
-    // persistent CTAs (4 per SM in total) striding over work units of (1024 B atoms) x (256 A atoms)
-    const size_t units = ((b.n + (size_t)kThreads * kPairJ - 1) / ((size_t)kThreads * kPairJ)) * ((a.n + kSliceA - 1) / kSliceA);
-    size_t nb = std::max<size_t>(1, ((size_t)kSMs * 4) / ctx->n_frames);
-    nb = std::min<size_t>(nb, units);
-    nb = std::max<size_t>(1, std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames)));
-    dim3 grid((unsigned)nb, (unsigned)ctx->n_frames);
-    const float c2 = cutoff_squared_threshold(cutoff);
-    if (o.count)
-        k_pairs_reduce_fast<DIM, true, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
-                                                                            (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
-                                                                            o.imin, o.dmax, o.imax, o.count);
-    else
-        k_pairs_reduce_fast<DIM, false, BOX><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(a), view_of(b), cutoff, c2,
-                                                                             (PairPartial *)ctx->d_pair_partials, ctx->d_tickets, o.dmin,
-                                                                             o.imin, o.dmax, o.imax, o.count);
-    LAUNCHED();
-    return GROAN_OK;
-}
-
-template <typename BOX>
-int dispatch_pairs_reduce(groan_gpu_ctx *ctx, int dim, const Group &a, const Group &b, float cutoff, const ReduceOut &o) {
-    if (std::is_same<BOX, BoxOrtho>::value) {
-        switch (dim) {
-        case 4: return launch_pairs_reduce_fast<4>(ctx, a, b, cutoff, o);
-        case 5: return launch_pairs_reduce_fast<5>(ctx, a, b, cutoff, o);
-        case 6: return launch_pairs_reduce_fast<6>(ctx, a, b, cutoff, o);
-        case 7: return launch_pairs_reduce_fast<7>(ctx, a, b, cutoff, o);
-        default: break;
-        }
-    } else {
-        // triclinic extension, 2-D / 3-D: the same kernel with the 27-image d^2 (kernels_pairs.cuh pair_d2_tric)
-        switch (dim) {
-        case 4: return launch_pairs_reduce_fast<4, BoxTric>(ctx, a, b, cutoff, o);
-        case 5: return launch_pairs_reduce_fast<5, BoxTric>(ctx, a, b, cutoff, o);
-        case 6: return launch_pairs_reduce_fast<6, BoxTric>(ctx, a, b, cutoff, o);
-        case 7: return launch_pairs_reduce_fast<7, BoxTric>(ctx, a, b, cutoff, o);
-        default: break;
-        }
-    }
-    switch (dim) {
-    case 0: return launch_pairs_reduce<0, BOX>(ctx, a, b, cutoff, o);
-    case 1: return launch_pairs_reduce<1, BOX>(ctx, a, b, cutoff, o);
-    case 2: return launch_pairs_reduce<2, BOX>(ctx, a, b, cutoff, o);
-    case 3: return launch_pairs_reduce<3, BOX>(ctx, a, b, cutoff, o);
-    case 4: return launch_pairs_reduce<4, BOX>(ctx, a, b, cutoff, o);
-    case 5: return launch_pairs_reduce<5, BOX>(ctx, a, b, cutoff, o);
-    case 6: return launch_pairs_reduce<6, BOX>(ctx, a, b, cutoff, o);
-    case 7: return launch_pairs_reduce<7, BOX>(ctx, a, b, cutoff, o);
-    default: return GROAN_EINVAL;
-    }
-}
-
-// Atom::distance checks self first, then the other atom (atom.rs:780-790); scan order is row-major
-int check_pair_positions(groan_gpu_ctx *ctx, const Group &a, const Group &b) {
-    if (ctx->valid.empty() || a.n == 0 || b.n == 0) return GROAN_OK;
-    for (size_t f = 0; f < ctx->n_frames; f++) {
-        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
-        auto at = [](const Group &g, size_t i) { return g.contiguous ? (size_t)g.first + i : (size_t)g.idx[i]; };
-        if (!v[at(a, 0)]) { ctx->err_a = f; ctx->err_b = at(a, 0); return GROAN_ENOPOS; }
-        for (size_t j = 0; j < b.n; j++)
-            if (!v[at(b, j)]) { ctx->err_a = f; ctx->err_b = at(b, j); return GROAN_ENOPOS; }
-        for (size_t i = 1; i < a.n; i++)
-            if (!v[at(a, i)]) { ctx->err_a = f; ctx->err_b = at(a, i); return GROAN_ENOPOS; }
-    }
-    return GROAN_OK;
-}
-
 int run_wrap(groan_gpu_ctx *ctx, const Group &g, bool translate, const float t[3], int8_t *shifts, bool tric) {
     int8_t *d_sh = nullptr;
     const size_t sh_bytes = ctx->n_frames * g.n * 3;
@@ -770,8 +387,8 @@ int check_wrap_args(groan_gpu_ctx *ctx, int gid, const Group **gp, bool *tric) {
 int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, float *center = nullptr, int center_weighted = 0) {
     if (!ctx) return GROAN_EINVAL;
     const Group *g = get_group(ctx, gid);
-    if (!g || gid < 0) return GROAN_ENOGROUP;
-    if (!ctx->refs[gid].set) return GROAN_ENOREF;
+    if (!g) return GROAN_ENOGROUP;
+    if (!ctx->refs[ref_slot(gid)].set) return GROAN_ENOREF;
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
     // extract_data_from_system(target): box first (rmsd.rs:430), then group_get_com's own checks
     int rc = check_box(ctx, false, nullptr);
@@ -781,7 +398,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     if (rc) return rc;
     rc = check_masses(ctx, *g);
     if (rc) return rc;
-    groan_gpu_ctx::Ref &R = ctx->refs[gid];
+    groan_gpu_ctx::Ref &R = ctx->refs[ref_slot(gid)];
     if (R.n != g->n) {  // number_of_positions_consistent, rmsd.rs:405-422
         ctx->err_a = R.n;
         ctx->err_b = g->n;
@@ -901,6 +518,8 @@ extern "C" {
 int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out) {
     if (!out || n_atoms == 0 || max_frames == 0 || n_atoms > 0xFFFFFFF0ull) return GROAN_EINVAL;
     *out = nullptr;
+    // frames map to gridDim.y (<= 65535), and maybe_launch_fallback counts finished frames in 16 bits
+    if (max_frames > kMaxFramesPerBatch) return GROAN_ECAPACITY;
     groan_gpu_ctx *ctx = new (std::nothrow) groan_gpu_ctx();
     if (!ctx) return GROAN_EINVAL;
     ctx->device = device;
@@ -919,7 +538,7 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         }
         const size_t slots = std::max(max_frames, kPartialSlots) + kMaxBlocksPerFrame;
         CK(cudaMalloc(&ctx->d_partials, slots * kMaxSums * sizeof(double)));
-        CK(cudaMalloc(&ctx->d_pair_partials, slots * sizeof(PairPartial)));
+        CK(cudaMalloc(&ctx->d_pair_partials, slots * kPairPartialBytes));
         CK(cudaMalloc(&ctx->d_tickets, (max_frames + 1) * sizeof(unsigned int)));
         CK(cudaMemset(ctx->d_tickets, 0, (max_frames + 1) * sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_c0, max_frames * 3 * sizeof(float)));
@@ -941,10 +560,6 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
         ctx->occ_rmsd_tma = 2;
-        if (const char *e = std::getenv("GROAN_DEBUG_SKIP_REF")) {
-            const int v = std::atoi(e);
-            CK(cudaMemcpyToSymbol(g_debug_skip_ref, &v, sizeof(int)));
-        }
         ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
         const int sq = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
         CK(cudaFuncSetAttribute(k_center_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
@@ -987,6 +602,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         if (g.d_idx) cudaFree(g.d_idx);
         if (g.d_mass) cudaFree(g.d_mass);
     }
+    if (ctx->all.d_mass) cudaFree(ctx->all.d_mass);
     for (auto &r : ctx->refs) {
         if (r.d_pc) cudaFree(r.d_pc);
         for (float *q : r.d_pq)
@@ -1066,6 +682,33 @@ int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n) {
 
 // ---- groups ---------------------------------------------------------------------------------------
 int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t n, const float *mass) {
+    if (ctx && gid == GROAN_GROUP_ALL) {
+        // the built-in "all" group (System::new creates "all" / "All" over every atom, groups.rs): its index list is fixed,
+        // only the masses can be attached (or removed: mass == NULL)
+        if (idx || n != ctx->n_atoms) return GROAN_EINVAL;
+        Group &g = ctx->all;
+        CK(cudaStreamSynchronize(ctx->compute));
+        if (g.d_mass) { cudaFree(g.d_mass); g.d_mass = nullptr; }
+        groan_gpu_ctx::Ref &R = ctx->refs[GROAN_MAX_GROUPS];
+        if (R.d_pc) { cudaFree(R.d_pc); R.d_pc = nullptr; }
+        for (float *&q : R.d_pq)
+            if (q) { cudaFree(q); q = nullptr; }
+        R.set = false;
+        g.has_mass = (mass != nullptr);
+        g.no_mass_at = -1;
+        g.mass.clear();
+        g.mass_sum = 0.0;
+        if (mass) {
+            g.mass.assign(mass, mass + n);
+            for (size_t i = 0; i < n; i++) {
+                g.mass_sum += (double)mass[i];
+                if (mass[i] < 0.0f && g.no_mass_at < 0) g.no_mass_at = (long)i;
+            }
+            CK(cudaMalloc(&g.d_mass, n * sizeof(float)));
+            CK(cudaMemcpy(g.d_mass, mass, n * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        return GROAN_OK;
+    }
     if (!ctx || gid < 0 || gid >= GROAN_MAX_GROUPS || (n && !idx)) return GROAN_EINVAL;
     for (size_t i = 0; i < n; i++) {
         if (idx[i] >= ctx->n_atoms) return GROAN_EINVAL;
@@ -1076,6 +719,8 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
     if (g.d_idx) { cudaFree(g.d_idx); g.d_idx = nullptr; }
     if (g.d_mass) { cudaFree(g.d_mass); g.d_mass = nullptr; }
     if (ctx->refs[gid].d_pc) { cudaFree(ctx->refs[gid].d_pc); ctx->refs[gid].d_pc = nullptr; }
+    for (float *&q : ctx->refs[gid].d_pq)
+        if (q) { cudaFree(q); q = nullptr; }
     ctx->refs[gid].set = false;
     g.set = true;
     g.n = n;
@@ -1107,7 +752,7 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
 // ---- frames ---------------------------------------------------------------------------------------
 }  // extern "C"
 
-namespace {
+namespace groan_host {
 // host -> device on the copy stream; a pageable source bounces through two pinned chunks so that the host memcpy of
 // chunk i + 1 overlaps the DMA of chunk i
 int h2d_on_copy_stream(groan_gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
@@ -1130,7 +775,7 @@ int h2d_on_copy_stream(groan_gpu_ctx *ctx, void *dst, const void *src, size_t by
     }
     return GROAN_OK;
 }
-}  // namespace
+}  // namespace groan_host
 
 extern "C" {
 
@@ -1142,8 +787,9 @@ int groan_gpu_push_frames(groan_gpu_ctx *ctx, const float *xyz, const float *box
     float *dst = ctx->d_slot[ctx->slot];
     ctx->cur_xyz = dst;
     rc = h2d_on_copy_stream(ctx, dst, xyz, n_frames * ctx->n_atoms * 3 * sizeof(float));
-    if (rc) return rc;
-    return end_batch(ctx);
+    if (!rc) rc = end_batch(ctx);
+    if (rc) ctx->have_frames = false;  // a failed upload leaves no current batch rather than a half-switched one
+    return rc;
 }
 
 int groan_gpu_push_frames_quantized(groan_gpu_ctx *ctx, const void *q, int elem_bytes, const int32_t *origin, float precision,
@@ -1279,173 +925,6 @@ int groan_gpu_group_distance(groan_gpu_ctx *ctx, int g1, int g2, int dim, float 
     return deliver(ctx, out, d_out, F * sizeof(float));
 }
 
-int groan_gpu_all_distances(groan_gpu_ctx *ctx, int g1, int g2, int dim, float *out) {
-    if (!ctx || dim < 0 || dim > 7) return GROAN_EINVAL;
-    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
-    if (!a || !b) return GROAN_ENOGROUP;  // group_get_n_atoms (analysis.rs:407-408)
-    bool tric = false;
-    int rc = check_box(ctx, true, &tric);
-    if (rc) return rc;
-    if (a->n == 0 || b->n == 0) return GROAN_OK;  // empty matrix, not an error (analysis.rs:412)
-    if (!out) return GROAN_EINVAL;
-    rc = check_pair_positions(ctx, *a, *b);
-    if (rc) return rc;
-    const size_t bytes = ctx->n_frames * a->n * b->n * sizeof(float);
-    float *d_out = out;
-    if (classify(out) != PK_DEVICE) {
-        rc = ensure_tmp(ctx, bytes);
-        if (rc) return rc;
-        d_out = (float *)ctx->d_tmp;
-    }
-    rc = tric ? dispatch_pairs<BoxTric>(ctx, dim, *a, *b, d_out) : dispatch_pairs<BoxOrtho>(ctx, dim, *a, *b, d_out);
-    if (rc) return rc;
-    return deliver(ctx, out, d_out, bytes);
-}
-
-int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, float cutoff, float *dmin, uint32_t *imin,
-                                   float *dmax, uint32_t *imax, uint64_t *count) {
-    if (!ctx || dim < 0 || dim > 7) return GROAN_EINVAL;
-    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
-    if (!a || !b) return GROAN_ENOGROUP;
-    bool tric = false;
-    int rc = check_box(ctx, true, &tric);
-    if (rc) return rc;
-    if (a->n == 0 || b->n == 0) return GROAN_EEMPTY;  // min/max of an empty matrix: Option::unwrap panics in the documented consumer
-    rc = check_pair_positions(ctx, *a, *b);
-    if (rc) return rc;
-    const size_t F = ctx->n_frames;
-    // scratch layout inside d_res (8 floats per frame): dmin | dmax | imin(2) | imax(2) | count(u64)
-    float *s = ctx->d_res;
-    ReduceOut o;
-    o.dmin = target_of<float>(dmin, s);
-    o.dmax = target_of<float>(dmax, s + F);
-    o.imin = target_of<uint32_t>(imin, (uint32_t *)(s + 2 * F));
-    o.imax = target_of<uint32_t>(imax, (uint32_t *)(s + 4 * F));
-    o.count = count ? target_of<unsigned long long>(count, (unsigned long long *)(s + 6 * F)) : nullptr;
-    rc = tric ? dispatch_pairs_reduce<BoxTric>(ctx, dim, *a, *b, cutoff, o) : dispatch_pairs_reduce<BoxOrtho>(ctx, dim, *a, *b, cutoff, o);
-    if (rc) return rc;
-    if ((rc = deliver(ctx, dmin, o.dmin, F * sizeof(float)))) return rc;
-    if ((rc = deliver(ctx, dmax, o.dmax, F * sizeof(float)))) return rc;
-    if ((rc = deliver(ctx, imin, o.imin, F * 2 * sizeof(uint32_t)))) return rc;
-    if ((rc = deliver(ctx, imax, o.imax, F * 2 * sizeof(uint32_t)))) return rc;
-    return deliver(ctx, count, o.count, F * sizeof(uint64_t));
-}
-
-// ---- cutoff pair search through a cell grid ---------------------------------------
-int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uint64_t *count, uint32_t *pairs, float *dist,
-                           size_t capacity) {
-    if (!ctx || !count || !(cutoff > 0.0f) || (dist && !pairs)) return GROAN_EINVAL;
-    const Group *a = get_group(ctx, g1), *b = get_group(ctx, g2);
-    if (!a || !b) return GROAN_ENOGROUP;
-    // CellGrid::new: the box must exist and be orthogonal (cellgrid.rs:308-312), then the positions of the group
-    int rc = check_box(ctx, false, nullptr);
-    if (rc) return rc;
-    rc = check_pair_positions(ctx, *a, *b);
-    if (rc) return rc;
-    const size_t F = ctx->n_frames, nb_atoms = b->n;
-    if (!pairs) capacity = 0;
-    // one grid geometry for the batch, from the smallest box: cells at least cutoff * (1 + 1e-4) wide in every frame
-    float lmin[3] = {3.0e38f, 3.0e38f, 3.0e38f};
-    for (size_t f = 0; f < F; f++)
-        for (int k = 0; k < 3; k++) lmin[k] = std::min(lmin[k], ctx->h_box[f * 9 + 4 * k]);
-    long nc[3];
-    for (int k = 0; k < 3; k++) nc[k] = std::max<long>(1, std::min<long>(1024, (long)std::floor((double)lmin[k] / ((double)cutoff * 1.0001))));
-    const size_t cell_cap = std::max<size_t>(4096, std::min<size_t>((size_t)8 << 20, 4 * nb_atoms + 4096));
-    while ((size_t)nc[0] * nc[1] * nc[2] > cell_cap) {  // wider cells are always correct, only slower
-        const int k = nc[0] >= nc[1] && nc[0] >= nc[2] ? 0 : (nc[1] >= nc[2] ? 1 : 2);
-        nc[k] = (nc[k] + 1) / 2;
-    }
-    CellGeom cg = {(int)nc[0], (int)nc[1], (int)nc[2]};
-    const float cutoff2 = cutoff_squared_threshold(cutoff);
-    const size_t cells = (size_t)nc[0] * nc[1] * nc[2];
-    // scratch layout (one allocation): results first, then per-frame grid storage for as many frames as fit ~1.5 GB.
-    // Group A is binned as well when it has at least one atom per cell on average: one warp then serves a whole cell of A
-    // (k_cell_query_tiled); sparse query groups keep one warp per atom (k_cell_query).
-    const size_t na_atoms = a->n;
-    const bool tiled = na_atoms >= cells && !(ctx->flags & GROAN_FLAG_NO_QUAD);
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    auto grid_bytes = [&](size_t atoms) { return up(atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(atoms * 16); };
-    const size_t per_frame = grid_bytes(nb_atoms) + (tiled ? grid_bytes(na_atoms) : 0);
-    const size_t fb = std::max<size_t>(1, std::min<size_t>(F, ((size_t)3 << 29) / std::max<size_t>(per_frame, 1)));
-    const bool stage_pairs = pairs && classify(pairs) != PK_DEVICE, stage_dist = dist && classify(dist) != PK_DEVICE;
-    const size_t o_count = 0, o_cursor = up(F * 8), o_far = o_cursor + up(F * 8), o_pairs = o_far + up(2 * F * 4),
-                 o_dist = o_pairs + (stage_pairs ? up(F * capacity * 8) : 0), o_grid = o_dist + (stage_dist ? up(F * capacity * 4) : 0);
-    rc = ensure_tmp(ctx, o_grid + fb * per_frame);
-    if (rc) return rc;
-    char *base = (char *)ctx->d_tmp;
-    unsigned long long *d_count = (unsigned long long *)(base + o_count), *d_cursor = (unsigned long long *)(base + o_cursor);
-    unsigned int *d_far_b = (unsigned int *)(base + o_far), *d_far_a = d_far_b + F;
-    uint32_t *d_pairs = pairs ? (stage_pairs ? (uint32_t *)(base + o_pairs) : pairs) : nullptr;
-    float *d_dist = dist ? (stage_dist ? (float *)(base + o_dist) : dist) : nullptr;
-    CK(cudaMemsetAsync(base, 0, o_pairs, ctx->compute));
-    struct CellLists {
-        uint32_t *cell_of, *counts, *fill, *offsets;
-        float4 *sorted;
-    };
-    auto carve = [&](char *p0, size_t atoms) {
-        CellLists c;
-        c.cell_of = (uint32_t *)p0;
-        c.counts = (uint32_t *)(p0 + fb * up(atoms * 4));
-        c.fill = (uint32_t *)((char *)c.counts + fb * up(cells * 4));
-        c.offsets = (uint32_t *)((char *)c.fill + fb * up(cells * 4));
-        c.sorted = (float4 *)((char *)c.offsets + fb * up((cells + 1) * 4));
-        return c;
-    };
-    const CellLists lb = carve(base + o_grid, nb_atoms);
-    const CellLists la = tiled ? carve(base + o_grid + fb * grid_bytes(nb_atoms), na_atoms) : CellLists();
-    const GroupView ga = view_of(*a), gb = view_of(*b);
-    for (size_t f0 = 0; f0 < F; f0 += fb) {
-        const size_t nf = std::min(fb, F - f0);
-        FrameView fv = frames_of(ctx);
-        fv.xyz += f0 * ctx->n_atoms * 3;
-        fv.box += f0 * 9;
-        // counting sort of a group by cell: histogram, prefix sum, scatter
-        auto build = [&](const GroupView &gv, size_t atoms, const CellLists &cl, unsigned int *far) -> int {
-            CK(cudaMemsetAsync(cl.counts, 0, nf * cells * 4, ctx->compute));
-            const unsigned nbk = (unsigned)std::max<size_t>(1, std::min<size_t>((atoms + kThreads - 1) / kThreads, (size_t)kSMs * 8));
-            if (atoms) {
-                k_cell_count<<<dim3(nbk, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gv, cg, cl.cell_of, cl.counts, cells, far + f0);
-                LAUNCHED();
-            }
-            k_cell_scan<<<(unsigned)nf, 1024, 0, ctx->compute>>>(cl.counts, cl.offsets, cl.fill, cells);
-            LAUNCHED();
-            if (atoms) {
-                k_cell_fill<<<dim3(nbk, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, gv, cl.cell_of, cl.fill, cl.sorted, cells);
-                LAUNCHED();
-            }
-            return GROAN_OK;
-        };
-        rc = build(gb, nb_atoms, lb, d_far_b);
-        if (rc) return rc;
-        uint32_t *pp = d_pairs ? d_pairs + f0 * capacity * 2 : nullptr;
-        float *dp = d_dist ? d_dist + f0 * capacity : nullptr;
-        if (tiled) {
-            rc = build(ga, na_atoms, la, d_far_a);
-            if (rc) return rc;
-            const unsigned nq = (unsigned)std::max<size_t>(1, std::min<size_t>(cells, (size_t)kSMs * 64));
-            if (pp)
-                k_cell_query_tiled<true><<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(
-                    fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets, la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
-                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0, d_far_b + f0);
-            else
-                k_cell_query_tiled<false><<<dim3(nq, (unsigned)nf), kThreads, 0, ctx->compute>>>(
-                    fv, (uint32_t)na_atoms, (uint32_t)nb_atoms, cg, la.offsets, la.sorted, lb.offsets, lb.sorted, cells, cutoff2, d_count + f0, pp,
-                    dp, (unsigned long long)capacity, d_cursor + f0, d_far_a + f0, d_far_b + f0);
-            LAUNCHED();
-        } else if (na_atoms) {
-            const unsigned nqa = (unsigned)std::max<size_t>(1, std::min<size_t>((na_atoms + 7) / 8, (size_t)kSMs * 16));
-            k_cell_query<<<dim3(nqa, (unsigned)nf), kThreads, 0, ctx->compute>>>(fv, ga, (uint32_t)nb_atoms, cg, lb.offsets, lb.sorted, cells, cutoff2,
-                                                                               d_count + f0, pp, dp, (unsigned long long)capacity, d_cursor + f0,
-                                                                               d_far_b + f0);
-            LAUNCHED();
-        }
-    }
-    if ((rc = deliver(ctx, count, d_count, F * sizeof(uint64_t)))) return rc;
-    if (stage_pairs && (rc = deliver(ctx, pairs, d_pairs, F * capacity * 8))) return rc;
-    if (stage_dist && (rc = deliver(ctx, dist, d_dist, F * capacity * 4))) return rc;
-    return GROAN_OK;
-}
-
 // ---- wrap / translate -----------------------------------------------------------------------------
 int groan_gpu_wrap(groan_gpu_ctx *ctx, int gid, int8_t *shifts) {
     const Group *g = nullptr;
@@ -1542,7 +1021,7 @@ int groan_gpu_atoms_center(groan_gpu_ctx *ctx, int gid, int weighted, int dim) {
 // ---- RMSD -----------------------------------------------------------------------------------------
 int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_xyz, size_t n_ref_atoms, const uint32_t *ref_idx,
                                  size_t n_ref, const float ref_box[9], const float *ref_mass) {
-    if (!ctx || !ref_xyz || gid < 0 || gid >= GROAN_MAX_GROUPS) return GROAN_EINVAL;
+    if (!ctx || !ref_xyz || gid < GROAN_GROUP_ALL || gid >= GROAN_MAX_GROUPS) return GROAN_EINVAL;
     const Group *g = get_group(ctx, gid);
     if (!g) return GROAN_ENOGROUP;
     if (!ref_box) return GROAN_ENOBOX;  // get_box_center (mod.rs:298-308) comes first in extract_data_from_system
@@ -1550,8 +1029,8 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
     if (ref_box[3] != 0.0f || ref_box[6] != 0.0f || ref_box[7] != 0.0f) return GROAN_ENOTORTHO;
     if (ref_box[0] == 0.0f || ref_box[4] == 0.0f || ref_box[8] == 0.0f) return GROAN_EZEROBOX;
     if (n_ref == 0) return GROAN_EEMPTY;
-    if (!ref_idx) return GROAN_EINVAL;
-    for (size_t i = 0; i < n_ref; i++) {
+    if (!ref_idx && n_ref > n_ref_atoms) return GROAN_EINVAL;  // ref_idx == NULL: the first n_ref atoms of the reference
+    for (size_t i = 0; ref_idx && i < n_ref; i++) {
         if (ref_idx[i] >= n_ref_atoms) return GROAN_EINVAL;
         if (i && ref_idx[i] <= ref_idx[i - 1]) return GROAN_EINVAL;
     }
@@ -1561,7 +1040,7 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         for (size_t i = 0; i < n_ref; i++)
             if (ref_mass[i] < 0.0f) {
                 ctx->err_a = 0;
-                ctx->err_b = ref_idx[i];
+                ctx->err_b = ref_idx ? ref_idx[i] : i;
                 return GROAN_ENOMASS;
             }
     } else {
@@ -1573,7 +1052,7 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
             return GROAN_EGROUPSIZE;
         }
     }
-    groan_gpu_ctx::Ref &R = ctx->refs[gid];
+    groan_gpu_ctx::Ref &R = ctx->refs[ref_slot(gid)];
     CK(cudaStreamSynchronize(ctx->compute));
     if (R.d_pc) { cudaFree(R.d_pc); R.d_pc = nullptr; }
     for (float *&q : R.d_pq)
@@ -1586,13 +1065,13 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         CK(cudaMalloc(&d_ref, n_ref_atoms * 3 * sizeof(float)));
         CK(cudaMalloc(&d_refbox, 9 * sizeof(float)));
         CK(cudaMalloc(&d_small, 6 * sizeof(float)));
-        CK(cudaMalloc(&d_ridx, n_ref * sizeof(uint32_t)));
+        if (ref_idx) CK(cudaMalloc(&d_ridx, n_ref * sizeof(uint32_t)));
         CK(cudaMalloc(&d_sums, kRefSums * sizeof(double)));
         CK(cudaMalloc(&R.d_pc, ref_floats(n_ref) * sizeof(float)));
         CK(cudaMemsetAsync(R.d_pc, 0, ref_floats(n_ref) * sizeof(float), ctx->compute));
         CK(cudaMemcpyAsync(d_ref, ref_xyz, n_ref_atoms * 3 * sizeof(float), cudaMemcpyDefault, ctx->compute));
         CK(cudaMemcpyAsync(d_refbox, ref_box, 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
-        CK(cudaMemcpyAsync(d_ridx, ref_idx, n_ref * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->compute));
+        if (ref_idx) CK(cudaMemcpyAsync(d_ridx, ref_idx, n_ref * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->compute));
         if (ref_mass) {
             CK(cudaMalloc(&d_rmass, n_ref * sizeof(float)));
             CK(cudaMemcpyAsync(d_rmass, ref_mass, n_ref * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));

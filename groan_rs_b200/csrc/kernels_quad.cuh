@@ -500,11 +500,6 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     };
     stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
-#ifdef GROAN_EXP_NOMATH
-        // experiment (profiles/exp/README.md): how fast does the ring alone stream?  Results are garbage.
-        sq = __fadd2_rn(sq, make_float2(c0.x + c1.y + c2.z, r[0].x + r[1].y + r[2].z + r[3].w));
-        return;
-#endif
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
         atom_pair(d01, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), r[0], r[1], bg.head + j);

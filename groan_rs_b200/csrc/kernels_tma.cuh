@@ -111,10 +111,6 @@ __device__ __forceinline__ BodyGeom body_geom(const FrameView &fv, const GroupVi
     return b;
 }
 
-// profiling experiment only (GROAN_DEBUG_SKIP_REF=1): do not copy the reference into the ring, to measure how much
-// of the RMSD kernel's time is its L2 -> SM traffic.  Results are garbage with it set; never set in tests or bench.
-__device__ int g_debug_skip_ref = 0;
-
 struct RefPair {
     float2 x, y, z, w; // (atom i0, atom i1) per component
 };
@@ -142,7 +138,7 @@ __device__ __forceinline__ void stream_pairs_tma(const FrameView &fv, const Grou
         const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
         const uint32_t atoms = min((uint32_t)CH, bg.body - c * CH);
         const uint32_t i0 = bg.head + c * CH, b0 = i0 >> 8; // reference blocks covering group atoms [i0, i0 + atoms)
-        const uint32_t ref_bytes = (WITH_REF && !g_debug_skip_ref) ? (((i0 + atoms - 1) >> 8) - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
+        const uint32_t ref_bytes = WITH_REF ? (((i0 + atoms - 1) >> 8) - b0 + 1) * (uint32_t)(kRefBlock * 16) : 0u;
         mbar_expect_tx(ctl.full + s, atoms * 12u * FPC + ref_bytes);
         unsigned char *dst = smem + s * C::kStageBytes;
         if (WITH_REF && ref_bytes) bulk_g2s(dst, ref_pc + (size_t)b0 * (4 * kRefBlock), ref_bytes, ctl.full + s, pol_ref);

@@ -8,6 +8,7 @@ there is no CPU fallback.
 """
 import ctypes as C
 import enum
+import weakref
 
 import numpy as np
 
@@ -154,6 +155,9 @@ class Group:
     def __len__(self):
         return int(self.indices.size)
 
+    def index_array(self, n_atoms):
+        return np.arange(n_atoms, dtype=np.uint32) if self.indices is None else self.indices
+
 
 class System:
     """A molecular system whose per-frame PBC geometry runs on one B200 (src/system/mod.rs:38-73).
@@ -176,9 +180,15 @@ class System:
         self.n_frames = 0
         self._host_frames = None
         self._boxes = None
-        self._version = 0
-        self._ref_cache = {}
+        self._version = 0   # bumped by everything that changes positions, boxes or groups (keys the RMSD reference cache)
+        self._ref_cache = {}  # target gid -> (weakref to the reference System, its _version when uploaded, group name)
         self._keep = []
+        self._all = None
+        self._atom_pair = None
+        if self.masses is not None:
+            # "all" / "All" exist from the start with the atoms' masses (System::new, src/system/mod.rs:150-170)
+            gm = np.where(np.isnan(self.masses), np.float32(-1.0), self.masses).astype(np.float32)
+            self._check(self._lib.groan_gpu_set_group(self._h, _lib.GROUP_ALL, None, self.n_atoms, _ptr(gm)), "set_group", "all")
         if triclinic:
             self.set_flags(_lib.FLAG_TRICLINIC)
 
@@ -278,7 +288,8 @@ class System:
         self._check(self._lib.groan_gpu_set_group(self._h, g.gid, _ptr(g.indices) if len(g) else None, len(g),
                                                   _ptr(gm) if gm is not None and len(g) else None), "set_group", name)
         self._groups[name] = g
-        self._ref_cache = {k: v for k, v in self._ref_cache.items() if k[1] != name}
+        self._ref_cache.pop(g.gid, None)  # set_group dropped the device-side reference of this gid
+        self._version += 1                # ... and a System used as somebody's reference has changed
         return g
 
     def group_create_from_ranges(self, name, ranges):
@@ -292,10 +303,22 @@ class System:
     def group_get_n_atoms(self, name):
         return self.n_atoms if name in ("all", "All") and name not in self._groups else len(self._group(name))
 
+    def _bump(self):
+        """positions changed in place: whoever cached this System as an RMSD reference must upload it again"""
+        self._host_frames = None
+        self._version += 1
+
     def group_isempty(self, name):
         return self.group_get_n_atoms(name) == 0
 
     def _group(self, name, rmsd=False):
+        if name in ("all", "All") and name not in self._groups:
+            if self._all is None:
+                self._all = Group.__new__(Group)
+                self._all.indices, self._all.gid = None, _lib.GROUP_ALL  # indices None: every atom, ascending
+                self._all.mass = None if self.masses is None else np.where(np.isnan(self.masses), np.float32(-1.0),
+                                                                          self.masses).astype(np.float32)
+            return self._all
         if name not in self._groups:
             if rmsd:
                 raise RMSDError("NonexistentGroup", name, _lib.ENOGROUP)
@@ -482,8 +505,10 @@ class System:
         for i in (index1, index2):
             if not 0 <= int(i) < self.n_atoms:
                 raise IndexError("atom index %d out of range" % i)
-        self.group_create_from_indices("__atom1", [int(index1)])
-        self.group_create_from_indices("__atom2", [int(index2)])
+        if self._atom_pair != (int(index1), int(index2)):
+            self.group_create_from_indices("__atom1", [int(index1)])
+            self.group_create_from_indices("__atom2", [int(index2)])
+            self._atom_pair = (int(index1), int(index2))
         return self.group_all_distances("__atom1", "__atom2", dim)[:, 0, 0]
 
     def group_all_distances_reduce(self, group1, group2, dim, cutoff=0.0, out=None):
@@ -511,10 +536,17 @@ class System:
     def group_wrap(self, name, shifts=False):
         """modifying.rs:215; shifts=True also returns the int8 image shifts [F, G, 3]"""
         gid = self._gid(name)
-        sh = np.empty((self.n_frames, self.group_get_n_atoms(name), 3), np.int8) if shifts is True else (shifts or None)
+        sh = self._shifts_arg(name, shifts)
         self._check(self._lib.groan_gpu_wrap(self._h, gid, _ptr(sh) if sh is not None else None), "group_wrap", name)
-        self._host_frames = None
+        self._bump()
         return sh
+
+    def _shifts_arg(self, name, shifts):
+        """shifts: False / None = not wanted, True = a fresh host array, anything else = the caller's int8 buffer
+        [F, G, 3] (numpy array or torch tensor, host or device)"""
+        if shifts is True:
+            return np.empty((self.n_frames, self.group_get_n_atoms(name), 3), np.int8)
+        return None if shifts is False or shifts is None else shifts
 
     def atoms_translate(self, t, shifts=False):
         """modifying.rs:73"""
@@ -523,9 +555,9 @@ class System:
     def group_translate(self, name, t, shifts=False):
         gid = self._gid(name)
         t3 = (C.c_float * 3)(*[float(v) for v in t])
-        sh = np.empty((self.n_frames, self.group_get_n_atoms(name), 3), np.int8) if shifts is True else (shifts or None)
+        sh = self._shifts_arg(name, shifts)
         self._check(self._lib.groan_gpu_translate(self._h, gid, t3, _ptr(sh) if sh is not None else None), "group_translate", name)
-        self._host_frames = None
+        self._bump()
         return sh
 
     # ------------------------------------------------------------------ cutoff pair search
@@ -576,23 +608,23 @@ class System:
             self._mol_ref = np.full(self.n_atoms, 0xFFFFFFFF, np.uint32)
             self._check(self._lib.groan_gpu_set_molecules(self._h, _ptr(self._mol_ref)), "make_molecules_whole")
         self._check(self._lib.groan_gpu_make_molecules_whole(self._h), "make_molecules_whole")
-        self._host_frames = None
+        self._bump()
 
     def make_group_whole(self, name):
         """System::make_group_whole (modifying.rs:437-465)"""
         self._check(self._lib.groan_gpu_make_group_whole(self._h, self._gid(name)), "make_group_whole", name)
-        self._host_frames = None
+        self._bump()
 
     def atoms_center(self, reference, dimension=Dimension.XYZ):
         """System::atoms_center (utility.rs:109-130)"""
         self._check(self._lib.groan_gpu_atoms_center(self._h, self._gid(reference), 0, int(dimension)), "atoms_center", reference)
-        self._host_frames = None
+        self._bump()
 
     def atoms_center_mass(self, reference, dimension=Dimension.XYZ):
         """System::atoms_center_mass (utility.rs:168-189)"""
         self._check(self._lib.groan_gpu_atoms_center(self._h, self._gid(reference), 1, int(dimension)), "atoms_center_mass",
                     reference)
-        self._host_frames = None
+        self._bump()
 
     # ------------------------------------------------------------------ RMSD (src/system/rmsd.rs)
     def _frame0(self):
@@ -601,27 +633,26 @@ class System:
         return self.get_frames()[0]
 
     def _set_reference(self, reference, group):
-        key = (id(reference), group, reference._version)
-        if self._ref_cache.get("cur") == key:
+        gid = self._gid(group, rmsd=True)
+        hit = self._ref_cache.get(gid)
+        if hit is not None and hit[0]() is reference and hit[1] == reference._version and hit[2] == group:
             return
         # extract_data_from_system(reference) runs first (rmsd.rs:146-147): box, then the group in the REFERENCE
         if reference._boxes is None:
             raise RMSDError("InvalidSimBox(SimBoxError::DoesNotExist)", "reference has no box", _lib.ENOBOX)
         rg = reference._group(group, rmsd=True)
-        gid = self._gid(group, rmsd=True)
-        if gid < 0:
-            raise RMSDError("NonexistentGroup", group, _lib.ENOGROUP)
         rmass = getattr(rg, "mass", None)
-        if rmass is None and len(rg):
-            e = RMSDError("InvalidMass(MassError::NoMass(%d))" % int(rg.indices[0]), "reference atom has no mass", _lib.ENOMASS)
-            raise e
+        if rmass is None and (rg.indices is None or len(rg)):
+            first = 0 if rg.indices is None else int(rg.indices[0])
+            raise RMSDError("InvalidMass(MassError::NoMass(%d))" % first, "reference atom has no mass", _lib.ENOMASS)
+        n_ref = reference.n_atoms if rg.indices is None else len(rg)
         ref_xyz = np.ascontiguousarray(reference._frame0(), dtype=np.float32)
         ref_box = np.ascontiguousarray(reference._boxes[0], dtype=np.float32)
         self._check(self._lib.groan_gpu_rmsd_set_reference(self._h, gid, _ptr(ref_xyz), reference.n_atoms,
-                                                           _ptr(rg.indices) if len(rg) else None, len(rg), _ptr(ref_box),
-                                                           _ptr(rmass) if len(rg) else None),
+                                                           _ptr(rg.indices) if n_ref and rg.indices is not None else None, n_ref,
+                                                           _ptr(ref_box), _ptr(rmass) if n_ref else None),
                     "rmsd_set_reference", group, rmsd=True)
-        self._ref_cache["cur"] = key
+        self._ref_cache[gid] = (weakref.ref(reference), reference._version, group)
 
     def calc_rmsd(self, reference, group, out=None, rot=None):
         """System::calc_rmsd / RMSDTrajRead::calc_rmsd (rmsd.rs:75,315): RMSD of every frame to `reference` (its frame 0)."""
@@ -647,5 +678,5 @@ class System:
         self._set_reference(reference, group)
         out = self._out(out, (self.n_frames,))
         self._check(self._lib.groan_gpu_rmsd_fit(self._h, self._gid(group, True), _ptr(out)), "calc_rmsd_and_fit", group, rmsd=True)
-        self._host_frames = None
+        self._bump()
         return out

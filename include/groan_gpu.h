@@ -89,7 +89,9 @@ int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n);
 
 /* ---- groups: Group::from_indices, container.rs:51-115 ---------------------------------------- */
 /* idx ascending and unique, each < n_atoms; mass nullable (ops that need masses then fail GROAN_ENOMASS,
- * mass[i] < 0 marks "atom idx[i] has no mass") */
+ * mass[i] < 0 marks "atom idx[i] has no mass").
+ * gid == GROAN_GROUP_ALL attaches masses to the built-in group of every atom ("all" / "All" exist from System::new on,
+ * src/system/mod.rs:150-170): idx must be NULL and n == n_atoms. */
 int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t n, const float *mass);
 
 /* ---- frames: FrameData::update_system, xdrfile_xtc.rs:88-104 ---------------------------------- */
@@ -176,7 +178,8 @@ int groan_gpu_atoms_center(groan_gpu_ctx *ctx, int gid, int weighted, int dim);
  * own index list for the same group name, rmsd.rs:823-841).  ref_mass: the n_ref masses of the REFERENCE
  * system's group (they weight the RMSD sum and reference.group_get_com, rmsd.rs:154,192); NULL = use the
  * masses given to groan_gpu_set_group (then n_ref must equal the group's size).  The target's own
- * group_get_com always uses the set_group masses. */
+ * group_get_com always uses the set_group masses.  ref_idx == NULL: the group is the first n_ref atoms of the reference
+ * (n_ref <= n_ref_atoms).  gid may be GROAN_GROUP_ALL. */
 int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_xyz, size_t n_ref_atoms,
                                  const uint32_t *ref_idx, size_t n_ref, const float ref_box[9], const float *ref_mass);
 /* System::calc_rmsd / RMSDTrajRead::calc_rmsd (rmsd.rs:75,315): rmsd F; rot (nullable) F x 9 row-major r */

@@ -85,8 +85,12 @@ class System {
     void set_masses(std::vector<float> masses) {
         if (masses.size() != n_atoms_) throw GpuError("InvalidArgument", "one mass per atom expected", GROAN_EINVAL);
         masses_ = std::move(masses);
+        // "all" exists from System::new on with the atoms' masses (src/system/mod.rs:150-170)
+        check(groan_gpu_set_group(ctx_, GROAN_GROUP_ALL, nullptr, n_atoms_, masses_.data()), "set_masses");
         for (auto &kv : groups_)
             if (kv.second.gid >= 0) upload_group(kv.second);
+        ref_keys_.clear();
+        version_++;
     }
 
     // System::group_create_from_indices (groups.rs) -> Group::from_indices (container.rs:51-115): sorted, de-duplicated
@@ -102,6 +106,8 @@ class System {
         g.indices = std::move(indices);
         upload_group(g);
         groups_[name] = std::move(g);
+        ref_keys_.erase(name); // groan_gpu_set_group dropped the device-side RMSD reference of this group id
+        version_++;            // a System that serves as somebody's reference has changed
     }
     void group_create_from_range(const std::string &name, uint32_t first, uint32_t last_inclusive) {
         std::vector<uint32_t> idx;
@@ -125,6 +131,7 @@ class System {
         check(groan_gpu_push_frames(ctx_, xyz, boxes ? b.data() : nullptr, n_frames), "set_frames");
         n_frames_ = n_frames;
         frame0_.assign(xyz, xyz + n_atoms_ * 3); // a System used as an RMSD reference is read on the host (rmsd.rs:186-203)
+        frame0_stale_ = false;
         has_box0_ = boxes != nullptr;
         if (boxes) box0_ = boxes[0];
         version_++;
@@ -186,13 +193,17 @@ class System {
     }
 
     // ---- modifying (src/system/modifying.rs, utility.rs): in place on every frame of the batch
-    void atoms_wrap() { check(groan_gpu_wrap(ctx_, GROAN_GROUP_ALL, nullptr), "atoms_wrap"); }
-    void group_wrap(const std::string &name) { check(groan_gpu_wrap(ctx_, group(name).gid, nullptr), "group_wrap", name); }
-    void atoms_translate(const Vector3D &t) { check(groan_gpu_translate(ctx_, GROAN_GROUP_ALL, t.data(), nullptr), "atoms_translate"); }
+    void atoms_wrap() { check(groan_gpu_wrap(ctx_, GROAN_GROUP_ALL, nullptr), "atoms_wrap"); touched(); }
+    void group_wrap(const std::string &name) { check(groan_gpu_wrap(ctx_, group(name).gid, nullptr), "group_wrap", name); touched(); }
+    void atoms_translate(const Vector3D &t) { check(groan_gpu_translate(ctx_, GROAN_GROUP_ALL, t.data(), nullptr), "atoms_translate"); touched(); }
     void group_translate(const std::string &name, const Vector3D &t) {
         check(groan_gpu_translate(ctx_, group(name).gid, t.data(), nullptr), "group_translate", name);
+        touched();
     }
-    void make_group_whole(const std::string &name) { check(groan_gpu_make_group_whole(ctx_, group(name).gid), "make_group_whole", name); }
+    void make_group_whole(const std::string &name) {
+        check(groan_gpu_make_group_whole(ctx_, group(name).gid), "make_group_whole", name);
+        touched();
+    }
     // bonds as index pairs (System::add_bonds_from_pdb); molecules and their reference atoms are worked out here, on the host
     void add_bonds(const std::vector<std::pair<uint32_t, uint32_t>> &bonds) {
         std::vector<uint32_t> parent(n_atoms_);
@@ -219,12 +230,15 @@ class System {
             check(groan_gpu_set_molecules(ctx_, mol_ref_.data()), "make_molecules_whole");
         }
         check(groan_gpu_make_molecules_whole(ctx_), "make_molecules_whole");
+        touched();
     }
     void atoms_center(const std::string &reference, Dimension dim) {
         check(groan_gpu_atoms_center(ctx_, group(reference).gid, 0, (int)dim), "atoms_center", reference);
+        touched();
     }
     void atoms_center_mass(const std::string &reference, Dimension dim) {
         check(groan_gpu_atoms_center(ctx_, group(reference).gid, 1, (int)dim), "atoms_center_mass", reference);
+        touched();
     }
 
     // ---- RMSD (src/system/rmsd.rs:75,129).  `reference` may be another System with its own atom count; the group is looked
@@ -239,6 +253,7 @@ class System {
         set_reference(reference, name);
         std::vector<float> out(n_frames_);
         check(groan_gpu_rmsd_fit(ctx_, group(name, true).gid, out.data()), "calc_rmsd_and_fit", name, true);
+        touched();
         return out;
     }
     // group_get_center (or group_get_com) AND calc_rmsd from one read of every frame
@@ -289,16 +304,25 @@ class System {
     void set_reference(const System &ref, const std::string &name) {
         const Group &mine = group(name, true);
         const Group &theirs = ref.group(name, true);
-        if (mine.gid < 0) throw RMSDError("NonexistentGroup", name + " (use a named group, not 'all')", GROAN_ENOGROUP);
         const auto key = std::make_pair(&ref, ref.version_);
         auto it = ref_keys_.find(name);
         if (it != ref_keys_.end() && it->second == key) return;
         if (ref.frame0_.empty()) throw GpuError("NoFrames", "the reference system has no frame", GROAN_ENOFRAMES);
+        if (ref.frame0_stale_) { // the reference was wrapped / translated / fitted in place since it was uploaded
+            std::vector<float> all(ref.n_frames_ * ref.n_atoms_ * 3);
+            ref.check(groan_gpu_get_frames(ref.ctx_, all.data()), "calc_rmsd (reading the reference back)");
+            ref.frame0_.assign(all.begin(), all.begin() + ref.n_atoms_ * 3);
+            ref.frame0_stale_ = false;
+        }
+        const bool all_atoms = theirs.gid == GROAN_GROUP_ALL;
+        const size_t n_ref = all_atoms ? ref.n_atoms_ : theirs.indices.size();
         std::vector<float> m;
-        if (!ref.masses_.empty())
-            for (uint32_t i : theirs.indices) m.push_back(ref.masses_[i]);
-        check(groan_gpu_rmsd_set_reference(ctx_, mine.gid, ref.frame0_.data(), ref.n_atoms_, theirs.indices.data(), theirs.indices.size(),
-                                           ref.has_box0_ ? ref.box0_.m : nullptr, m.empty() ? nullptr : m.data()),
+        if (!ref.masses_.empty()) {
+            if (all_atoms) m = ref.masses_;
+            else for (uint32_t i : theirs.indices) m.push_back(ref.masses_[i]);
+        }
+        check(groan_gpu_rmsd_set_reference(ctx_, mine.gid, ref.frame0_.data(), ref.n_atoms_, all_atoms ? nullptr : theirs.indices.data(),
+                                           n_ref, ref.has_box0_ ? ref.box0_.m : nullptr, m.empty() ? nullptr : m.data()),
               "calc_rmsd", name, true);
         ref_keys_[name] = key;
     }
@@ -362,7 +386,13 @@ class System {
     std::map<std::string, Group> groups_;
     std::vector<float> masses_;
     std::vector<uint32_t> mol_ref_;
-    std::vector<float> frame0_;
+    // positions changed on the device: the host copy of frame 0 is stale and RMSD references taken from this System are too
+    void touched() {
+        frame0_stale_ = true;
+        version_++;
+    }
+    mutable std::vector<float> frame0_;
+    mutable bool frame0_stale_ = false;
     SimBox box0_;
     bool has_box0_ = false;
     unsigned long version_ = 0;
