@@ -66,7 +66,16 @@ SIGNATURES = {
     "groan_gpu_synth_uniform": (_int, [_vp, _u64, _u64, _sz, C.POINTER(_f), C.POINTER(_f), _vp]),
     "groan_gpu_synth_blob": (_int, [_vp, _u64, _u64, _sz, _f, _f, _vp, _vp, _vp, _int]),
     "groan_gpu_synth_blob_ref": (_int, [_vp, _u64, _f, C.POINTER(_f), _vp]),
+    # include/groan_xtc.h
+    "groan_xtc_scan": (_int, [_vp, _sz, _sz, _vp, C.POINTER(C.c_int32), C.POINTER(_sz)]),
+    "groan_xtc_decode": (_int, [_vp, _sz, _vp, _sz, _int, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "groan_xtc_encode": (_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp, _f, _int, _vp, _sz, C.POINTER(_sz)]),
+    "groan_gpu_push_xtc": (_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "groan_gpu_xtc_bad_frames": (_int, [_vp, C.POINTER(_sz)]),
+    "groan_gpu_push_group_frames": (_int, [_vp, _vp, _vp, _sz, _vp, _sz]),
+    "groan_gpu_write_xtc": (_int, [_vp, _f, _vp, _vp, _int, _vp, _sz, C.POINTER(_sz)]),
 }
+XTC_OK, XTC_EOF, XTC_EMAGIC, XTC_ETRUNC, XTC_EFORMAT, XTC_ERAW, XTC_ECAPACITY, XTC_ERANGE, XTC_EINVAL = range(9)
 
 _LIB = None
 

@@ -83,6 +83,17 @@ struct groan_gpu_ctx {
     void *d_quant[2] = {nullptr, nullptr};       // quantised frames as uploaded (groan_gpu_push_frames_quantized), one per slot
     size_t quant_bytes = 0;
     int32_t *d_origin[2] = {nullptr, nullptr};   // their per-frame integer origins (F x 3)
+    // xtc streams decoded on the device (groan_xtc.cu): the file's bytes as uploaded, per-frame parameters, damage flags
+    void *d_xtc[2] = {nullptr, nullptr};
+    size_t xtc_cap = 0;
+    void *d_xtc_params[2] = {nullptr, nullptr};
+    int *d_xtc_status = nullptr;
+    size_t xtc_frames = 0;
+    // partial frames (groan_gpu_push_group_frames): compact upload + the atom list
+    void *d_sel[2] = {nullptr, nullptr};
+    size_t sel_cap = 0;
+    uint32_t *d_sel_atoms = nullptr;
+    size_t sel_atoms_cap = 0;
     float *h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 

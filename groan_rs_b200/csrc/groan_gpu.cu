@@ -595,6 +595,9 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         if (ctx->h_stage[s]) cudaFreeHost(ctx->h_stage[s]);
         if (ctx->d_quant[s]) cudaFree(ctx->d_quant[s]);
         if (ctx->d_origin[s]) cudaFree(ctx->d_origin[s]);
+        if (ctx->d_xtc[s]) cudaFree(ctx->d_xtc[s]);
+        if (ctx->d_xtc_params[s]) cudaFree(ctx->d_xtc_params[s]);
+        if (ctx->d_sel[s]) cudaFree(ctx->d_sel[s]);
         if (ctx->ev_done[s]) cudaEventDestroy(ctx->ev_done[s]);
         if (ctx->ev_stage[s]) cudaEventDestroy(ctx->ev_stage[s]);
     }
@@ -608,7 +611,8 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         for (float *q : r.d_pq)
             if (q) cudaFree(q);
     }
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done, ctx->d_mol_ref};
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done, ctx->d_mol_ref,
+                    ctx->d_xtc_status, ctx->d_sel_atoms};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);

@@ -393,6 +393,72 @@ class System:
         self._boxes = bm
         self._version += 1
 
+    def set_frames_xtc(self, xtc, first=0, count=None):
+        """Stage frames [first, first + count) of an xtc.XtcFile straight from the file's bytes: they cross PCIe compressed
+        (about a third of the floats for a solvated system) and are decoded on the GPU (groan_gpu_push_xtc); boxes come from
+        the frame headers.  Returns dict(step, time, precision)."""
+        count = xtc.n_frames - first if count is None else int(count)
+        if first < 0 or count <= 0 or first + count > xtc.n_frames:
+            raise IndexError("frames [%d, %d) of %d" % (first, first + count, xtc.n_frames))
+        offs = np.ascontiguousarray(xtc.offsets[first:first + count + 1])
+        meta = {"step": np.zeros(count, np.int32), "time": np.zeros(count, np.float32), "precision": np.zeros(count, np.float32)}
+        self._check(self._lib.groan_gpu_push_xtc(self._h, _ptr(xtc.data), xtc.nbytes, _ptr(offs), count, _ptr(meta["step"]),
+                                                 _ptr(meta["time"]), _ptr(meta["precision"])), "set_frames_xtc")
+        self._host_frames = None
+        self._keep = [xtc.data, offs]
+        self.n_frames = count
+        bm = np.zeros((count, 9), np.float32)
+        for f in range(count):  # the header's box: 9 big-endian floats at byte 16 of the frame
+            o = int(offs[f]) + 16
+            raw = xtc.data[o:o + 36]
+            raw = raw.numpy() if _is_torch(raw) else np.asarray(raw)
+            bm[f] = np.frombuffer(raw.tobytes(), dtype=">f4")
+        self._boxes = bm
+        self._version += 1
+        return meta
+
+    def xtc_bad_frames(self):
+        n = C.c_size_t(0)
+        self._check(self._lib.groan_gpu_xtc_bad_frames(self._h, C.byref(n)), "xtc_bad_frames")
+        return int(n.value)
+
+    def set_group_frames(self, xyz_sel, atoms, boxes):
+        """Partial frames (GroupXtcReader, molly_xtc.rs:404-470): xyz_sel [F, len(atoms), 3] holds only the atoms `atoms`
+        (ascending).  Only those bytes cross PCIe; the other atoms of the System keep their previous values."""
+        sel = np.ascontiguousarray(atoms, dtype=np.uint32)
+        if _is_torch(xyz_sel):
+            a = xyz_sel if xyz_sel.dim() == 3 else xyz_sel.unsqueeze(0)
+            if str(a.dtype) != "torch.float32" or not a.is_contiguous() or a.is_cuda:
+                raise ValueError("partial frames must be contiguous float32 host tensors")
+        else:
+            a = np.ascontiguousarray(xyz_sel, dtype=np.float32)
+            if a.ndim == 2:
+                a = a[None]
+        F = int(a.shape[0])
+        if tuple(a.shape[1:]) != (int(sel.size), 3):
+            raise ValueError("partial frames must be [F, %d, 3]" % sel.size)
+        bm = _boxes_to_matrices(boxes, F)
+        self._check(self._lib.groan_gpu_push_group_frames(self._h, _ptr(a), _ptr(sel), int(sel.size), _ptr(bm), F), "set_group_frames")
+        self._host_frames = None
+        self._keep = [a, sel]
+        self.n_frames = F
+        self._boxes = bm
+        self._version += 1
+
+    def write_xtc(self, precision=1000.0, step=None, time=None, n_threads=None):
+        """The current batch as xtc frames (numpy uint8), byte-identical to XtcWriter::write_frame (xtc_io/mod.rs:300-330):
+        quantised on the device with the writer's rounding, encoded by a pool of host threads."""
+        from . import xtc as _xtc
+        F = self.n_frames
+        st = None if step is None else np.ascontiguousarray(step, dtype=np.int32)
+        tm = None if time is None else np.ascontiguousarray(time, dtype=np.float32)
+        cap = F * (self.n_atoms * 12 + 128) + 64
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        self._check(self._lib.groan_gpu_write_xtc(self._h, C.c_float(precision), _ptr(st), _ptr(tm),
+                                                  int(n_threads or _xtc.default_threads()), _ptr(out), cap, C.byref(n)), "write_xtc")
+        return out[: n.value]
+
     def set_valid(self, valid):
         """Option<Vector3D> positions (atom.rs:23-71): valid[f, i] == 0 means atom i has no position in frame f."""
         v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8).reshape(self.n_frames, self.n_atoms)

@@ -10,12 +10,16 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "groan_gpu.h")
+HEADERS = [HEADER, os.path.join(ROOT, "include", "groan_xtc.h")]
 
 
 def declared_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(groan_gpu_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in HEADERS:
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(groan_(?:gpu|xtc)_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 @pytest.fixture(scope="module")
