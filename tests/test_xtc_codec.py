@@ -194,7 +194,7 @@ def test_gpu_decoder_flags_damaged_streams(tmp_path):
     raw = np.fromfile(os.path.join(XTC, "short_trajectory.xtc"), dtype=np.uint8).copy()
     x = g.xtc.XtcFile(raw)
     lo, hi = int(x.offsets[2]), int(x.offsets[3])
-    raw[lo + 200:hi - 8] = 0xFF  # every flag bit set, maximal runs: the stream of frame 2 overruns its end
+    raw[lo + 200:hi - 8] = 0  # no flag ever set: one large atom per group, the stream of frame 2 runs past its end
     s = g.System(x.n_atoms, max_frames=x.n_frames)
     s.set_frames_xtc(g.xtc.XtcFile(raw))
     assert s.xtc_bad_frames() >= 1
