@@ -140,13 +140,16 @@ def ncu_traffic(frames_per_step):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(steps, warmup, sample_frames=None, threads=None):
-    """Restated groan_rs CPU trajectory path (oracle/groan_oracle.c: orc_baseline_traj, following
-    parallel.rs:208-269,425-448): T threads, interleaved frames, AoS 240-byte atom records, f32 sequential sums."""
+def cpu_reference_run(steps, warmup, frames_per_step, threads=None, sample_frames=None):
+    """Restated groan_rs CPU trajectory path (oracle/groan_oracle.c: orc_baseline_traj_cyclic, following
+    parallel.rs:208-269,425-448): T threads, each with its own clone of the System (AoS 240-byte atom records), the frames of
+    the WHOLE run interleaved among them (thread t takes frames t, t + T, ...), f32 sequential sums.
+    A step is `frames_per_step` frames like in the GPU arm; `sample_frames` distinct frames are held in memory and visited
+    cyclically (37 x 48 MB; a run of 20 steps would otherwise need 35 GB)."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     T = threads or max(1, min(cores, 32))
-    Fs = sample_frames or T
+    Fs = sample_frames or frames_per_step
     m = masses(N_ATOMS)
     idx = np.arange(N_ATOMS, dtype=np.uint32)
     L = np.array([BOX, BOX, BOX], np.float32)
@@ -156,29 +159,30 @@ def cpu_reference_run(steps, warmup, sample_frames=None, threads=None):
     for f in range(Fs):
         frames[f] = orc.synth_blob_frame(N_ATOMS, SEED, f, BLOB_SCALE, NOISE_SCALE, rot[f], cen[f], L, wrap=True)
     boxes = np.tile(L, (Fs, 1))
-    times = []
-    for it in range(warmup + steps):
-        sec, _, _ = orc.baseline_traj(frames, boxes, idx, m, ref_xyz, L, ops=1 | 2, n_threads=T)
-        if it >= warmup:
-            times.append(sec)
-    sec = float(np.mean(times))
-    return {"value": Fs / sec, "unit": "frames/s", "cores": T, "kind": "port",
-            "sample": "%d frames x %d atoms (group_get_center + calc_rmsd), %d threads, interleaved frames; restated groan_rs CPU "
-                      "path (oracle/), generation excluded" % (Fs, N_ATOMS, T), "ms_per_step": sec * 1e3, "frames": Fs}
+    if warmup > 0:
+        orc.baseline_traj(frames, boxes, idx, m, ref_xyz, L, ops=1 | 2, n_threads=T, total_frames=warmup * frames_per_step)
+    total = max(1, steps) * frames_per_step
+    sec, _, _ = orc.baseline_traj(frames, boxes, idx, m, ref_xyz, L, ops=1 | 2, n_threads=T, total_frames=total)
+    return {"value": total / sec, "unit": "frames/s", "cores": T, "kind": "port",
+            "sample": "%d frames (= %d steps x %d; %d distinct frames visited cyclically) x %d atoms (group_get_center + calc_rmsd), "
+                      "%d threads, frames interleaved among the threads like traj_iter_map_reduce; restated groan_rs CPU path (oracle/), "
+                      "generation excluded" % (total, max(1, steps), frames_per_step, Fs, N_ATOMS, T),
+            "ms_per_step": sec * 1e3 / max(1, steps), "frames": frames_per_step}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(max(1, args.steps), min(args.warmup, 1), sample_frames=args.cpu_frames)
+    W = max(args.warmup, 0)
+    r = cpu_reference_run(max(1, args.steps), W, args.frames, sample_frames=args.cpu_frames)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded generator shared with the GPU arm)",
             "config": workload_config(r["frames"]),
             "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "warmup_steps_run": W, "gpu_launches": 0}
     emit(line)
 
 
@@ -189,6 +193,31 @@ def workload_config(frames_per_step):
             "batching": "one call per step over a batch of %d frames (%d MB resident in HBM)" % (frames_per_step,
                                                                                                  frames_per_step * N_ATOMS * 12 // 1000000),
             "l2_policy": "inputs larger than L2: %d MB per step vs 126 MB L2" % (frames_per_step * N_ATOMS * 12 // 1000000)}
+
+
+def pin_to_gpu_numa(local):
+    """Run this rank's host side (threads, first-touch of its pinned buffers) on the NUMA node its GPU hangs off.
+    Returns what was found for the JSON line; a VM that exposes no topology reports node -1 and nothing is changed."""
+    info = {"node": None, "cpus": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        info["pci"] = bus
+        info["node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpus"] = len(allowed)
+    except Exception as e:  # no sysfs topology (containers, VMs): leave the affinity alone
+        info["error"] = type(e).__name__
+    return info
 
 
 def check_frames_against_oracle(ref_xyz, m, rot, cen, frame0, which, got_center, got_rmsd):
@@ -249,8 +278,6 @@ def run_gpu_arm(args):
     cen_all = torch.empty((n_slots * F, 3), dtype=torch.float32, device=dev)
     rmsd_all = torch.empty((n_slots * F,), dtype=torch.float32, device=dev)
     d_cen, d_rmsd = cen_all[:F], rmsd_all[:F]  # slot 0, also used by the per-op timings below
-    g_cen = torch.empty((world * n_slots * F, 3), dtype=torch.float32, device=dev) if world > 1 else None
-    g_rmsd = torch.empty((world * n_slots * F,), dtype=torch.float32, device=dev) if world > 1 else None
     step_no = [0]
 
     def step():
@@ -259,11 +286,14 @@ def run_gpu_arm(args):
         s.group_center_and_rmsd(ref, "G", center_out=cen_all[i * F:(i + 1) * F], rmsd_out=rmsd_all[i * F:(i + 1) * F])
         step_no[0] += 1
 
+    gathered = [None, None]
+
     def drain():
+        # the path's only exchange, through the product's own gather: groan_rs_b200.parallel.gather_frames
         step_no[0] = 0
         if world > 1:
-            dist.all_gather_into_tensor(g_cen, cen_all)
-            dist.all_gather_into_tensor(g_rmsd, rmsd_all)
+            gathered[0] = g.gather_frames(cen_all, world * n_slots * F)
+            gathered[1] = g.gather_frames(rmsd_all, world * n_slots * F)
 
     def barrier():
         if world > 1:
@@ -351,81 +381,111 @@ def run_gpu_arm(args):
                 "achieved_burst": ops[dom]["gbs"], "frac_burst": ops[dom]["gbs"] / peak, "ops": ops,
                 "fallback_frames": fallback}
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + kernels + D2H every step
+    # ---- end to end through the public API with HOST buffers (pinned): H2D + decode + kernels + D2H every step.
+    # Four feeds of the SAME frames (rounded to the xtc lattice for the last three):
+    #   f32        what read_xtc hands out (12 B/atom)                                 -> System.set_frames
+    #   int16      the decoder's lattice integers + a per-frame origin (6 B/atom)      -> System.set_frames_quantized
+    #   xtc        the FILE'S BYTES as they lie on disk, decoded on the GPU            -> System.set_frames_xtc
+    #   xtc_host   the file's bytes decoded by the host thread pool inside the step    -> XtcFile.decode + set_frames_quantized
+    # The headline `value` is the xtc feed: its host buffer is the trajectory file itself, nothing is prepared on the host.
     e2e = None
     if not args.no_e2e:
+        numa = pin_to_gpu_numa(local)
         h_in = [torch.empty((F, N_ATOMS, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
         s.get_frames(out=h_in[0])
         s.sync()
+        t0 = time.perf_counter()
         h_in[1].copy_(h_in[0])
+        host_memcpy_gbs = 2 * F * N_ATOMS * 12 * 1e-9 / (time.perf_counter() - t0)  # read + write, one thread
         h_cen = torch.empty((F, 3), dtype=torch.float32).pin_memory()
         h_rmsd = torch.empty((F,), dtype=torch.float32).pin_memory()
         boxes = np.tile(np.array([BOX, BOX, BOX], np.float32), (F, 1))
+        Ke = max(3, min(K, 50))  # 8-30 ms per step: bounded so that the default run stays short
 
-        def e2e_step(k):
-            s.set_frames(h_in[k & 1], boxes)
-            s.group_center_and_rmsd(ref, "G", center_out=h_cen, rmsd_out=h_rmsd)
-
-        Ke = max(3, min(K, 50))  # 7 ms per step: bounded so that the default run stays short
-        for k in range(2):
-            e2e_step(k)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(Ke):
-            e2e_step(k)
-        s.sync()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert np.abs(h_rmsd.numpy() - r0).max() <= 2e-6 and np.abs(h_cen.numpy() - c0).max() <= 4e-6  # same frames, same results
-        e2e = {"value": world * F * Ke / dt, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 12 + F * 36,
-               "d2h_bytes_per_step": F * 16, "ms_per_step": dt * 1e3 / Ke, "steps": Ke,
-               "timing": "host wall clock around the steps, sync both sides"}
-
-        # the same steps fed with the xtc decoder's integers (int16 lattice points at precision 1000 + a per-frame origin,
-        # groan_gpu_push_frames_quantized): the frames are those of h_in rounded to the xtc grid, half the PCIe bytes.
-        # Single-GPU runs only: it is a property of the link, and N ranks would pin N x 1.8 GB more host memory for it.
-        if world == 1:
-            prec = 1000.0
-            x = h_in[0].numpy()
-            h_q = [torch.empty((F, N_ATOMS, 3), dtype=torch.int16).pin_memory() for _ in range(2)]
-            origin = np.zeros((F, 3), np.int32)
-            for f in range(F):  # frame by frame: no multi-GB temporaries
-                lat = np.rint(x[f].astype(np.float64) * prec).astype(np.int32)
-                origin[f] = ((lat.min(axis=0).astype(np.int64) + lat.max(axis=0)) // 2).astype(np.int32)
-                rel = lat - origin[f]
-                assert np.abs(rel).max() < 32768
-                h_q[0][f] = torch.from_numpy(rel.astype(np.int16))
-            h_q[1].copy_(h_q[0])
-            del lat, rel
-
-            def e2e_q_step(k):
-                s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin)
+        def run_feed(push, steps):
+            def one(k):
+                push(k)
                 s.group_center_and_rmsd(ref, "G", center_out=h_cen, rmsd_out=h_rmsd)
-
             for k in range(2):
-                e2e_q_step(k)
+                one(k)
             barrier()
             t0 = time.perf_counter()
-            for k in range(Ke):
-                e2e_q_step(k)
+            for k in range(steps):
+                one(k)
             s.sync()
             torch.cuda.synchronize()
-            dtq = time.perf_counter() - t0
+            dt = time.perf_counter() - t0
             if world > 1:
-                t = torch.tensor([dtq], device=dev)
+                t = torch.tensor([dt], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dtq = float(t.item())
-            assert np.all(np.abs(h_rmsd.numpy() - 0.0866) < 2e-3)
-            e2e["quantized_int16"] = {"value": world * F * Ke / dtq, "unit": "frames/s", "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48,
-                                      "ms_per_step": dtq * 1e3 / Ke,
-                                      "note": "frames rounded to the xtc grid (precision 1000) and uploaded as the decoder's int16 lattice "
-                                              "points; floats rebuilt on the device with the reader's expression"}
-            s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
-            del h_q
+                dt = float(t.item())
+            return dt
+
+        feeds = {}
+        dt = run_feed(lambda k: s.set_frames(h_in[k & 1], boxes), Ke)
+        assert np.abs(h_rmsd.numpy() - r0).max() <= 2e-6 and np.abs(h_cen.numpy() - c0).max() <= 4e-6  # same frames, same results
+        feeds["f32"] = {"value": world * F * Ke / dt, "h2d_bytes_per_step": F * N_ATOMS * 12 + F * 36, "ms_per_step": dt * 1e3 / Ke,
+                        "steps": Ke, "h2d_gbs_per_gpu": (F * N_ATOMS * 12) * 1e-9 / (dt / Ke)}
+
+        # the trajectory file: the batch written as xtc (precision 1000) by the product's encoder -- byte-identical to the
+        # reference's write_xtc (tests/test_xtc_codec.py) -- held in pinned memory like a file read into a pinned buffer
+        prec = 1000.0
+        stream = g.xtc.encode(xyz=h_in[0].numpy(), boxes=boxes, precision=prec)
+        h_x = [torch.empty(stream.size, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for t_ in h_x:
+            t_.numpy()[:] = stream
+        xf = [g.xtc.XtcFile(t_) for t_ in h_x]
+        del stream
+        assert xf[0].n_frames == F and xf[0].n_atoms == N_ATOMS
+        dt = run_feed(lambda k: s.set_frames_xtc(xf[k & 1]), Ke)
+        assert s.xtc_bad_frames() == 0
+        cx, rx = h_cen.numpy().copy(), h_rmsd.numpy().copy()
+        # parity of this feed: frame 0 as the REFERENCE's reader semantics decode it (host decoder, bit-identical to read_xtc)
+        # through the exact64 oracle
+        from oracle import oracle as orc
+        fr0 = xf[0].decode(first=0, count=1)["xyz"][0]
+        idx_all = np.arange(N_ATOMS, dtype=np.uint32)
+        Lb = np.array([BOX] * 3, np.float32)
+        c64 = orc.get_center_x64(fr0, idx_all, Lb)
+        r64, _ = orc.calc_rmsd_x64(ref_xyz, idx_all, Lb, m, fr0, idx_all, Lb)
+        assert np.abs(cx[0] - c64).max() <= 1e-5 and abs(float(rx[0]) - float(r64)) <= 1e-4, (cx[0], c64, rx[0], r64)
+        xtc_bytes = int(xf[0].offsets[-1])
+        feeds["xtc"] = {"value": world * F * Ke / dt, "h2d_bytes_per_step": xtc_bytes + F * 56, "ms_per_step": dt * 1e3 / Ke, "steps": Ke,
+                        "h2d_gbs_per_gpu": xtc_bytes * 1e-9 / (dt / Ke), "bytes_per_atom": xtc_bytes / (F * N_ATOMS),
+                        "parity_frame0_vs_exact64": {"center_err_nm": float(np.abs(cx[0] - c64).max()),
+                                                     "rmsd_err_nm": abs(float(rx[0]) - float(r64))},
+                        "note": "host buffer = the xtc file's bytes (precision 1000); uploaded as they are, decoded on the GPU"}
+
+        h_q = [torch.empty((F, N_ATOMS, 3), dtype=torch.int16).pin_memory() for _ in range(2)]
+        origin = [np.zeros((F, 3), np.int32) for _ in range(2)]
+        xf[0].decode(want="q16", out=h_q[0].numpy(), origin_out=origin[0])
+        h_q[1].copy_(h_q[0])
+        origin[1][:] = origin[0]
+        dt = run_feed(lambda k: s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin[k & 1]), Ke)
+        assert np.array_equal(h_rmsd.numpy(), rx) and np.array_equal(h_cen.numpy(), cx)  # the same floats reach the kernels
+        feeds["int16"] = {"value": world * F * Ke / dt, "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48, "ms_per_step": dt * 1e3 / Ke,
+                          "steps": Ke, "h2d_gbs_per_gpu": (F * N_ATOMS * 6) * 1e-9 / (dt / Ke),
+                          "note": "the xtc decoder's lattice integers (int16 + per-frame origin), floats rebuilt on the device"}
+        if world == 1:
+            # the host decoder inside the step: what a host-side reader sustains on this box's cores
+            nthr = g.xtc.default_threads()
+
+            def push_host_decoded(k):
+                xf[k & 1].decode(want="q16", out=h_q[k & 1].numpy(), origin_out=origin[k & 1], n_threads=nthr)
+                s.set_frames_quantized(h_q[k & 1], prec, boxes, origin=origin[k & 1])
+
+            dt = run_feed(push_host_decoded, 3)
+            assert np.array_equal(h_rmsd.numpy(), rx)
+            feeds["xtc_host_decode"] = {"value": F * 3 / dt, "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48, "ms_per_step": dt * 1e3 / 3,
+                                        "steps": 3, "host_threads": nthr,
+                                        "note": "xtc bytes -> int16 lattice by the host thread pool (groan_xtc_decode) inside the step"}
+        head = feeds["xtc"]
+        e2e = {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": F * 16,
+               "ms_per_step": head["ms_per_step"], "steps": Ke, "feed": "xtc (file bytes, GPU decode)",
+               "f32_equivalent_h2d_bytes_per_step": F * N_ATOMS * 12 + F * 36, "timing": "host wall clock around the steps, sync both sides",
+               "feeds": feeds, "host_memcpy_gbs_one_thread": host_memcpy_gbs, "numa": numa}
+        s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
+        del h_q, h_x, xf
 
     extras = None
     if rank == 0 and not args.no_extras:
@@ -433,7 +493,7 @@ def run_gpu_arm(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_run(1, 0, sample_frames=args.cpu_frames)
+        cpu = cpu_reference_run(3, 0, F, sample_frames=args.cpu_frames)  # ~15 s of CPU work: 3 steps of F frames
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -592,7 +652,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=37,
                     help="frames per step (48 MB each); 37 frames x 8 CTAs per frame = 296 CTAs = one wave of 2 CTAs per SM")
-    ap.add_argument("--cpu-frames", type=int, default=None, help="frames in the CPU sample (default: one per thread)")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="distinct frames held by the CPU arm (default: frames per step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

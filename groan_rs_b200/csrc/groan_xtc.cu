@@ -219,6 +219,8 @@ int groan_gpu_push_xtc(groan_gpu_ctx *ctx, const uint8_t *data, size_t len, cons
         p.bitsize = fi.bitsize;
         p.smallidx = fi.smallidx;
         p.inv_precision = gx::inv_precision(fi.precision);
+        p.recip1 = xtc_recip(fi.sizeint[1]);
+        p.recip2 = xtc_recip(fi.sizeint[2]);
         std::memcpy(&boxes[f * 9], fi.box, sizeof(fi.box));
         if (step) step[f] = fi.step;
         if (time) time[f] = fi.time;
@@ -242,6 +244,9 @@ int groan_gpu_push_xtc(groan_gpu_ctx *ctx, const uint8_t *data, size_t len, cons
             }
             CK(cudaMalloc(&ctx->d_xtc_status, ctx->max_frames * sizeof(int)));
             ctx->xtc_cap = cap;
+            unsigned long long recips[73];
+            for (int k = 0; k < 73; k++) recips[k] = xtc_recip((uint32_t)gx::kMagicInts[k]);
+            CK(cudaMemcpyToSymbol(g_xtc_magic_recip, recips, sizeof(recips)));
         }
         int r = h2d_on_copy_stream(ctx, ctx->d_xtc[slot], data + lo, bytes);
         if (r) return r;
@@ -249,10 +254,18 @@ int groan_gpu_push_xtc(groan_gpu_ctx *ctx, const uint8_t *data, size_t len, cons
         CK(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_xtc[slot]) + bytes, 0, 16, ctx->copy));
         // pageable source: the runtime stages it before the call returns, `params` may go out of scope
         CK(cudaMemcpyAsync(ctx->d_xtc_params[slot], params.data(), n_frames * sizeof(XtcFrameParams), cudaMemcpyHostToDevice, ctx->copy));
-        const unsigned nb = (unsigned)((n_frames + kXtcWarpsPerCta - 1) / kXtcWarpsPerCta);
-        // on the COPY stream: ordered behind its own upload, overlapping the kernels still running on the previous batch
-        k_xtc_decode<<<nb, kXtcWarpsPerCta * 32, 0, ctx->copy>>>((const uint32_t *)ctx->d_xtc[slot], (const XtcFrameParams *)ctx->d_xtc_params[slot],
-                                                                (int)n_frames, ctx->cur_xyz, ctx->n_atoms * 3, ctx->d_xtc_status);
+        // on the COPY stream: ordered behind its own upload, overlapping the kernels still running on the previous batch.
+        // Many frames: one warp each; few large ones (fewer frames than the GPU has warp slots to fill): a CTA each.
+        const uint32_t *d_stream = (const uint32_t *)ctx->d_xtc[slot];
+        const XtcFrameParams *d_params = (const XtcFrameParams *)ctx->d_xtc_params[slot];
+        if (n_frames >= (size_t)kSMs * 4 || ctx->n_atoms < 4096) {
+            const unsigned nb = (unsigned)((n_frames + kXtcWarpsPerCta - 1) / kXtcWarpsPerCta);
+            k_xtc_decode<1><<<nb, kXtcWarpsPerCta * 32, 0, ctx->copy>>>(d_stream, d_params, (int)n_frames, ctx->cur_xyz, ctx->n_atoms * 3,
+                                                                       ctx->d_xtc_status);
+        } else {
+            k_xtc_decode<kXtcWideWarps><<<(unsigned)n_frames, kXtcWideWarps * 32, 0, ctx->copy>>>(d_stream, d_params, (int)n_frames, ctx->cur_xyz,
+                                                                                                 ctx->n_atoms * 3, ctx->d_xtc_status);
+        }
         LAUNCHED();
         ctx->xtc_frames = n_frames;
         return end_batch(ctx);

@@ -42,6 +42,12 @@ def gather_frames(local, n_frames_total, device=None):
     lo, hi = sizes[rank]
     if t.shape[0] != hi - lo:
         raise ValueError("rank %d holds %d frames, expected %d" % (rank, t.shape[0], hi - lo))
+    if (dist.get_backend() == "nccl" and n_frames_total % world == 0 and isinstance(local, torch.Tensor) and t.is_cuda
+            and t.is_contiguous()):
+        # equal shards already on the exchange device: one collective straight into the result, no padding copies
+        full = torch.empty((n_frames_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t)
+        return full
     pad = torch.zeros((longest,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
     pad[: hi - lo] = t.to(device)
     parts = [torch.empty_like(pad) for _ in range(world)]

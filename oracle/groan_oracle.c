@@ -790,6 +790,7 @@ _Static_assert(sizeof(atom_rec) == 240, "atom record must be 240 bytes");
 typedef struct {
     const float *frames, *boxes;
     size_t F, n;
+    size_t F_store; /* frames actually held in `frames` (0 = F): frame f of the trajectory is stored frame f % F_store */
     const uint32_t *idx, *idx2;
     size_t g, g2;
     const float *mass_all;
@@ -822,7 +823,9 @@ static void *traj_thread(void *arg) {
         for (size_t i = 0; i < J->g; i++) ref_idx[i] = J->idx[i];
     }
     /* interleaved assignment parallel.rs:425-448 */
-    for (size_t f = (size_t)J->tid; f < J->F; f += (size_t)J->T) {
+    const size_t F_store = J->F_store ? J->F_store : J->F;
+    for (size_t ft = (size_t)J->tid; ft < J->F; ft += (size_t)J->T) {
+        const size_t f = ft % F_store;
         const float *fr = J->frames + f * n * 3;
         const float *L = J->boxes + f * 3;
         /* FrameData::update_system xdrfile_xtc.rs:88-104: set position, reset velocity and force */
@@ -889,6 +892,19 @@ double orc_baseline_traj(const float *frames, const float *boxes, size_t F, size
     traj_job J;
     memset(&J, 0, sizeof(J));
     J.frames = frames; J.boxes = boxes; J.F = F; J.n = n; J.idx = idx; J.g = g; J.mass_all = mass_all;
+    J.ref_xyz = ref_xyz; J.ref_L = ref_L; J.ops = ops & 15; J.centers = centers; J.rmsd = rmsd;
+    return run_jobs(&J, T);
+}
+
+/* the same path over a trajectory of F_total frames of which only F_store distinct ones are held in memory (frame f is
+ * stored frame f % F_store): lets the bench time many steps' worth of frames the way the reference splits a whole
+ * trajectory among its threads (parallel.rs:425-448), without holding them all.  Outputs: F_store entries. */
+double orc_baseline_traj_cyclic(const float *frames, const float *boxes, size_t F_store, size_t F_total, size_t n, const uint32_t *idx,
+                                size_t g, const float *mass_all, const float *ref_xyz, const float ref_L[3], int ops, int T,
+                                float *centers, float *rmsd) {
+    traj_job J;
+    memset(&J, 0, sizeof(J));
+    J.frames = frames; J.boxes = boxes; J.F = F_total; J.F_store = F_store; J.n = n; J.idx = idx; J.g = g; J.mass_all = mass_all;
     J.ref_xyz = ref_xyz; J.ref_L = ref_L; J.ops = ops & 15; J.centers = centers; J.rmsd = rmsd;
     return run_jobs(&J, T);
 }

@@ -129,6 +129,9 @@ void orc_synth_blob_frame(float *xyz, size_t n_atoms, uint64_t seed, uint64_t fr
 double orc_baseline_traj(const float *frames /* F*n*3 */, const float *boxes /* F*3 lengths */, size_t F, size_t n_atoms,
                          const uint32_t *idx, size_t g, const float *mass_all /* n_atoms */, const float *ref_xyz,
                          const float ref_L[3], int ops, int n_threads, float *centers /* F*3 */, float *rmsd /* F */);
+double orc_baseline_traj_cyclic(const float *frames, const float *boxes, size_t F_store, size_t F_total, size_t n_atoms,
+                                const uint32_t *idx, size_t g, const float *mass_all, const float *ref_xyz, const float ref_L[3],
+                                int ops, int n_threads, float *centers, float *rmsd);
 double orc_baseline_pairs(const float *frames, const float *boxes, size_t F, size_t n_atoms, const uint32_t *idx1, size_t g1,
                           const uint32_t *idx2, size_t g2, int dim, int n_threads, float *dmin /* F */, float *dmax /* F */);
 

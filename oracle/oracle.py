@@ -405,10 +405,24 @@ def synth_blob_frame(n, seed, frame, scale, nscale, rot, centre, L, wrap=True):
 # ---------------------------------------------------------------- restated CPU trajectory path (baseline)
 
 
-def baseline_traj(frames, boxes_L, idx, mass_all, ref_xyz, ref_L, ops, n_threads):
-    """ops bitmask: 1 group_get_center, 2 calc_rmsd, 4 fit, 8 atoms_wrap.  Returns (seconds, centers, rmsd)."""
+def baseline_traj(frames, boxes_L, idx, mass_all, ref_xyz, ref_L, ops, n_threads, total_frames=None):
+    """ops bitmask: 1 group_get_center, 2 calc_rmsd, 4 fit, 8 atoms_wrap.  Returns (seconds, centers, rmsd).
+    total_frames: length of the trajectory to process; the stored frames are visited cyclically (frame f = frames[f % F])."""
     fr = _f32(frames)
     F, n = fr.shape[0], fr.shape[1]
+    if total_frames is not None:
+        bx = _f32(boxes_L).reshape(F, 3)
+        i = _idx(idx)
+        cen, rm = np.zeros((F, 3), np.float32), np.zeros(F, np.float32)
+        m = _f32(mass_all) if mass_all is not None else None
+        rx = _f32(ref_xyz) if ref_xyz is not None else None
+        rl = _f32(ref_L) if ref_L is not None else None
+        fn = lib().orc_baseline_traj_cyclic
+        fn.restype = C.c_double
+        sec = fn(_fp(fr), _fp(bx), _sz(F), _sz(int(total_frames)), _sz(n), i.ctypes.data_as(_u), _sz(i.size),
+                 _fp(m) if m is not None else None, _fp(rx) if rx is not None else None, _fp(rl) if rl is not None else None,
+                 C.c_int(ops), C.c_int(n_threads), _fp(cen), _fp(rm))
+        return sec, cen, rm
     bx = _f32(boxes_L).reshape(F, 3)
     i = _idx(idx)
     cen = np.zeros((F, 3), np.float32)

@@ -167,11 +167,12 @@ def test_gpu_decoder_is_read_xtc_bit_for_bit(name):
 
 @pytest.mark.gpu
 @needs_ref
-@pytest.mark.parametrize("kind,n,prec", [("water", 30000, 1000.0), ("gas", 25000, 1000.0), ("huge", 4000, 1000.0), ("chain", 50000, 1000.0),
-                                         ("chain", 7777, 10000.0), ("water", 10, 100.0)])
-def test_gpu_decoder_synthetic_streams(kind, n, prec, tmp_path):
+@pytest.mark.parametrize("kind,n,prec,F", [("water", 30000, 1000.0, 6), ("gas", 25000, 1000.0, 6), ("huge", 4000, 1000.0, 6),
+                                           ("chain", 50000, 1000.0, 6), ("chain", 7777, 10000.0, 6), ("water", 10, 100.0, 6),
+                                           ("water", 5000, 1000.0, 600), ("gas", 4100, 1000.0, 3)])
+def test_gpu_decoder_synthetic_streams(kind, n, prec, F, tmp_path):
+    """one warp per frame (many frames, or small ones) and one CTA per frame (few large frames)"""
     import groan_rs_b200 as g
-    F = 6
     xyz, box, step, time = _synthetic(kind, n, F, 5)
     box[:, [3, 6, 7]] = 0
     raw = ref.write_xtc(str(tmp_path / "ref.xtc"), xyz, box, step, time, prec)
