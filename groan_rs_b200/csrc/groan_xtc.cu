@@ -254,21 +254,25 @@ int groan_gpu_push_xtc(groan_gpu_ctx *ctx, const uint8_t *data, size_t len, cons
         CK(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_xtc[slot]) + bytes, 0, 16, ctx->copy));
         // pageable source: the runtime stages it before the call returns, `params` may go out of scope
         CK(cudaMemcpyAsync(ctx->d_xtc_params[slot], params.data(), n_frames * sizeof(XtcFrameParams), cudaMemcpyHostToDevice, ctx->copy));
-        // on the COPY stream: ordered behind its own upload, overlapping the kernels still running on the previous batch.
+        int r2 = end_batch(ctx);
+        if (r2) return r2;
+        // The decoder runs on the COMPUTE stream, behind the upload (end_batch made it wait for the copy stream): while it
+        // decodes batch k and the analysis kernels run, the copy stream is already uploading batch k + 1 into the other
+        // buffer (begin_batch orders that upload behind everything the compute stream did with the buffer before).
         // Many frames: one warp each; few large ones (fewer frames than the GPU has warp slots to fill): a CTA each.
         const uint32_t *d_stream = (const uint32_t *)ctx->d_xtc[slot];
         const XtcFrameParams *d_params = (const XtcFrameParams *)ctx->d_xtc_params[slot];
         if (n_frames >= (size_t)kSMs * 4 || ctx->n_atoms < 4096) {
             const unsigned nb = (unsigned)((n_frames + kXtcWarpsPerCta - 1) / kXtcWarpsPerCta);
-            k_xtc_decode<1><<<nb, kXtcWarpsPerCta * 32, 0, ctx->copy>>>(d_stream, d_params, (int)n_frames, ctx->cur_xyz, ctx->n_atoms * 3,
-                                                                       ctx->d_xtc_status);
+            k_xtc_decode<1><<<nb, kXtcWarpsPerCta * 32, 0, ctx->compute>>>(d_stream, d_params, (int)n_frames, ctx->cur_xyz, ctx->n_atoms * 3,
+                                                                          ctx->d_xtc_status);
         } else {
-            k_xtc_decode<kXtcWideWarps><<<(unsigned)n_frames, kXtcWideWarps * 32, 0, ctx->copy>>>(d_stream, d_params, (int)n_frames, ctx->cur_xyz,
-                                                                                                 ctx->n_atoms * 3, ctx->d_xtc_status);
+            k_xtc_decode<kXtcWideWarps><<<(unsigned)n_frames, kXtcWideWarps * 32, 0, ctx->compute>>>(d_stream, d_params, (int)n_frames,
+                                                                                                    ctx->cur_xyz, ctx->n_atoms * 3, ctx->d_xtc_status);
         }
         LAUNCHED();
         ctx->xtc_frames = n_frames;
-        return end_batch(ctx);
+        return GROAN_OK;
     }();
     if (rc) ctx->have_frames = false;
     return rc;
@@ -280,6 +284,7 @@ int groan_gpu_xtc_bad_frames(groan_gpu_ctx *ctx, size_t *n) {
     if (!ctx->d_xtc_status || ctx->xtc_frames == 0) return GROAN_OK;
     std::vector<int> h(ctx->xtc_frames);
     CK(cudaStreamSynchronize(ctx->copy));
+    CK(cudaStreamSynchronize(ctx->compute));
     CK(cudaMemcpy(h.data(), ctx->d_xtc_status, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int v : h) *n += (v != 0);
     return GROAN_OK;

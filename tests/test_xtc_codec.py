@@ -191,14 +191,21 @@ def test_gpu_decoder_synthetic_streams(kind, n, prec, F, tmp_path):
 
 @pytest.mark.gpu
 def test_gpu_decoder_flags_damaged_streams(tmp_path):
+    """a frame whose bit stream is shorter than its atoms need (here: the length field of the third frame halved) is reported,
+    the frames before it are intact"""
     import groan_rs_b200 as g
     raw = np.fromfile(os.path.join(XTC, "short_trajectory.xtc"), dtype=np.uint8).copy()
     x = g.xtc.XtcFile(raw)
-    lo, hi = int(x.offsets[2]), int(x.offsets[3])
-    raw[lo + 200:hi - 8] = 0  # no flag ever set: one large atom per group, the stream of frame 2 runs past its end
-    s = g.System(x.n_atoms, max_frames=x.n_frames)
-    s.set_frames_xtc(g.xtc.XtcFile(raw))
-    assert s.xtc_bad_frames() >= 1
+    good = x.decode(count=2)["xyz"]
+    lo = int(x.offsets[2])
+    nbytes = int.from_bytes(raw[lo + 88:lo + 92].tobytes(), "big")
+    raw[lo + 88:lo + 92] = np.frombuffer((nbytes // 2 // 4 * 4).to_bytes(4, "big"), dtype=np.uint8)
+    cut = g.xtc.XtcFile(raw, max_frames=3)
+    assert cut.n_frames == 3
+    s = g.System(x.n_atoms, max_frames=3)
+    s.set_frames_xtc(cut)
+    assert s.xtc_bad_frames() == 1
+    assert np.array_equal(bits(s.get_frames()[:2]), bits(good))
     s.close()
 
 
