@@ -39,6 +39,7 @@ SIGNATURES = {
     "groan_gpu_error_detail": (_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "groan_gpu_launch_count": (_u64, [_vp]),
     "groan_gpu_fallback_frames": (_int, [_vp, C.POINTER(_sz)]),
+    "groan_gpu_second_pass_frames": (_int, [_vp, C.POINTER(_sz)]),
     "groan_gpu_set_group": (_int, [_vp, _int, _vp, _sz, _vp]),
     "groan_gpu_push_frames": (_int, [_vp, _vp, _vp, _sz]),
     "groan_gpu_push_frames_quantized": (_int, [_vp, _vp, _int, _vp, _f, _vp, _sz]),

@@ -107,6 +107,10 @@ struct groan_gpu_ctx {
     float *d_c0 = nullptr, *d_cen = nullptr, *d_cen2 = nullptr, *d_res = nullptr, *d_rot = nullptr;
     int *d_flags = nullptr;  // per frame: 1 = the single-pass kernel could not certify its result, redo exactly
     unsigned int *d_frames_done = nullptr;  // device-side fallback launch: frames finished by the running single-pass kernel
+    int *d_flags2 = nullptr;                // per frame: 1 = the fused centre + RMSD kernel sent the frame through the sine-sum centre pass
+    unsigned int *d_second_any = nullptr;   // device-side launch of that pass: how many frames of the running launch want it
+    int *d_second_list = nullptr;           // ... and which
+    bool second_valid = false;              // d_flags2 belongs to the last call
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
     int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
     int occ_center_quad = 0;                   // quad kernels (kernels_quad.cuh)

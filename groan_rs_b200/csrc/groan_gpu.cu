@@ -180,6 +180,7 @@ int set_quad_attr(groan_gpu_ctx *ctx) {
     return GROAN_OK;
 }
 
+int blocks_per_frame_quad(size_t g, size_t F, int occ, size_t chunk);
 FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
                            float *rmsd_out, float *rot_out) {
     FallbackPlan fp;
@@ -196,6 +197,20 @@ FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center,
     fp.com = ctx->d_cen;
     fp.rmsd_out = rmsd_out;
     fp.rot_out = rot_out;
+    fp.second_flags = ctx->d_flags2;
+    fp.second_count = ctx->d_second_any;
+    fp.second_list = ctx->d_second_list;
+    fp.n_report = (int)ctx->n_frames;
+    // the second tier normally runs for one or two frames of a batch (the CTAs of every other frame exit at once): enough CTAs
+    // per frame to fill the GPU with a single frame
+    {
+        const size_t chunk = QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kAtoms;
+        size_t nb = std::max<size_t>(1, (g.n + chunk - 1) / chunk);
+        nb = std::min<size_t>(nb, (size_t)kSMs * (size_t)std::max(1, ctx->occ_center_quad));
+        nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(ctx->n_frames, 1)));
+        fp.nb_second = (int)nb;
+    }
+    fp.second_smem = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
     return fp;
 }
 
@@ -282,10 +297,10 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
         const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
         if (weighted)
             k_center_quad<true><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                           out, ctx->d_flags, fp);
+                                                                           out, ctx->d_flags, fp, nullptr, 0);
         else
             k_center_quad<false><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                            out, ctx->d_flags, fp);
+                                                                            out, ctx->d_flags, fp, nullptr, 0);
         LAUNCHED();
         if (fp.enabled) return GROAN_OK;
         flags = ctx->d_flags;
@@ -418,7 +433,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     rv.sum_m_target = g->mass_sum;
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
-    bool center_done = false, device_fallback = false;
+    bool center_done = false, device_fallback = false, second_tier = false;
     if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && quad_ok(ctx, *g)) {
         // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
         QuadRef qr;
@@ -431,6 +446,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         if (rc) return rc;
         flags = ctx->d_flags;
         center_done = fused;
+        second_tier = fused;
     } else if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
         // centre + RMSD from one read of the frame (kernels_tma.cuh)
         const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
@@ -471,6 +487,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     // reference-order passes (all frames, or only the flagged ones): group_get_com of the target
     // (geometric estimate, mass-weighted unwrap), then shift + wrap + covariance in f64.  Skipped here when the
     // single-pass kernel tail-launches them itself for the frames that need them.
+    ctx->second_valid = second_tier;
     if (!device_fallback) {
         rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
         if (rc) return rc;
@@ -495,6 +512,23 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
             // frames the fused pass flagged: reference-order centre passes for those frames only (d_c0 already
             // holds their Bai-Breen estimate from the RMSD fallback above)
             if (!device_fallback) {
+                if (ctx->second_valid) {
+                    // host-launched second tier of the fused quad kernel: the sine-sum centre pass over the frames it marked;
+                    // what that pass cannot certify either gets bit 1 of its flag set and is redone below
+                    typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
+                    FallbackPlan f2 = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, false, nullptr, nullptr);
+                    f2.second_count = nullptr;
+                    dim3 sgrid((unsigned)f2.nb_second, (unsigned)ctx->n_frames);
+                    if (center_weighted)
+                        k_center_quad<true><<<sgrid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(
+                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1);
+                    else
+                        k_center_quad<false><<<sgrid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(
+                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1);
+                    LAUNCHED();
+                    rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
+                    if (rc) return rc;
+                }
                 rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
                 if (rc) return rc;
             }
@@ -550,6 +584,11 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaMemset(ctx->d_frames_done, 0, sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_flags, max_frames * sizeof(int)));
         CK(cudaMemset(ctx->d_flags, 0, max_frames * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_flags2, max_frames * sizeof(int)));
+        CK(cudaMemset(ctx->d_flags2, 0, max_frames * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_second_list, max_frames * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_second_any, sizeof(unsigned int)));
+        CK(cudaMemset(ctx->d_second_any, 0, sizeof(unsigned int)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center, k_center_fast<false>, kThreads, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
@@ -611,7 +650,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         for (float *q : r.d_pq)
             if (q) cudaFree(q);
     }
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_frames_done, ctx->d_mol_ref,
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_flags2, ctx->d_second_any, ctx->d_second_list, ctx->d_frames_done, ctx->d_mol_ref,
                     ctx->d_xtc_status, ctx->d_sel_atoms};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -679,6 +718,17 @@ int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n) {
     if (!ctx->have_frames) return GROAN_OK;
     std::vector<int> h(ctx->n_frames);
     CK(cudaMemcpyAsync(h.data(), ctx->d_flags, ctx->n_frames * sizeof(int), cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    for (int v : h) *n += (v != 0);
+    return GROAN_OK;
+}
+
+int groan_gpu_second_pass_frames(groan_gpu_ctx *ctx, size_t *n) {
+    if (!ctx || !n) return GROAN_EINVAL;
+    *n = 0;
+    if (!ctx->have_frames || !ctx->second_valid) return GROAN_OK;
+    std::vector<int> h(ctx->n_frames);
+    CK(cudaMemcpyAsync(h.data(), ctx->d_flags2, ctx->n_frames * sizeof(int), cudaMemcpyDeviceToHost, ctx->compute));
     CK(cudaStreamSynchronize(ctx->compute));
     for (int v : h) *n += (v != 0);
     return GROAN_OK;

@@ -31,6 +31,10 @@
 #pragma once
 #include "kernels_tma.cuh"
 
+#ifndef GROAN_QUAD_EARLY_RELEASE
+#define GROAN_QUAD_EARLY_RELEASE 0
+#endif
+
 namespace groan {
 
 constexpr int kQuadCenterThreads = 256;            // CTA size of k_center_quad; a chunk is one quad per thread
@@ -212,14 +216,15 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     uint32_t ring;
     asm volatile("{\n\t.reg .u64 a;\n\tcvta.to.shared.u64 a, %1;\n\tcvt.u32.u64 %0, a;\n\t}" : "=r"(ring) : "l"(smem));
     const uint32_t full0 = ring + STAGES * kSt, empty0 = full0 + STAGES * 8u;
+    const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
     auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES (one thread)
         const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
         const uint32_t atoms = min(CH, bg.body - c * CH);
         const uint32_t ref_bytes = WITH_REF ? ((atoms + kQuadRefBlock - 1) / kQuadRefBlock) * (uint32_t)(kQuadRefBlock * 16) : 0u;
         mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
         unsigned char *dst = smem + s * C::kStageBytes;
-        bulk_g2s(dst, src0 + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, l2_policy_evict_first());
-        if (WITH_REF) bulk_g2s(dst + C::kFrameBytes, ref_pq + (size_t)c * CH * 4, ref_bytes, ctl.full + s, l2_policy_evict_last());
+        bulk_g2s(dst, src0 + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, pol_frame);
+        if (WITH_REF) bulk_g2s(dst + C::kFrameBytes, ref_pq + (size_t)c * CH * 4, ref_bytes, ctl.full + s, pol_ref);
     };
     if (t == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -266,16 +271,30 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
         const uint32_t nst = st ^ (2u * kSt), nph = ph ^ (uint32_t)(st != 0);
         QuadRegs q;
         load(st, q);
-        mbar_wait_a(fb + 8u, ph);
-        fn(j, q.c0, q.c1, q.c2, q.r);
+#if GROAN_QUAD_EARLY_RELEASE
+        // the stage is released as soon as its bytes are in registers (the arrive is ordered behind the loads), a whole
+        // quad of arithmetic earlier than "when done with it": the refill gets that much more time to arrive
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
+#endif
+        mbar_wait_a(fb + 8u, ph);
+        fn(j, q.c0, q.c1, q.c2, q.r);
+#if !GROAN_QUAD_EARLY_RELEASE
+        __syncwarp();
+        if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
+#endif
         j += jstep;
         load(st + kSt, q);
-        if (it + 2 < my_chunks) mbar_wait_a(full0 + (nst ? 16u : 0u), nph);
-        fn(j, q.c0, q.c1, q.c2, q.r);
+#if GROAN_QUAD_EARLY_RELEASE
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
+#endif
+        if (it + 2 < my_chunks) mbar_wait_a(full0 + (nst ? 16u : 0u), nph);
+        fn(j, q.c0, q.c1, q.c2, q.r);
+#if !GROAN_QUAD_EARLY_RELEASE
+        __syncwarp();
+        if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
+#endif
         j += jstep;
         ph = nph;
         st = nst;
@@ -310,6 +329,47 @@ __device__ inline void finish_center_sin(const double tot_md[3], double M, const
         out3[k] = (float)(um - m * Lk);                 // c0 = c~ - m L lies in [0, L): the image within L/2 of c0
     }
     *flag = redo;
+}
+
+// finishing thread of the fused centre + RMSD kernels: the same placement of the mean, but WITHOUT any trigonometric sum.
+// The loop accumulates Sd = sum d and Qd = sum d^2 per axis (unweighted; the image decision is geometric, iterators.rs:1407)
+// instead of sum sin -- one FFMA per coordinate instead of FMUL + FMUL.RZ + MUFU.SIN + FADD, a quarter of the loop's issue slots.
+// With theta_i = 2 pi (u_i - b) / L the angles of the unwrapped atoms about the straddled boundary b, tbar their mean and
+// a_i = theta_i - tbar (sum a_i = 0):
+//     S = sum sin theta_i = sin tbar * sum cos a_i + cos tbar * sum sin a_i,
+//     sum cos a_i >= n - Q/2,   |sum sin a_i| = |sum (sin a_i - a_i)| <= sum |a_i|^3 / 6 <= A Q / 6,
+// Q = sum a_i^2 (from Sd, Qd), A = max |a_i| (from the extent).  If |sin tbar| (n - Q/2) - |cos tbar| A Q / 6 >= kSinGuard n
+// the sign of S -- the side of b the circular mean lies on -- is the sign of tbar, certified with the same margin the sine
+// sum itself is held to.  Otherwise (*second = 1) the frame goes through the sine-sum pass (k_center_quad, gated), which
+// is one more read of that frame; only what IT cannot certify reaches the reference-order passes.
+__device__ inline void finish_center_moments(const double tot_md[3], double M, const double Sd[3], const double Qd[3], const float *tmn,
+                                             const float *tmx, const float p[3], const float *L, uint32_t n, float *out3, int *flag,
+                                             int *second) {
+    int redo = 0, again = 0;
+    const double inv_m = fast_rcp(M), inv_n = fast_rcp((double)n);
+    for (int k = 0; k < 3; k++) {
+        const double Lk = (double)L[k], inv_l = fast_rcp(Lk);
+        if (!((double)tmx[k] - (double)tmn[k] < 0.5 * Lk * kExtentSlack)) redo = 1; // not compact: images may differ
+        const double lo = (double)p[k] + (double)tmn[k], hi = (double)p[k] + (double)tmx[k];
+        const double mlo = floor_div(lo, Lk, inv_l), mhi = floor_div(hi, Lk, inv_l);
+        double m = mlo;
+        if (mlo != mhi) { // the group straddles the boundary mhi * L: which side is the circular mean on?
+            const double s = 6.283185307179586 * inv_l, dbar = Sd[k] * inv_n;
+            const double tbar = s * (((double)p[k] - mhi * Lk) + dbar); // |tbar| < pi: b lies inside the extent, which is < L/2
+            double var = Qd[k] * inv_n - dbar * dbar;                   // f32 partial sums: keep a relative slack
+            var = (var > 0.0 ? var : 0.0) * 1.001 + 1e-9;
+            const double q = s * s * var;                               // Q / n
+            const double a = s * fmax((double)tmx[k] - dbar, dbar - (double)tmn[k]);
+            const float st = __sinf((float)tbar), ct = __cosf((float)tbar);
+            const double bound = fabs((double)st) * (1.0 - 0.5 * q) - fabs((double)ct) * a * q * (1.0 / 6.0);
+            if (!(bound >= kSinGuard)) again = 1;
+            m = tbar > 0.0 ? mhi : mlo;
+        }
+        const double um = (double)p[k] + tot_md[k] * inv_m; // mean of the unwrapped group
+        out3[k] = (float)(um - m * Lk);                 // c0 = c~ - m L lies in [0, L): the image within L/2 of c0
+    }
+    *flag = redo;
+    *second = redo ? 0 : again; // a frame that is not compact goes to the reference-order passes right away
 }
 
 // Per-frame constants, computed by one thread, parked in shared memory and read back by everybody with volatile loads.
@@ -382,11 +442,17 @@ __device__ __forceinline__ double edge_sin(float x, float L) {
 // ---------------------------------------------------------------- group_get_center / group_get_com
 // sums: [0..2] sum m d, [3] sum m, [4..6] sum sin
 template <bool WEIGHTED>
+// sel_mode != 0: the second tier of the fused centre + RMSD kernels -- only the selected frames are done (1: frames with
+// sel[f] != 0, launched from the host over the whole batch; 2: frames sel[blockIdx.y], launched from the device over exactly
+// the frames that need it), and a frame this pass cannot certify either gets bit 1 of its flag ORed in (the fused kernel's
+// flag word: bit 0 RMSD, bit 1 centre).
 __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                                 float *out, int *flags, FallbackPlan fp) {
+                                                                 float *out, int *flags, FallbackPlan fp, const int *sel, int sel_mode) {
+    static_assert(kQuadCenterThreads == 256, "maybe_launch_fallback launches this kernel with 256 threads");
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     FrameReduceSmem<7, 3, kQuadCenterThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<7, 3, kQuadCenterThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
-    const int f = blockIdx.y, nb = gridDim.x;
+    const int f = sel_mode == 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
+    if (sel_mode == 1 && sel[f] == 0) return; // uniform for the CTA (host-launched: nobody counts finished frames)
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
@@ -437,15 +503,79 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
         }
         int flag = 0;
         finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, &flag);
-        flags[f] = flag;
+        if (sel_mode) {
+            if (flag) flags[f] |= 2;
+        } else {
+            flags[f] = flag;
+        }
         maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag);
     }
 }
 
 // ---------------------------------------------------------------- calc_rmsd (+ optionally the centre)
 // CENTER: 0 = RMSD only, 1 = also group_get_center, 2 = also group_get_com.
-// canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum sin
+// canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum d^2 or sum sin (unweighted)
 constexpr int kQuadSums = kFastSums + 6;
+
+// Which way will the centre's image be decided in this frame?  A strided sample of 256 atoms (one per thread, the same
+// atoms in every CTA of the frame, so all of them come to the same answer) estimates the mean, the variance and the extent
+// of the group per axis, and the certificate of finish_center_moments is evaluated on those with generous margins: the
+// mean moved towards the nearest box face by four standard errors, the variance and the extent enlarged.  If it would
+// not hold, the frame accumulates the sine sums instead of the second moments (the loop of the previous generation, ~13 %
+// slower) and is finished by finish_center_sin.  A wrong guess costs time, never the result: the moments are checked
+// again, exactly, by the finishing thread, which sends the frame through the sine-sum pass if they fall short.
+// `scratch`: 8 x 12 floats of shared memory nobody else uses yet.  Contains __syncthreads().
+__device__ __forceinline__ bool predict_sine_mode(const float *fr, const GroupView &g, const float p[3], const float L[3], float *scratch) {
+    constexpr int K = kQuadRmsdThreads;
+    const uint32_t t = threadIdx.x;
+    const uint32_t i = (uint32_t)(((uint64_t)t * g.n) / K);
+    const float *q = fr + ((size_t)g.first + i) * 3;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float d = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+        v[k] = d;
+        v[3 + k] = d * d;
+        v[6 + k] = d;
+        v[9 + k] = d;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) v[k] = warp_sum(v[k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        v[6 + k] = warp_min(v[6 + k]);
+        v[9 + k] = warp_max(v[9 + k]);
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) scratch[(t >> 5) * 12 + k] = v[k];
+    }
+    __syncthreads();
+    if (t == 0) {
+        float a[12];
+        for (int k = 0; k < 12; k++) a[k] = scratch[k];
+        for (int w = 1; w < K / 32; w++)
+            for (int k = 0; k < 12; k++) {
+                const float x = scratch[w * 12 + k];
+                a[k] = k < 6 ? a[k] + x : (k < 9 ? fminf(a[k], x) : fmaxf(a[k], x));
+            }
+        int sine = 0;
+        for (int k = 0; k < 3; k++) {
+            const float s = 6.2831853f / L[k], dbar = a[k] * (1.0f / K);
+            const float var = fmaxf(a[3 + k] * (1.0f / K) - dbar * dbar, 0.0f);
+            const float u = p[k] + dbar, dist = fabsf(u - L[k] * rintf(u / L[k]));  // sample mean to the nearest box face
+            const float th = fmaxf(s * (dist - 4.0f * sqrtf(var * (1.0f / K))), 0.0f);
+            const float qv = 1.3f * s * s * var, ext = 1.25f * s * (a[9 + k] - a[6 + k]);
+            const float bound = (th >= 1.5707963f ? 1.0f : __sinf(th)) * (1.0f - 0.5f * qv) - ext * qv * (1.0f / 6.0f);
+            if (!(bound >= 4.0f * (float)kSinGuard)) sine = 1;
+        }
+        scratch[96] = sine ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    const bool r = scratch[96] != 0.0f;
+    __syncthreads(); // the scratch is about to become the ring
+    return r;
+}
 
 template <bool SAME_MASS, int CENTER>
 __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, double *partials,
@@ -460,15 +590,17 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    const bool sine_mode = CENTER ? predict_sine_mode(fr, g, p, L, reinterpret_cast<float *>(dyn_smem)) : false;
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero();
-    float sd[3] = {0.f, 0.f, 0.f}, ss[3] = {0.f, 0.f, 0.f}; // centre sums as scalars: six registers less than two pattern sums
+    // centre (CENTER != 0): sum d, and sum d^2 (moments) or sum sin (sine mode) per axis, all unweighted, as pattern sums
+    V3 sdv = v3_zero(), cqv = v3_zero();
 #pragma unroll
     for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
     float2 sq = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
-    auto atom_pair = [&](const V3 &d, float2 xa, float2 xb, float2 xc, const float4 &r0, const float4 &r1, uint32_t i) {
+    auto atom_pair = [&](const V3 &d, const float4 &r0, const float4 &r1, uint32_t i) {
         const float2 pc[3] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y)};
         const float2 w = make_float2(r1.z, r1.w);
         const V3 wd = v3_mul(w, d); // w d also serves Hw = sum pc (w d)^T: no separate w pc products
@@ -481,30 +613,39 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         sq = __ffma2_rn(wd.a, d.a, sq);
         sq = __ffma2_rn(wd.b, d.b, sq);
         sq = __ffma2_rn(wd.c, d.c, sq);
-        if (CENTER == 1) {
-            sd[0] = (sd[0] + d.a.x) + d.b.y;
-            sd[1] = (sd[1] + d.a.y) + d.c.x;
-            sd[2] = (sd[2] + d.b.x) + d.c.y;
-        }
-        if (CENTER) {
-            const float2 sa = quad_sin(xa, qc.sc[0], qc.sc[1]), sb = quad_sin(xb, qc.sc[2], qc.sc[0]), sc = quad_sin(xc, qc.sc[1], qc.sc[2]);
-            ss[0] = (ss[0] + sa.x) + sb.y;
-            ss[1] = (ss[1] + sa.y) + sc.x;
-            ss[2] = (ss[2] + sb.x) + sc.y;
-        }
+        if (CENTER) v3_add(sdv, d);
         quad_minmax(mm, d);
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
             v3_fma(smd, m, d); // sum m is a constant of the group: ref.sum_m_target, no accumulator
         }
     };
-    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
-                                        [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
-        V3 d01, d23;
-        quad_deltas(qc, c0, c1, c2, d01, d23);
-        atom_pair(d01, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), r[0], r[1], bg.head + j);
-        atom_pair(d23, make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w), r[2], r[3], bg.head + j + 2);
-    });
+    auto moments = [&](const V3 &d) {
+        cqv.a = __ffma2_rn(d.a, d.a, cqv.a);
+        cqv.b = __ffma2_rn(d.b, d.b, cqv.b);
+        cqv.c = __ffma2_rn(d.c, d.c, cqv.c);
+    };
+    if (!sine_mode) {
+        stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+            V3 d01, d23;
+            quad_deltas(qc, c0, c1, c2, d01, d23);
+            atom_pair(d01, r[0], r[1], bg.head + j);
+            if (CENTER) moments(d01);
+            atom_pair(d23, r[2], r[3], bg.head + j + 2);
+            if (CENTER) moments(d23);
+        });
+    } else {
+        stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+            V3 d01, d23;
+            quad_deltas(qc, c0, c1, c2, d01, d23);
+            atom_pair(d01, r[0], r[1], bg.head + j);
+            quad_sines(qc, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), cqv);
+            atom_pair(d23, r[2], r[3], bg.head + j + 2);
+            quad_sines(qc, make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w), cqv);
+        });
+    }
     __syncthreads(); // every warp has left the ring: its memory becomes the reduction scratch
     float a[KS];
 #pragma unroll
@@ -517,8 +658,8 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     a[22] = v3_x(smd); a[23] = v3_y(smd); a[24] = v3_z(smd);
     a[25] = 0.0f;
     if (CENTER) {
-        a[KS - 6] = sd[0]; a[KS - 5] = sd[1]; a[KS - 4] = sd[2];
-        a[KS - 3] = ss[0]; a[KS - 2] = ss[1]; a[KS - 1] = ss[2];
+        a[KS - 6] = v3_x(sdv); a[KS - 5] = v3_y(sdv); a[KS - 4] = v3_z(sdv);
+        a[KS - 3] = v3_x(cqv); a[KS - 2] = v3_y(cqv); a[KS - 1] = v3_z(cqv);
     }
     double tot[KS];
     float tmn[3], tmx[3];
@@ -538,7 +679,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
                 tmx[k] = fmaxf(tmx[k], dk);
                 if (CENTER) {
                     tot[KS - 6 + k] += d[k];
-                    tot[KS - 3 + k] += edge_sin(xk, L[k]);
+                    tot[KS - 3 + k] += sine_mode ? edge_sin(xk, L[k]) : d[k] * d[k];
                 }
             }
             for (int u = 0; u < 3; u++)
@@ -558,17 +699,19 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         tot[25] = ref.sum_m_target;
         double rt[kFastSums];
         for (int k = 0; k < kFastSums; k++) rt[k] = tot[k];
-        int flag_r = 0, flag_c = 0;
+        int flag_r = 0, flag_c = 0, second = 0;
         finish_rmsd<SAME_MASS>(rt, tmn, tmx, p[0], p[1], p[2], L, ref, rmsd_out + f, rot_out + f * 9, com_out + f * 3, &flag_r);
         if (CENTER) {
             // centre: geometric (sum d / n) or mass-weighted with the target group's masses (= the COM of the RMSD)
             double md[3];
             for (int k = 0; k < 3; k++) md[k] = CENTER == 2 ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[KS - 6 + k];
             const double M = CENTER == 2 ? (SAME_MASS ? ref.sum_w : tot[25]) : (double)g.n;
-            finish_center_sin(md, M, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
+            if (sine_mode) finish_center_sin(md, M, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
+            else finish_center_moments(md, M, tot + (KS - 6), tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c, &second);
+            fp.second_flags[f] = second;
         }
         flags[f] = flag_r | (flag_c << 1);
-        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags, flag_r | flag_c);
+        maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags, flag_r | flag_c, second, f);
     }
 }
 

@@ -259,29 +259,63 @@ struct FallbackPlan {
     int want_center, center_weighted, want_rmsd;
     float *center_out;        // want_center
     float *com, *rmsd_out, *rot_out; // want_rmsd
+    // second tier of the fused centre + RMSD kernels (kernels_quad.cuh, finish_center_moments): frames whose image could
+    // not be certified from the moments go through the sine-sum centre pass (k_center_quad, gated by second_flags) first
+    int *second_flags;          // per frame, written by the fused kernel (diagnostics, and the gate of the host-launched pass)
+    unsigned int *second_count; // device-launched pass: number of such frames of the running launch (re-armed by the thread that reads it)
+    int *second_list;           // ... and which (any order): the pass is launched over exactly these frames
+    int nb_second;              // CTAs per frame of that k_center_quad launch
+    int second_smem;            // its dynamic shared memory
+    int n_report;               // finishing threads that will call maybe_launch_fallback (n_frames, or the length of the list)
 };
+
+// sel_mode 0: every frame of the batch; 1: frames with sel[f] != 0 (host-launched second tier); 2: frames sel[0 .. gridDim.y)
+template <bool WEIGHTED>
+__global__ void k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets, float *out, int *flags, FallbackPlan fp,
+                              const int *sel, int sel_mode);
 
 // frames_done counts finished frames in its low 16 bits and flagged ones above, so that the thread that finishes the last
 // frame learns from its own atomic whether any frame needs the passes: no read-back of the flags (8 dependent L2 round
 // trips at the very end of the kernel, ~3 us, in the first version).  Batches are far below 65535 frames (kPartialSlots).
 __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, const FrameView &fv, const GroupView &g, const RefView &ref,
-                                                      double *partials, unsigned int *tickets, const int *flags, int my_flag) {
+                                                      double *partials, unsigned int *tickets, int *flags, int my_flag, int my_second = 0,
+                                                      int my_frame = 0) {
     if (!fp.enabled) return;
+    if (my_second) fp.second_list[atomicAdd(fp.second_count, 1u)] = my_frame;
     __threadfence();
     const unsigned int done = atomicAdd(fp.frames_done, my_flag ? 0x10001u : 1u);
-    if ((done & 0xffffu) != (unsigned)fp.n_frames - 1) return;
+    if ((done & 0xffffu) != (unsigned)fp.n_report - 1) return;
     *fp.frames_done = 0u; // re-arm
-    if (!my_flag && (done >> 16) == 0u) return;
+    const bool slow = my_flag || (done >> 16) != 0u;
+    const unsigned int n_second = fp.second_count != nullptr ? atomicExch(fp.second_count, 0u) : 0u;
+    if (!slow && n_second == 0u) return;
     __threadfence();
     const dim3 ge(fp.nb_exact, fp.n_frames), gc(fp.nb_cov, fp.n_frames);
-    k_trig<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.c0, flags);
-    if (fp.want_rmsd) {
-        k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.com, flags);
-        k_cov<<<gc, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, ref, fp.com, partials, tickets, fp.rmsd_out, fp.rot_out, flags);
+    if (slow) {
+        k_trig<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.c0, flags);
+        if (fp.want_rmsd) {
+            k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.com, flags);
+            k_cov<<<gc, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, ref, fp.com, partials, tickets, fp.rmsd_out, fp.rot_out, flags);
+        }
+        if (fp.want_center) {
+            if (fp.center_weighted) k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
+            else k_unwrap<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
+        }
     }
-    if (fp.want_center) {
-        if (fp.center_weighted) k_unwrap<true><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
-        else k_unwrap<false><<<ge, kThreads, 0, cudaStreamTailLaunch>>>(fv, g, fp.c0, partials, tickets, fp.center_out, flags);
+    if (n_second) {
+        // the sine-sum centre pass over exactly the frames the moments could not certify (tail launches run in order: behind
+        // the reference-order passes above, which have consumed this launch's flags by then).  It is itself a single-pass
+        // kernel with a device-side fallback: a centre-only plan, no third tier.
+        FallbackPlan f2 = fp;
+        f2.want_rmsd = 0;
+        f2.want_center = 1;
+        f2.second_count = nullptr;
+        f2.n_report = (int)n_second;
+        const dim3 gs(fp.nb_second, n_second);
+        if (fp.center_weighted)
+            k_center_quad<true><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, fp.second_list, 2);
+        else
+            k_center_quad<false><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, fp.second_list, 2);
     }
 }
 

@@ -229,6 +229,12 @@ class System:
         self._check(self._lib.groan_gpu_fallback_frames(self._h, C.byref(n)), "fallback_frames")
         return int(n.value)
 
+    def second_pass_frames(self):
+        """frames of the last group_center_and_rmsd call whose centre went through the sine-sum pass (second tier)"""
+        n = C.c_size_t(0)
+        self._check(self._lib.groan_gpu_second_pass_frames(self._h, C.byref(n)), "second_pass_frames")
+        return int(n.value)
+
     def _detail(self):
         a, b = C.c_size_t(0), C.c_size_t(0)
         self._lib.groan_gpu_error_detail(self._h, C.byref(a), C.byref(b))

@@ -86,6 +86,10 @@ uint64_t groan_gpu_launch_count(groan_gpu_ctx *ctx);
 /* diagnostics (synchronises): how many frames of the last get_center / get_com / rmsd call the single-pass kernel could
  * not certify and handed to the reference-order passes (non-compact group, centre on the box edge, RMSD below f32 resolution) */
 int groan_gpu_fallback_frames(groan_gpu_ctx *ctx, size_t *n);
+/* diagnostics (synchronises): how many frames of the last centre + RMSD call (groan_gpu_center_rmsd) went through the second,
+ * sine-sum centre pass because the moments the fused kernel accumulates could not decide the centre's periodic image (the mean
+ * of the group within ~0.1 nm of a box face); still a single-pass kernel, one more read of those frames only */
+int groan_gpu_second_pass_frames(groan_gpu_ctx *ctx, size_t *n);
 
 /* ---- groups: Group::from_indices, container.rs:51-115 ---------------------------------------- */
 /* idx ascending and unique, each < n_atoms; mass nullable (ops that need masses then fail GROAN_ENOMASS,

@@ -910,6 +910,70 @@ def test_quad_kernels_match_pair_kernels_and_x64(n):
             assert abs(rq[f] - r64) <= 2e-5, (name, f, rq[f], r64)
 
 
+def test_fused_centre_second_tier():
+    """The fused centre + RMSD kernel decides the centre's periodic image from the moments sum d, sum d^2
+    (finish_center_moments, kernels_quad.cuh) unless a 256-atom sample predicts that they will not do (mean too close to a box
+    face): such frames accumulate the sine sums instead (predict_sine_mode).  When the prediction is wrong -- here the
+    sampled atoms are moved 1 nm away from the face on purpose -- the finishing thread notices and the frame goes through the
+    sine-sum centre pass (second tier), launched from the device or from the host (GROAN_FLAG_HOST_FALLBACK); neither is
+    a fallback to the reference-order passes.  All frames must match the exact64 oracle and the separate calls."""
+    import groan_rs_b200 as g
+    n, F = 262_144 + 4, 8
+    L = np.array([12.0, 11.0, 13.0], np.float32)
+    masses = np.random.default_rng(21).uniform(1.0, 100.0, n).astype(np.float32)
+    scale, nscale = 1.3 / 131070.0, 0.02 / 37837.23
+    rot = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (F, 1))
+    cen = np.array([[6.0, 5.5, 6.5],       # inside the box: no face straddled, no trigonometry
+                    [0.5, 5.5, 6.5],       # straddles x = 0 with the mean 0.5 nm inside: the moments certify it
+                    [0.003, 5.5, 6.5],     # mean 3 pm from the face
+                    [11.998, 5.5, 6.5],    # the same from the other side
+                    [6.0, 10.997, 0.004],  # two faces at once
+                    [11.5, 10.5, 12.4],    # three faces straddled, all certified by the moments
+                    [6.0, 5.5, 12.9999],   # 0.1 pm: the sine sum cannot decide either -> reference-order passes (third tier)
+                    [3.0, 3.0, 3.0]], np.float32)
+    idx = np.arange(2, n - 1, dtype=np.uint32)
+    sampled = 2 + (np.arange(256, dtype=np.uint64) * len(idx) // 256).astype(np.int64)  # predict_sine_mode's atoms
+    gen = g.System(n, masses=masses, max_frames=F)
+    gen.synth_blob(33, 0, F, scale, nscale, rot, cen, L, wrap=True)
+    ref_xyz = gen.synth_blob_ref(33, scale, L / 2)
+    honest = gen.get_frames().copy()
+    fooled = honest.copy()
+    for f in (2, 3, 4):  # the sample now says "1 nm from every face": the kernel takes the moments and finds them wanting
+        axes = [0] if f != 4 else [1, 2]
+        for k in axes:
+            shift = 1.0 if cen[f, k] < L[k] / 2 else -1.0
+            fooled[f, sampled, k] = np.mod(fooled[f, sampled, k] + np.float32(shift), L[k])
+    gen.close()
+    res = {}
+    for name, flags, frames, want_second in (("device", 0, fooled, 3), ("host", g.FLAG_HOST_FALLBACK, fooled, 3), ("honest", 0, honest, 0)):
+        s = g.System(n, masses=masses, max_frames=F)
+        s.set_flags(flags)
+        s.set_frames(frames, np.tile(L, (F, 1)))
+        ref = g.System(n, masses=masses)
+        ref.set_frames(ref_xyz, L)
+        for x in (s, ref):
+            x.group_create_from_indices("G", idx)
+        out = {}
+        for weighted in (False, True):
+            c2, r2 = s.group_center_and_rmsd(ref, "G", weighted=weighted)
+            second, slow = s.second_pass_frames(), s.fallback_frames()
+            assert second == want_second, (name, weighted, second)
+            assert slow <= 1, (name, weighted, slow)         # frame 6 only, if the sine sum gives up on it
+            sep = s.group_get_com("G") if weighted else s.group_get_center("G")
+            assert np.abs(c2 - sep).max() <= 4e-6, (name, weighted, c2, sep)
+            out[weighted] = (c2, r2)
+        res[name] = out
+        if name != "host":
+            for f in range(F):
+                e64 = orc.get_center_x64(frames[f], idx, L)
+                assert np.abs(out[False][0][f] - e64).max() <= 1e-5, (name, f, out[False][0][f], e64)
+                r64, _ = orc.calc_rmsd_x64(ref_xyz, idx, L, masses[idx], frames[f], idx, L)
+                assert abs(out[False][1][f] - r64) <= 1e-4
+    for w in (False, True):
+        assert np.array_equal(bits(res["device"][w][0]), bits(res["host"][w][0]))
+        assert np.array_equal(bits(res["device"][w][1]), bits(res["host"][w][1]))
+
+
 def test_back_to_back_calls_keep_stream_order():
     """Back-to-back calls that write the SAME result buffers -- one on a group every frame of which needs the device-launched
     fallback passes (tail-launched grids), one on a compact group -- must leave the results of the call issued last, and
