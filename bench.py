@@ -479,6 +479,41 @@ def run_gpu_arm(args):
             feeds["xtc_host_decode"] = {"value": F * 3 / dt, "h2d_bytes_per_step": F * N_ATOMS * 6 + F * 48, "ms_per_step": dt * 1e3 / 3,
                                         "steps": 3, "host_threads": nthr,
                                         "note": "xtc bytes -> int16 lattice by the host thread pool (groan_xtc_decode) inside the step"}
+        # partial frames (GroupXtcReader semantics, molly_xtc.rs:441-462): the analysis needs a 400 000-atom group (every 10th
+        # atom, SURVEY 8d cfg5 "G = 400 000 scattered"), so only those atoms are read and uploaded -- 10x fewer PCIe bytes
+        sel = np.arange(0, N_ATOMS, 10, dtype=np.uint32)
+        for sysm in (s, ref):
+            sysm.group_create_from_indices("S10", sel)
+        s.set_frames(h_in[0], boxes)
+        want_c, want_r = s.group_center_and_rmsd(ref, "S10")  # the same frames through the full upload
+        h_sel = [torch.from_numpy(np.ascontiguousarray(h_in[0].numpy()[:, sel, :])).pin_memory() for _ in range(2)]
+
+        def run_group_feed(steps):
+            def one(k):
+                s.set_group_frames(h_sel[k & 1], sel, boxes)
+                s.group_center_and_rmsd(ref, "S10", center_out=h_cen, rmsd_out=h_rmsd)
+            for k in range(2):
+                one(k)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                one(k)
+            s.sync()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        dt = run_group_feed(Ke)
+        assert np.array_equal(h_rmsd.numpy(), want_r) and np.array_equal(h_cen.numpy(), want_c)
+        feeds["group_f32"] = {"value": world * F * Ke / dt, "h2d_bytes_per_step": F * int(sel.size) * 12 + F * 36 + int(sel.size) * 4,
+                              "ms_per_step": dt * 1e3 / Ke, "steps": Ke, "group_atoms": int(sel.size),
+                              "h2d_gbs_per_gpu": F * int(sel.size) * 12 * 1e-9 / (dt / Ke),
+                              "note": "only the group's atoms are uploaded (System.set_group_frames) and scattered into the resident frames; "
+                                      "centre + RMSD of that 400 000-atom index-list group"}
         head = feeds["xtc"]
         e2e = {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": F * 16,
                "ms_per_step": head["ms_per_step"], "steps": Ke, "feed": "xtc (file bytes, GPU decode)",
@@ -568,6 +603,43 @@ def run_extras(torch, g, local, peak):
     out["calc_rmsd_and_fit"] = {"ms": t, "frames_per_s": F / (t * 1e-3),
                                 "gbs": ((12 + 24) * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3),
                                 "frac_of_hbm_peak": ((12 + 24) * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
+    # the cliff behind the single pass: the same batch through the reference-order passes only
+    # (GROAN_FLAG_EXACT_ONLY) -- what a frame costs when the single pass cannot certify it
+    b.set_flags(g.FLAG_EXACT_ONLY)
+    t = time_op(lambda: b.group_get_center("G", out=d_c), reps=3)
+    out["exact_only_group_get_center"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "gbs": 12 * N_ATOMS * F * 1e-9 / (t * 1e-3),
+                                          "frac_of_hbm_peak": 12 * N_ATOMS * F * 1e-9 / (t * 1e-3) / peak}
+    t = time_op(lambda: b.calc_rmsd(r, "G", out=d_r), reps=3)
+    out["exact_only_calc_rmsd"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "gbs": (12 * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3),
+                                   "frac_of_hbm_peak": (12 * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
+    b.set_flags(0)
+    # a box-spanning slab (a membrane: uniform in x and y, 4 nm thick in z): never compact in x / y, so every frame takes the
+    # path behind the single pass
+    b.synth_uniform(SEED, 0, F, [0.0, 0.0, 15.0], [BOX, BOX, 4.0], [BOX] * 3)
+    r.set_frames(b.get_frames()[0], [BOX] * 3)
+    t = time_op(lambda: b.group_get_center("G", out=d_c), reps=3)
+    out["slab_group_get_center"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "fallback_frames": b.fallback_frames(),
+                                    "frac_of_hbm_peak": 12 * N_ATOMS * F * 1e-9 / (t * 1e-3) / peak}
+    t = time_op(lambda: b.calc_rmsd(r, "G", out=d_r), reps=3)
+    out["slab_calc_rmsd"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "fallback_frames": b.fallback_frames(),
+                             "frac_of_hbm_peak": (12 * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
+    b.close()
+    r.close()
+    # calc_rmsd_and_fit at the headline's batch size (configs[4] names "RMSD/Kabsch fit"): 37 frames, all 4M atoms rewritten
+    F37 = 37
+    b = g.System(N_ATOMS, masses=m, device=local, max_frames=F37)
+    r = g.System(N_ATOMS, masses=m, device=local, max_frames=1)
+    b.set_stream(torch.cuda.current_stream().cuda_stream)
+    for sysm in (b, r):
+        sysm.group_create_from_indices("G", np.arange(N_ATOMS, dtype=np.uint32))
+    r.set_frames(b.synth_blob_ref(SEED, BLOB_SCALE, [BOX / 2] * 3), [BOX] * 3)
+    rot, cen = frame_params(0, F37)
+    b.synth_blob(SEED, 0, F37, BLOB_SCALE, NOISE_SCALE, rot, cen, [BOX] * 3, wrap=True)
+    d_r37 = torch.empty((F37,), dtype=torch.float32, device=dev)
+    t = time_op(lambda: b.calc_rmsd_and_fit(r, "G", out=d_r37), reps=3)
+    out["calc_rmsd_and_fit_37_frames"] = {"ms": t, "frames_per_s": F37 / (t * 1e-3),
+                                          "gbs": ((12 + 24) * F37 + 16) * N_ATOMS * 1e-9 / (t * 1e-3),
+                                          "frac_of_hbm_peak": ((12 + 24) * F37 + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
     b.close()
     r.close()
     # configs[3]: 1M atoms, box 21.5, 2 000 x 200 000 all-pairs

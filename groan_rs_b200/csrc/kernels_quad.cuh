@@ -31,10 +31,6 @@
 #pragma once
 #include "kernels_tma.cuh"
 
-#ifndef GROAN_QUAD_EARLY_RELEASE
-#define GROAN_QUAD_EARLY_RELEASE 0
-#endif
-
 namespace groan {
 
 constexpr int kQuadCenterThreads = 256;            // CTA size of k_center_quad; a chunk is one quad per thread
@@ -147,7 +143,7 @@ struct QuadCfg {
     static constexpr size_t kFrameBytes = (size_t)kAtoms * 12;
     static constexpr size_t kRefBytes = WITH_REF ? (size_t)kAtoms * 16 : 0;
     static constexpr size_t kStageBytes = kFrameBytes + kRefBytes;
-    static constexpr size_t kConstOff = STAGES * kStageBytes + 128; // ring, QuadCtl, then 24 floats of per-frame constants
+    static constexpr size_t kConstOff = STAGES * kStageBytes + 256; // ring, barriers, then 24 floats of per-frame constants
     static constexpr size_t kBytes = kConstOff + 128;
 };
 constexpr int kQuadCenterStages = 4; // 48 KB ring: 4 CTAs per SM
@@ -271,30 +267,16 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
         const uint32_t nst = st ^ (2u * kSt), nph = ph ^ (uint32_t)(st != 0);
         QuadRegs q;
         load(st, q);
-#if GROAN_QUAD_EARLY_RELEASE
-        // the stage is released as soon as its bytes are in registers (the arrive is ordered behind the loads), a whole
-        // quad of arithmetic earlier than "when done with it": the refill gets that much more time to arrive
-        __syncwarp();
-        if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
-#endif
         mbar_wait_a(fb + 8u, ph);
         fn(j, q.c0, q.c1, q.c2, q.r);
-#if !GROAN_QUAD_EARLY_RELEASE
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb) == 1u && it + STAGES < my_chunks) issue(it + STAGES);
-#endif
         j += jstep;
         load(st + kSt, q);
-#if GROAN_QUAD_EARLY_RELEASE
-        __syncwarp();
-        if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
-#endif
         if (it + 2 < my_chunks) mbar_wait_a(full0 + (nst ? 16u : 0u), nph);
         fn(j, q.c0, q.c1, q.c2, q.r);
-#if !GROAN_QUAD_EARLY_RELEASE
         __syncwarp();
         if (lane == 0 && mbar_arrive_pending(eb + 8u) == 1u && it + 1 + STAGES < my_chunks) issue(it + 1 + STAGES);
-#endif
         j += jstep;
         ph = nph;
         st = nst;

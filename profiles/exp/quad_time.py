@@ -43,12 +43,15 @@ d_c2 = torch.empty((F, 3), dtype=torch.float32, device=dev)
 d_r2 = torch.empty((F,), dtype=torch.float32, device=dev)
 
 
-def burst(fn, reps=50):
+REPS = int(os.environ.get("REPS", "50"))
+
+
+def burst(fn, reps=REPS):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     t = []
-    for _ in range(5):
+    for _ in range(5 if reps <= 50 else 3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
