@@ -5,7 +5,7 @@ thin Python host side that mirrors the reference's System / Group / SimBox / Dim
 path.  Importing the package does not load the library; creating a System does, and fails loudly when the
 CUDA library is missing (there is no CPU fallback).
 """
-from ._lib import FLAG_EXACT_ONLY, FLAG_HOST_FALLBACK, FLAG_FRAME_SHARING, FLAG_NO_TMA, FLAG_NO_QUAD, FLAG_TRICLINIC, GroanLibraryMissing  # noqa: F401
+from ._lib import FLAG_EXACT_ONLY, FLAG_HOST_FALLBACK, FLAG_NO_TMA, FLAG_TRICLINIC, GroanLibraryMissing  # noqa: F401
 from .system import (Dimension, GpuError, GroanError, Group, GroupError, MassError, PositionError, RMSDError,  # noqa: F401
                      SimBox, SimBoxError, System)
 from . import xtc  # noqa: F401
@@ -13,4 +13,4 @@ from .parallel import frame_range, gather_frames, traj_iter_map_reduce  # noqa: 
 
 __all__ = ["System", "Group", "SimBox", "Dimension", "GroanError", "GroupError", "SimBoxError", "PositionError",
            "MassError", "RMSDError", "GpuError", "frame_range", "gather_frames", "traj_iter_map_reduce",
-           "xtc", "FLAG_TRICLINIC", "FLAG_EXACT_ONLY", "FLAG_NO_TMA", "FLAG_NO_QUAD", "FLAG_FRAME_SHARING", "FLAG_HOST_FALLBACK", "GroanLibraryMissing"]
+           "xtc", "FLAG_TRICLINIC", "FLAG_EXACT_ONLY", "FLAG_NO_TMA", "FLAG_HOST_FALLBACK", "GroanLibraryMissing"]

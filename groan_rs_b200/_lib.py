@@ -17,8 +17,6 @@ MAX_GROUPS = 64
 FLAG_TRICLINIC = 1
 FLAG_EXACT_ONLY = 2
 FLAG_NO_TMA = 4
-FLAG_NO_QUAD = 32
-FLAG_FRAME_SHARING = 8
 FLAG_HOST_FALLBACK = 16
 
 _vp = C.c_void_p

@@ -110,11 +110,14 @@ struct groan_gpu_ctx {
     int *d_flags2 = nullptr;                // per frame: 1 = the fused centre + RMSD kernel sent the frame through the sine-sum centre pass
     unsigned int *d_second_any = nullptr;   // device-side launch of that pass: how many frames of the running launch want it
     int *d_second_list = nullptr;           // ... and which
+    unsigned int *d_slow_count = nullptr;   // the same for the frames a single pass of a contiguous group flags (exact quad passes)
+    int *d_slow_list = nullptr;
+    int *d_head_list = nullptr;             // frames of the batch sorted by the 16-byte phase of a group (launch_rmsd_quad), cached per key
+    size_t head_list_key_frames = 0;
+    uint32_t head_list_key_first = 0xffffffffu;
     bool second_valid = false;              // d_flags2 belongs to the last call
     int occ_center = 4, occ_rmsd = 2;  // resident CTAs per SM of the single-pass kernels
-    int occ_center_tma = 0, occ_rmsd_tma = 0;  // same for the TMA-fed versions (0 = unavailable)
     int occ_center_quad = 0;                   // quad kernels (kernels_quad.cuh)
-    bool rmsd_attr_set[2][3][2] = {};           // k_rmsd_tma<SAME_MASS, CENTER, FPC>: shared-memory attribute set on this device
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     uint32_t *d_mol_ref = nullptr;      // make_molecules_whole: reference atom of every atom's molecule (groan_gpu_set_molecules)

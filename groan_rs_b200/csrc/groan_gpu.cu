@@ -40,84 +40,18 @@ int blocks_per_frame_fast(size_t g, size_t F, int occ) {
     return (int)nb;
 }
 
-// TMA-fed kernels need a contiguous group (one byte range per frame), enough atoms to fill the ring, and a
+// The ring-fed kernels need a contiguous group (one byte range per frame), enough atoms to fill the ring, and a
 // 16-byte aligned coordinate buffer (cudaMalloc'ed slots always are; attached buffers are checked)
 bool tma_ok(const groan_gpu_ctx *ctx, const Group &g, int occ) {
     return occ > 0 && g.contiguous && g.n >= 4096 && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
            !(ctx->flags & GROAN_FLAG_NO_TMA);
 }
 
-int blocks_per_frame_tma(size_t g, size_t F, int occ) {
-    size_t nb = (g + 1023) / 1024;  // at least one chunk per CTA
-    nb = std::max<size_t>(nb, 1);
-    nb = std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * (size_t)occ) / std::max<size_t>(F, 1)));
-    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(F, 1)));
-    return (int)nb;
-}
-
-// frames served by one CTA of the TMA-fed RMSD kernels.  Opt-in (GROAN_FLAG_FRAME_SHARING): 4 frames share one copy of
-// each reference chunk when the batch has a multiple of 4 frames and every frame puts the group at the same offset modulo
-// 4 atoms (n_atoms % 4 == 0).  It cuts the reference's L2 -> SM traffic 4x, but measured on B200 it is SLOWER than one
-// frame per CTA (0.200 vs 0.127 ms per 8 x 4M-atom batch, profiles/r1_summary.md): the per-frame constants stop being
-// CTA-uniform, which costs registers (spills in the fused variant) and issue slots.
-int frames_per_cta(const groan_gpu_ctx *ctx) {
-    if (!(ctx->flags & GROAN_FLAG_FRAME_SHARING)) return 1;
-    return (ctx->n_atoms % 4 == 0 && ctx->n_frames % 4 == 0) ? 4 : 1;
-}
-
-template <bool SAME_MASS, int CENTER, int FPC>
-int launch_rmsd_tma_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, float *d_center, float *d_rmsd, float *d_rot,
-                      const FallbackPlan &fp) {
-    typedef TmaCfg<true, kRmsdStages, FPC> C;
-    // the dynamic shared memory limit is a per-device function attribute: remember it per ctx, not per process
-    bool &attr_set = ctx->rmsd_attr_set[SAME_MASS ? 1 : 0][CENTER][FPC == 4 ? 1 : 0];
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(k_rmsd_tma<SAME_MASS, CENTER, FPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes));
-        attr_set = true;
-    }
-    const size_t groups = ctx->n_frames / FPC;
-    size_t nb = (g.n + C::CH - 1) / C::CH;  // at least one chunk per CTA
-    nb = std::max<size_t>(1, std::min<size_t>(nb, std::max<size_t>(1, ((size_t)kSMs * 2) / groups)));
-    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / ctx->n_frames));
-    dim3 grid((unsigned)nb, (unsigned)groups);
-    k_rmsd_tma<SAME_MASS, CENTER, FPC><<<grid, kTmaThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, ctx->d_partials,
-                                                                                       ctx->d_tickets, d_center, d_rmsd, d_rot,
-                                                                                       ctx->d_cen, ctx->d_flags, fp);
-    LAUNCHED();
-    return GROAN_OK;
-}
-
-// center_mode: 0 = RMSD only, 1 = + geometric centre, 2 = + centre of mass
-int launch_rmsd_tma(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, bool same_mass, int center_mode, float *d_center,
-                    float *d_rmsd, float *d_rot, const FallbackPlan &fp) {
-    const int fpc = frames_per_cta(ctx);
-#define GO(SM, CM)                                                                                      \
-    return fpc == 4 ? launch_rmsd_tma_t<SM, CM, 4>(ctx, g, rv, d_center, d_rmsd, d_rot, fp)              \
-                    : launch_rmsd_tma_t<SM, CM, 1>(ctx, g, rv, d_center, d_rmsd, d_rot, fp)
-    if (same_mass) {
-        if (center_mode == 0) GO(true, 0);
-        if (center_mode == 1) GO(true, 1);
-        GO(true, 2);
-    }
-    if (center_mode == 0) GO(false, 0);
-    if (center_mode == 1) GO(false, 1);
-    GO(false, 2);
-#undef GO
-}
-
 // ---- quad kernels (kernels_quad.cuh) -----------------------------------------------------------------
-// They need what the TMA-fed kernels need, plus the same 16-byte phase of the group in every frame of the batch
-// (n_atoms % 4 == 0, or a single frame): the permuted reference is laid out relative to the aligned body.
-// They need what the TMA-fed kernels need.  The centre kernels take any frame size (the 16-byte phase of the group is worked
-// out per frame).  The RMSD kernels read a reference laid out relative to the aligned body, one copy per phase: a single
-// copy when every frame puts the group at the same phase (n_atoms % 4 == 0, or one frame), otherwise up to four -- which is
-// only worth it while they all stay in L2 (<= 64 MB); larger groups with odd frame sizes keep the pair kernels.
-bool quad_center_ok(const groan_gpu_ctx *ctx, const Group &g) {
-    return tma_ok(ctx, g, 2) && !(ctx->flags & GROAN_FLAG_NO_QUAD);
-}
-bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) {
-    return quad_center_ok(ctx, g) && (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1 || g.n <= (1u << 20));
-}
+// The centre kernels take any frame size (the 16-byte phase of the group is worked out per frame).  The RMSD kernels read a
+// reference laid out relative to the aligned body, one copy per phase (launch_rmsd_quad_t).
+bool quad_center_ok(const groan_gpu_ctx *ctx, const Group &g) { return tma_ok(ctx, g, 2); }
+bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) { return quad_center_ok(ctx, g); }
 
 uint32_t quad_head(const groan_gpu_ctx *ctx, const Group &g, size_t f) { return (uint32_t)((4 - ((f * ctx->n_atoms + g.first) & 3)) & 3); }
 
@@ -146,15 +80,60 @@ int ensure_quad_ref(groan_gpu_ctx *ctx, groan_gpu_ctx::Ref &R, const Group &g, Q
     return GROAN_OK;
 }
 
+// The permuted reference is laid out relative to the 16-byte aligned body of the group, and where that body starts depends on
+// the frame when a frame is not a multiple of four atoms long: frame f puts the group at phase (f * n_atoms + first) mod 4.
+// All frames of one phase ("head") share one permuted copy.  Launching the whole batch at once would stream up to four
+// 64 MB copies through the 126 MB L2 at the same time; instead the frames are sorted by phase and each phase gets its own
+// launch (one wave of CTAs each), so that one copy at a time is resident.  n_atoms % 4 == 0 (or a single frame) is the
+// one-launch case.
+int quad_head_lists(groan_gpu_ctx *ctx, const Group &g, int counts[4], int offsets[4]) {
+    const size_t F = ctx->n_frames;
+    std::vector<int> order;
+    order.reserve(F);
+    int off = 0;
+    for (int h = 0; h < 4; h++) {
+        offsets[h] = off;
+        for (size_t f = 0; f < F; f++)
+            if (quad_head(ctx, g, f) == (uint32_t)h) order.push_back((int)f);
+        counts[h] = (int)order.size() - off;
+        off = (int)order.size();
+    }
+    if (ctx->head_list_key_frames != F || ctx->head_list_key_first != g.first) {
+        if (!ctx->d_head_list) CK(cudaMalloc(&ctx->d_head_list, ctx->max_frames * sizeof(int)));
+        CK(cudaMemcpyAsync(ctx->d_head_list, order.data(), F * sizeof(int), cudaMemcpyHostToDevice, ctx->compute));
+        CK(cudaStreamSynchronize(ctx->compute));  // `order` is a local; once per (batch size, group start)
+        ctx->head_list_key_frames = F;
+        ctx->head_list_key_first = g.first;
+    }
+    return GROAN_OK;
+}
+
 template <bool SAME_MASS, int CENTER>
 int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, float *d_center, float *d_rmsd,
-                       float *d_rot, const FallbackPlan &fp) {
+                       float *d_rot, FallbackPlan fp) {
     typedef QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads> C;
-    dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2, C::kAtoms), (unsigned)ctx->n_frames);
-    k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
-                                                                                   ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
-                                                                                   ctx->d_flags, fp);
-    LAUNCHED();
+    if (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1) {
+        dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2, C::kAtoms), (unsigned)ctx->n_frames);
+        k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+                                                                                       ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
+                                                                                       ctx->d_flags, fp, nullptr);
+        LAUNCHED();
+        return GROAN_OK;
+    }
+    int counts[4], offsets[4];
+    int rc = quad_head_lists(ctx, g, counts, offsets);
+    if (rc) return rc;
+    for (int h = 0; h < 4; h++) {
+        if (!counts[h]) continue;
+        size_t nb = (size_t)blocks_per_frame_quad(g.n, (size_t)counts[h], 2, C::kAtoms);
+        nb = std::max<size_t>(1, std::min<size_t>(nb, kPartialSlots / ctx->n_frames));  // partial records are indexed by the frame number
+        dim3 grid((unsigned)nb, (unsigned)counts[h]);
+        fp.n_report = counts[h];
+        k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+                                                                                       ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
+                                                                                       ctx->d_flags, fp, ctx->d_head_list + offsets[h]);
+        LAUNCHED();
+    }
     return GROAN_OK;
 }
 
@@ -181,8 +160,19 @@ int set_quad_attr(groan_gpu_ctx *ctx) {
 }
 
 int blocks_per_frame_quad(size_t g, size_t F, int occ, size_t chunk);
+// CTAs per frame of the exact quad passes (k_trig_quad / k_center_quad with ext_pilot; k_cov_quad).  They depend on the batch
+// only, never on how many frames are re-done, so that a frame gets the same bits whether it is re-done from the device, from
+// the host or under GROAN_FLAG_EXACT_ONLY.
+int nb_exact_quad(const groan_gpu_ctx *ctx, const Group &g, bool cov) {
+    const size_t chunk = 1024;
+    size_t nb = std::max<size_t>(1, (g.n + chunk - 1) / chunk);
+    nb = std::min<size_t>(nb, (size_t)kSMs * (cov ? 2 : (size_t)std::max(1, ctx->occ_center_quad)));
+    nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(ctx->n_frames, 1)));
+    return (int)nb;
+}
+
 FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
-                           float *rmsd_out, float *rot_out) {
+                           float *rmsd_out, float *rot_out, bool quad_exact = false, const QuadRef *qr = nullptr) {
     FallbackPlan fp;
     fp.enabled = (ctx->flags & GROAN_FLAG_HOST_FALLBACK) ? 0 : 1;
     fp.n_frames = (int)ctx->n_frames;
@@ -211,6 +201,13 @@ FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center,
         fp.nb_second = (int)nb;
     }
     fp.second_smem = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
+    fp.quad_exact = quad_exact ? 1 : 0;
+    fp.slow_count = ctx->d_slow_count;
+    fp.slow_list = ctx->d_slow_list;
+    fp.nb_xc = nb_exact_quad(ctx, g, false);
+    fp.nb_xv = nb_exact_quad(ctx, g, true);
+    fp.cov_smem = (int)QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kBytes;
+    for (int h = 0; h < 4; h++) fp.ref_pq.v[h] = qr ? qr->v[h] : nullptr;
     return fp;
 }
 
@@ -285,38 +282,58 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
     return GROAN_OK;
 }
 
+// The exact passes of a contiguous group on the ring (kernels_quad.cuh).  sel == nullptr: every frame of the batch; otherwise
+// the frames whose flag is set.
+int run_exact_center_quad(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out, const int *sel) {
+    typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
+    FallbackPlan off = fallback_plan(ctx, g, false, false, nullptr, false, nullptr, nullptr);
+    off.enabled = 0;
+    dim3 grid((unsigned)off.nb_xc, (unsigned)ctx->n_frames);
+    const int mode = sel ? 1 : 0;
+    k_trig_quad<<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, ctx->d_c0, sel, mode);
+    LAUNCHED();
+    if (weighted)
+        k_center_quad<true><<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+                                                                                   ctx->d_flags, off, sel, mode, ctx->d_c0);
+    else
+        k_center_quad<false><<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+                                                                                    ctx->d_flags, off, sel, mode, ctx->d_c0);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
+// group_get_com of the target (-> ctx->d_cen), then the f64 covariance around it
+int run_exact_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &qr, float *d_rmsd, float *d_rot, const int *sel) {
+    int rc = run_exact_center_quad(ctx, g, true, ctx->d_cen, sel);
+    if (rc) return rc;
+    typedef QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads> C;
+    dim3 grid((unsigned)nb_exact_quad(ctx, g, true), (unsigned)ctx->n_frames);
+    k_cov_quad<<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, qr, ctx->d_cen, ctx->d_partials, ctx->d_tickets,
+                                                                     d_rmsd, d_rot, sel, sel ? 1 : 0);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
 // group_get_center / group_get_com.  Single pass first (kernels_center.cuh); the reference-order passes --
 // estimate (always geometric, iterators.rs:1407) then unwrap -- then re-do only the frames it flagged
 // (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
+    if (ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
+        if (ctx->flags & GROAN_FLAG_EXACT_ONLY) return run_exact_center_quad(ctx, g, weighted, out, nullptr);
         typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
         dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad, C::kAtoms), (unsigned)ctx->n_frames);
         const size_t smem = C::kBytes;
-        const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
+        const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr, true);
         if (weighted)
             k_center_quad<true><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                           out, ctx->d_flags, fp, nullptr, 0);
+                                                                           out, ctx->d_flags, fp, nullptr, 0, nullptr);
         else
             k_center_quad<false><<<grid, kQuadCenterThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                            out, ctx->d_flags, fp, nullptr, 0);
+                                                                            out, ctx->d_flags, fp, nullptr, 0, nullptr);
         LAUNCHED();
         if (fp.enabled) return GROAN_OK;
-        flags = ctx->d_flags;
-    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, g, ctx->occ_center_tma)) {
-        dim3 grid(blocks_per_frame_tma(g.n, ctx->n_frames, ctx->occ_center_tma), (unsigned)ctx->n_frames);
-        const size_t smem = TmaCfg<false, kCenterStages, 1>::kBytes;
-        const FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr);
-        if (weighted)
-            k_center_tma<true><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                          out, ctx->d_flags, fp);
-        else
-            k_center_tma<false><<<grid, kTmaThreads, smem, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
-                                                                           out, ctx->d_flags, fp);
-        LAUNCHED();
-        if (fp.enabled) return GROAN_OK;  // the kernel launches the reference-order passes itself when a frame needs them
-        flags = ctx->d_flags;
+        return run_exact_center_quad(ctx, g, weighted, out, ctx->d_flags);
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, ctx->occ_center);
         dim3 grid(nb, (unsigned)ctx->n_frames);
@@ -434,34 +451,22 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     const int *flags = nullptr;
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
     bool center_done = false, device_fallback = false, second_tier = false;
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && quad_ok(ctx, *g)) {
-        // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
-        QuadRef qr;
+    const bool qx = quad_ok(ctx, *g);  // contiguous group on the ring: fast and exact passes of kernels_quad.cuh
+    QuadRef qr;
+    if (qx) {
         rc = ensure_quad_ref(ctx, R, *g, &qr);
         if (rc) return rc;
+    }
+    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && qx) {
+        // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
         const bool fused = center != nullptr && R.same_mass;  // see launch_rmsd_quad
-        const FallbackPlan fp = fallback_plan(ctx, *g, fused, center_weighted != 0, d_center, true, d_rmsd, d_rot);
+        const FallbackPlan fp = fallback_plan(ctx, *g, fused, center_weighted != 0, d_center, true, d_rmsd, d_rot, true, &qr);
         device_fallback = fp.enabled != 0;
         rc = launch_rmsd_quad(ctx, *g, rv, qr, R.same_mass, fused ? (center_weighted ? 2 : 1) : 0, d_center, d_rmsd, d_rot, fp);
         if (rc) return rc;
         flags = ctx->d_flags;
         center_done = fused;
         second_tier = fused;
-    } else if (center && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
-        // centre + RMSD from one read of the frame (kernels_tma.cuh)
-        const FallbackPlan fp = fallback_plan(ctx, *g, true, center_weighted != 0, d_center, true, d_rmsd, d_rot);
-        device_fallback = fp.enabled != 0;
-        rc = launch_rmsd_tma(ctx, *g, rv, R.same_mass, center_weighted ? 2 : 1, d_center, d_rmsd, d_rot, fp);
-        if (rc) return rc;
-        flags = ctx->d_flags;
-        center_done = true;
-    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && tma_ok(ctx, *g, ctx->occ_rmsd_tma)) {
-        // single pass, TMA-fed (kernels_tma.cuh)
-        const FallbackPlan fp = fallback_plan(ctx, *g, false, false, nullptr, true, d_rmsd, d_rot);
-        device_fallback = fp.enabled != 0;
-        rc = launch_rmsd_tma(ctx, *g, rv, R.same_mass, 0, nullptr, d_rmsd, d_rot, fp);
-        if (rc) return rc;
-        flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
         const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
@@ -488,7 +493,10 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     // (geometric estimate, mass-weighted unwrap), then shift + wrap + covariance in f64.  Skipped here when the
     // single-pass kernel tail-launches them itself for the frames that need them.
     ctx->second_valid = second_tier;
-    if (!device_fallback) {
+    if (!device_fallback && qx) {
+        rc = run_exact_rmsd_quad(ctx, *g, rv, qr, d_rmsd, d_rot, flags);
+        if (rc) return rc;
+    } else if (!device_fallback) {
         rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
         if (rc) return rc;
         rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags);
@@ -521,15 +529,17 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
                     dim3 sgrid((unsigned)f2.nb_second, (unsigned)ctx->n_frames);
                     if (center_weighted)
                         k_center_quad<true><<<sgrid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(
-                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1);
+                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1, nullptr);
                     else
                         k_center_quad<false><<<sgrid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(
-                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1);
+                            frames_of(ctx), view_of(*g), ctx->d_partials, ctx->d_tickets, d_center, ctx->d_flags, f2, ctx->d_flags2, 1, nullptr);
                     LAUNCHED();
-                    rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
-                    if (rc) return rc;
                 }
-                rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
+                if (qx) {
+                    rc = run_exact_center_quad(ctx, *g, center_weighted != 0, d_center, flags);
+                } else {
+                    rc = run_unwrap(ctx, *g, center_weighted != 0, ctx->d_c0, d_center, flags);
+                }
                 if (rc) return rc;
             }
         } else {
@@ -587,22 +597,21 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaMalloc(&ctx->d_flags2, max_frames * sizeof(int)));
         CK(cudaMemset(ctx->d_flags2, 0, max_frames * sizeof(int)));
         CK(cudaMalloc(&ctx->d_second_list, max_frames * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_slow_list, max_frames * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_slow_count, sizeof(unsigned int)));
+        CK(cudaMemset(ctx->d_slow_count, 0, sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_second_any, sizeof(unsigned int)));
         CK(cudaMemset(ctx->d_second_any, 0, sizeof(unsigned int)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center, k_center_fast<false>, kThreads, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));
         ctx->occ_rmsd = std::max(1, std::min(ctx->occ_rmsd, 8));
-        // TMA-fed versions: dynamic shared memory ring (48 KB centre, ~100 KB RMSD: set per instantiation at first launch)
-        const int sc = (int)TmaCfg<false, kCenterStages, 1>::kBytes;
-        CK(cudaFuncSetAttribute(k_center_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
-        CK(cudaFuncSetAttribute(k_center_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_tma, k_center_tma<false>, kTmaThreads, sc));
-        ctx->occ_rmsd_tma = 2;
-        ctx->occ_center_tma = std::min(ctx->occ_center_tma, 4);
         const int sq = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
         CK(cudaFuncSetAttribute(k_center_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
         CK(cudaFuncSetAttribute(k_center_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaFuncSetAttribute(k_trig_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaFuncSetAttribute(k_cov_quad, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kBytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center_quad, k_center_quad<false>, kQuadCenterThreads, sq));
         ctx->occ_center_quad = std::min(ctx->occ_center_quad, 4);
         int qrc = set_quad_attr<true, 0>(ctx);
@@ -650,7 +659,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         for (float *q : r.d_pq)
             if (q) cudaFree(q);
     }
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_flags2, ctx->d_second_any, ctx->d_second_list, ctx->d_frames_done, ctx->d_mol_ref,
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_flags2, ctx->d_second_any, ctx->d_second_list, ctx->d_slow_list, ctx->d_slow_count, ctx->d_head_list, ctx->d_frames_done, ctx->d_mol_ref,
                     ctx->d_xtc_status, ctx->d_sel_atoms};
     for (void *b : bufs)
         if (b) cudaFree(b);

@@ -234,7 +234,7 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
     // Group A is binned as well when it has at least one atom per cell on average: one warp then serves a whole cell of A
     // (k_cell_query_tiled); sparse query groups keep one warp per atom (k_cell_query).
     const size_t na_atoms = a->n;
-    const bool tiled = na_atoms >= cells && !(ctx->flags & GROAN_FLAG_NO_QUAD);
+    const bool tiled = na_atoms >= cells && !(ctx->flags & GROAN_FLAG_NO_TMA);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     auto grid_bytes = [&](size_t atoms) { return up(atoms * 4) + up(cells * 4) * 2 + up((cells + 1) * 4) + up(atoms * 16); };
     const size_t per_frame = grid_bytes(nb_atoms) + (tiled ? grid_bytes(na_atoms) : 0);

@@ -60,10 +60,6 @@ __global__ void __launch_bounds__(kThreads) k_ref_permute(const float *pc, float
     }
 }
 
-// the permuted reference, one copy per head (0..3 atoms before the first 16-byte boundary of the group in a frame)
-struct QuadRef {
-    const float *v[4];
-};
 
 // a 3-vector sum held as three register pairs in the patterns of the quad: a = (x,y), b = (z,x), c = (y,z)
 struct V3 {
@@ -423,22 +419,27 @@ __device__ __forceinline__ double edge_sin(float x, float L) {
 
 // ---------------------------------------------------------------- group_get_center / group_get_com
 // sums: [0..2] sum m d, [3] sum m, [4..6] sum sin
+// sel_mode != 0: only the selected frames are done (1: frames with sel[f] != 0, launched over the whole batch; 2: frames
+// sel[blockIdx.y], launched from the device over exactly the frames that need it).
+// ext_pilot == nullptr: the single pass -- pilot = the group's first atom, image of the mean decided by the sine sum; with
+//   sel_mode != 0 this is the second tier of the fused centre + RMSD kernels, and a frame it cannot certify either gets bit 1
+//   of its flag ORed in (the fused kernel's flag word: bit 0 RMSD, bit 1 centre).
+// ext_pilot != nullptr: the EXACT pass -- the reference's second loop itself (iterators.rs:1237-1266): pilot = c0, the
+//   Bai-Breen estimate of the frame (k_trig_quad), result = c0 + mean(min-image displacement from c0).  No compactness is
+//   needed and nothing is flagged: this is what frames the single pass could not certify are re-done with.
 template <bool WEIGHTED>
-// sel_mode != 0: the second tier of the fused centre + RMSD kernels -- only the selected frames are done (1: frames with
-// sel[f] != 0, launched from the host over the whole batch; 2: frames sel[blockIdx.y], launched from the device over exactly
-// the frames that need it), and a frame this pass cannot certify either gets bit 1 of its flag ORed in (the fused kernel's
-// flag word: bit 0 RMSD, bit 1 centre).
 __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                                 float *out, int *flags, FallbackPlan fp, const int *sel, int sel_mode) {
+                                                                 float *out, int *flags, FallbackPlan fp, const int *sel, int sel_mode,
+                                                                 const float *ext_pilot) {
     static_assert(kQuadCenterThreads == 256, "maybe_launch_fallback launches this kernel with 256 threads");
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     FrameReduceSmem<7, 3, kQuadCenterThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<7, 3, kQuadCenterThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
     const int f = sel_mode == 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
-    if (sel_mode == 1 && sel[f] == 0) return; // uniform for the CTA (host-launched: nobody counts finished frames)
+    if (sel_mode == 1 && sel[f] == 0) return; // uniform for the CTA (nobody counts finished frames in this mode)
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
-    const float *p0 = fr + (size_t)g.first * 3;
+    const float *p0 = ext_pilot ? ext_pilot + (size_t)f * 3 : fr + (size_t)g.first * 3;
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
@@ -483,6 +484,11 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
                 tmx[k] = fmaxf(tmx[k], d);
             }
         }
+        if (ext_pilot) {
+            const double inv_m = 1.0 / (WEIGHTED ? tot[3] : (double)g.n);
+            for (int k = 0; k < 3; k++) out[f * 3 + k] = (float)((double)p[k] + tot[k] * inv_m);
+            return;
+        }
         int flag = 0;
         finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, &flag);
         if (sel_mode) {
@@ -490,7 +496,7 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
         } else {
             flags[f] = flag;
         }
-        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag);
+        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag, 0, f);
     }
 }
 
@@ -562,11 +568,13 @@ __device__ __forceinline__ bool predict_sine_mode(const float *fr, const GroupVi
 template <bool SAME_MASS, int CENTER>
 __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, double *partials,
                                                                unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
-                                                               float *com_out, int *flags, FallbackPlan fp) {
+                                                               float *com_out, int *flags, FallbackPlan fp, const int *sel) {
     constexpr int KS = CENTER ? kQuadSums : kFastSums;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     FrameReduceSmem<KS, 3, kQuadRmsdThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<KS, 3, kQuadRmsdThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
-    const int f = blockIdx.y, nb = gridDim.x;
+    // sel: the frames of this launch (one launch per 16-byte phase of the group when the frame size is not a multiple of four
+    // atoms, see launch_rmsd_quad); nullptr = the whole batch
+    const int f = sel ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
@@ -694,6 +702,136 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         }
         flags[f] = flag_r | (flag_c << 1);
         maybe_launch_fallback(fp, fv, g, ref, partials, tickets, flags, flag_r | flag_c, second, f);
+    }
+}
+
+// ---------------------------------------------------------------- the exact passes of a contiguous group
+// What a frame costs when the single pass cannot certify it (a group that spans the box: any membrane) used to be three
+// reference-order passes at a tenth of the memory bandwidth (k_trig, k_unwrap, k_cov: precise sincosf, fmodf chains, f64
+// sums behind 32-bit scalar loads).  These are the same passes on the ring + quad machinery: the Bai-Breen estimate with the
+// SFU (k_trig_quad), the unwrap around it (k_center_quad with ext_pilot), the covariance in f64 (k_cov_quad).
+//
+// k_trig_quad -- estimate_center (iterators.rs:1152-1191, auxiliary.rs:59-99), geometric: c0 = (atan2(-sum sin th, -sum cos th)
+// + pi) / s, th = 2 pi wrap(x) / L.  sin and cos are periodic, so th is taken from frac(x / L) in [-1/2, 1/2] -- where the
+// SFU is at its best (|err| < 5e-7) whatever the coordinate -- instead of wrapping first.  The estimate only picks periodic
+// images in the next pass; its error moves an atom to another image only if the atom lies within ~1e-7 nm of the point
+// opposite to c0, where the reference's own f32 sums decide by rounding as well.
+// sums: [0..2] sum cos, [3..5] sum sin
+__global__ void __launch_bounds__(kQuadCenterThreads, 3) k_trig_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
+                                                               float *c0_out, const int *sel, int sel_mode) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    FrameReduceSmem<6, 0, kQuadCenterThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<6, 0, kQuadCenterThreads / 32> *>(dyn_smem);
+    const int f = sel_mode == 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
+    if (sel_mode == 1 && sel[f] == 0) return;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *fr = fv.frame(f);
+    const float zero[3] = {0.f, 0.f, 0.f};
+    const QuadConst qc = quad_constants(zero, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kConstOff));
+    const BodyGeom bg = body_geom(fv, g, f);
+    V3 sc = v3_zero(), ss = v3_zero();
+    auto turn = [](float2 x, float2 inv) { // frac(x / L) in [-1/2, 1/2], both halves
+        const float2 t = __fmul2_rn(x, inv), k = __fadd2_rn(__fadd2_rn(t, splat(kMagic)), splat(-kMagic));
+        return __fadd2_rn(t, make_float2(-k.x, -k.y));
+    };
+    auto pair = [&](float2 xa, float2 xb, float2 xc) {
+        const float2 ta = turn(xa, qc.inv.a), tb = turn(xb, qc.inv.b), tc = turn(xc, qc.inv.c);
+        const float tp = 6.283185307179586f;
+        sc.a = __fadd2_rn(sc.a, make_float2(__cosf(ta.x * tp), __cosf(ta.y * tp)));
+        ss.a = __fadd2_rn(ss.a, make_float2(__sinf(ta.x * tp), __sinf(ta.y * tp)));
+        sc.b = __fadd2_rn(sc.b, make_float2(__cosf(tb.x * tp), __cosf(tb.y * tp)));
+        ss.b = __fadd2_rn(ss.b, make_float2(__sinf(tb.x * tp), __sinf(tb.y * tp)));
+        sc.c = __fadd2_rn(sc.c, make_float2(__cosf(tc.x * tp), __cosf(tc.y * tp)));
+        ss.c = __fadd2_rn(ss.c, make_float2(__sinf(tc.x * tp), __sinf(tc.y * tp)));
+    };
+    stream_quads<false, kQuadCenterStages, kQuadCenterThreads>(fv, g, f, bg, nullptr, dyn_smem,
+                                           [&](uint32_t, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&)[4]) {
+        pair(make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y));
+        pair(make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w));
+    });
+    __syncthreads();
+    const float a[6] = {v3_x(sc), v3_y(sc), v3_z(sc), v3_x(ss), v3_y(ss), v3_z(ss)};
+    double tot[6];
+    if (frame_reduce<6, 0>(a, nullptr, nullptr, partials + (size_t)f * nb * 6, tickets + f, nb, sm, tot, nullptr, nullptr) && threadIdx.x == 0) {
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            for (int k = 0; k < 3; k++) {
+                const float u = __ldg(q + k) * (1.0f / L[k]), v = (u - rintf(u)) * 6.283185307179586f;
+                tot[k] += (double)__cosf(v);
+                tot[3 + k] += (double)__sinf(v);
+            }
+        }
+        for (int k = 0; k < 3; k++)
+            c0_out[f * 3 + k] = (float)((atan2(-tot[3 + k], -tot[k]) + 3.14159265358979323846) * (double)L[k] * (1.0 / 6.283185307179586));
+    }
+}
+
+// k_cov_quad -- kabsch_rmsd's sums for frames the f32 single pass cannot serve (not compact, or RMSD below what f32 products
+// resolve).  q_i = wrap(x_i + (bc - com)) - bc (rmsd.rs:479-492) is the min-image displacement of x_i from com, whatever the
+// shape of the group: com (the exact pass's group_get_com) is the pilot, and every product pc_u q_v, w pc_u q_v, w q_v q_v is
+// formed and summed in f64 (exact products of two f32), like k_cov does -- on the FP64 pipe, which B200 has at half the FP32
+// rate and which the rest of the library never touches.
+__global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_cov_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, const float *com_in,
+                                                              double *partials, unsigned int *tickets, float *rmsd_out, float *rot_out,
+                                                              const int *sel, int sel_mode) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    FrameReduceSmem<kCovSums, 0, kQuadRmsdThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<kCovSums, 0, kQuadRmsdThreads / 32> *>(dyn_smem);
+    const int f = sel_mode == 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
+    if (sel_mode == 1 && sel[f] == 0) return;
+    float L[3];
+    fv.lengths(f, L[0], L[1], L[2]);
+    const float *fr = fv.frame(f);
+    const float p[3] = {__ldg(com_in + f * 3), __ldg(com_in + f * 3 + 1), __ldg(com_in + f * 3 + 2)};
+    const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
+    const BodyGeom bg = body_geom(fv, g, f);
+    double acc[kCovSums];
+#pragma unroll
+    for (int k = 0; k < kCovSums; k++) acc[k] = 0.0;
+    auto atom = [&](float dx, float dy, float dz, float px, float py, float pz, float w) {
+        const double q[3] = {(double)dx, (double)dy, (double)dz}, pc[3] = {(double)px, (double)py, (double)pz}, m = (double)w;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const double mp = m * pc[u];
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                acc[u * 3 + v] = fma(pc[u], q[v], acc[u * 3 + v]);
+                acc[9 + u * 3 + v] = fma(mp, q[v], acc[9 + u * 3 + v]);
+            }
+        }
+        acc[18] = fma(m, fma(q[0], q[0], fma(q[1], q[1], q[2] * q[2])), acc[18]);
+    };
+    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+                                        [&](uint32_t, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+        V3 d01, d23;
+        quad_deltas(qc, c0, c1, c2, d01, d23);
+        // unit k = 0: pcx(0) pcx(1) pcy(0) pcy(1); 1: pcz(0) pcz(1) w(0) w(1); 2, 3: the same for atoms 2, 3 (k_ref_permute)
+        atom(d01.a.x, d01.a.y, d01.b.x, r[0].x, r[0].z, r[1].x, r[1].z);
+        atom(d01.b.y, d01.c.x, d01.c.y, r[0].y, r[0].w, r[1].y, r[1].w);
+        atom(d23.a.x, d23.a.y, d23.b.x, r[2].x, r[2].z, r[3].x, r[3].z);
+        atom(d23.b.y, d23.c.x, d23.c.y, r[2].y, r[2].w, r[3].y, r[3].w);
+    });
+    __syncthreads();
+    double tot[kCovSums];
+    if (frame_reduce<kCovSums, 0>(acc, nullptr, nullptr, partials + (size_t)f * nb * kCovSums, tickets + f, nb, sm, tot, nullptr, nullptr) &&
+        threadIdx.x == 0) {
+        for (uint32_t t = 0; t < bg.head + bg.tail; t++) {
+            const uint32_t i = t < bg.head ? t : bg.head + bg.body + (t - bg.head);
+            const float *q = fr + ((size_t)g.first + i) * 3;
+            const float4 r = ref_at(ref.pc, i);
+            double d[3];
+            for (int k = 0; k < 3; k++) d[k] = (double)pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
+            const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
+            for (int u = 0; u < 3; u++)
+                for (int v = 0; v < 3; v++) {
+                    tot[u * 3 + v] += pcd[u] * d[v];
+                    tot[9 + u * 3 + v] += w * pcd[u] * d[v];
+                }
+            tot[18] += w * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        }
+        double r[9];
+        rmsd_out[f] = (float)finish_kabsch(tot, tot + 9, tot[18], ref, r, nullptr);
+        for (int k = 0; k < 9; k++) rot_out[f * 9 + k] = (float)r[k];
     }
 }
 

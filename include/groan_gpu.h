@@ -61,14 +61,11 @@ enum groan_dim {
 /* ctx flags */
 #define GROAN_FLAG_TRICLINIC 1u  /* enable the triclinic EXTENSION (wrap, min-image distances); without it a
                                     non-orthogonal box returns GROAN_ENOTORTHO exactly like the reference */
-#define GROAN_FLAG_EXACT_ONLY 2u /* disable the single-pass fast paths; always run the reference-order passes */
-#define GROAN_FLAG_FRAME_SHARING 8u /* opt in: RMSD kernels serve four frames per CTA, sharing each reference chunk (less L2
-                                       traffic, but measured slower than one frame per CTA on B200; see profiles/) */
-#define GROAN_FLAG_HOST_FALLBACK 16u /* launch the reference-order fallback passes from the host after every single-pass kernel
+#define GROAN_FLAG_EXACT_ONLY 2u /* disable the single-pass fast paths; always run the exact (reference-order) passes */
+#define GROAN_FLAG_NO_TMA 4u     /* contiguous groups through the gather kernels (register-staged 256-bit loads) instead of the
+                                    TMA-fed ring kernels; for tests (two independent implementations of the same sums) */
+#define GROAN_FLAG_HOST_FALLBACK 16u /* launch the passes that re-do flagged frames from the host after every single-pass kernel
                                         instead of letting the kernel tail-launch them from the device when a frame needs them */
-#define GROAN_FLAG_NO_TMA 4u     /* single-pass kernels with register-staged 256-bit loads instead of the TMA-fed ring */
-#define GROAN_FLAG_NO_QUAD 32u   /* single-pass kernels of kernels_tma.cuh (pairs of atoms, sin + cos sums) instead of the quad
-                                    kernels of kernels_quad.cuh; for A/B measurements and tests */
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
 int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ctx **out);

@@ -22,7 +22,7 @@ import groan_rs_b200 as g  # noqa: E402
 import bench  # noqa: E402
 
 F = int(os.environ.get("FRAMES", "37"))
-N = bench.N_ATOMS
+N = int(os.environ.get("NATOMS", bench.N_ATOMS))
 m = bench.masses(N)
 s = g.System(N, masses=m, device=0, max_frames=F)
 ref = g.System(N, masses=m, device=0, max_frames=1)

@@ -609,38 +609,6 @@ def test_single_pass_falls_back_when_it_cannot_certify(example):
     assert np.allclose(out[0][0], orc.get_center(two, [0, 1], [10.0] * 3), atol=TOL_CENTER)
 
 
-def test_frame_sharing_matches_one_frame_per_cta():
-    """RMSD kernels: four frames per CTA sharing each reference chunk (opt-in, GROAN_FLAG_FRAME_SHARING) against the
-    default of one frame per CTA"""
-    import groan_rs_b200 as g
-    n, F, L = 400_000, 8, np.array([20.0, 21.0, 19.0], np.float32)
-    masses = np.random.default_rng(2).uniform(1.0, 100.0, n).astype(np.float32)
-    scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
-    shared = _blob_system(n, F, L, 5, scale, nscale, masses, flags=g.FLAG_FRAME_SHARING)
-    single = _blob_system(n, F, L, 5, scale, nscale, masses)
-    ref = g.System(n, masses=masses)
-    ref.set_frames(shared.synth_blob_ref(5, scale, L / 2), L)
-    idx = np.arange(4, n - 8)   # first % 4 == 0 -> no head atoms; a ragged tail
-    for s in (shared, single, ref):
-        s.group_create_from_indices("G", idx)
-        s.group_create_from_indices("H", np.arange(3, n - 1))  # head of 1 atom, tail of 0..3
-    for grp in ("G", "H"):
-        r0, r1 = shared.calc_rmsd(ref, grp), single.calc_rmsd(ref, grp)
-        assert shared.fallback_frames() == 0 and single.fallback_frames() == 0
-        c0, q0 = shared.group_center_and_rmsd(ref, grp)
-        c1, q1 = single.group_center_and_rmsd(ref, grp)
-        m0, p0 = shared.group_center_and_rmsd(ref, grp, weighted=True)
-        m1, p1 = single.group_center_and_rmsd(ref, grp, weighted=True)
-        assert np.abs(r0 - r1).max() <= 2e-6 and np.abs(q0 - q1).max() <= 2e-6 and np.abs(p0 - p1).max() <= 2e-6
-        assert np.abs(c0 - c1).max() <= 4e-6 and np.abs(m0 - m1).max() <= 4e-6
-        frames = shared.get_frames()
-        ii = np.asarray(shared._groups[grp].indices)
-        for f in (0, 5):
-            r64, _ = orc.calc_rmsd_x64(ref._frame0(), ii, L, masses[ii], frames[f], ii, L)
-            assert abs(r0[f] - r64) <= 2e-5 and abs(q0[f] - r64) <= 2e-5
-
-
-# ------------------------------------------------------------------ all-pairs fast paths (packed one-step min-image)
 @pytest.mark.parametrize("far", [False, True])
 def test_all_pairs_fast_paths_bitexact(far):
     """2-D / 3-D all-pairs on an orthogonal box: coordinates up to 10 % outside the box take the packed one-step fold,
@@ -864,8 +832,8 @@ def test_device_side_fallback_matches_exact_only():
 # ------------------------------------------------------------------ quad kernels (kernels_quad.cuh)
 @pytest.mark.parametrize("n", [300_000, 300_001, 300_002])
 def test_quad_kernels_match_pair_kernels_and_x64(n):
-    """kernels_quad.cuh (quads of atoms, permuted reference, sine-only image decision) against kernels_tma.cuh
-    (GROAN_FLAG_NO_QUAD) and the exact64 oracle: heads of 0..3 atoms, ragged tails, a group smaller than one chunk per
+    """kernels_quad.cuh (quads of atoms on the TMA-fed ring, permuted reference, sine-only image decision) against the gather
+    kernels (GROAN_FLAG_NO_TMA: an independent implementation of the same sums) and the exact64 oracle: heads of 0..3 atoms, ragged tails, a group smaller than one chunk per
     CTA, blobs straddling box faces (frame 0 of _blob_system sits on two of them), non-cubic box, and frame sizes that
     are not multiples of four atoms (the group's 16-byte phase then changes from frame to frame: one permuted reference
     per phase)."""
@@ -874,7 +842,7 @@ def test_quad_kernels_match_pair_kernels_and_x64(n):
     masses = np.random.default_rng(4).uniform(1.0, 100.0, n).astype(np.float32)
     scale, nscale = 3.0 / 131070.0, 0.03 / 37837.23
     quad = _blob_system(n, F, L, 11, scale, nscale, masses)
-    pair = _blob_system(n, F, L, 11, scale, nscale, masses, flags=g.FLAG_NO_QUAD)
+    pair = _blob_system(n, F, L, 11, scale, nscale, masses, flags=g.FLAG_NO_TMA)
     ref = g.System(n, masses=masses)
     ref_xyz = quad.synth_blob_ref(11, scale, L / 2)
     ref.set_frames(ref_xyz, L)
