@@ -52,6 +52,8 @@ SIGNATURES = {
     "groan_gpu_all_distances": (_int, [_vp, _int, _int, _int, _vp]),
     "groan_gpu_all_distances_reduce": (_int, [_vp, _int, _int, _int, _f, _vp, _vp, _vp, _vp, _vp]),
     "groan_gpu_pairs_within": (_int, [_vp, _int, _int, _f, _vp, _vp, _vp, _sz]),
+    "groan_gpu_guess_bonds": (_int, [_vp, _vp, _f, _vp, _vp, _sz]),
+    "groan_gpu_hbonds": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, _sz]),
     "groan_gpu_wrap": (_int, [_vp, _int, _vp]),
     "groan_gpu_translate": (_int, [_vp, _int, C.POINTER(_f), _vp]),
     "groan_gpu_make_group_whole": (_int, [_vp, _int]),

@@ -28,7 +28,7 @@ def units():
 
 
 def headers():
-    h = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h")))
+    h = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h", ".inl")))
     return h + [os.path.join(ROOT, "include", "groan_gpu.h")]
 
 

@@ -370,10 +370,42 @@ struct GroupView {
     __device__ __forceinline__ uint32_t atom(uint32_t i) const { return idx ? __ldg(idx + i) : first + i; }
 };
 
+// Triclinic extension of the centre / RMSD path (the reference rejects such boxes).  A GROMACS box
+// v1 = (a, 0, 0), v2 = (bx, by, 0), v3 = (cx, cy, cz) becomes an ORTHOGONAL periodic box of lengths (a, by, cz) under the shear
+//     uz = z,   uy = y - z cy / cz,   ux = x - uy bx / by - z cx / cz
+// (v2 -> (0, by, 0), v3 -> (0, 0, cz)); fractional coordinates are u_k / L_k, so "Bai-Breen on fractional coordinates" is
+// the orthogonal algorithm on u, and because the map is linear, means and displacements computed in u map back with to_x.
+// With bx = cx = cy = 0 both maps are the identity bit for bit (y - z * 0 == y).
+struct Shear {
+    float a21, a31, a32;
+    __device__ __forceinline__ void to_u(float &x, float &y, float &z) const {
+        y = y - z * a32;
+        x = (x - y * a21) - z * a31;
+    }
+    __device__ __forceinline__ void to_x(float &x, float &y, float &z) const {
+        x = (x + y * a21) + z * a31;
+        y = y + z * a32;
+    }
+};
+
 struct FrameView {
     const float *xyz; // F x N x 3
     const float *box; // F x 9
     size_t n_atoms;
+    int tric;         // 1: the kernels see sheared coordinates (for_each_group_atom applies Shear::to_u)
+    __device__ __forceinline__ Shear shear(int f) const {
+        Shear s;
+        s.a21 = __ldg(box + f * 9 + 3) / __ldg(box + f * 9 + 4);
+        s.a31 = __ldg(box + f * 9 + 6) / __ldg(box + f * 9 + 8);
+        s.a32 = __ldg(box + f * 9 + 7) / __ldg(box + f * 9 + 8);
+        return s;
+    }
+    // the first atom of the group as the kernels see it (pilot of the single-pass kernels)
+    __device__ __forceinline__ void load_atom(int f, uint32_t atom, float &x, float &y, float &z) const {
+        const float *p = frame(f) + (size_t)atom * 3;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+        if (tric) shear(f).to_u(x, y, z);
+    }
     __device__ __forceinline__ const float *frame(int f) const { return xyz + (size_t)f * n_atoms * 3; }
     __device__ __forceinline__ void lengths(int f, float &lx, float &ly, float &lz) const {
         lx = __ldg(box + f * 9 + 0);
@@ -387,7 +419,22 @@ struct FrameView {
 // eight atoms per thread, issued before any of them is used); the up-to-7 atoms before the first
 // 32-byte boundary and after the last full octet, and index-list groups, use scalar loads.
 template <typename F>
+__device__ __forceinline__ void for_each_group_atom_raw(const FrameView &fv, const GroupView &g, int f, F &&fn);
+// ... with the coordinates sheared into the orthogonal picture when the frame view says so (triclinic extension)
+template <typename F>
 __device__ __forceinline__ void for_each_group_atom(const FrameView &fv, const GroupView &g, int f, F &&fn) {
+    if (fv.tric) {
+        const Shear sh = fv.shear(f);
+        for_each_group_atom_raw(fv, g, f, [&](uint32_t i, float x, float y, float z) {
+            sh.to_u(x, y, z);
+            fn(i, x, y, z);
+        });
+    } else {
+        for_each_group_atom_raw(fv, g, f, fn);
+    }
+}
+template <typename F>
+__device__ __forceinline__ void for_each_group_atom_raw(const FrameView &fv, const GroupView &g, int f, F &&fn) {
     const float *fr = fv.frame(f);
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (g.idx) {

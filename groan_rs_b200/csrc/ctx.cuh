@@ -75,9 +75,20 @@ struct groan_gpu_ctx {
     float *cur_xyz = nullptr;   // slot buffer or attached caller buffer
     bool attached = false;
     bool have_frames = false, have_box = false;
+    bool batch_tric = false;    // some frame of the batch has a triclinic box (set by check_box)
     size_t n_frames = 0;
     std::vector<float> h_box;   // F x 9 of the current batch
-    std::vector<uint8_t> valid; // F x N, empty = all valid
+    // Option<Vector3D> positions (groan_gpu_set_valid): the bitmap lives on the device; an op asks "first atom of this group
+    // without a position" once per (bitmap, group) -- the answer is cached, so the per-op cost is a table lookup
+    uint8_t *d_valid = nullptr;  // F x N, allocated on first use
+    bool has_valid = false;
+    struct ValidAnswer {
+        const void *group;  // Group the question was asked for (nullptr: atoms of polyatomic molecules)
+        bool found;
+        size_t frame, atom;
+    };
+    std::vector<ValidAnswer> valid_cache;
+    unsigned long long *d_valid_first = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_done[2] = {nullptr, nullptr};
     bool done_recorded[2] = {false, false};
     void *d_quant[2] = {nullptr, nullptr};       // quantised frames as uploaded (groan_gpu_push_frames_quantized), one per slot
@@ -183,12 +194,22 @@ inline FrameView frames_of(groan_gpu_ctx *ctx) {
     fv.xyz = ctx->cur_xyz;
     fv.box = ctx->d_box[ctx->slot];
     fv.n_atoms = ctx->n_atoms;
+    fv.tric = 0;
+    return fv;
+}
+
+// the same, for the centre / RMSD kernels of the triclinic extension: they see sheared coordinates when the batch has a
+// triclinic frame (the shear of an orthogonal frame is the identity bit for bit)
+inline FrameView frames_of_geom(groan_gpu_ctx *ctx) {
+    FrameView fv = frames_of(ctx);
+    fv.tric = ctx->batch_tric ? 1 : 0;
     return fv;
 }
 
 // simbox_check (simbox.rs:230-236) over every frame of the batch; zero box = the reference's panic
 inline int check_box(groan_gpu_ctx *ctx, bool allow_triclinic, bool *any_triclinic) {
     if (any_triclinic) *any_triclinic = false;
+    ctx->batch_tric = false;
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
     if (!ctx->have_box) return GROAN_ENOBOX;
     for (size_t f = 0; f < ctx->n_frames; f++) {
@@ -198,28 +219,18 @@ inline int check_box(groan_gpu_ctx *ctx, bool allow_triclinic, bool *any_triclin
         if (tric) {
             if (!allow_triclinic || !(ctx->flags & GROAN_FLAG_TRICLINIC)) return GROAN_ENOTORTHO;
             if (any_triclinic) *any_triclinic = true;
+            ctx->batch_tric = true;
         }
         if (b[0] == 0.0f || b[4] == 0.0f || b[8] == 0.0f) return GROAN_EZEROBOX;
     }
     return GROAN_OK;
 }
 
-// first atom of the group (group order) without a position, in the first frame that has one
-inline int check_positions(groan_gpu_ctx *ctx, const Group &g) {
-    if (ctx->valid.empty()) return GROAN_OK;
-    for (size_t f = 0; f < ctx->n_frames; f++) {
-        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
-        for (size_t i = 0; i < g.n; i++) {
-            const size_t a = g.contiguous ? g.first + i : g.idx[i];
-            if (!v[a]) {
-                ctx->err_a = f;
-                ctx->err_b = a;
-                return GROAN_ENOPOS;
-            }
-        }
-    }
-    return GROAN_OK;
-}
+// first atom of the group (group order) without a position, in the first frame that has one (groan_gpu.cu; device scan,
+// cached per bitmap and group)
+int check_positions(groan_gpu_ctx *ctx, const Group &g);
+// the same question for an arbitrary group or, with g == nullptr, for the atoms of polyatomic molecules (ctx->d_mol_ref)
+int first_invalid(groan_gpu_ctx *ctx, const Group *g, bool *found, size_t *frame, size_t *pos);
 
 inline int check_masses(groan_gpu_ctx *ctx, const Group &g) {
     if (!g.has_mass) {
@@ -274,19 +285,7 @@ inline float cutoff_squared_threshold(float c) {
 }
 
 // Atom::distance checks self first, then the other atom (atom.rs:780-790); scan order is row-major
-inline int check_pair_positions(groan_gpu_ctx *ctx, const Group &a, const Group &b) {
-    if (ctx->valid.empty() || a.n == 0 || b.n == 0) return GROAN_OK;
-    for (size_t f = 0; f < ctx->n_frames; f++) {
-        const uint8_t *v = &ctx->valid[f * ctx->n_atoms];
-        auto at = [](const Group &g, size_t i) { return g.contiguous ? (size_t)g.first + i : (size_t)g.idx[i]; };
-        if (!v[at(a, 0)]) { ctx->err_a = f; ctx->err_b = at(a, 0); return GROAN_ENOPOS; }
-        for (size_t j = 0; j < b.n; j++)
-            if (!v[at(b, j)]) { ctx->err_a = f; ctx->err_b = at(b, j); return GROAN_ENOPOS; }
-        for (size_t i = 1; i < a.n; i++)
-            if (!v[at(a, i)]) { ctx->err_a = f; ctx->err_b = at(a, i); return GROAN_ENOPOS; }
-    }
-    return GROAN_OK;
-}
+int check_pair_positions(groan_gpu_ctx *ctx, const Group &a, const Group &b);
 
 // batch bookkeeping (groan_gpu.cu): switch to the other device slot / make the uploaded batch visible to the compute stream
 int begin_batch(groan_gpu_ctx *ctx, size_t F, const float *box, bool use_slot);

@@ -44,7 +44,7 @@ int blocks_per_frame_fast(size_t g, size_t F, int occ) {
 // 16-byte aligned coordinate buffer (cudaMalloc'ed slots always are; attached buffers are checked)
 bool tma_ok(const groan_gpu_ctx *ctx, const Group &g, int occ) {
     return occ > 0 && g.contiguous && g.n >= 4096 && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
-           !(ctx->flags & GROAN_FLAG_NO_TMA);
+           !(ctx->flags & GROAN_FLAG_NO_TMA) && !ctx->batch_tric;  // triclinic extension: gather kernels only
 }
 
 // ---- quad kernels (kernels_quad.cuh) -----------------------------------------------------------------
@@ -219,7 +219,93 @@ int ensure_slots(groan_gpu_ctx *ctx) {
 }
 
 }  // namespace
+namespace groan {
+// first (frame, position in the group) whose atom has no position: min over f * n + i of the zero entries of the bitmap.
+// mol_ref != nullptr restricts the scan to atoms of polyatomic molecules (make_molecules_whole, modifying.rs:362-380).
+__global__ void __launch_bounds__(kThreads) k_first_invalid(const uint8_t *valid, size_t n_atoms, GroupView g, size_t n_frames,
+                                                             const uint32_t *mol_ref, unsigned long long *first) {
+    const size_t total = n_frames * (size_t)g.n;
+    unsigned long long best = ~0ull;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = k / g.n;
+        const uint32_t a = g.atom((uint32_t)(k - f * g.n));
+        if (mol_ref && __ldg(mol_ref + a) == kNoMolecule) continue;
+        if (!__ldg(valid + f * n_atoms + a)) {
+            best = k;
+            break;  // k only grows along a thread's stride
+        }
+    }
+    if (best != ~0ull) atomicMin(first, best);
+}
+}  // namespace groan
+
 namespace groan_host {
+int first_invalid(groan_gpu_ctx *ctx, const Group *gq, bool *found, size_t *frame, size_t *pos) {
+    *found = false;
+    if (!ctx->has_valid) return GROAN_OK;
+    for (const auto &c : ctx->valid_cache)
+        if (c.group == (const void *)gq) {
+            *found = c.found;
+            *frame = c.frame;
+            *pos = c.atom;
+            return GROAN_OK;
+        }
+    const Group &g = gq ? *gq : ctx->all;
+    groan_gpu_ctx::ValidAnswer ans = {(const void *)gq, false, 0, 0};
+    if (g.n) {
+        if (!ctx->d_valid_first) CK(cudaMalloc(&ctx->d_valid_first, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->d_valid_first, 0xff, sizeof(unsigned long long), ctx->compute));
+        const size_t total = ctx->n_frames * g.n;
+        const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((total + kThreads - 1) / kThreads, (size_t)kSMs * 16));
+        k_first_invalid<<<nb, kThreads, 0, ctx->compute>>>(ctx->d_valid, ctx->n_atoms, view_of(g), ctx->n_frames,
+                                                          gq ? nullptr : ctx->d_mol_ref, ctx->d_valid_first);
+        LAUNCHED();
+        unsigned long long h = ~0ull;
+        CK(cudaMemcpyAsync(&h, ctx->d_valid_first, sizeof(h), cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaStreamSynchronize(ctx->compute));
+        if (h != ~0ull) {
+            ans.found = true;
+            ans.frame = (size_t)(h / g.n);
+            ans.atom = (size_t)(h % g.n);
+        }
+    }
+    ctx->valid_cache.push_back(ans);
+    *found = ans.found;
+    *frame = ans.frame;
+    *pos = ans.atom;
+    return GROAN_OK;
+}
+
+static size_t atom_of(const Group &g, size_t i) { return g.contiguous ? (size_t)g.first + i : (size_t)g.idx[i]; }
+
+int check_positions(groan_gpu_ctx *ctx, const Group &g) {
+    bool found;
+    size_t f = 0, i = 0;
+    int rc = first_invalid(ctx, &g, &found, &f, &i);
+    if (rc) return rc;
+    if (!found) return GROAN_OK;
+    ctx->err_a = f;
+    ctx->err_b = atom_of(g, i);
+    return GROAN_ENOPOS;
+}
+
+// per frame the reference looks at a[0], then every atom of b, then a[1..] (atom.rs:780-790, row-major scan): with the first
+// missing position of each group (frame-major, group order) the first failure of that scan follows
+int check_pair_positions(groan_gpu_ctx *ctx, const Group &a, const Group &b) {
+    if (!ctx->has_valid || a.n == 0 || b.n == 0) return GROAN_OK;
+    bool fa, fb;
+    size_t af = 0, ai = 0, bf = 0, bi = 0;
+    int rc = first_invalid(ctx, &a, &fa, &af, &ai);
+    if (rc) return rc;
+    rc = first_invalid(ctx, &b, &fb, &bf, &bi);
+    if (rc) return rc;
+    if (!fa && !fb) return GROAN_OK;
+    const bool take_a = fa && (!fb || af < bf || (af == bf && ai == 0));
+    ctx->err_a = take_a ? af : bf;
+    ctx->err_b = take_a ? atom_of(a, ai) : atom_of(b, bi);
+    return GROAN_ENOPOS;
+}
+
 // switch to the other slot; the copy stream may only overwrite it once every kernel that used it is done
 int begin_batch(groan_gpu_ctx *ctx, size_t F, const float *box, bool use_slot) {
     if (F == 0) return GROAN_EINVAL;
@@ -237,7 +323,8 @@ int begin_batch(groan_gpu_ctx *ctx, size_t F, const float *box, bool use_slot) {
     ctx->slot = next;
     ctx->n_frames = F;
     ctx->have_frames = true;
-    ctx->valid.clear();
+    ctx->has_valid = false;
+    ctx->valid_cache.clear();
     ctx->have_box = (box != nullptr);
     ctx->h_box.assign(F * 9, 0.0f);
     if (box) {
@@ -260,24 +347,29 @@ int end_batch(groan_gpu_ctx *ctx) {
 namespace {
 
 // ---- centre passes -------------------------------------------------------------------------------
-int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out, const int *flags) {
+// to_cartesian matters for triclinic batches only: intermediate results stay in the sheared picture (0), results go back (1)
+int run_trig(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *c0_out, const int *flags, int to_cartesian = 0) {
     const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
     dim3 grid(nb, (unsigned)ctx->n_frames);
     if (weighted)
-        k_trig<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags);
+        k_trig<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags,
+                                                          to_cartesian);
     else
-        k_trig<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags);
+        k_trig<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, c0_out, flags,
+                                                           to_cartesian);
     LAUNCHED();
     return GROAN_OK;
 }
 
-int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c0, float *out, const int *flags) {
+int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c0, float *out, const int *flags, int to_cartesian = 1) {
     const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
     dim3 grid(nb, (unsigned)ctx->n_frames);
     if (weighted)
-        k_unwrap<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags);
+        k_unwrap<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags,
+                                                            to_cartesian);
     else
-        k_unwrap<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags);
+        k_unwrap<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), c0, ctx->d_partials, ctx->d_tickets, out, flags,
+                                                             to_cartesian);
     LAUNCHED();
     return GROAN_OK;
 }
@@ -338,10 +430,10 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
         const int nb = blocks_per_frame_fast(g.n, ctx->n_frames, ctx->occ_center);
         dim3 grid(nb, (unsigned)ctx->n_frames);
         if (weighted)
-            k_center_fast<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+            k_center_fast<true><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
                                                                      ctx->d_flags);
         else
-            k_center_fast<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
+            k_center_fast<false><<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials, ctx->d_tickets, out,
                                                                       ctx->d_flags);
         LAUNCHED();
         flags = ctx->d_flags;
@@ -352,13 +444,13 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
 }
 
 // validation shared by the centre ops, in the reference's order (analysis.rs:105-120, iterators.rs:1152-1191)
-int check_center_args(groan_gpu_ctx *ctx, int gid, bool weighted, const Group **gp) {
+int check_center_args(groan_gpu_ctx *ctx, int gid, bool weighted, const Group **gp, bool allow_triclinic = false) {
     if (!ctx) return GROAN_EINVAL;
     const Group *g = get_group(ctx, gid);
     if (!g) return GROAN_ENOGROUP;
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
     if (g->n == 0) return GROAN_EEMPTY;
-    int rc = check_box(ctx, false, nullptr);
+    int rc = check_box(ctx, allow_triclinic, nullptr);  // triclinic boxes: extension of the centre ops only (GROAN_FLAG_TRICLINIC)
     if (rc) return rc;
     rc = check_positions(ctx, *g);
     if (rc) return rc;
@@ -423,7 +515,8 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     if (!ctx->refs[ref_slot(gid)].set) return GROAN_ENOREF;
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
     // extract_data_from_system(target): box first (rmsd.rs:430), then group_get_com's own checks
-    int rc = check_box(ctx, false, nullptr);
+    bool tric = false;
+    int rc = check_box(ctx, !fit, &tric);  // triclinic extension: RMSD and rotation, not the fit (fit_structure stays orthogonal)
     if (rc) return rc;
     if (g->n == 0) return GROAN_EEMPTY;
     rc = check_positions(ctx, *g);
@@ -471,7 +564,7 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
         const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
         dim3 fgrid(nbf, (unsigned)ctx->n_frames);
-        if (center && R.same_mass) {
+        if (center && R.same_mass && !tric) {
             // centre and RMSD from one gather of the group (kernels_quad.cuh k_rmsd_fast_center)
             if (center_weighted)
                 k_rmsd_fast_center<2><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
@@ -481,10 +574,10 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
                                                                              d_center, d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
             center_done = true;
         } else if (R.same_mass)
-            k_rmsd_fast<true><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+            k_rmsd_fast<true><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
                                                                      d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
         else
-            k_rmsd_fast<false><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
+            k_rmsd_fast<false><<<fgrid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(*g), rv, ctx->d_partials, ctx->d_tickets,
                                                                       d_rmsd, d_rot, ctx->d_cen, ctx->d_flags);
         LAUNCHED();
         flags = ctx->d_flags;
@@ -499,11 +592,11 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     } else if (!device_fallback) {
         rc = run_trig(ctx, *g, false, ctx->d_c0, flags);
         if (rc) return rc;
-        rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags);
+        rc = run_unwrap(ctx, *g, true, ctx->d_c0, ctx->d_cen, flags, 0);  // the COM stays in the picture k_cov wraps in
         if (rc) return rc;
         const int nb = blocks_per_frame_fast(g->n, ctx->n_frames, 2);
         dim3 grid(nb, (unsigned)ctx->n_frames);
-        k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
+        k_cov<<<grid, kThreads, 0, ctx->compute>>>(frames_of_geom(ctx), view_of(*g), rv, ctx->d_cen, ctx->d_partials, ctx->d_tickets, d_rmsd,
                                                     d_rot, flags);
         LAUNCHED();
     }
@@ -659,7 +752,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
         for (float *q : r.d_pq)
             if (q) cudaFree(q);
     }
-    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_flags2, ctx->d_second_any, ctx->d_second_list, ctx->d_slow_list, ctx->d_slow_count, ctx->d_head_list, ctx->d_frames_done, ctx->d_mol_ref,
+    void *bufs[] = {ctx->d_partials, ctx->d_pair_partials, ctx->d_tickets, ctx->d_c0, ctx->d_cen, ctx->d_cen2, ctx->d_res, ctx->d_rot, ctx->d_tmp, ctx->d_flags, ctx->d_flags2, ctx->d_second_any, ctx->d_second_list, ctx->d_slow_list, ctx->d_slow_count, ctx->d_head_list, ctx->d_valid, ctx->d_valid_first, ctx->d_frames_done, ctx->d_mol_ref,
                     ctx->d_xtc_status, ctx->d_sel_atoms};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -778,6 +871,7 @@ int groan_gpu_set_group(groan_gpu_ctx *ctx, int gid, const uint32_t *idx, size_t
         if (i && idx[i] <= idx[i - 1]) return GROAN_EINVAL;  // container.rs:51-115: sorted, unique
     }
     Group &g = ctx->groups[gid];
+    ctx->valid_cache.clear();
     CK(cudaStreamSynchronize(ctx->compute));
     if (g.d_idx) { cudaFree(g.d_idx); g.d_idx = nullptr; }
     if (g.d_mass) { cudaFree(g.d_mass); g.d_mass = nullptr; }
@@ -903,8 +997,14 @@ int groan_gpu_attach_frames(groan_gpu_ctx *ctx, float *d_xyz, const float *box, 
 int groan_gpu_set_valid(groan_gpu_ctx *ctx, const uint8_t *valid) {
     if (!ctx) return GROAN_EINVAL;
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
-    if (!valid) ctx->valid.clear();
-    else ctx->valid.assign(valid, valid + ctx->n_frames * ctx->n_atoms);
+    ctx->valid_cache.clear();
+    ctx->has_valid = false;
+    if (!valid) return GROAN_OK;
+    if (!ctx->d_valid) CK(cudaMalloc(&ctx->d_valid, ctx->max_frames * ctx->n_atoms));
+    // host or device source; ordered on the compute stream like the ops that will ask about it
+    CK(cudaMemcpyAsync(ctx->d_valid, valid, ctx->n_frames * ctx->n_atoms, cudaMemcpyDefault, ctx->compute));
+    if (classify(valid) == PK_PAGEABLE) CK(cudaStreamSynchronize(ctx->compute));
+    ctx->has_valid = true;
     return GROAN_OK;
 }
 
@@ -933,18 +1033,18 @@ int groan_gpu_get_frames_quantized(groan_gpu_ctx *ctx, int32_t *q_out, float pre
 // ---- centres --------------------------------------------------------------------------------------
 int groan_gpu_estimate_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out) {
     const Group *g = nullptr;
-    int rc = check_center_args(ctx, gid, weighted != 0, &g);
+    int rc = check_center_args(ctx, gid, weighted != 0, &g, true);
     if (rc) return rc;
     if (!out) return GROAN_EINVAL;
     float *d_out = target_of<float>(out, ctx->d_cen);
-    rc = run_trig(ctx, *g, weighted != 0, d_out, nullptr);
+    rc = run_trig(ctx, *g, weighted != 0, d_out, nullptr, 1);
     if (rc) return rc;
     return deliver(ctx, out, d_out, ctx->n_frames * 3 * sizeof(float));
 }
 
 int groan_gpu_get_center(groan_gpu_ctx *ctx, int gid, int weighted, float *out) {
     const Group *g = nullptr;
-    int rc = check_center_args(ctx, gid, weighted != 0, &g);
+    int rc = check_center_args(ctx, gid, weighted != 0, &g, true);
     if (rc) return rc;
     if (!out) return GROAN_EINVAL;
     float *d_out = target_of<float>(out, ctx->d_cen);
@@ -1035,6 +1135,7 @@ int groan_gpu_set_molecules(groan_gpu_ctx *ctx, const uint32_t *mol_ref) {
     CK(cudaStreamSynchronize(ctx->compute));
     if (!ctx->d_mol_ref) CK(cudaMalloc(&ctx->d_mol_ref, ctx->n_atoms * sizeof(uint32_t)));
     ctx->mol_ref.assign(mol_ref, mol_ref + ctx->n_atoms);
+    ctx->valid_cache.clear();
     CK(cudaMemcpy(ctx->d_mol_ref, mol_ref, ctx->n_atoms * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return GROAN_OK;
 }
@@ -1045,14 +1146,16 @@ int groan_gpu_make_molecules_whole(groan_gpu_ctx *ctx) {
     if (!ctx->have_frames) return GROAN_ENOFRAMES;
     int rc = check_box(ctx, false, nullptr);  // simbox_check first (modifying.rs:350)
     if (rc) return rc;
-    if (!ctx->valid.empty()) {  // first atom of a polyatomic molecule without a position (modifying.rs:362-380)
-        for (size_t f = 0; f < ctx->n_frames; f++)
-            for (size_t i = 0; i < ctx->n_atoms; i++)
-                if (ctx->mol_ref[i] != kNoMolecule && !ctx->valid[f * ctx->n_atoms + i]) {
-                    ctx->err_a = f;
-                    ctx->err_b = i;
-                    return GROAN_ENOPOS;
-                }
+    {  // first atom of a polyatomic molecule without a position (modifying.rs:362-380)
+        bool found;
+        size_t f = 0, i = 0;
+        rc = first_invalid(ctx, nullptr, &found, &f, &i);
+        if (rc) return rc;
+        if (found) {
+            ctx->err_a = f;
+            ctx->err_b = i;
+            return GROAN_ENOPOS;
+        }
     }
     size_t nb = (ctx->n_atoms + kThreads - 1) / kThreads;
     nb = std::max<size_t>(1, std::min<size_t>(nb, (size_t)kMaxBlocksPerFrame * 4));
@@ -1089,7 +1192,8 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
     if (!g) return GROAN_ENOGROUP;
     if (!ref_box) return GROAN_ENOBOX;  // get_box_center (mod.rs:298-308) comes first in extract_data_from_system
     if (ref_box[1] != 0.0f || ref_box[2] != 0.0f || ref_box[5] != 0.0f) return GROAN_EINVAL;
-    if (ref_box[3] != 0.0f || ref_box[6] != 0.0f || ref_box[7] != 0.0f) return GROAN_ENOTORTHO;
+    const bool ref_tric = ref_box[3] != 0.0f || ref_box[6] != 0.0f || ref_box[7] != 0.0f;
+    if (ref_tric && !(ctx->flags & GROAN_FLAG_TRICLINIC)) return GROAN_ENOTORTHO;
     if (ref_box[0] == 0.0f || ref_box[4] == 0.0f || ref_box[8] == 0.0f) return GROAN_EZEROBOX;
     if (n_ref == 0) return GROAN_EEMPTY;
     if (!ref_idx && n_ref > n_ref_atoms) return GROAN_EINVAL;  // ref_idx == NULL: the first n_ref atoms of the reference
@@ -1143,6 +1247,7 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
         fv.xyz = d_ref;
         fv.box = d_refbox;
         fv.n_atoms = n_ref_atoms;
+        fv.tric = ref_tric ? 1 : 0;
         GroupView gv;
         gv.idx = d_ridx;
         gv.first = 0;
@@ -1154,7 +1259,7 @@ int groan_gpu_rmsd_set_reference(groan_gpu_ctx *ctx, int gid, const float *ref_x
                                                                    nullptr);
         LAUNCHED();
         k_unwrap<true><<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small, ctx->d_partials, ctx->d_tickets + ctx->max_frames,
-                                                                    d_small + 3, nullptr);
+                                                                    d_small + 3, nullptr, 0);
         LAUNCHED();
         k_ref_prepare<<<dim3(nb, 1), kThreads, 0, ctx->compute>>>(fv, gv, d_small + 3, R.d_pc, ctx->d_partials,
                                                                    ctx->d_tickets + ctx->max_frames, d_sums);

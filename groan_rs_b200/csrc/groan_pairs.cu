@@ -318,3 +318,5 @@ int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uin
     return GROAN_OK;
 }
 }  // extern "C"
+
+#include "groan_bonds.inl"

@@ -33,7 +33,7 @@ __device__ __forceinline__ bool frame_skipped(const int *flags, int f) { return 
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads) k_trig(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
-                                                    float *c0_out, const int *flags) {
+                                                    float *c0_out, const int *flags, int to_cartesian = 0) {
     __shared__ FrameReduceSmem<6, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
     if (frame_skipped(flags, f)) return;
@@ -70,13 +70,16 @@ __global__ void __launch_bounds__(kThreads) k_trig(FrameView fv, GroupView g, do
             const float xi = (float)tot[k], ze = (float)tot[3 + k];
             c0_out[f * 3 + k] = (atan2f(-ze, -xi) + 3.14159265358979323846f) / sc[k];
         }
+        if (fv.tric && to_cartesian) fv.shear(f).to_x(c0_out[f * 3], c0_out[f * 3 + 1], c0_out[f * 3 + 2]);
     }
 }
 
 // centre = sum(m * (c0 + vector_to(c0, x))) / sum(m); geometry: m = 1, divisor = n
 template <bool WEIGHTED>
+// to_cartesian (triclinic extension only): 1 = `out` is a result and goes back through Shear::to_x; 0 = it is the COM the
+// covariance pass will use, which works in the sheared picture too
 __global__ void __launch_bounds__(kThreads) k_unwrap(FrameView fv, GroupView g, const float *c0_in, double *partials,
-                                                      unsigned int *tickets, float *out, const int *flags) {
+                                                      unsigned int *tickets, float *out, const int *flags, int to_cartesian = 1) {
     __shared__ FrameReduceSmem<4, 0> sm;
     const int f = blockIdx.y, nb = gridDim.x;
     if (frame_skipped(flags, f)) return;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_unwrap(FrameView fv, GroupView g, 
         threadIdx.x == 0) {
         const double div = WEIGHTED ? tot[3] : (double)g.n;
         for (int k = 0; k < 3; k++) out[f * 3 + k] = (float)(tot[k] / div);
+        if (fv.tric && to_cartesian) fv.shear(f).to_x(out[f * 3], out[f * 3 + 1], out[f * 3 + 2]);
     }
 }
 
@@ -185,8 +189,8 @@ __global__ void __launch_bounds__(kThreads) k_center_fast(FrameView fv, GroupVie
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
-    const float *p0 = fv.frame(f) + (size_t)g.atom(0) * 3;
-    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
+    float px, py, pz;
+    fv.load_atom(f, g.atom(0), px, py, pz);
     const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
     const float sx = pi_x2() * ix, sy = pi_x2() * iy, sz = pi_x2() * iz;
     float a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -210,8 +214,10 @@ __global__ void __launch_bounds__(kThreads) k_center_fast(FrameView fv, GroupVie
     });
     double tot[10];
     float tmn[3], tmx[3];
-    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0)
+    if (frame_reduce<10, 3>(a, mn, mx, partials + (size_t)f * nb * 16, tickets + f, nb, sm, tot, tmn, tmx) && threadIdx.x == 0) {
         finish_center<WEIGHTED>(tot, tmn, tmx, px, py, pz, L, g.n, out + f * 3, flags + f);
+        if (fv.tric) fv.shear(f).to_x(out[f * 3], out[f * 3 + 1], out[f * 3 + 2]);  // the centre back from the sheared picture
+    }
 }
 
 // Vector3D::distance between two per-frame centres (System::group_distance, analysis.rs:348-360)

@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast_center(FrameView fv, 
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float4 r = ref_at(ref.pc, i);
         const float d[3] = {pilot_delta(x, p[0], L[0], inv[0]), pilot_delta(y, p[1], L[1], inv[1]), pilot_delta(z, p[2], L[2], inv[2])};
-        rmsd_accumulate<true>(a, mn, mx, d, r, 0.0f);
+        rmsd_accumulate<true>(a, mn, mx, d, r, 0.0f, d);
         if (CENTER == 1) { c[0] += d[0]; c[1] += d[1]; c[2] += d[2]; }
         c[3] += __sinf(__fmul_rn(x, sc[0])); // same definition as quad_sin / edge_sin
         c[4] += __sinf(__fmul_rn(y, sc[1]));

@@ -49,11 +49,13 @@ __global__ void __launch_bounds__(kThreads) k_ref_prepare(FrameView fv, GroupVie
     const float bx = lx / 2.0f, by = ly / 2.0f, bz = lz / 2.0f; // get_box_center, mod.rs:298-308
     const float shx = bx - com[0], shy = by - com[1], shz = bz - com[2];
     double d[kRefSums] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const Shear shr = fv.shear(0);
     for_each_group_atom(fv, g, 0, [&](uint32_t i, float x, float y, float z) {
         const float m = __ldg(g.mass + i);
-        const float px = wrap_coordinate(x + shx, lx) - bx;
-        const float py = wrap_coordinate(y + shy, ly) - by;
-        const float pz = wrap_coordinate(z + shz, lz) - bz;
+        float px = wrap_coordinate(x + shx, lx) - bx;
+        float py = wrap_coordinate(y + shy, ly) - by;
+        float pz = wrap_coordinate(z + shz, lz) - bz;
+        if (fv.tric) shr.to_x(px, py, pz);  // wrapped in the sheared picture, stored (and rotated) in Cartesian coordinates
         float *o = pc_out + ref_word(i);
         o[0] = px; o[kRefBlock] = py; o[2 * kRefBlock] = pz; o[3 * kRefBlock] = m;
         d[0] += (double)m * ((double)px * px + (double)py * py + (double)pz * pz);
@@ -95,11 +97,13 @@ __global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, Ref
     double d[kCovSums];
 #pragma unroll
     for (int k = 0; k < kCovSums; k++) d[k] = 0.0;
+    const Shear shr = fv.shear(f);
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float4 r = ref_at(ref.pc, i);
         // shift_and_wrap_coordinates (rmsd.rs:479-492) then q - centroid_q (rmsd.rs:564), f32 like the reference
-        const double q[3] = {(double)(wrap_coordinate(x + shx, lx) - bx), (double)(wrap_coordinate(y + shy, ly) - by),
-                             (double)(wrap_coordinate(z + shz, lz) - bz)};
+        float qx = wrap_coordinate(x + shx, lx) - bx, qy = wrap_coordinate(y + shy, ly) - by, qz = wrap_coordinate(z + shz, lz) - bz;
+        if (fv.tric) shr.to_x(qx, qy, qz);
+        const double q[3] = {(double)qx, (double)qy, (double)qz};
         const double pc[3] = {(double)r.x, (double)r.y, (double)r.z};
         const double m = (double)r.w;
 #pragma unroll
@@ -137,9 +141,11 @@ __global__ void __launch_bounds__(kThreads) k_cov(FrameView fv, GroupView g, Ref
 constexpr int kFastSums = 26;
 constexpr double kCancelGuard = 2e-5;
 
+// d: displacement the sums are formed with (Cartesian); du: the same displacement in the picture the box is orthogonal in
+// (identical unless the triclinic extension is on), whose extent certifies the pass
 template <bool SAME_MASS>
 __device__ __forceinline__ void rmsd_accumulate(float (&a)[kFastSums], float (&mn)[3], float (&mx)[3], const float (&d)[3],
-                                                const float4 &r, float m) {
+                                                const float4 &r, float m, const float (&du)[3]) {
     const float pc[3] = {r.x, r.y, r.z};
     const float w = r.w;
 #pragma unroll
@@ -156,8 +162,8 @@ __device__ __forceinline__ void rmsd_accumulate(float (&a)[kFastSums], float (&m
         const float wd = w * d[v];
         a[18 + v] += wd;
         a[21] = __fmaf_rn(wd, d[v], a[21]);
-        mn[v] = fminf(mn[v], d[v]);
-        mx[v] = fmaxf(mx[v], d[v]);
+        mn[v] = fminf(mn[v], du[v]);
+        mx[v] = fmaxf(mx[v], du[v]);
     }
     if (!SAME_MASS) {
 #pragma unroll
@@ -202,17 +208,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_rmsd_fast(FrameView fv, GroupVi
     const int f = blockIdx.y, nb = gridDim.x;
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
-    const float *p0 = fv.frame(f) + (size_t)g.atom(0) * 3;
-    const float px = __ldg(p0), py = __ldg(p0 + 1), pz = __ldg(p0 + 2);
+    float px, py, pz;
+    fv.load_atom(f, g.atom(0), px, py, pz);
     const float ix = 1.0f / L[0], iy = 1.0f / L[1], iz = 1.0f / L[2];
     float a[kFastSums];
 #pragma unroll
     for (int k = 0; k < kFastSums; k++) a[k] = 0.0f;
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    const Shear shr = fv.shear(f);
     for_each_group_atom(fv, g, f, [&](uint32_t i, float x, float y, float z) {
         const float4 r = ref_at(ref.pc, i);
-        const float d[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
-        rmsd_accumulate<SAME_MASS>(a, mn, mx, d, r, SAME_MASS ? 0.0f : __ldg(g.mass + i));
+        const float du[3] = {pilot_delta(x, px, L[0], ix), pilot_delta(y, py, L[1], iy), pilot_delta(z, pz, L[2], iz)};
+        float d[3] = {du[0], du[1], du[2]};
+        if (fv.tric) shr.to_x(d[0], d[1], d[2]);  // linear map: sums of the Cartesian displacements are what Kabsch needs
+        rmsd_accumulate<SAME_MASS>(a, mn, mx, d, r, SAME_MASS ? 0.0f : __ldg(g.mass + i), du);
     });
     double tot[kFastSums];
     float tmn[3], tmx[3];

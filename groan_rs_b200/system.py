@@ -649,6 +649,58 @@ class System:
                                                      _ptr(dist), capacity), "group_pairs_within", g1)
         return count, pairs, dist
 
+    # ------------------------------------------------------------------ users of the cell grid
+    def guess_bonds(self, vdw, radius_factor=0.55, capacity=None, assign=True):
+        """System::guess_bonds (guess.rs:362-395): per frame the bonds i < j with distance(i, j) < (vdw[i] + vdw[j]) *
+        radius_factor, found through a cell grid of the longest possible bond.  `vdw`: one van der Waals radius per atom, None /
+        NaN / negative = the atom has none (the reference's `no_vdw` warning list: returned as 1-based atom numbers, like
+        BondsGuessInfo).  Returns (bonds, no_vdw) with bonds = one sorted [n, 2] array per frame; with `assign`, the bonds of
+        frame 0 become the System's topology (assign_bonds + reset_mol_references, guess.rs:409-425)."""
+        v = np.array([-1.0 if (x is None or not (x == x) or x < 0) else float(x) for x in vdw], np.float32)
+        if v.size != self.n_atoms:
+            raise ValueError("one radius per atom")
+        F = self.n_frames
+        cap = int(capacity) if capacity else 8 * self.n_atoms + 64
+        count = np.zeros(F, np.uint64)
+        pairs = np.zeros((F, cap, 2), np.uint32)
+        self._check(self._lib.groan_gpu_guess_bonds(self._h, _ptr(v), C.c_float(radius_factor), _ptr(count), _ptr(pairs), cap), "guess_bonds")
+        if int(count.max()) > cap:
+            return self.guess_bonds(vdw, radius_factor, capacity=int(count.max()), assign=assign)
+        bonds = []
+        for f in range(F):
+            p = pairs[f, :int(count[f])].astype(np.int64)
+            bonds.append(p[np.lexsort((p[:, 1], p[:, 0]))])
+        if assign and F:
+            self.add_bonds(bonds[0])
+        return bonds, [int(i) + 1 for i in np.nonzero(v < 0)[0]]
+
+    def hbonds_single(self, acceptors, donors, max_distance, min_angle, capacity=None):
+        """HBondAnalysis::analyze_single (hbonds.rs:240-320): `acceptors` = a group name, `donors` = [(donor atom, [hydrogen
+        atoms])].  Per frame a structured array (donor, hydrogen, acceptor, distance, angle) sorted by (donor, acceptor, hydrogen)."""
+        don = np.array([d for d, _ in donors], np.uint32)
+        off = np.zeros(len(donors) + 1, np.uint32)
+        off[1:] = np.cumsum([len(h) for _, h in donors])
+        hyd = np.array([x for _, h in donors for x in h], np.uint32)
+        F = self.n_frames
+        cap = int(capacity) if capacity else 4 * int(hyd.size) + 64
+        count = np.zeros(F, np.uint64)
+        dha = np.zeros((F, cap, 3), np.uint32)
+        da = np.zeros((F, cap, 2), np.float32)
+        self._check(self._lib.groan_gpu_hbonds(self._h, self._gid(acceptors), _ptr(don), _ptr(off), _ptr(hyd if hyd.size else np.zeros(1, np.uint32)),
+                                               int(don.size), C.c_float(max_distance), C.c_float(min_angle), _ptr(count), _ptr(dha), _ptr(da), cap),
+                    "hbonds", acceptors)
+        if int(count.max()) > cap:
+            return self.hbonds_single(acceptors, donors, max_distance, min_angle, capacity=int(count.max()))
+        out = []
+        dt = np.dtype([("donor", np.int64), ("hydrogen", np.int64), ("acceptor", np.int64), ("distance", np.float32), ("angle", np.float32)])
+        for f in range(F):
+            n = int(count[f])
+            r = np.zeros(n, dt)
+            r["donor"], r["hydrogen"], r["acceptor"] = dha[f, :n, 0], dha[f, :n, 1], dha[f, :n, 2]
+            r["distance"], r["angle"] = da[f, :n, 0], da[f, :n, 1]
+            out.append(r[np.lexsort((r["hydrogen"], r["acceptor"], r["donor"]))])
+        return out
+
     # ------------------------------------------------------------------ whole molecules / groups, centering (SURVEY 8f rank 1)
     def add_bonds(self, pairs):
         """Bonds as (i, j) index pairs, e.g. from CONECT records (System::add_bonds_from_pdb, pdb_io.rs:129-200).  The
@@ -672,6 +724,7 @@ class System:
         for i in np.nonzero(bonded)[0]:
             mol_ref[i] = find(i)
         self._mol_ref = mol_ref
+        self._bonds = getattr(self, "_bonds", set()) | {(int(min(a, b)), int(max(a, b))) for a, b in np.asarray(pairs, dtype=np.int64).reshape(-1, 2)}
         self._check(self._lib.groan_gpu_set_molecules(self._h, _ptr(mol_ref)), "add_bonds")
 
     def make_molecules_whole(self):

@@ -151,6 +151,22 @@ int groan_gpu_all_distances_reduce(groan_gpu_ctx *ctx, int g1, int g2, int dim, 
 int groan_gpu_pairs_within(groan_gpu_ctx *ctx, int g1, int g2, float cutoff, uint64_t *count, uint32_t *pairs, float *dist,
                            size_t capacity);
 
+/* ---- users of the cell grid ---------------------------------------------------- */
+/* System::guess_bonds (src/system/guess.rs:362-470): per frame, every pair of atoms i < j with van der Waals radii whose
+ * minimum-image distance is below (vdw[i] + vdw[j]) * radius_factor (reference default 0.55).  vdw: n_atoms floats, < 0 = the
+ * atom has no radius (it gets no bonds; the reference lists it in its BondsGuessWarning).  count: F; pairs (nullable):
+ * F x capacity x 2 atom indices, unordered; pairs beyond the capacity are counted but not stored.  Assigning the bonds to
+ * atoms and the sanity checks on their number stay on the host (guess.rs:409-425,472-). */
+int groan_gpu_guess_bonds(groan_gpu_ctx *ctx, const float *vdw, float radius_factor, uint64_t *count, uint32_t *pairs, size_t capacity);
+/* HBondAnalysis::analyze_single (src/system/hbonds.rs:240-320) for one acceptor group and one list of donors, per frame:
+ * donors[d] carries the hydrogens hydrogens[hyd_offsets[d] .. hyd_offsets[d + 1]) (HBondChainGroups, hbonds.rs:108-150).
+ * A record for every (donor, hydrogen, acceptor) with acceptor != donor, distance(acceptor, donor) <= max_distance and
+ * angle(donor - hydrogen - acceptor) >= min_angle (degrees; calc_angle hbonds.rs:322-335).  count: F; dha (nullable, together
+ * with dist_angle): F x capacity x 3 atom indices; dist_angle: F x capacity x 2 (distance in nm, angle in degrees).
+ * The order of the records is undefined (as is the order of CellGrid::neighbors_iter, cellgrid.rs:141-144). */
+int groan_gpu_hbonds(groan_gpu_ctx *ctx, int acc_gid, const uint32_t *donors, const uint32_t *hyd_offsets, const uint32_t *hydrogens,
+                     size_t n_donors, float max_distance, float min_angle, uint64_t *count, uint32_t *dha, float *dist_angle, size_t capacity);
+
 /* ---- wrap / translate (in place on the current batch) ------------------------------------------ */
 /* System::atoms_wrap / group_wrap (modifying.rs:201,215; vector3d.rs:380-417).  shifts (nullable):
  * F x G x 3 int8, net number of +L steps per axis (for the triclinic extension: multiples of box vectors) */

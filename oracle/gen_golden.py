@@ -171,6 +171,14 @@ def main():
                         boxes=abx, time=atm, orig_index=keep, Peptide=np.arange(363, dtype=np.uint32),
                         Phosphates=np.arange(363, 491, dtype=np.uint32))
 
+    # ---- the water of the same system for the hbonds.rs goldens (hbonds.rs:505-587): indices only -- the
+    # trajectory itself is tests/golden/xtc/aa_membrane_peptide.xtc, decoded by the product's xtc reader in the test
+    ow = np.array([i for i, (r, a) in enumerate(zip(resn, atn)) if r == "SOL" and a == "OW"], np.uint32)
+    hw1 = np.array([i for i, (r, a) in enumerate(zip(resn, atn)) if r == "SOL" and a == "HW1"], np.uint32)
+    hw2 = np.array([i for i, (r, a) in enumerate(zip(resn, atn)) if r == "SOL" and a == "HW2"], np.uint32)
+    assert len(ow) == len(hw1) == len(hw2) == 5091 and np.all(hw1 == ow + 1) and np.all(hw2 == ow + 2)
+    np.savez_compressed(os.path.join(OUT, "aa_membrane_water.npz"), OW=ow, HW1=hw1, HW2=hw2, n_atoms=np.array([len(resn)], np.int64))
+
     # ---- cfg3: triclinic / dodecahedron / octahedron (50 atoms x 11 frames)
     tri = {}
     for name in ("triclinic", "dodecahedron", "octahedron"):

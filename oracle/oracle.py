@@ -380,6 +380,160 @@ def tric_all_distances(xyz, idx1, idx2, dim, box9):
     return out
 
 
+
+# Triclinic centre / RMSD: the DEFINITION of the extension ("Bai-Breen on fractional coordinates, mapped back"),
+# restated in numpy float64.  A box v1 = (a, 0, 0), v2 = (bx, by, 0), v3 = (cx, cy, cz) becomes the orthogonal periodic box
+# (a, by, cz) under the shear u_z = z, u_y = y - z cy/cz, u_x = x - u_y bx/by - z cx/cz; every orthogonal algorithm of this
+# file is applied to u and the result mapped back (the map is linear).  Pins: tests/test_gpu_parity.py
+# test_triclinic_centre_and_rmsd_* (brute-force nearest-image unwrapping of compact groups; identity on orthogonal boxes).
+def _tric_params(box9):
+    b = np.asarray(box9, np.float64).reshape(3, 3)
+    L = np.array([b[0, 0], b[1, 1], b[2, 2]])
+    return b[1, 0] / b[1, 1], b[2, 0] / b[2, 2], b[2, 1] / b[2, 2], L
+
+
+def tric_to_u(x, box9):
+    a21, a31, a32, _ = _tric_params(box9)
+    x = np.asarray(x, np.float64).reshape(-1, 3)
+    uy = x[:, 1] - x[:, 2] * a32
+    ux = x[:, 0] - uy * a21 - x[:, 2] * a31
+    return np.stack([ux, uy, x[:, 2]], axis=1)
+
+
+def tric_to_x(u, box9):
+    a21, a31, a32, _ = _tric_params(box9)
+    u = np.asarray(u, np.float64).reshape(-1, 3)
+    return np.stack([u[:, 0] + u[:, 1] * a21 + u[:, 2] * a31, u[:, 1] + u[:, 2] * a32, u[:, 2]], axis=1)
+
+
+def _center_u64(u, L, mass=None):
+    th = 2.0 * np.pi * np.mod(u, L) / L
+    c0 = (np.arctan2(-np.sin(th).sum(axis=0), -np.cos(th).sum(axis=0)) + np.pi) * L / (2.0 * np.pi)  # geometric estimate
+    v = np.mod(u - c0 + L / 2.0, L) - L / 2.0
+    w = np.ones(len(u)) if mass is None else np.asarray(mass, np.float64)
+    return ((c0 + v) * w[:, None]).sum(axis=0) / w.sum(), c0
+
+
+def tric_estimate_center_x64(xyz, idx, box9):
+    u = tric_to_u(np.asarray(xyz, np.float64).reshape(-1, 3)[np.asarray(idx, np.int64)], box9)
+    return tric_to_x(_center_u64(u, _tric_params(box9)[3])[1], box9)[0]
+
+
+def tric_get_center_x64(xyz, idx, box9, mass=None):
+    u = tric_to_u(np.asarray(xyz, np.float64).reshape(-1, 3)[np.asarray(idx, np.int64)], box9)
+    return tric_to_x(_center_u64(u, _tric_params(box9)[3], mass)[0], box9)[0]
+
+
+def _tric_extract(xyz, idx, box9, mass):
+    L = _tric_params(box9)[3]
+    u = tric_to_u(np.asarray(xyz, np.float64).reshape(-1, 3)[np.asarray(idx, np.int64)], box9)
+    com = _center_u64(u, L, mass)[0]
+    return tric_to_x(np.mod(u + (L / 2.0 - com), L) - L / 2.0, box9)  # wrapped around the COM, centred, Cartesian
+
+
+def tric_calc_rmsd_x64(ref_xyz, ref_idx, ref_box9, mass, tgt_xyz, tgt_idx, tgt_box9):
+    pc = _tric_extract(ref_xyz, ref_idx, ref_box9, mass)
+    qc = _tric_extract(tgt_xyz, tgt_idx, tgt_box9, mass)
+    w = np.asarray(mass, np.float64)
+    U, _, Vt = np.linalg.svd(pc.T @ qc)
+    D = np.diag([1.0, 1.0, -1.0 if np.linalg.det(U @ Vt) < 0 else 1.0])
+    r = U @ D @ Vt
+    diff = pc @ r - qc  # r^T pc_i as rows
+    return float(np.sqrt((w * (diff * diff).sum(axis=1)).sum() / w.sum())), r
+
+
+
+# ---------------------------------------------------------------- users of the cell grid (guess.rs:362-470, hbonds.rs:240-335)
+# numpy float32 restatements with the reference's operation order; brute force over all pairs instead of the cell grid (the
+# grid only prunes: cells are at least as wide as the cutoff, so neighbors_iter offers every atom within it).
+def _minimg_vec(d, L):
+    """min_image per axis with the reference's loops (vector3d.rs:575-592), vectorised, float32"""
+    d = d.astype(np.float32).copy()
+    L = np.asarray(L, np.float32)
+    h = (L / np.float32(2.0)).astype(np.float32)
+    for _ in range(64):
+        hi = d > h
+        if not hi.any():
+            break
+        d = np.where(hi, (d - L).astype(np.float32), d)
+    for _ in range(64):
+        lo = d < -h
+        if not lo.any():
+            break
+        d = np.where(lo, (d + L).astype(np.float32), d)
+    return d
+
+
+def _dist32(a, b, L):
+    """Vector3D::distance, Dimension::XYZ: sqrt((dx*dx + dy*dy) + dz*dz) in float32"""
+    d = _minimg_vec((np.asarray(a, np.float32) - np.asarray(b, np.float32)).astype(np.float32), L)
+    q = ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32)
+    q = (q + (d[..., 2] * d[..., 2]).astype(np.float32)).astype(np.float32)
+    return np.sqrt(q).astype(np.float32)
+
+
+def guess_bonds(xyz, vdw, box, radius_factor=0.55):
+    """identify_bonds (guess.rs:427-470): sorted array of (i, j), i < j; vdw < 0 / NaN = no radius"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3)
+    v = np.asarray(vdw, np.float32)
+    has = v >= 0
+    out = []
+    rf = np.float32(radius_factor)
+    for i in np.nonzero(has)[0]:
+        js = np.nonzero(has & (np.arange(len(v)) > i))[0]
+        if js.size == 0:
+            continue
+        d = _dist32(x[i][None, :], x[js], L)
+        lim = ((v[i] + v[js]).astype(np.float32) * rf).astype(np.float32)
+        for j in js[d < lim]:
+            out.append((int(i), int(j)))
+    return np.array(sorted(out), np.int64).reshape(-1, 2)
+
+
+def _vector_to32(c, p, L):
+    L = np.asarray(L, np.float32)
+    h = (L / np.float32(2.0)).astype(np.float32)
+    t = ((np.asarray(p, np.float32) - np.asarray(c, np.float32)).astype(np.float32) + h).astype(np.float32)
+    m = np.fmod((np.fmod(t, L).astype(np.float32) + L).astype(np.float32), L).astype(np.float32)
+    return (m - h).astype(np.float32)
+
+
+def hbond_angle(donor, hydrogen, acceptor, box):
+    """HBondAnalysis::calc_angle (hbonds.rs:322-350), degrees, float32"""
+    st, L = _L(box)
+    _chk(st)
+    hd, ha = _vector_to32(hydrogen, donor, L), _vector_to32(hydrogen, acceptor, L)
+    dot = np.float32(np.float32(np.float32(hd[0] * ha[0]) + np.float32(hd[1] * ha[1])) + np.float32(hd[2] * ha[2]))
+    n1 = np.sqrt(np.float32(np.float32(np.float32(hd[0] * hd[0]) + np.float32(hd[1] * hd[1])) + np.float32(hd[2] * hd[2])))
+    n2 = np.sqrt(np.float32(np.float32(np.float32(ha[0] * ha[0]) + np.float32(ha[1] * ha[1])) + np.float32(ha[2] * ha[2])))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ang = np.float32(np.arccos(np.float32(dot / np.float32(n1 * n2))) * np.float32(57.29577951308232))
+    if np.isnan(ang):
+        return np.float32(180.0) if _dist32(hydrogen, acceptor, L) < _dist32(donor, acceptor, L) else np.float32(0.0)
+    return ang
+
+
+def hbonds_single(xyz, acceptors, donors, box, max_distance, min_angle):
+    """HBondAnalysis::analyze_single (hbonds.rs:240-320): list of (donor, hydrogen, acceptor, distance, angle), sorted by
+    (donor, acceptor, hydrogen); donors = [(donor, [hydrogens])]"""
+    st, L = _L(box)
+    _chk(st)
+    x = _f32(xyz).reshape(-1, 3)
+    acc = np.asarray(acceptors, np.int64)
+    out = []
+    for d, hs in donors:
+        dist = _dist32(x[acc], x[d][None, :], L)
+        for a, dd in zip(acc[(dist <= np.float32(max_distance)) & (acc != d)], dist[(dist <= np.float32(max_distance)) & (acc != d)]):
+            for h in hs:
+                ang = hbond_angle(x[d], x[h], x[a], L)
+                if ang < np.float32(min_angle):
+                    continue
+                out.append((int(d), int(h), int(a), float(dd), float(ang)))
+    return sorted(out, key=lambda r: (r[0], r[2], r[1]))
+
+
 # ---------------------------------------------------------------- synthetic workloads
 
 

@@ -412,10 +412,106 @@ def test_triclinic_cfg3(tric, name):
         exp, esh = orc.tric_wrap(moved[f], range(n), bx[f])
         assert np.array_equal(sh[f], esh), f
         assert np.array_equal(bits(w[f]), bits(exp)), f
-    # centre / RMSD stay the reference's behaviour on a triclinic box
+    # centre / RMSD: the reference's behaviour without the flag (with it: test_triclinic_centre_and_rmsd_*)
     with pytest.raises(g.GroanError) as ei:
-        s.group_get_center("all")
+        plain.group_get_center("all")
     assert "NotOrthogonal" in ei.value.variant
+
+
+@pytest.mark.parametrize("name", ["triclinic", "dodecahedron", "octahedron"])
+def test_triclinic_centre_and_rmsd_fixtures(tric, name):
+    """Triclinic EXTENSION of group_estimate_center / group_get_center / group_get_com / calc_rmsd (parity unpinned: the
+    reference returns NotOrthogonal).  Definition = oracle.tric_*_x64 (Bai-Breen on fractional coordinates, i.e. the
+    orthogonal algorithm in the sheared picture); here on the reference's three 50-atom triclinic trajectories."""
+    fr, bx = tric[name + "_frames"], tric[name + "_boxes"]
+    F, n = fr.shape[0], fr.shape[1]
+    masses = np.random.default_rng(12).uniform(1.0, 30.0, n).astype(np.float32)
+    s = _sys(n, masses=masses, max_frames=F, triclinic=True)
+    s.set_frames(fr, bx)
+    idx = np.arange(3, n - 2)
+    s.group_create_from_indices("G", idx)
+    ref = _sys(n, masses=masses, triclinic=True)
+    ref.set_frames(fr[0], bx[0].reshape(1, 9))
+    ref.group_create_from_indices("G", idx)
+    est, cen, com = s.group_estimate_center("G"), s.group_get_center("G"), s.group_get_com("G")
+    rm = s.calc_rmsd(ref, "G")
+    assert abs(float(rm[0])) <= TOL_RMSD  # frame 0 against itself
+    for f in range(F):
+        assert np.abs(est[f] - orc.tric_estimate_center_x64(fr[f], idx, bx[f])).max() <= 2e-5, (f, est[f])
+        assert np.abs(cen[f] - orc.tric_get_center_x64(fr[f], idx, bx[f])).max() <= TOL_CENTER, (f, cen[f])
+        assert np.abs(com[f] - orc.tric_get_center_x64(fr[f], idx, bx[f], masses[idx])).max() <= TOL_CENTER, (f, com[f])
+        e, _ = orc.tric_calc_rmsd_x64(fr[0], idx, bx[0], masses[idx], fr[f], idx, bx[f])
+        assert abs(float(rm[f]) - e) <= TOL_RMSD, (f, rm[f], e)
+    # the fit stays orthogonal-only, with or without the flag (fit_structure is not part of the extension)
+    import groan_rs_b200 as g
+    with pytest.raises(g.GroanError) as ei:
+        s.calc_rmsd_and_fit(ref, "G")
+    assert "NotOrthogonal" in ei.value.variant
+
+
+def test_triclinic_centre_and_rmsd_blob_and_orthogonal_identity():
+    """Self-pins of the triclinic centre / RMSD extension.
+    (ii) a compact blob, rigidly moved and wrapped into a triclinic cell: the centre must be the plain mean of the blob
+         unwrapped by brute force (nearest of 5^3 periodic images to its first atom, Cartesian metric, float64) up to a whole
+         box vector combination, and the RMSD the noise level it was built with -- neither involves the shear.
+    (i)  orthogonal frames of a batch that also holds a triclinic frame go through the sheared code path (the shear of an
+         orthogonal box is the identity) and must equal the orthogonal-only run of the same kernels bit for bit."""
+    import groan_rs_b200 as g
+    n, F = 120_000, 4
+    box = np.array([12.0, 0, 0, 3.0, 11.0, 0, 2.5, -3.5, 10.0], np.float32)
+    orth = np.array([12.0, 0, 0, 0, 11.0, 0, 0, 0, 10.0], np.float32)
+    masses = np.random.default_rng(3).uniform(1.0, 100.0, n).astype(np.float32)
+    scale, nscale = 1.2 / 131070.0, 0.03 / 37837.23
+    rot = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (F, 1))
+    rot[1] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
+    rot[2] = [1, 0, 0, 0, 0, -1, 0, 1, 0]
+    cen = np.array([[6.0, 5.0, 5.0], [0.4, 10.6, 9.8], [13.5, 3.0, 0.2], [2.0, 2.0, 2.0]], np.float32)
+    gen = g.System(n, masses=masses, max_frames=F)
+    gen.synth_blob(17, 0, F, scale, nscale, rot, cen, [50.0] * 3, wrap=False)  # unwrapped blobs; the box given here is not used
+    raw = gen.get_frames().copy()
+    ref_xyz = gen.synth_blob_ref(17, scale, [6.0, 5.0, 5.0])
+    gen.close()
+    boxes = np.tile(box, (F, 1))
+    boxes[3] = orth
+    s = g.System(n, masses=masses, max_frames=F, triclinic=True)
+    s.set_frames(raw, boxes)
+    s.atoms_wrap()  # into the triclinic cell (frame 3: the orthogonal box)
+    wrapped = s.get_frames().copy()
+    idx = np.arange(5, n - 3)
+    s.group_create_from_indices("G", idx)
+    ref = g.System(n, masses=masses, triclinic=True)
+    ref.set_frames(ref_xyz, box.reshape(1, 9))
+    ref.group_create_from_indices("G", idx)
+    cen_g, com_g, rm = s.group_get_center("G"), s.group_get_com("G"), s.calc_rmsd(ref, "G")
+    imgs = np.array([[i, j, k] for i in range(-2, 3) for j in range(-2, 3) for k in range(-2, 3)], np.float64)
+    for f in range(F):
+        B = boxes[f].reshape(3, 3).astype(np.float64)
+        x = wrapped[f, idx].astype(np.float64)
+        shifts = imgs @ B
+        d2 = (((x - x[0])[:, None, :] + shifts[None, :, :]) ** 2).sum(axis=2)
+        un = x + shifts[np.argmin(d2, axis=1)]
+        for got, want in ((cen_g[f], un.mean(axis=0)), (com_g[f], (un * masses[idx, None]).sum(axis=0) / masses[idx].sum())):
+            k = np.linalg.solve(B.T, got.astype(np.float64) - want)  # difference in units of the box vectors
+            assert np.abs(k - np.rint(k)).max() * 12.0 <= 2e-5, (f, got, want, k)
+        assert abs(float(rm[f]) - 0.03 * np.sqrt(3.0)) <= 2e-3, (f, rm[f])  # noise sigma 0.03 nm per axis
+        e, _ = orc.tric_calc_rmsd_x64(ref_xyz, idx, box, masses[idx], wrapped[f], idx, boxes[f])
+        assert abs(float(rm[f]) - e) <= TOL_RMSD, (f, rm[f], e)
+        assert np.abs(cen_g[f] - orc.tric_get_center_x64(wrapped[f], idx, boxes[f])).max() <= TOL_CENTER
+    # (i): frame 3 (orthogonal box) inside the mixed batch == the same frame through the orthogonal code (gather kernels)
+    o = g.System(n, masses=masses, max_frames=F)  # the same batch size: the same grids, hence the same order of the partial sums
+    o.set_flags(g.FLAG_NO_TMA)
+    o.set_frames(wrapped, np.tile(orth, (F, 1)))
+    o.group_create_from_indices("G", idx)
+    oref = g.System(n, masses=masses)
+    oref.set_frames(ref_xyz, orth.reshape(1, 9))
+    oref.group_create_from_indices("G", idx)
+    sref = g.System(n, masses=masses, triclinic=True)
+    sref.set_frames(ref_xyz, orth.reshape(1, 9))
+    sref.group_create_from_indices("G", idx)
+    rm_mixed = s.calc_rmsd(sref, "G")
+    assert np.array_equal(bits(o.group_get_center("G")[3]), bits(cen_g[3]))
+    assert np.array_equal(bits(o.group_get_com("G")[3]), bits(com_g[3]))
+    assert np.array_equal(bits(o.calc_rmsd(oref, "G")[3:4]), bits(rm_mixed[3:4]))
 
 
 def test_triclinic_code_on_orthogonal_box_is_identical(example):
@@ -1424,3 +1520,124 @@ def test_caller_provided_shift_buffers(example):
     s.atoms_translate([30.0, -17.0, 5.0], shifts=dev)
     s.sync()
     assert np.array_equal(dev.cpu().numpy()[0], esh)
+
+
+# ------------------------------------------------------------------ users of the cell grid: guess_bonds, HBondAnalysis
+def _water_box(n_mol, L, seed):
+    """rigid three-site waters at random positions and orientations in a cubic box: O, H, H per molecule"""
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(0, L, size=(n_mol, 3))
+    q = rng.normal(size=(n_mol, 4))
+    q /= np.linalg.norm(q, axis=1)[:, None]
+    w, x, y, z = q.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
+                  2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1).reshape(n_mol, 3, 3)
+    h1 = np.array([0.0957, 0.0, 0.0]), np.array([-0.024, 0.0927, 0.0])
+    xyz = np.empty((n_mol, 3, 3))
+    xyz[:, 0] = o
+    xyz[:, 1] = o + R @ h1[0]
+    xyz[:, 2] = o + R @ h1[1]
+    return np.mod(xyz.reshape(-1, 3), L).astype(np.float32)
+
+
+def test_guess_bonds_matches_restatement():
+    """groan_gpu_guess_bonds against the restated identify_bonds (guess.rs:427-470): the same set of (i, j) pairs in every
+    frame -- water boxes dense enough for chance contacts, atoms without a radius, bonds through the box faces -- and the
+    topology it assigns (mol_ref of make_molecules_whole)."""
+    import groan_rs_b200 as g
+    n_mol, L, F = 3000, 4.2, 3
+    frames = np.stack([_water_box(n_mol, L, 100 + f) for f in range(F)])
+    n = frames.shape[1]
+    vdw = np.tile(np.array([0.152, 0.12, 0.12], np.float32), n_mol)
+    vdw[5::97] = -1.0  # some hydrogens without a radius
+    s = g.System(n, max_frames=F)
+    s.set_frames(frames, [L] * 3)
+    bonds, no_vdw = s.guess_bonds(vdw, 0.55)
+    assert no_vdw == [int(i) + 1 for i in np.nonzero(vdw < 0)[0]]
+    for f in range(F):
+        exp = orc.guess_bonds(frames[f], vdw, [L] * 3, 0.55)
+        assert np.array_equal(bonds[f], exp), (f, len(bonds[f]), len(exp))
+        assert len(exp) > 2 * n_mol - 100  # the O-H bonds, plus chance contacts
+    # the bonds of frame 0 became the topology: every water is one molecule with its oxygen as reference atom
+    mol = s._mol_ref.reshape(n_mol, 3)
+    intact = (vdw.reshape(n_mol, 3) >= 0).all(axis=1)
+    assert (mol[intact, 1] <= np.arange(n_mol)[intact] * 3).all() and (mol[intact, 1] == mol[intact, 2]).all()
+    # a larger radius factor, capacity exceeded on the first try (the call is repeated with the count it reported)
+    b2, _ = s.guess_bonds(vdw, 0.8, capacity=16, assign=False)
+    assert np.array_equal(b2[1], orc.guess_bonds(frames[1], vdw, [L] * 3, 0.8))
+    # nobody has a radius: no bonds
+    b3, nv = s.guess_bonds([None] * n, assign=False)
+    assert all(len(b) == 0 for b in b3) and len(nv) == n
+
+
+def test_hbonds_water_goldens_gpu():
+    """hbonds.rs:505-587 through groan_gpu_hbonds: the reference's own numbers -- bonds per frame (exact) and the first / last
+    bond of each of the 21 frames (1e-3) -- on aa_membrane_peptide.xtc read by the product's xtc reader; two frames in full
+    against the restated analyze_single."""
+    import os
+    import groan_rs_b200 as g
+    import hbond_goldens as hg
+    here = os.path.dirname(os.path.abspath(__file__))
+    xf = g.xtc.XtcFile.open(os.path.join(here, "golden", "xtc", "aa_membrane_peptide.xtc"))
+    water = np.load(os.path.join(here, "golden", "aa_membrane_water.npz"))
+    ow = water["OW"].astype(np.int64)
+    n = int(water["n_atoms"][0])
+    assert xf.n_atoms == n and xf.n_frames == 21
+    s = g.System(n, max_frames=21)
+    s.set_frames_xtc(xf)
+    s.group_create_from_indices("OW", ow)
+    s.group_create_from_indices("HW", np.sort(np.concatenate([ow + 1, ow + 2])))
+    s.add_bonds(np.concatenate([np.stack([ow, ow + 1], 1), np.stack([ow, ow + 2], 1)]))
+    from groan_rs_b200.hbonds import HBondAnalysis, HBondChain
+    an = HBondAnalysis(s, [HBondChain("OW", "OW", "HW")], [(0, 0)], hg.MAX_DISTANCE, hg.MIN_ANGLE)
+    maps = an.analyze()
+    frames = s.get_frames()
+    for f in range(21):
+        rec = maps[f][(0, 0)]
+        hg.check_frame(f, zip(rec["donor"], rec["hydrogen"], rec["acceptor"], rec["distance"], rec["angle"]))
+    donors = [(int(o), [int(o) + 1, int(o) + 2]) for o in ow]
+    for f in (3, 17):
+        L = s._boxes[f].reshape(3, 3).diagonal().copy()
+        exp = orc.hbonds_single(frames[f], ow, donors, L, hg.MAX_DISTANCE, hg.MIN_ANGLE)
+        rec = maps[f][(0, 0)]
+        assert [(int(a), int(b), int(c)) for a, b, c in zip(rec["donor"], rec["hydrogen"], rec["acceptor"])] == [r[:3] for r in exp]
+        assert np.abs(rec["distance"] - np.array([r[3] for r in exp], np.float32)).max() <= TOL_DIST
+        assert np.abs(rec["angle"] - np.array([r[4] for r in exp], np.float32)).max() <= 2e-2  # acosf near 180 degrees
+
+
+def test_hbonds_two_chains_and_errors():
+    """analyze_pair (hbonds.rs:214-238: acceptors of chain 1 with donors of chain 2 and the other way round), an acceptor that
+    is also a donor (never its own partner), the inclusive distance and angle limits, and the constructor's checks."""
+    import groan_rs_b200 as g
+    from groan_rs_b200.hbonds import HBondAnalysis, HBondChain, HBondError
+    L, n_mol = 3.1, 900
+    xyz = _water_box(n_mol, L, 7)
+    n = xyz.shape[0]
+    s = g.System(n)
+    s.set_frames(xyz, [L] * 3)
+    o = np.arange(0, n, 3)
+    a_o, b_o = o[: n_mol // 2], o[n_mol // 2:]
+    for name, oo in (("A_O", a_o), ("B_O", b_o)):
+        s.group_create_from_indices(name, oo)
+    s.group_create_from_indices("H", np.sort(np.concatenate([o + 1, o + 2])))
+    s.add_bonds(np.concatenate([np.stack([o, o + 1], 1), np.stack([o, o + 2], 1)]))
+    an = HBondAnalysis(s, [HBondChain("A_O", "A_O", "H"), HBondChain("B_O", "B_O", "H")], [(0, 1), (1, 1)], 0.33, 140.0)
+    m = an.analyze()[0]
+    da = [(int(i), [int(i) + 1, int(i) + 2]) for i in a_o]
+    db = [(int(i), [int(i) + 1, int(i) + 2]) for i in b_o]
+    exp01 = orc.hbonds_single(xyz, a_o, db, [L] * 3, 0.33, 140.0) + orc.hbonds_single(xyz, b_o, da, [L] * 3, 0.33, 140.0)
+    exp11 = orc.hbonds_single(xyz, b_o, db, [L] * 3, 0.33, 140.0)
+    for key, exp in (((0, 1), exp01), ((1, 1), exp11)):
+        rec = m[key]
+        assert len(exp) > 20
+        assert [(int(a), int(b), int(c)) for a, b, c in zip(rec["donor"], rec["hydrogen"], rec["acceptor"])] == [r[:3] for r in exp], key
+        assert np.abs(rec["angle"] - np.array([r[4] for r in exp], np.float32)).max() <= 2e-2
+    assert all(int(d) != int(a) for d, a in zip(m[(1, 1)]["donor"], m[(1, 1)]["acceptor"]))
+    with pytest.raises(HBondError):
+        HBondAnalysis(s, [HBondChain("A_O", "A_O", "H")], [(0, 1)], 0.3, 150.0)          # pair names a chain that does not exist
+    with pytest.raises(HBondError):
+        HBondAnalysis(s, [HBondChain("A_O", "A_O", "H")], [(0, 0), (0, 0)], 0.3, 150.0)  # the same pair twice
+    with pytest.raises(g.GroanError) as ei:  # triclinic box: CellGrid::new rejects it (cellgrid.rs:308-312)
+        s.set_frames(xyz, np.array([L, 0, 0, 0.5, L, 0, 0, 0, L], np.float32).reshape(1, 9))
+        an.analyze()
+    assert "NotOrthogonal" in ei.value.variant

@@ -330,3 +330,30 @@ def test_error_codes(example):
         orc.get_center(xyz, [0], np.zeros((3, 3), np.float32))
     assert e.value.code == orc.EZEROBOX
     assert np.isnan(orc.estimate_center(xyz, [], example["box"])).all()  # iterators.rs:1183-1185
+
+
+# ---- hbonds.rs:505-587: the restated analyze_single against the reference's golden counts and bonds
+@pytest.mark.parametrize("frame", [0, 11, 20])
+def test_hbonds_water_goldens(frame):
+    import os
+    from oracle import xdrfile_ref
+    import hbond_goldens as hg
+    here = os.path.dirname(os.path.abspath(__file__))
+    traj = xdrfile_ref.read_xtc(os.path.join(here, "golden", "xtc", "aa_membrane_peptide.xtc"))
+    water = np.load(os.path.join(here, "golden", "aa_membrane_water.npz"))
+    ow = water["OW"].astype(np.int64)
+    donors = [(int(o), [int(o) + 1, int(o) + 2]) for o in ow]
+    L = traj["box"][frame].reshape(3, 3).diagonal().copy()
+    hg.check_frame(frame, orc.hbonds_single(traj["xyz"][frame], ow, donors, L, hg.MAX_DISTANCE, hg.MIN_ANGLE))
+
+
+def test_guess_bonds_restatement_small():
+    """identify_bonds (guess.rs:427-470) on a hand-made case: the limit is (vdw1 + vdw2) * factor, strict; atoms without a
+    radius get no bonds; periodic images count"""
+    L = [3.0, 3.0, 3.0]
+    x = np.array([[0.1, 0.1, 0.1], [0.196, 0.1, 0.1], [0.07, 0.19, 0.1], [0.38, 0.1, 0.1], [2.95, 0.1, 0.1], [2.99, 0.1, 0.1]], np.float32)
+    vdw = [0.152, 0.12, 0.12, 0.152, -1.0, 0.12]
+    got = orc.guess_bonds(x, vdw, L, 0.55)
+    # O(0)-H(1) 0.096 < 0.1496; O(0)-H(2) 0.0949; H(1)-H(2): 0.155 > 0.132; O(0)-O(3) 0.28 > 0.167; atom 4 has no radius;
+    # atom 5 sits 0.11 nm from atom 0 and 0.12 nm from atom 2 THROUGH the box face: 0.11 < 0.1496, 0.12 < 0.132 -> bonds
+    assert got.tolist() == [[0, 1], [0, 2], [0, 5], [2, 5]]
