@@ -523,7 +523,7 @@ def run_gpu_arm(args):
         del h_q, h_x, xf
 
     extras = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:  # secondary single-GPU numbers: not while other ranks would wait
         extras = run_extras(torch, g, local, peak)
 
     cpu = None
@@ -625,6 +625,27 @@ def run_extras(torch, g, local, peak):
                              "frac_of_hbm_peak": (12 * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak}
     b.close()
     r.close()
+    # configs[4] names a TRICLINIC box: the extension of the centre / RMSD path (parity unpinned: the reference
+    # returns NotOrthogonal), on the box variant of SURVEY 8d cfg5 (v2x = 8.5, v3x = 8.5, v3y = -8.5); gather kernels
+    bt = g.System(N_ATOMS, masses=m, device=local, max_frames=F, triclinic=True)
+    rt = g.System(N_ATOMS, masses=m, device=local, max_frames=1, triclinic=True)
+    bt.set_stream(torch.cuda.current_stream().cuda_stream)
+    for sysm in (bt, rt):
+        sysm.group_create_from_indices("G", np.arange(N_ATOMS, dtype=np.uint32))
+    rt.set_frames(bt.synth_blob_ref(SEED, BLOB_SCALE, [BOX / 2] * 3), tri)
+    rot, cen = frame_params(0, F)
+    bt.synth_blob(SEED, 0, F, BLOB_SCALE, NOISE_SCALE, rot, cen, tri, wrap=False)
+    bt.atoms_wrap()  # into the triclinic cell
+    t = time_op(lambda: bt.group_get_center("G", out=d_c), reps=3)
+    out["triclinic_group_get_center"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "fallback_frames": bt.fallback_frames(),
+                                         "frac_of_hbm_peak": 12 * N_ATOMS * F * 1e-9 / (t * 1e-3) / peak, "note": "parity unpinned (extension)"}
+    t = time_op(lambda: bt.calc_rmsd(rt, "G", out=d_r), reps=3)
+    rr = d_r.cpu().numpy()
+    assert np.all(np.abs(rr - 0.0866) < 2e-3), rr
+    out["triclinic_calc_rmsd"] = {"ms": t, "frames_per_s": F / (t * 1e-3), "fallback_frames": bt.fallback_frames(),
+                                  "frac_of_hbm_peak": (12 * F + 16) * N_ATOMS * 1e-9 / (t * 1e-3) / peak, "note": "parity unpinned (extension)"}
+    bt.close()
+    rt.close()
     # calc_rmsd_and_fit at the headline's batch size (configs[4] names "RMSD/Kabsch fit"): 37 frames, all 4M atoms rewritten
     F37 = 37
     b = g.System(N_ATOMS, masses=m, device=local, max_frames=F37)
