@@ -397,6 +397,22 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         h_in[1].copy_(h_in[0])
         host_memcpy_gbs = 2 * F * N_ATOMS * 12 * 1e-9 / (time.perf_counter() - t0)  # read + write, one thread
+        # the platform's ceiling for any host-fed path: plain pinned -> device copies of the same buffer, all ranks at once,
+        # nothing else running (at N = 8 the ranks share the host's memory system and PCIe root complexes)
+        d_raw = torch.empty((F * N_ATOMS * 3,), dtype=torch.float32, device=dev)
+        d_raw.copy_(h_in[0].view(-1), non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            d_raw.copy_(h_in[0].view(-1), non_blocking=True)
+        torch.cuda.synchronize()
+        dt_raw = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_raw], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_raw = float(t.item())
+        h2d_raw_gbs = 4 * F * N_ATOMS * 12 * 1e-9 / dt_raw
+        del d_raw
         h_cen = torch.empty((F, 3), dtype=torch.float32).pin_memory()
         h_rmsd = torch.empty((F,), dtype=torch.float32).pin_memory()
         boxes = np.tile(np.array([BOX, BOX, BOX], np.float32), (F, 1))
@@ -518,7 +534,10 @@ def run_gpu_arm(args):
         e2e = {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": F * 16,
                "ms_per_step": head["ms_per_step"], "steps": Ke, "feed": "xtc (file bytes, GPU decode)",
                "f32_equivalent_h2d_bytes_per_step": F * N_ATOMS * 12 + F * 36, "timing": "host wall clock around the steps, sync both sides",
-               "feeds": feeds, "host_memcpy_gbs_one_thread": host_memcpy_gbs, "numa": numa}
+               "feeds": feeds, "host_memcpy_gbs_one_thread": host_memcpy_gbs, "numa": numa,
+               "h2d_raw_gbs_per_gpu": h2d_raw_gbs, "h2d_raw_gbs_all_gpus": h2d_raw_gbs * world,
+               "h2d_raw_note": "plain cudaMemcpyAsync of the f32 batch from pinned memory on every rank at once, slowest rank: the ceiling "
+                               "of any host-fed feed on this box at this N"}
         s.set_frames(h_in[0], boxes)  # back to the f32 batch for whatever follows
         del h_q, h_x, xf
 

@@ -11,6 +11,9 @@
 //   System::calc_rmsd (rmsd.rs:75)                       System::calc_rmsd(reference, name) -> std::vector<float>
 //   GroupError::NotFound / EmptyGroup / InvalidSimBox    exceptions GroupError{variant = "NotFound" / ...}
 //   traj_iter_map_reduce body (parallel.rs:208-269)      FrameBatcher: buffers frames, flushes a batch to the GPU every B frames
+//   XtcReader / GroupXtcReader (xtc_io/mod.rs, molly_xtc.rs)  XtcFile + System::set_frames_xtc / set_group_frames / write_xtc
+//   System::guess_bonds (guess.rs:362)                   System::guess_bonds(vdw, factor) -> bonds per frame
+//   HBondAnalysis (hbonds.rs:160-335)                    HBondAnalysis{chains, pairs, max_distance, min_angle}.analyze(system)
 #pragma once
 #include <algorithm>
 #include <array>
@@ -19,11 +22,13 @@
 #include <functional>
 #include <map>
 #include <stdexcept>
+#include <tuple>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "groan_gpu.h"
+#include "groan_xtc.h"
 
 namespace groan {
 
@@ -223,6 +228,9 @@ class System {
         for (size_t i = 0; i < n_atoms_; i++)
             if (bonded[i]) mol_ref_[i] = find((uint32_t)i); // System::create_mol_references, modifying.rs:258-283
         check(groan_gpu_set_molecules(ctx_, mol_ref_.data()), "add_bonds");
+        for (const auto &bd : bonds) bonds_.emplace_back(std::min(bd.first, bd.second), std::max(bd.first, bd.second));
+        std::sort(bonds_.begin(), bonds_.end());
+        bonds_.erase(std::unique(bonds_.begin(), bonds_.end()), bonds_.end());
     }
     void make_molecules_whole() {
         if (mol_ref_.empty()) {
@@ -265,6 +273,114 @@ class System {
         check(groan_gpu_center_rmsd(ctx_, group(name, true).gid, weighted ? 1 : 0, &c[0][0], r.data(), nullptr), "group_center_and_rmsd",
               name, true);
         return {std::move(c), std::move(r)};
+    }
+
+    // ---- xtc frames (include/groan_xtc.h; XtcReader xtc_io/mod.rs:97-330, GroupXtcReader molly_xtc.rs:404-470)
+    // frames [first, first + count) of an xtc file held in memory: the file's bytes are uploaded and decoded on the GPU
+    void set_frames_xtc(const uint8_t *data, size_t len, const std::vector<uint64_t> &offsets, size_t first, size_t count) {
+        if (first + count + 1 > offsets.size() || count == 0 || count > max_frames_) throw GpuError("Gpu", "frame range", GROAN_EINVAL);
+        check(groan_gpu_push_xtc(ctx_, data, len, offsets.data() + first, count, nullptr, nullptr, nullptr), "set_frames_xtc");
+        n_frames_ = count;
+        touched();
+    }
+    // partial frames: xyz_sel holds only the atoms `atoms` (ascending) of every frame; the others keep their previous values
+    void set_group_frames(const float *xyz_sel, const std::vector<uint32_t> &atoms, const SimBox *boxes, size_t n_frames) {
+        std::vector<float> b(n_frames * 9);
+        for (size_t f = 0; f < n_frames; f++) std::copy(boxes[f].m, boxes[f].m + 9, b.begin() + f * 9);
+        check(groan_gpu_push_group_frames(ctx_, xyz_sel, atoms.data(), atoms.size(), b.data(), n_frames), "set_group_frames");
+        n_frames_ = n_frames;
+        touched();
+    }
+    // the current batch as xtc frames, byte for byte what XtcWriter::write_frame would append (xtc_io/mod.rs:300-330)
+    std::vector<uint8_t> write_xtc(float precision, const std::vector<int32_t> &step, const std::vector<float> &time, int n_threads = 4) {
+        std::vector<uint8_t> out(n_frames_ * (n_atoms_ * 12 + 128) + 64);
+        size_t len = 0;
+        check(groan_gpu_write_xtc(ctx_, precision, step.empty() ? nullptr : step.data(), time.empty() ? nullptr : time.data(), n_threads,
+                                  out.data(), out.size(), &len), "write_xtc");
+        out.resize(len);
+        return out;
+    }
+
+    // ---- System::guess_bonds (guess.rs:362-395): bonds i < j with distance < (vdw[i] + vdw[j]) * radius_factor, per frame, sorted.
+    // vdw[i] < 0: the atom has no van der Waals radius.  The bonds of frame 0 become the topology (assign_bonds, guess.rs:409-425).
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> guess_bonds(const std::vector<float> &vdw, float radius_factor = 0.55f,
+                                                                        bool assign = true) {
+        if (vdw.size() != n_atoms_) throw GpuError("Gpu", "one radius per atom", GROAN_EINVAL);
+        std::vector<uint64_t> count(n_frames_, 0);
+        size_t cap = 8 * n_atoms_ + 64;
+        std::vector<uint32_t> pairs;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            pairs.assign(n_frames_ * cap * 2, 0);
+            check(groan_gpu_guess_bonds(ctx_, vdw.data(), radius_factor, count.data(), pairs.data(), cap), "guess_bonds");
+            const uint64_t most = *std::max_element(count.begin(), count.end());
+            if (most <= cap) break;
+            cap = (size_t)most;
+        }
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> out(n_frames_);
+        for (size_t f = 0; f < n_frames_; f++) {
+            for (uint64_t k = 0; k < count[f]; k++) out[f].emplace_back(pairs[(f * cap + k) * 2], pairs[(f * cap + k) * 2 + 1]);
+            std::sort(out[f].begin(), out[f].end());
+        }
+        if (assign && n_frames_) add_bonds(out[0]);
+        return out;
+    }
+
+    // ---- HBondAnalysis::analyze_single (hbonds.rs:240-320) for one acceptor group and one list of donors with their hydrogens
+    struct HBond {
+        uint32_t donor, hydrogen, acceptor;
+        float distance, angle;
+    };
+    struct Donor {
+        uint32_t donor;
+        std::vector<uint32_t> hydrogens;
+    };
+    std::vector<std::vector<HBond>> hbonds_single(const std::string &acceptors, const std::vector<Donor> &donors, float max_distance,
+                                                  float min_angle) {
+        std::vector<uint32_t> don, off(1, 0), hyd;
+        for (const Donor &d : donors) {
+            don.push_back(d.donor);
+            hyd.insert(hyd.end(), d.hydrogens.begin(), d.hydrogens.end());
+            off.push_back((uint32_t)hyd.size());
+        }
+        if (hyd.empty()) hyd.push_back(0);
+        std::vector<uint64_t> count(n_frames_, 0);
+        size_t cap = 4 * hyd.size() + 64;
+        std::vector<uint32_t> dha;
+        std::vector<float> da;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            dha.assign(n_frames_ * cap * 3, 0);
+            da.assign(n_frames_ * cap * 2, 0.0f);
+            check(groan_gpu_hbonds(ctx_, group(acceptors).gid, don.data(), off.data(), hyd.data(), don.size(), max_distance, min_angle,
+                                   count.data(), dha.data(), da.data(), cap), "hbonds", acceptors);
+            const uint64_t most = *std::max_element(count.begin(), count.end());
+            if (most <= cap) break;
+            cap = (size_t)most;
+        }
+        std::vector<std::vector<HBond>> out(n_frames_);
+        for (size_t f = 0; f < n_frames_; f++) {
+            for (uint64_t k = 0; k < count[f]; k++) {
+                const size_t at = f * cap + k;
+                out[f].push_back({dha[at * 3], dha[at * 3 + 1], dha[at * 3 + 2], da[at * 2], da[at * 2 + 1]});
+            }
+            std::sort(out[f].begin(), out[f].end(), [](const HBond &a, const HBond &b) {
+                return std::tie(a.donor, a.acceptor, a.hydrogen) < std::tie(b.donor, b.acceptor, b.hydrogen);
+            });
+        }
+        return out;
+    }
+    const std::vector<std::pair<uint32_t, uint32_t>> &bonds() const { return bonds_; }
+    std::vector<uint32_t> group_indices(const std::string &name) const { return group(name).indices; }
+
+    // diagnostics of the last centre / RMSD call (groan_gpu.h)
+    size_t fallback_frames() {
+        size_t n = 0;
+        check(groan_gpu_fallback_frames(ctx_, &n), "fallback_frames");
+        return n;
+    }
+    size_t second_pass_frames() {
+        size_t n = 0;
+        check(groan_gpu_second_pass_frames(ctx_, &n), "second_pass_frames");
+        return n;
     }
 
     groan_gpu_ctx *raw() { return ctx_; }
@@ -382,6 +498,7 @@ class System {
 
     groan_gpu_ctx *ctx_ = nullptr;
     size_t n_atoms_, max_frames_, n_frames_ = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> bonds_;  // topology given through add_bonds / guess_bonds (i < j, sorted)
     int next_gid_ = 0;
     std::map<std::string, Group> groups_;
     std::vector<float> masses_;
@@ -398,6 +515,98 @@ class System {
     unsigned long version_ = 0;
     std::map<std::string, std::pair<const System *, unsigned long>> ref_keys_;
 };
+
+// src/system/hbonds.rs: chains of (acceptors, donors, hydrogens) given as groups of the System (the reference takes selection
+// queries; the selection language stays outside this library), pairs of chains to analyse, the two criteria.
+struct HBondChain {
+    std::string acceptors, donors, hydrogens;
+};
+class HBondAnalysis {
+  public:
+    using HBondMap = std::map<std::pair<size_t, size_t>, std::vector<System::HBond>>;
+    // HBondAnalysis construction = HBondChainGroups::new per chain (hbonds.rs:108-150: hydrogens of a donor = its bonded atoms
+    // that are in the hydrogen group; donors without one are dropped) + sanity_check_pairs (:337-370)
+    HBondAnalysis(System &system, const std::vector<HBondChain> &chains, std::vector<std::pair<size_t, size_t>> pairs, float max_distance,
+                  float min_angle)
+        : sys_(system), pairs_(std::move(pairs)), max_distance_(max_distance), min_angle_(min_angle) {
+        std::map<uint32_t, std::vector<uint32_t>> bonded;
+        for (const auto &b : system.bonds()) {
+            bonded[b.first].push_back(b.second);
+            bonded[b.second].push_back(b.first);
+        }
+        for (const HBondChain &c : chains) {
+            const std::vector<uint32_t> hyd = system.group_indices(c.hydrogens);
+            Chain ch;
+            ch.acceptors = c.acceptors;
+            for (uint32_t d : system.group_indices(c.donors)) {
+                System::Donor don{d, {}};
+                std::vector<uint32_t> nb = bonded[d];
+                std::sort(nb.begin(), nb.end());
+                for (uint32_t h : nb)
+                    if (std::binary_search(hyd.begin(), hyd.end(), h)) don.hydrogens.push_back(h);
+                if (!don.hydrogens.empty()) ch.donors.push_back(std::move(don));
+            }
+            if (system.group_get_n_atoms(c.acceptors) == 0 && ch.donors.empty()) throw GroanError("EmptyChain", "hydrogen-bond chain is empty", GROAN_EINVAL);
+            chains_.push_back(std::move(ch));
+        }
+        std::vector<std::pair<size_t, size_t>> seen;
+        for (const auto &p : pairs_) {
+            if (p.first >= chains_.size() || p.second >= chains_.size()) throw GroanError("InvalidPair", "pair names a chain that does not exist", GROAN_EINVAL);
+            const std::pair<size_t, size_t> key(std::min(p.first, p.second), std::max(p.first, p.second));
+            if (std::find(seen.begin(), seen.end(), key) != seen.end()) throw GroanError("DuplicatePair", "pair requested twice", GROAN_EINVAL);
+            seen.push_back(key);
+        }
+    }
+    // FrameAnalyze::analyze (hbonds.rs:160-210) for every frame of the System's current batch
+    std::vector<HBondMap> analyze() {
+        std::vector<HBondMap> maps(sys_.n_frames());
+        for (const auto &p : pairs_) {
+            std::vector<std::vector<std::vector<System::HBond>>> parts;
+            if (p.first == p.second) {
+                parts.push_back(sys_.hbonds_single(chains_[p.first].acceptors, chains_[p.first].donors, max_distance_, min_angle_));
+            } else {  // analyze_pair (hbonds.rs:214-238)
+                parts.push_back(sys_.hbonds_single(chains_[p.first].acceptors, chains_[p.second].donors, max_distance_, min_angle_));
+                parts.push_back(sys_.hbonds_single(chains_[p.second].acceptors, chains_[p.first].donors, max_distance_, min_angle_));
+            }
+            for (size_t f = 0; f < sys_.n_frames(); f++)
+                for (auto &part : parts) {
+                    auto &dst = maps[f][p];
+                    dst.insert(dst.end(), part[f].begin(), part[f].end());
+                }
+        }
+        return maps;
+    }
+
+  private:
+    struct Chain {
+        std::string acceptors;
+        std::vector<System::Donor> donors;
+    };
+    System &sys_;
+    std::vector<Chain> chains_;
+    std::vector<std::pair<size_t, size_t>> pairs_;
+    float max_distance_, min_angle_;
+};
+
+// An xtc trajectory held in memory (std::ifstream / mmap of the file): frame offsets from groan_xtc_scan
+struct XtcFile {
+    std::vector<uint8_t> data;
+    std::vector<uint64_t> offsets;  // n_frames + 1
+    int32_t n_atoms = 0;
+    explicit XtcFile(std::vector<uint8_t> bytes) : data(std::move(bytes)) {
+        size_t cap = 1024, n = 0;
+        for (;;) {
+            offsets.assign(cap + 1, 0);
+            const int st = groan_xtc_scan(data.data(), data.size(), cap, offsets.data(), &n_atoms, &n);
+            if (st != GROAN_XTC_OK && st != GROAN_XTC_EOF) throw GpuError("Xtc", "not an xtc file", st);
+            if (n < cap) break;
+            cap *= 8;
+        }
+        offsets.resize(n + 1);
+    }
+    size_t n_frames() const { return offsets.size() - 1; }
+};
+
 
 // The seam the reference offers to per-frame code is `body: Fn(&System, &mut Data)` of traj_iter_map_reduce
 // (parallel.rs:208-269) / FrameAnalyze::analyze (traj_convert.rs:76-83): one frame at a time.  A GPU operator wants batches:

@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <string>
 #include <vector>
 
 #include "groan_gpu.hpp"
@@ -22,7 +24,8 @@ static bool approx3(const Vector3D &v, float x, float y, float z, float eps = 1e
     return approx(v[0], x, eps) && approx(v[1], y, eps) && approx(v[2], z, eps);
 }
 
-int main() {
+int main(int argc, char **argv) {
+    const std::string golden = argc > 1 ? argv[1] : "tests/golden";
     // ---- analysis.rs:488-560 (center_single_atom / center_two_atoms / center_several_atoms), box 10^3
     {
         System s(5);
@@ -167,6 +170,60 @@ int main() {
         bool ok = true;
         for (size_t k = 0; k < expect; k++) ok = ok && D[pl.pairs[k][0] * 2950 + pl.pairs[k][1]] == pl.dist[k] && pl.dist[k] < cutoff;
         CHECK(ok);
+    }
+    // ---- hbonds.rs:505-587 (test_hbonds_analyze_simple_water): water-water hydrogen bonds of aa_membrane_peptide.xtc, 0.3 nm / 150
+    // degrees; the trajectory is read by the library's own xtc reader (file bytes uploaded, decoded on the GPU).  Water starts at
+    // atom 17515 (OW, HW1, HW2 per molecule; aa_membrane_peptide.gro), 5 091 molecules.
+    {
+        std::ifstream in(golden + "/xtc/aa_membrane_peptide.xtc", std::ios::binary);
+        std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        CHECK(!bytes.empty());
+        if (!bytes.empty()) {
+            XtcFile xf(std::move(bytes));
+            CHECK(xf.n_atoms == 32817 && xf.n_frames() == 21);
+            System s((size_t)xf.n_atoms, xf.n_frames());
+            s.set_frames_xtc(xf.data.data(), xf.data.size(), xf.offsets, 0, xf.n_frames());
+            std::vector<uint32_t> ow, hw;
+            std::vector<std::pair<uint32_t, uint32_t>> bonds;
+            for (uint32_t k = 0; k < 5091; k++) {
+                const uint32_t o = 17515 + 3 * k;
+                ow.push_back(o);
+                hw.push_back(o + 1);
+                hw.push_back(o + 2);
+                bonds.emplace_back(o, o + 1);
+                bonds.emplace_back(o, o + 2);
+            }
+            s.group_create_from_indices("OW", ow);
+            s.group_create_from_indices("HW", hw);
+            s.add_bonds(bonds);
+            HBondAnalysis an(s, {{"OW", "OW", "HW"}}, {{0, 0}}, 0.3f, 150.0f);
+            const auto maps = an.analyze();
+            const size_t expected_n[21] = {4675, 4644, 4629, 4617, 4651, 4532, 4649, 4611, 4621, 4701, 4694, 4650, 4565, 4681,
+                                           4699, 4711, 4652, 4649, 4697, 4652, 4644};
+            for (size_t f = 0; f < 21; f++) CHECK(maps[f].at({0, 0}).size() == expected_n[f]);
+            // the first bond of the reference's list for frame 0: HBond::new(17527, 17528, 21100, 0.262, 157.241)
+            bool found = false;
+            for (const auto &h : maps[0].at({0, 0}))
+                if (h.donor == 17527 && h.hydrogen == 17528 && h.acceptor == 21100) found = approx(h.distance, 0.262f, 1e-3f) && approx(h.angle, 157.241f, 1e-3f);
+            CHECK(found);
+            // guess_bonds on the same frames: with the radii of elements.yaml (O 0.152, H 0.12 ... here only the water) every
+            // water must come out as O-H, O-H and nothing else inside the water
+            std::vector<float> vdw((size_t)xf.n_atoms, -1.0f);
+            for (uint32_t o : ow) { vdw[o] = 0.152f; vdw[o + 1] = 0.12f; vdw[o + 2] = 0.12f; }
+            const auto gb = s.guess_bonds(vdw, 0.55f, false);
+            CHECK(gb.size() == 21 && gb[0].size() == 2 * 5091);
+            bool all_oh = true;
+            for (const auto &b : gb[0]) all_oh = all_oh && (b.first - 17515) % 3 == 0 && b.second > b.first && b.second <= b.first + 2;
+            CHECK(all_oh);
+            // write the batch back at the file's precision: decoding what we wrote gives the same lattice, so the bytes of the
+            // coordinates section are the file's (headers carry step / time, passed through here as zeros)
+            const std::vector<uint8_t> again = s.write_xtc(100.0f, {}, {});
+            XtcFile back(again);
+            CHECK(back.n_frames() == 21 && back.n_atoms == 32817);
+            System s2((size_t)back.n_atoms, back.n_frames());
+            s2.set_frames_xtc(back.data.data(), back.data.size(), back.offsets, 0, back.n_frames());
+            CHECK(s.get_frames() == s2.get_frames());
+        }
     }
     // ---- FrameBatcher: frames arrive one by one (traj_iter_map_reduce body), results come back per batch, in order
     {

@@ -26,6 +26,6 @@ def test_cpp_mirror_compiles_and_links():
 @pytest.mark.gpu
 def test_cpp_mirror_reference_style_tests():
     exe = _compile()
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "all checks passed" in out.stdout
