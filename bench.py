@@ -128,8 +128,8 @@ def measured_peak():
 
 def ncu_traffic(frames_per_step):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the last `ncu --set full`
-    capture of this workload (profiles/r1_dominant_kernel.json); None if the capture was made with another batch size"""
-    p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
+    capture of this workload (profiles/r2_dominant_kernel.json); None if the capture was made with another batch size"""
+    p = os.path.join(ROOT, "profiles", "r2_dominant_kernel.json")
     try:
         d = json.load(open(p))
         if d.get("frames_per_step") == frames_per_step:

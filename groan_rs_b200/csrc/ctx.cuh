@@ -123,6 +123,9 @@ struct groan_gpu_ctx {
     int *d_second_list = nullptr;           // ... and which
     unsigned int *d_slow_count = nullptr;   // the same for the frames a single pass of a contiguous group flags (exact quad passes)
     int *d_slow_list = nullptr;
+    // feedback of the device-side fallback protocol, one word per group slot (pinned, mapped): see FallbackPlan::feedback
+    unsigned long long *h_feedback = nullptr, *d_feedback = nullptr;
+    unsigned fast_skips[GROAN_MAX_GROUPS + 1] = {};  // consecutive calls that went straight to the exact passes
     int *d_head_list = nullptr;             // frames of the batch sorted by the 16-byte phase of a group (launch_rmsd_quad), cached per key
     size_t head_list_key_frames = 0;
     uint32_t head_list_key_first = 0xffffffffu;

@@ -174,6 +174,8 @@ int nb_exact_quad(const groan_gpu_ctx *ctx, const Group &g, bool cov) {
 FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center, bool center_weighted, float *center_out, bool want_rmsd,
                            float *rmsd_out, float *rot_out, bool quad_exact = false, const QuadRef *qr = nullptr) {
     FallbackPlan fp;
+    const int slot = &g == &ctx->all ? GROAN_MAX_GROUPS : (int)(&g - ctx->groups);
+    fp.feedback = (quad_exact && slot >= 0 && slot <= GROAN_MAX_GROUPS) ? ctx->d_feedback + slot : nullptr;
     fp.enabled = (ctx->flags & GROAN_FLAG_HOST_FALLBACK) ? 0 : 1;
     fp.n_frames = (int)ctx->n_frames;
     fp.nb_exact = blocks_per_frame_fast(g.n, ctx->n_frames, 4);
@@ -374,6 +376,28 @@ int run_unwrap(groan_gpu_ctx *ctx, const Group &g, bool weighted, const float *c
     return GROAN_OK;
 }
 
+// A group whose every frame was flagged by the last single pass (a membrane: it spans the box on every frame) goes straight
+// to the exact passes: no wasted pass, no device-side launch (~45 us per call).  The answer of the previous call arrives
+// through a host-mapped word the last finishing thread writes; nothing is waited for, a stale answer only costs time.  Every
+// 32nd call tries the single pass again.
+bool skip_single_pass(groan_gpu_ctx *ctx, const Group &g) {
+    if (ctx->flags & GROAN_FLAG_HOST_FALLBACK) return false;
+    const int slot = &g == &ctx->all ? GROAN_MAX_GROUPS : (int)(&g - ctx->groups);
+    if (slot < 0 || slot > GROAN_MAX_GROUPS) return false;
+    const unsigned long long w = *(volatile unsigned long long *)(ctx->h_feedback + slot);
+    const unsigned flagged = (unsigned)(w >> 32), frames = (unsigned)(w & 0xffffffffu);
+    if (frames == 0 || flagged != frames) {
+        ctx->fast_skips[slot] = 0;
+        return false;
+    }
+    if (++ctx->fast_skips[slot] % 32 == 0) return false;
+    return true;
+}
+int mark_all_flagged(groan_gpu_ctx *ctx) {  // groan_gpu_fallback_frames counts non-zero flags
+    CK(cudaMemsetAsync(ctx->d_flags, 1, ctx->n_frames * sizeof(int), ctx->compute));
+    return GROAN_OK;
+}
+
 // The exact passes of a contiguous group on the ring (kernels_quad.cuh).  sel == nullptr: every frame of the batch; otherwise
 // the frames whose flag is set.
 int run_exact_center_quad(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out, const int *sel) {
@@ -413,6 +437,10 @@ int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out
     const int *flags = nullptr;
     if (ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
         if (ctx->flags & GROAN_FLAG_EXACT_ONLY) return run_exact_center_quad(ctx, g, weighted, out, nullptr);
+        if (skip_single_pass(ctx, g)) {
+            int rc = mark_all_flagged(ctx);
+            return rc ? rc : run_exact_center_quad(ctx, g, weighted, out, nullptr);
+        }
         typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
         dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad, C::kAtoms), (unsigned)ctx->n_frames);
         const size_t smem = C::kBytes;
@@ -550,7 +578,11 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         rc = ensure_quad_ref(ctx, R, *g, &qr);
         if (rc) return rc;
     }
-    if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && qx) {
+    const bool skip = qx && !(ctx->flags & GROAN_FLAG_EXACT_ONLY) && skip_single_pass(ctx, *g);
+    if (skip) {
+        rc = mark_all_flagged(ctx);  // flags stays nullptr: the exact passes below run for every frame
+        if (rc) return rc;
+    } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY) && qx) {
         // quad kernels: RMSD, optionally with the centre, from one read of the frame (kernels_quad.cuh)
         const bool fused = center != nullptr && R.same_mass;  // see launch_rmsd_quad
         const FallbackPlan fp = fallback_plan(ctx, *g, fused, center_weighted != 0, d_center, true, d_rmsd, d_rot, true, &qr);
@@ -691,6 +723,9 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaMemset(ctx->d_flags2, 0, max_frames * sizeof(int)));
         CK(cudaMalloc(&ctx->d_second_list, max_frames * sizeof(int)));
         CK(cudaMalloc(&ctx->d_slow_list, max_frames * sizeof(int)));
+        CK(cudaHostAlloc(&ctx->h_feedback, (GROAN_MAX_GROUPS + 1) * sizeof(unsigned long long), cudaHostAllocMapped));
+        std::memset(ctx->h_feedback, 0, (GROAN_MAX_GROUPS + 1) * sizeof(unsigned long long));
+        CK(cudaHostGetDevicePointer(&ctx->d_feedback, ctx->h_feedback, 0));
         CK(cudaMalloc(&ctx->d_slow_count, sizeof(unsigned int)));
         CK(cudaMemset(ctx->d_slow_count, 0, sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->d_second_any, sizeof(unsigned int)));
@@ -756,6 +791,7 @@ void groan_gpu_destroy(groan_gpu_ctx *ctx) {
                     ctx->d_xtc_status, ctx->d_sel_atoms};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (ctx->h_feedback) cudaFreeHost(ctx->h_feedback);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);

@@ -112,6 +112,8 @@ struct FallbackPlan {
     int nb_xc, nb_xv;           // CTAs per frame of the centre-type passes and of k_cov_quad (the same in every mode: bit-identical results)
     int cov_smem;               // dynamic shared memory of k_cov_quad
     QuadRef ref_pq;             // permuted reference (want_rmsd)
+    unsigned long long *feedback; // host-mapped word: (flagged frames << 32) | frames of the launch, written by the last finisher;
+                                  // the host reads it before the NEXT call on the group and skips the single pass if it was all flagged
 };
 
 // sel_mode 0: every frame of the batch; 1: frames with sel[f] != 0; 2: frames sel[0 .. gridDim.y)
@@ -138,6 +140,7 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
     const bool slow = my_flag || (done >> 16) != 0u;
     const unsigned int n_second = fp.second_count != nullptr ? atomicExch(fp.second_count, 0u) : 0u;
     const unsigned int n_slow = fp.quad_exact ? atomicExch(fp.slow_count, 0u) : 0u;
+    if (fp.quad_exact && fp.feedback) *fp.feedback = ((unsigned long long)n_slow << 32) | (unsigned long long)(unsigned)fp.n_report;
     if (!slow && n_second == 0u) return;
     __threadfence();
     if (slow && fp.quad_exact) {
@@ -176,6 +179,7 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
         f2.want_rmsd = 0;
         f2.want_center = 1;
         f2.second_count = nullptr;
+        f2.feedback = nullptr;  // what happens to a handful of frames says nothing about the group
         f2.n_report = (int)n_second;
         const dim3 gs(fp.nb_second, n_second);
         if (fp.center_weighted)

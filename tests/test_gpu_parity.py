@@ -1650,3 +1650,44 @@ def test_hbonds_two_chains_and_errors():
         s.set_frames(xyz, np.array([L, 0, 0, 0.5, L, 0, 0, 0, L], np.float32).reshape(1, 9))
         an.analyze()
     assert "NotOrthogonal" in ei.value.variant
+
+
+def test_box_spanning_group_skips_the_single_pass_after_the_first_call():
+    """A group that spans the box (a membrane slab) fails the single pass on every frame.  The first call finds that out (single
+    pass + exact passes launched from the device); from the second call on the host goes straight to the exact passes
+    (FallbackPlan::feedback).  Results are the same bits either way and equal GROAN_FLAG_EXACT_ONLY; a compact group on the same
+    System is not affected."""
+    import groan_rs_b200 as g
+    n, F = 150_000, 5
+    L = np.array([14.0, 13.0, 12.0], np.float32)
+    masses = np.random.default_rng(5).uniform(1.0, 60.0, n).astype(np.float32)
+    out = {}
+    for name, flags in (("default", 0), ("exact", g.FLAG_EXACT_ONLY)):
+        s = g.System(n, masses=masses, max_frames=F)
+        s.set_flags(flags)
+        s.synth_uniform(21, 0, F, [0.0, 0.0, 4.0], [L[0], L[1], 3.0], L)  # a slab: uniform in x and y, 3 nm thick in z
+        ref = g.System(n, masses=masses)
+        ref.set_frames(s.get_frames()[0], L)
+        for x in (s, ref):
+            x.group_create_from_indices("slab", np.arange(8, n - 4))
+        calls = []
+        for k in range(4):
+            c = s.group_get_center("slab")
+            nf = s.fallback_frames()
+            r = s.calc_rmsd(ref, "slab")
+            calls.append((c, r))
+            if name == "default":
+                assert nf == F, (k, nf)
+        launches_before = s.launch_count()
+        s.group_get_center("slab")
+        per_call = s.launch_count() - launches_before
+        if name == "default":
+            assert per_call == 2, per_call  # k_trig_quad + k_center_quad(ext_pilot): no single pass, nothing launched from the device
+        for c, r in calls[1:]:
+            assert np.array_equal(bits(c), bits(calls[0][0])) and np.array_equal(bits(r), bits(calls[0][1]))
+        out[name] = calls[0]
+        frames = s.get_frames()
+        idx = np.arange(8, n - 4)
+        for f in (0, F - 1):  # z is compact, x / y span the box: compare the well-defined axis with the exact64 oracle
+            assert abs(calls[0][0][f][2] - orc.get_center_x64(frames[f], idx, L)[2]) <= TOL_CENTER
+    assert np.array_equal(bits(out["default"][0]), bits(out["exact"][0])) and np.array_equal(bits(out["default"][1]), bits(out["exact"][1]))
