@@ -108,6 +108,25 @@ int quad_head_lists(groan_gpu_ctx *ctx, const Group &g, int counts[4], int offse
     return GROAN_OK;
 }
 
+// The second tier of the fused centre + RMSD kernels (kernels_quad.cuh, finish_center_moments): the sine-sum centre pass over the
+// frames the fused launch just counted, launched behind EVERY fused launch with room for kSecondCap frames (the CTAs of unused
+// slots exit at once: ~4 us).  Launching it from the device only when needed costs ~45 us each time, and predicting the frames
+// inside the fused kernel makes a whole one-wave grid wait for its slowest frame (profiles/r2_ring.md).
+constexpr int kSecondCap = 4;
+template <int CENTER>
+int launch_second_tier(groan_gpu_ctx *ctx, const Group &g, float *d_center, FallbackPlan fp) {
+    if (CENTER == 0 || !fp.enabled) return GROAN_OK;  // GROAN_FLAG_HOST_FALLBACK: rmsd_common gates the pass by the per-frame flags
+    typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
+    fp.want_rmsd = 0;
+    fp.want_center = 1;
+    fp.feedback = nullptr;
+    dim3 grid((unsigned)fp.nb_second, (unsigned)kSecondCap);
+    k_center_quad<CENTER == 2><<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), ctx->d_partials, ctx->d_tickets,
+                                                                                     d_center, ctx->d_flags, fp, ctx->d_second_list, 3, nullptr);
+    LAUNCHED();
+    return GROAN_OK;
+}
+
 template <bool SAME_MASS, int CENTER>
 int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, float *d_center, float *d_rmsd,
                        float *d_rot, FallbackPlan fp) {
@@ -118,7 +137,7 @@ int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, co
                                                                                        ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
                                                                                        ctx->d_flags, fp, nullptr);
         LAUNCHED();
-        return GROAN_OK;
+        return launch_second_tier<CENTER>(ctx, g, d_center, fp);
     }
     int counts[4], offsets[4];
     int rc = quad_head_lists(ctx, g, counts, offsets);
@@ -133,6 +152,8 @@ int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, co
                                                                                        ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
                                                                                        ctx->d_flags, fp, ctx->d_head_list + offsets[h]);
         LAUNCHED();
+        rc = launch_second_tier<CENTER>(ctx, g, d_center, fp);
+        if (rc) return rc;
     }
     return GROAN_OK;
 }
@@ -191,14 +212,16 @@ FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center,
     fp.rot_out = rot_out;
     fp.second_flags = ctx->d_flags2;
     fp.second_count = ctx->d_second_any;
+    fp.second_ticket = ctx->d_second_any + 1;
+    fp.second_cap = kSecondCap;
     fp.second_list = ctx->d_second_list;
     fp.n_report = (int)ctx->n_frames;
-    // the second tier normally runs for one or two frames of a batch (the CTAs of every other frame exit at once): enough CTAs
-    // per frame to fill the GPU with a single frame
+    // the second tier runs for one or two frames of a batch (the CTAs of its other slots exit at once): one CTA per SM and frame
     {
         const size_t chunk = QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kAtoms;
         size_t nb = std::max<size_t>(1, (g.n + chunk - 1) / chunk);
-        nb = std::min<size_t>(nb, (size_t)kSMs * (size_t)std::max(1, ctx->occ_center_quad));
+        static const int per_sm = getenv("GROAN_EXP_SECOND_PER_SM") ? atoi(getenv("GROAN_EXP_SECOND_PER_SM")) : 1;
+        nb = std::min<size_t>(nb, (size_t)kSMs * per_sm);
         nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(ctx->n_frames, 1)));
         fp.nb_second = (int)nb;
     }
@@ -728,8 +751,8 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         CK(cudaHostGetDevicePointer(&ctx->d_feedback, ctx->h_feedback, 0));
         CK(cudaMalloc(&ctx->d_slow_count, sizeof(unsigned int)));
         CK(cudaMemset(ctx->d_slow_count, 0, sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_second_any, sizeof(unsigned int)));
-        CK(cudaMemset(ctx->d_second_any, 0, sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_second_any, 2 * sizeof(unsigned int)));  // [frames counted by the fused launch, tickets of the pass]
+        CK(cudaMemset(ctx->d_second_any, 0, 2 * sizeof(unsigned int)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_center, k_center_fast<false>, kThreads, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_rmsd, k_rmsd_fast<true>, kThreads, 0));
         ctx->occ_center = std::max(1, std::min(ctx->occ_center, 8));

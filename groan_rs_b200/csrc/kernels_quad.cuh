@@ -434,7 +434,26 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
     static_assert(kQuadCenterThreads == 256, "maybe_launch_fallback launches this kernel with 256 threads");
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     FrameReduceSmem<7, 3, kQuadCenterThreads / 32> &sm = *reinterpret_cast<FrameReduceSmem<7, 3, kQuadCenterThreads / 32> *>(dyn_smem); // reuses the ring once it has drained
-    const int f = sel_mode == 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
+    // sel_mode 3: the second tier of the fused kernels, launched from the host behind EVERY fused launch with room for
+    // gridDim.y frames: the frames are sel[0 .. n), n = what the fused launch counted (capped; the rest was launched from the
+    // device).  Every CTA takes a ticket when it is done; the last one re-arms the counter for the next fused launch.
+    unsigned int n_sel = 0;
+    if (sel_mode == 3) {
+        n_sel = min(*reinterpret_cast<volatile unsigned int *>(fp.second_count), gridDim.y);
+        fp.n_report = (int)n_sel;
+    }
+    auto done = [&]() {
+        if (sel_mode != 3 || threadIdx.x != 0) return;
+        if (atomicAdd(fp.second_ticket, 1u) == gridDim.x * gridDim.y - 1u) {
+            *fp.second_ticket = 0u;
+            *fp.second_count = 0u;
+        }
+    };
+    if (sel_mode == 3 && blockIdx.y >= n_sel) {
+        done();
+        return;
+    }
+    const int f = sel_mode >= 2 ? sel[blockIdx.y] : (int)blockIdx.y, nb = gridDim.x;
     if (sel_mode == 1 && sel[f] == 0) return; // uniform for the CTA (nobody counts finished frames in this mode)
     float L[3];
     fv.lengths(f, L[0], L[1], L[2]);
@@ -496,74 +515,17 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
         } else {
             flags[f] = flag;
         }
-        maybe_launch_fallback(fp, fv, g, RefView(), partials, tickets, flags, flag, 0, f);
+        FallbackPlan mine = fp;  // this pass produces no second-tier frames of its own
+        if (sel_mode == 3) mine.second_count = nullptr;
+        maybe_launch_fallback(mine, fv, g, RefView(), partials, tickets, flags, flag, 0, f);
     }
+    done();
 }
 
 // ---------------------------------------------------------------- calc_rmsd (+ optionally the centre)
 // CENTER: 0 = RMSD only, 1 = also group_get_center, 2 = also group_get_com.
-// canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum d^2 or sum sin (unweighted)
+// canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum d^2 (unweighted)
 constexpr int kQuadSums = kFastSums + 6;
-
-// Which way will the centre's image be decided in this frame?  A strided sample of 256 atoms (one per thread, the same
-// atoms in every CTA of the frame, so all of them come to the same answer) estimates the mean, the variance and the extent
-// of the group per axis, and the certificate of finish_center_moments is evaluated on those with generous margins: the
-// mean moved towards the nearest box face by four standard errors, the variance and the extent enlarged.  If it would
-// not hold, the frame accumulates the sine sums instead of the second moments (the loop of the previous generation, ~13 %
-// slower) and is finished by finish_center_sin.  A wrong guess costs time, never the result: the moments are checked
-// again, exactly, by the finishing thread, which sends the frame through the sine-sum pass if they fall short.
-// `scratch`: 8 x 12 floats of shared memory nobody else uses yet.  Contains __syncthreads().
-__device__ __forceinline__ bool predict_sine_mode(const float *fr, const GroupView &g, const float p[3], const float L[3], float *scratch) {
-    constexpr int K = kQuadRmsdThreads;
-    const uint32_t t = threadIdx.x;
-    const uint32_t i = (uint32_t)(((uint64_t)t * g.n) / K);
-    const float *q = fr + ((size_t)g.first + i) * 3;
-    float v[12];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const float d = pilot_delta(__ldg(q + k), p[k], L[k], 1.0f / L[k]);
-        v[k] = d;
-        v[3 + k] = d * d;
-        v[6 + k] = d;
-        v[9 + k] = d;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++) v[k] = warp_sum(v[k]);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        v[6 + k] = warp_min(v[6 + k]);
-        v[9 + k] = warp_max(v[9 + k]);
-    }
-    if ((t & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < 12; k++) scratch[(t >> 5) * 12 + k] = v[k];
-    }
-    __syncthreads();
-    if (t == 0) {
-        float a[12];
-        for (int k = 0; k < 12; k++) a[k] = scratch[k];
-        for (int w = 1; w < K / 32; w++)
-            for (int k = 0; k < 12; k++) {
-                const float x = scratch[w * 12 + k];
-                a[k] = k < 6 ? a[k] + x : (k < 9 ? fminf(a[k], x) : fmaxf(a[k], x));
-            }
-        int sine = 0;
-        for (int k = 0; k < 3; k++) {
-            const float s = 6.2831853f / L[k], dbar = a[k] * (1.0f / K);
-            const float var = fmaxf(a[3 + k] * (1.0f / K) - dbar * dbar, 0.0f);
-            const float u = p[k] + dbar, dist = fabsf(u - L[k] * rintf(u / L[k]));  // sample mean to the nearest box face
-            const float th = fmaxf(s * (dist - 4.0f * sqrtf(var * (1.0f / K))), 0.0f);
-            const float qv = 1.3f * s * s * var, ext = 1.25f * s * (a[9 + k] - a[6 + k]);
-            const float bound = (th >= 1.5707963f ? 1.0f : __sinf(th)) * (1.0f - 0.5f * qv) - ext * qv * (1.0f / 6.0f);
-            if (!(bound >= 4.0f * (float)kSinGuard)) sine = 1;
-        }
-        scratch[96] = sine ? 1.0f : 0.0f;
-    }
-    __syncthreads();
-    const bool r = scratch[96] != 0.0f;
-    __syncthreads(); // the scratch is about to become the ring
-    return r;
-}
 
 template <bool SAME_MASS, int CENTER>
 __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, double *partials,
@@ -580,11 +542,10 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
     const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
-    const bool sine_mode = CENTER ? predict_sine_mode(fr, g, p, L, reinterpret_cast<float *>(dyn_smem)) : false;
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero();
-    // centre (CENTER != 0): sum d, and sum d^2 (moments) or sum sin (sine mode) per axis, all unweighted, as pattern sums
+    // centre (CENTER != 0): sum d and sum d^2 per axis, unweighted, as pattern sums -- the moments finish_center_moments decides with
     V3 sdv = v3_zero(), cqv = v3_zero();
 #pragma unroll
     for (int u = 0; u < 3; u++) h[u] = hw[u] = v3_zero();
@@ -615,27 +576,15 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         cqv.b = __ffma2_rn(d.b, d.b, cqv.b);
         cqv.c = __ffma2_rn(d.c, d.c, cqv.c);
     };
-    if (!sine_mode) {
-        stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
-                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
-            V3 d01, d23;
-            quad_deltas(qc, c0, c1, c2, d01, d23);
-            atom_pair(d01, r[0], r[1], bg.head + j);
-            if (CENTER) moments(d01);
-            atom_pair(d23, r[2], r[3], bg.head + j + 2);
-            if (CENTER) moments(d23);
-        });
-    } else {
-        stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
-                                            [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
-            V3 d01, d23;
-            quad_deltas(qc, c0, c1, c2, d01, d23);
-            atom_pair(d01, r[0], r[1], bg.head + j);
-            quad_sines(qc, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), cqv);
-            atom_pair(d23, r[2], r[3], bg.head + j + 2);
-            quad_sines(qc, make_float2(c1.z, c1.w), make_float2(c2.x, c2.y), make_float2(c2.z, c2.w), cqv);
-        });
-    }
+    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+                                        [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+        V3 d01, d23;
+        quad_deltas(qc, c0, c1, c2, d01, d23);
+        atom_pair(d01, r[0], r[1], bg.head + j);
+        if (CENTER) moments(d01);
+        atom_pair(d23, r[2], r[3], bg.head + j + 2);
+        if (CENTER) moments(d23);
+    });
     __syncthreads(); // every warp has left the ring: its memory becomes the reduction scratch
     float a[KS];
 #pragma unroll
@@ -669,7 +618,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
                 tmx[k] = fmaxf(tmx[k], dk);
                 if (CENTER) {
                     tot[KS - 6 + k] += d[k];
-                    tot[KS - 3 + k] += sine_mode ? edge_sin(xk, L[k]) : d[k] * d[k];
+                    tot[KS - 3 + k] += d[k] * d[k];
                 }
             }
             for (int u = 0; u < 3; u++)
@@ -696,8 +645,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             double md[3];
             for (int k = 0; k < 3; k++) md[k] = CENTER == 2 ? (SAME_MASS ? tot[18 + k] : tot[22 + k]) : tot[KS - 6 + k];
             const double M = CENTER == 2 ? (SAME_MASS ? ref.sum_w : tot[25]) : (double)g.n;
-            if (sine_mode) finish_center_sin(md, M, tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c);
-            else finish_center_moments(md, M, tot + (KS - 6), tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c, &second);
+            finish_center_moments(md, M, tot + (KS - 6), tot + (KS - 3), tmn, tmx, p, L, g.n, center_out + f * 3, &flag_c, &second);
             fp.second_flags[f] = second;
         }
         flags[f] = flag_r | (flag_c << 1);

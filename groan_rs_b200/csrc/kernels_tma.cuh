@@ -98,9 +98,11 @@ struct FallbackPlan {
     float *com, *rmsd_out, *rot_out; // want_rmsd
     // second tier of the fused centre + RMSD kernels (kernels_quad.cuh, finish_center_moments): frames whose image could
     // not be certified from the moments go through the sine-sum centre pass (k_center_quad, gated by second_flags) first
-    int *second_flags;          // per frame, written by the fused kernel (diagnostics, and the gate of the host-launched pass)
-    unsigned int *second_count; // device-launched pass: number of such frames of the running launch (re-armed by the thread that reads it)
-    int *second_list;           // ... and which (any order): the pass is launched over exactly these frames
+    int *second_flags;          // per frame, written by the fused kernel (diagnostics, and the gate under GROAN_FLAG_HOST_FALLBACK)
+    unsigned int *second_count; // number of such frames of the running fused launch (re-armed by the second-tier pass, sel_mode 3)
+    int *second_list;           // ... and which (any order): the pass runs over exactly these frames
+    unsigned int *second_ticket; // CTAs of the second-tier pass that are done
+    int second_cap;             // frames the host-launched pass has room for; more than that: the rest is launched from the device
     int nb_second;              // CTAs per frame of that k_center_quad launch
     int second_smem;            // its dynamic shared memory
     int n_report;               // finishing threads that will call maybe_launch_fallback (n_frames, or the length of the list)
@@ -138,7 +140,10 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
     if ((done & 0xffffu) != (unsigned)fp.n_report - 1) return;
     *fp.frames_done = 0u; // re-arm
     const bool slow = my_flag || (done >> 16) != 0u;
-    const unsigned int n_second = fp.second_count != nullptr ? atomicExch(fp.second_count, 0u) : 0u;
+    // second tier: the host launches it behind every fused launch for up to second_cap frames; only what exceeds that is
+    // launched from here (a device-side launch costs ~45 us, profiles/r2_ring.md)
+    const unsigned int n_all = fp.second_count != nullptr ? *reinterpret_cast<volatile unsigned int *>(fp.second_count) : 0u;
+    const unsigned int n_second = n_all > (unsigned)fp.second_cap ? n_all - (unsigned)fp.second_cap : 0u;
     const unsigned int n_slow = fp.quad_exact ? atomicExch(fp.slow_count, 0u) : 0u;
     if (fp.quad_exact && fp.feedback) *fp.feedback = ((unsigned long long)n_slow << 32) | (unsigned long long)(unsigned)fp.n_report;
     if (!slow && n_second == 0u) return;
@@ -172,9 +177,9 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
         }
     }
     if (n_second) {
-        // the sine-sum centre pass over exactly the frames the moments could not certify (tail launches run in order: behind
-        // the exact passes above, which have consumed this launch's lists by then).  It is itself a single-pass kernel with a
-        // device-side fallback: a centre-only plan, no third tier.
+        // the sine-sum centre pass over the frames the moments could not certify BEYOND the host-launched pass's capacity (tail
+        // launches run in order: behind the exact passes above, which have consumed this launch's lists by then).  It is itself
+        // a single-pass kernel with a device-side fallback: a centre-only plan, no third tier.
         FallbackPlan f2 = fp;
         f2.want_rmsd = 0;
         f2.want_center = 1;
@@ -182,10 +187,11 @@ __device__ __forceinline__ void maybe_launch_fallback(const FallbackPlan &fp, co
         f2.feedback = nullptr;  // what happens to a handful of frames says nothing about the group
         f2.n_report = (int)n_second;
         const dim3 gs(fp.nb_second, n_second);
+        const int *rest = fp.second_list + fp.second_cap;
         if (fp.center_weighted)
-            k_center_quad<true><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, fp.second_list, 2, nullptr);
+            k_center_quad<true><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, rest, 2, nullptr);
         else
-            k_center_quad<false><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, fp.second_list, 2, nullptr);
+            k_center_quad<false><<<gs, 256, fp.second_smem, cudaStreamTailLaunch>>>(fv, g, partials, tickets, fp.center_out, flags, f2, rest, 2, nullptr);
     }
 }
 
