@@ -216,12 +216,11 @@ FallbackPlan fallback_plan(groan_gpu_ctx *ctx, const Group &g, bool want_center,
     fp.second_cap = kSecondCap;
     fp.second_list = ctx->d_second_list;
     fp.n_report = (int)ctx->n_frames;
-    // the second tier runs for one or two frames of a batch (the CTAs of its other slots exit at once): one CTA per SM and frame
+    // the second tier runs for one or two frames of a batch (the CTAs of its other slots exit at once): two CTAs per SM and frame
     {
         const size_t chunk = QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kAtoms;
         size_t nb = std::max<size_t>(1, (g.n + chunk - 1) / chunk);
-        static const int per_sm = getenv("GROAN_EXP_SECOND_PER_SM") ? atoi(getenv("GROAN_EXP_SECOND_PER_SM")) : 1;
-        nb = std::min<size_t>(nb, (size_t)kSMs * per_sm);
+        nb = std::min<size_t>(nb, (size_t)kSMs * 2);
         nb = std::min<size_t>(nb, std::max<size_t>(1, kPartialSlots / std::max<size_t>(ctx->n_frames, 1)));
         fp.nb_second = (int)nb;
     }
