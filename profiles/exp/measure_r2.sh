@@ -7,6 +7,6 @@ python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --no-e2e > gpurun_out/
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --no-e2e > gpurun_out/r2_ncu_launches.log 2>&1
 python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --no-e2e > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_rmsd_quad -s 8 -c 1 -o gpurun_out/r2_dominant -f \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_rmsd_quad<.bool.1, .int.1>" -s 4 -c 1 -o gpurun_out/r2_dominant -f \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extras --no-e2e > gpurun_out/r2_ncu_full.log 2>&1
 tail -4 gpurun_out/r2_gputest.log
