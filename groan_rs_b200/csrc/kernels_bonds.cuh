@@ -12,17 +12,28 @@ namespace groan {
 template <typename F>
 __device__ __forceinline__ void for_each_neighbour(float ax, float ay, float az, const BoxOrtho &B, const CellGeom &cg, const uint32_t *of,
                                                    const float4 *sb, bool fold, int lane, F &&fn) {
-    int xs[3], ys[3], zs[3], mx, my, mz;
-    axis_cells(cell_coord(ax, B.lx, cg.nx), cg.nx, xs, mx);
+    // The binned atoms are sorted by cell index with x running fastest, so the (up to three) neighbour cells of one (y, z) row
+    // are ONE contiguous range of the sorted array -- plus the cell at the other end of the row when the atom's cell is the first
+    // or the last one (periodic wrap).  9 ranges (+ up to 9 wrap cells) instead of 27: with the small cells of bond guessing
+    // (0.17 nm: half an atom per cell) most of a walk is range bookkeeping.
+    int ys[3], zs[3], my, mz;
+    const int cx = cell_coord(ax, B.lx, cg.nx);
     axis_cells(cell_coord(ay, B.ly, cg.ny), cg.ny, ys, my);
     axis_cells(cell_coord(az, B.lz, cg.nz), cg.nz, zs, mz);
-    const int ncell = mx * my * mz;
+    const int x_lo = cg.nx >= 3 ? max(cx - 1, 0) : 0, x_hi = cg.nx >= 3 ? min(cx + 1, cg.nx - 1) : cg.nx - 1;
+    const int x_wrap = cg.nx >= 3 ? (cx == 0 ? cg.nx - 1 : (cx == cg.nx - 1 ? 0 : -1)) : -1;
+    const int rows = my * mz, ncell = x_wrap >= 0 ? 2 * rows : rows;
     uint32_t my_lo = 0, my_hi = 0;
     if (lane < ncell) {
-        const int kx = lane % mx, ky = (lane / mx) % my, kz = lane / (mx * my);
-        const uint32_t c = ((uint32_t)zs[kz] * cg.ny + ys[ky]) * cg.nx + xs[kx];
-        my_lo = of[c];
-        my_hi = of[c + 1];
+        const int r = lane < rows ? lane : lane - rows, ky = r % my, kz = r / my;
+        const uint32_t row = ((uint32_t)zs[kz] * cg.ny + ys[ky]) * cg.nx;
+        if (lane < rows) {
+            my_lo = of[row + x_lo];
+            my_hi = of[row + x_hi + 1];
+        } else {
+            my_lo = of[row + x_wrap];
+            my_hi = of[row + x_wrap + 1];
+        }
     }
     for (int k = 0; k < ncell; k++) {
         const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
