@@ -37,7 +37,10 @@ int plan_grid(groan_gpu_ctx *ctx, float width, size_t n_binned, size_t out_bytes
         for (int k = 0; k < 3; k++) lmin[k] = std::min(lmin[k], ctx->h_box[f * 9 + 4 * k]);
     long nc[3];
     for (int k = 0; k < 3; k++) nc[k] = std::max<long>(1, std::min<long>(1024, (long)std::floor((double)lmin[k] / ((double)width * 1.0001))));
-    const size_t cell_cap = std::max<size_t>(4096, std::min<size_t>((size_t)8 << 20, 4 * n_binned + 4096));
+    // at most one cell per four binned atoms: a warp walks a neighbourhood 32 candidates at a time, so cells much emptier than
+    // that only add range bookkeeping (bond guessing asks for 0.17 nm cells: half an atom each) and make the one-CTA prefix sum
+    // over the cells the longest kernel of the call
+    const size_t cell_cap = std::max<size_t>(4096, n_binned / 4);
     while ((size_t)nc[0] * nc[1] * nc[2] > cell_cap) {  // wider cells are always correct, only slower
         const int k = nc[0] >= nc[1] && nc[0] >= nc[2] ? 0 : (nc[1] >= nc[2] ? 1 : 2);
         nc[k] = (nc[k] + 1) / 2;
