@@ -195,6 +195,23 @@ def workload_config(frames_per_step):
             "l2_policy": "inputs larger than L2: %d MB per step vs 126 MB L2" % (frames_per_step * N_ATOMS * 12 // 1000000)}
 
 
+class CentreRows:
+    """ParallelTrajData of the bench's traj_iter_map_reduce check (module level: it travels between ranks by pickle)"""
+
+    def __init__(self):
+        self.rows = {}
+
+    def initialize(self, rank):  # parallel.rs:40
+        pass
+
+    @staticmethod
+    def reduce(items):  # parallel.rs:48
+        out = CentreRows()
+        for it in items:
+            out.rows.update(it.rows)
+        return out
+
+
 def pin_to_gpu_numa(local):
     """Run this rank's host side (threads, first-touch of its pinned buffers) on the NUMA node its GPU hangs off.
     Returns what was found for the JSON line; a VM that exposes no topology reports node -1 and nothing is changed."""
@@ -554,12 +571,44 @@ def run_gpu_arm(args):
         cpu = cpu_reference_run(3, 0, F, sample_frames=args.cpu_frames)  # ~15 s of CPU work: 3 steps of F frames
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # the product's rank-sharded map-reduce (groan_rs_b200.parallel.traj_iter_map_reduce = System::traj_iter_map_reduce,
+    # parallel.rs:208-269) over this launch's process group, outside the timed region: a small trajectory, every rank
+    # analyses its contiguous shard in batches, the Data objects are reduced on every rank and must equal what one rank
+    # computes for all frames
+    parallel_check = None
+    if world > 1:
+        nP, FP = 65_536, 4 * world + 3  # ragged shards on purpose
+        small = g.System(nP, device=local, max_frames=FP)
+        small.set_stream(torch.cuda.current_stream().cuda_stream)
+        small.group_create_from_indices("G", np.arange(16, nP - 5, dtype=np.uint32))
+        rotP, cenP = frame_params(10_000, FP)
+        cenP = (cenP * (12.0 / BOX)).astype(np.float32)
+
+        def load(idx):
+            small.synth_blob(SEED, int(idx[0]), len(idx), 1.5 / 131070.0, 0.02 / 37837.23, rotP[idx], cenP[idx], [12.0] * 3, wrap=True)
+            return small
+
+        def body(sysm, idx, data):
+            c = sysm.group_get_center("G")
+            for k, f in enumerate(idx):
+                data.rows[int(f)] = c[k].copy()
+
+        red = g.traj_iter_map_reduce(FP, load, body, CentreRows(), batch_frames=3)
+        small.synth_blob(SEED, 0, FP, 1.5 / 131070.0, 0.02 / 37837.23, rotP, cenP, [12.0] * 3, wrap=True)
+        direct = small.group_get_center("G")
+        # a frame generated inside a batch that starts elsewhere is the same frame: the generator is counter-based per frame
+        # (different batch sizes use different grids: the partial sums are folded in another order, hence a tolerance)
+        okp = len(red.rows) == FP and all(np.abs(red.rows[f] - direct[f]).max() <= 4e-6 for f in range(FP))
+        parallel_check = {"frames": FP, "ranks": world, "ok": bool(okp), "what": "traj_iter_map_reduce over NCCL == one rank over all frames"}
+        assert okp
+        small.close()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic: seeded rigid blob + noise generated on the device, batch resident in HBM and reused every step",
                 "config": workload_config(F), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "parity": parity, "extras": extras}
+                "clocks": clocks, "parity": parity, "parallel_check": parallel_check, "extras": extras}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
