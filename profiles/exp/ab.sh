@@ -1,9 +1,6 @@
-# A/B timing of library variants through bench.py (tuning experiments): bash profiles/exp/ab.sh libgroan_gpu [libexp1 ...]
-for v in "${@:-libgroan_gpu}"; do
-GROAN_GPU_LIB=$PWD/groan_rs_b200/$v.so timeout 120 python bench.py --steps 100 --warmup 3 --no-extras --no-cpu --no-e2e > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -3 gpurun_out/ab_$v.err
-python - <<P
-import json
-d=json.loads(open("gpurun_out/ab_$v.json").read().strip().splitlines()[-1])
-print("$v", round(d["ms_per_step"],4), [round(v["ms"],4) for v in d["roofline"]["ops"].values()], d["clocks"]["sm_mhz"], d["roofline"]["fallback_frames"])
-P
+# A/B timing of library builds (tuning experiments): bash profiles/exp/ab.sh groan_rs_b200/libgroan_gpu.so [groan_rs_b200/libquad_x.so ...]
+# Builds of variants: profiles/exp/quad_variants.sh name:"-DKNOB=1"; the timing itself is profiles/exp/quad_time.py (bursts of 50
+# launches of the three ring-fed ops on the bench's workload; REPS=300 for the sustained regime, FRAME0 to pick the frames).
+for lib in "${@:-groan_rs_b200/libgroan_gpu.so}"; do
+  timeout 200 python profiles/exp/quad_time.py "$lib" 2>&1 | tail -1
 done
