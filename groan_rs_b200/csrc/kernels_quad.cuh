@@ -183,15 +183,140 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint32_t bar) {
     return cnt;
 }
 
+// ---------------------------------------------------------------- per-warp ring (frame + reference), cp.async
+// What the CTA-wide TMA ring costs the RMSD kernels (profiles/r2_async.md): the arithmetic alone runs the bench batch in
+// 0.27 ms, the barrier protocol around it (two waits, two warp-elected arrivals with their answer looked at, the refill code)
+// adds 0.065 ms even when the copies are 16 bytes long, and with real data every warp waits for the slowest of the CTA's
+// eight before a stage is refilled.  Here every warp owns its slice of the ring outright: 32 quads = 1536 B of frame +
+// one 2 KB block of the permuted reference per stage, filled by its own lanes with 16-byte cp.async (coalesced 512 B per
+// warp instruction, the same L2 policies as the bulk copies) and waited for with cp.async.wait_group + __syncwarp: no
+// mbarrier, no elected thread, no dependence on any other warp.  Chunk c of the frame still goes to CTA c % gridDim.x and
+// warp w still takes quads [32 w, 32 w + 32) of it, so the sums are bit-identical to the TMA ring's.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int STAGES, int NT, typename F>
+__device__ __forceinline__ void stream_quads_warp(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *ref_pq,
+                                                  unsigned char *smem, F &&fn) {
+    constexpr uint32_t CH = NT * 4, W = NT / 32;
+    constexpr uint32_t kSlotF = 32 * 48, kSlotR = kQuadRefBlock * 16, kSlot = kSlotF + kSlotR;
+    static_assert(kQuadRefBlock == 128, "one reference block per warp and stage");
+    static_assert((size_t)W * STAGES * kSlot <= QuadCfg<true, STAGES, NT>::kStageBytes * STAGES, "per-warp rings fit the CTA ring");
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    const uint32_t lane = t & 31, w = t >> 5;
+    const uint32_t chunks = (bg.body + CH - 1) / CH;
+    const uint32_t n = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (n == 0) return;
+    uint32_t ring;
+    asm volatile("{\n\t.reg .u64 a;\n\tcvta.to.shared.u64 a, %1;\n\tcvt.u32.u64 %0, a;\n\t}" : "=r"(ring) : "l"(smem));
+    ring += w * (uint32_t)(STAGES * kSlot);
+    const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
+    // this lane's 16-byte units of the warp's slice of chunk blockIdx.x; a chunk further on: + gridDim.x chunks
+    const char *gf = reinterpret_cast<const char *>(fv.frame(f) + ((size_t)g.first + bg.head) * 3) +
+                     ((size_t)blockIdx.x * CH + w * 128u) * 12 + lane * 16u;
+    const char *gr = reinterpret_cast<const char *>(ref_pq) + ((size_t)blockIdx.x * CH + w * 128u) * 16 + lane * 16u;
+    const size_t fstep = (size_t)gridDim.x * CH * 12, rstep = (size_t)gridDim.x * CH * 16;
+    const uint32_t dst0 = ring + lane * 16u;
+    // The destination of a stage is carried as a per-thread address (d, below), not as dst0 + a warp-uniform stage offset:
+    // with the offset in a uniform register ptxas 12.9 emits LDGSTS [R + UR + imm], desc[UR] with the offset copied over the
+    // cache-policy descriptor, which the B200 rejects as an illegal instruction.
+    auto issue_full = [&](uint32_t d) { // the warp's slice of a full chunk into the stage whose lane address is d
+        cp_async16(d, gf, pol_frame);
+        cp_async16(d + 512u, gf + 512, pol_frame);
+        cp_async16(d + 1024u, gf + 1024, pol_frame);
+        cp_async16(d + kSlotF, gr, pol_ref);
+        cp_async16(d + kSlotF + 512u, gr + 512, pol_ref);
+        cp_async16(d + kSlotF + 1024u, gr + 1024, pol_ref);
+        cp_async16(d + kSlotF + 1536u, gr + 1536, pol_ref);
+        gf += fstep;
+        gr += rstep;
+    };
+    // the CTA's last chunk may be ragged (a multiple of 4 atoms): quads [0, lastq) exist, the reference is padded to blocks
+    const uint32_t last_atoms = min(CH, bg.body - (blockIdx.x + (n - 1) * gridDim.x) * CH), lastq = last_atoms >> 2;
+    auto issue_last = [&](uint32_t d) {
+#pragma unroll
+        for (uint32_t k = 0; k < 3; k++)
+            if (w * 96u + k * 32u + lane < lastq * 3u) cp_async16(d + k * 512u, gf + k * 512u, pol_frame);
+        if (w * 128u < last_atoms) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) cp_async16(d + kSlotF + k * 512u, gr + k * 512u, pol_ref);
+        }
+    };
+    const uint32_t off_f = ring + lane * 48u, off_r = ring + kSlotF + lane * 16u;
+    struct QuadRegs {
+        float4 c0, c1, c2, r[4];
+    };
+    auto load = [&](uint32_t so, QuadRegs &q) {
+        q.c0 = lds128(off_f + so); q.c1 = lds128(off_f + so + 16u); q.c2 = lds128(off_f + so + 32u);
+        q.r[0] = lds128(off_r + so);
+        q.r[1] = lds128(off_r + so + 512u);
+        q.r[2] = lds128(off_r + so + 1024u);
+        q.r[3] = lds128(off_r + so + 1536u);
+    };
+    // prologue: the first STAGES chunks (always one group per stage, so that the wait below counts the same everywhere)
+#pragma unroll
+    for (uint32_t i = 0; i < (uint32_t)STAGES; i++) {
+        if (i + 1 < n) issue_full(dst0 + i * kSlot);
+        else if (i + 1 == n) issue_last(dst0 + i * kSlot);
+        cp_async_commit();
+    }
+    uint32_t j = blockIdx.x * CH + t * 4, so = 0, i = 0, d = dst0;
+    const uint32_t dend = dst0 + (STAGES - 1) * kSlot;
+    const uint32_t jstep = gridDim.x * CH;
+    // hot loop: this chunk and the one refilled behind it are full
+    const uint32_t hot = n > (uint32_t)STAGES + 1 ? n - STAGES - 1 : 0;
+    for (; i < hot; i++) {
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        QuadRegs q;
+        load(so, q);
+        fn(j, q.c0, q.c1, q.c2, q.r);
+        __syncwarp(); // every lane has its quad in registers: the stage may be overwritten
+        issue_full(d);
+        cp_async_commit();
+        j += jstep;
+        so = so == (STAGES - 1) * kSlot ? 0u : so + kSlot;
+        d = d == dend ? dst0 : d + kSlot;
+    }
+    for (; i < n; i++) {
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        if (i + 1 < n || (t < lastq)) {
+            QuadRegs q;
+            load(so, q);
+            fn(j, q.c0, q.c1, q.c2, q.r);
+        }
+        __syncwarp();
+        if (i + STAGES + 1 < n) issue_full(d);
+        else if (i + STAGES + 1 == n) issue_last(d);
+        cp_async_commit();
+        j += jstep;
+        so = so == (STAGES - 1) * kSlot ? 0u : so + kSlot;
+        d = d == dend ? dst0 : d + kSlot;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------- CTA-wide TMA ring (frame bytes only)
+// The centre kernels (k_center_quad, k_trig_quad: no reference, 4 CTAs per SM, at the HBM roofline) stream through this ring;
+// the kernels that also read the reference use stream_quads_warp above.
 // Stream the 16-byte aligned body of the group through the ring; fn(j, c0, c1, c2, r) per quad with j the body index of
-// the quad's first atom, c0..c2 the twelve coordinates and r the four reference units (undefined when !WITH_REF).
+// the quad's first atom, c0..c2 the twelve coordinates and r unused (the signature of stream_quads_warp).
 // Chunk c of the frame goes to CTA c % gridDim.x.  Only the last chunk of a frame can be ragged (a multiple of 4 atoms),
 // so every chunk of a CTA but its last runs the unchecked, stage-unrolled loop.
 // Dynamic shared memory: [ring: STAGES x (frame chunk | reference chunk)] [QuadCtl].  After the call the ring is free
 // (every copy issued has been consumed) and the caller may reuse it once the CTA has synchronised.
 template <bool WITH_REF, int STAGES, int NT, typename F>
-__device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *ref_pq,
+__device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupView &g, int f, const BodyGeom &bg, const float *,
                                              unsigned char *smem, F &&fn) {
+    static_assert(!WITH_REF, "frame + reference go through stream_quads_warp");
     typedef QuadCfg<WITH_REF, STAGES, NT> C;
     constexpr uint32_t CH = C::kAtoms, kSt = (uint32_t)C::kStageBytes;
     // threadIdx.x through a volatile asm: the value then lives in a register.  Left to itself the allocator re-reads
@@ -208,15 +333,12 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     uint32_t ring;
     asm volatile("{\n\t.reg .u64 a;\n\tcvta.to.shared.u64 a, %1;\n\tcvt.u32.u64 %0, a;\n\t}" : "=r"(ring) : "l"(smem));
     const uint32_t full0 = ring + STAGES * kSt, empty0 = full0 + STAGES * 8u;
-    const uint64_t pol_frame = l2_policy_evict_first(), pol_ref = l2_policy_evict_last();
-    auto issue = [&](uint32_t it) { // copies of this CTA's chunk `it` into stage it % STAGES (one thread)
+    const uint64_t pol_frame = l2_policy_evict_first();
+    auto issue = [&](uint32_t it) { // copy of this CTA's chunk `it` into stage it % STAGES (one thread)
         const uint32_t s = it % STAGES, c = blockIdx.x + it * gridDim.x;
         const uint32_t atoms = min(CH, bg.body - c * CH);
-        const uint32_t ref_bytes = WITH_REF ? ((atoms + kQuadRefBlock - 1) / kQuadRefBlock) * (uint32_t)(kQuadRefBlock * 16) : 0u;
-        mbar_expect_tx(ctl.full + s, atoms * 12u + ref_bytes);
-        unsigned char *dst = smem + s * C::kStageBytes;
-        bulk_g2s(dst, src0 + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, pol_frame);
-        if (WITH_REF) bulk_g2s(dst + C::kFrameBytes, ref_pq + (size_t)c * CH * 4, ref_bytes, ctl.full + s, pol_ref);
+        mbar_expect_tx(ctl.full + s, atoms * 12u);
+        bulk_g2s(smem + s * C::kStageBytes, src0 + (size_t)c * CH * 12, atoms * 12u, ctl.full + s, pol_frame);
     };
     if (t == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -228,8 +350,8 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     }
     __syncthreads();
     if (my_chunks == 0) return;
-    // this thread's quad inside a stage: coordinates at t * 48 B, reference unit k at (warp * 128 + k * 32 + lane) * 16 B
-    const uint32_t off_f = ring + t * 48u, off_r = ring + (uint32_t)C::kFrameBytes + ((t >> 5) * 128u + lane) * 16u;
+    // this thread's quad inside a stage: coordinates at t * 48 B
+    const uint32_t off_f = ring + t * 48u;
     uint32_t j = blockIdx.x * CH + t * 4;
     const uint32_t jstep = gridDim.x * CH;
     struct QuadRegs {
@@ -237,12 +359,6 @@ __device__ __forceinline__ void stream_quads(const FrameView &fv, const GroupVie
     };
     auto load = [&](uint32_t st, QuadRegs &q) { // st = byte offset of the stage
         q.c0 = lds128(off_f + st); q.c1 = lds128(off_f + st + 16u); q.c2 = lds128(off_f + st + 32u);
-        if (WITH_REF) {
-            q.r[0] = lds128(off_r + st);
-            q.r[1] = lds128(off_r + st + 512u);
-            q.r[2] = lds128(off_r + st + 1024u);
-            q.r[3] = lds128(off_r + st + 1536u);
-        }
     };
     auto quad = [&](uint32_t st) {
         QuadRegs q;
@@ -576,7 +692,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         cqv.b = __ffma2_rn(d.b, d.b, cqv.b);
         cqv.c = __ffma2_rn(d.c, d.c, cqv.c);
     };
-    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+    stream_quads_warp<kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
                                         [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
@@ -749,7 +865,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_cov_quad(FrameView fv, 
         }
         acc[18] = fma(m, fma(q[0], q[0], fma(q[1], q[1], q[2] * q[2])), acc[18]);
     };
-    stream_quads<true, kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
+    stream_quads_warp<kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
                                         [&](uint32_t, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
