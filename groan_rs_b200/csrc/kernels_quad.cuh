@@ -28,6 +28,9 @@
 //    mean from below, so a fixed threshold on it (kSinGuard) replaces the edge-band test; frames below it are flagged
 //    and re-done by the reference-order passes like before.
 //  * Loop control: stage/phase counters instead of divisions, full chunks only in the hot loop.
+//  * Two rings feed the quads: the kernels that also read the reference (k_rmsd_quad, k_cov_quad) run one
+//    private cp.async ring per warp (stream_quads_warp: no barrier protocol at all), the centre kernels the CTA-wide TMA ring
+//    (stream_quads: bulk copies on mbarriers, last reader refills).
 #pragma once
 #include "kernels_tma.cuh"
 
