@@ -86,3 +86,18 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.GroanLibraryMissing):
         _lib.lib()
+
+
+def test_async_copies_keep_their_cache_policy_descriptor(libpath):
+    """ptxas 12.9 can emit LDGSTS [R + UR + imm], desc[UR] with the warp-uniform stage offset copied over the cache-policy
+    descriptor (B200: 'illegal instruction', profiles/r2_async.md).  stream_quads_warp carries the destination as a per-thread
+    address to avoid that form: no cp.async of the RMSD kernels may use a uniform register in its shared-memory address,
+    and the kernels must still be fed by LDGSTS with L2 cache hints (desc[...])."""
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "k_rmsd_quad", libpath], capture_output=True, text=True).stdout
+    if "LDGSTS" not in sass:  # older cuobjdump: no -fun filter on mangled substrings
+        sass = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
+    copies = [l for l in sass.splitlines() if "LDGSTS" in l]
+    assert len(copies) >= 14, "the RMSD kernels are fed by cp.async (LDGSTS)"
+    assert all("desc[" in l for l in copies), "every async copy carries an L2 cache-policy descriptor"
+    bad = [l.strip() for l in copies if re.search(r"\[R\d+\+UR\d+", l)]
+    assert not bad, "LDGSTS with a uniform-register shared-memory offset:\n" + "\n".join(bad[:4])
