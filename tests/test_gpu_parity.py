@@ -1686,3 +1686,40 @@ def test_box_spanning_group_skips_the_single_pass_after_the_first_call():
         for f in (0, F - 1):  # z is compact, x / y span the box: compare the well-defined axis with the exact64 oracle
             assert abs(calls[0][0][f][2] - orc.get_center_x64(frames[f], idx, L)[2]) <= TOL_CENTER
     assert np.array_equal(bits(out["default"][0]), bits(out["exact"][0])) and np.array_equal(bits(out["default"][1]), bits(out["exact"][1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks_per_cta", [1, 2, 3, 4, 5, 6, 7, 9])
+def test_warp_ring_every_depth(chunks_per_cta):
+    """stream_quads_warp (the per-warp cp.async ring of the RMSD kernels, kernels_quad.cuh) with 1 .. 9 chunks per CTA: fewer
+    chunks than stages, exactly as many, one more (the first trip of the hot loop), ragged last chunks that end inside a warp's
+    slice, inside a 128-atom reference block and on a chunk boundary, heads of 0 .. 3 atoms, and a frame size that is not a
+    multiple of four atoms (one launch per 16-byte phase).  Centre, RMSD and the fused call against the exact64 oracle."""
+    import groan_rs_b200 as g
+    F, L = 37, np.array([14.0, 15.0, 13.0], np.float32)  # 37 frames: 8 CTAs per frame, like the bench
+    body = 8 * 1024 * chunks_per_cta
+    n = body + 1032 + (3 if chunks_per_cta == 9 else 0)  # the last case: a phase per frame, CTAs per frame from the phase's frame count
+    masses = np.random.default_rng(9).uniform(1.0, 100.0, n).astype(np.float32)
+    scale, nscale = 1.5 / 131070.0, 0.02 / 37837.23
+    s = _blob_system(n, F, L, 31 + chunks_per_cta, scale, nscale, masses)
+    ref = g.System(n, masses=masses)
+    ref_xyz = s.synth_blob_ref(31 + chunks_per_cta, scale, L / 2)
+    ref.set_frames(ref_xyz, L)
+    frames = s.get_frames()
+    groups = {"full": np.arange(0, body), "slice": np.arange(1, body - 1024 + 36 + 1), "block": np.arange(2, body - 300),
+              "plus": np.arange(3, body + 1024 + 4)}
+    for name, idx in groups.items():
+        for sysm in (s, ref):
+            sysm.group_create_from_indices(name, idx)
+        c = s.group_get_center(name)
+        r = s.calc_rmsd(ref, name)
+        assert s.fallback_frames() == 0
+        c2, r2 = s.group_center_and_rmsd(ref, name)
+        assert np.abs(c2 - c).max() <= 4e-6 and np.abs(r2 - r).max() <= 2e-6, name
+        for f in (0, 1, 2, 3, F - 1):
+            c64 = orc.get_center_x64(frames[f], idx, L)
+            r64, _ = orc.calc_rmsd_x64(ref_xyz, idx, L, masses[idx], frames[f], idx, L)
+            assert np.abs(c2[f] - c64).max() <= TOL_CENTER, (name, f, c2[f], c64)
+            assert abs(r[f] - r64) <= 2e-5 and abs(r2[f] - r64) <= 2e-5, (name, f, r[f], r2[f], r64)
+    s.close()
+    ref.close()
