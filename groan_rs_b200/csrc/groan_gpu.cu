@@ -44,14 +44,15 @@ int blocks_per_frame_fast(size_t g, size_t F, int occ) {
 // 16-byte aligned coordinate buffer (cudaMalloc'ed slots always are; attached buffers are checked)
 bool tma_ok(const groan_gpu_ctx *ctx, const Group &g, int occ) {
     return occ > 0 && g.contiguous && g.n >= 4096 && (reinterpret_cast<uintptr_t>(ctx->cur_xyz) & 15) == 0 &&
-           !(ctx->flags & GROAN_FLAG_NO_TMA) && !ctx->batch_tric;  // triclinic extension: gather kernels only
+           !(ctx->flags & GROAN_FLAG_NO_TMA);
 }
 
 // ---- quad kernels (kernels_quad.cuh) -----------------------------------------------------------------
 // The centre kernels take any frame size (the 16-byte phase of the group is worked out per frame).  The RMSD kernels read a
 // reference laid out relative to the aligned body, one copy per phase (launch_rmsd_quad_t).
+// Triclinic extension: the single-pass centre runs on the ring as well (k_center_quad<., TRIC>); RMSD stays with the gather kernels.
 bool quad_center_ok(const groan_gpu_ctx *ctx, const Group &g) { return tma_ok(ctx, g, 2); }
-bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) { return quad_center_ok(ctx, g); }
+bool quad_ok(const groan_gpu_ctx *ctx, const Group &g) { return quad_center_ok(ctx, g) && !ctx->batch_tric; }
 
 uint32_t quad_head(const groan_gpu_ctx *ctx, const Group &g, size_t f) { return (uint32_t)((4 - ((f * ctx->n_atoms + g.first) & 3)) & 3); }
 
@@ -457,7 +458,24 @@ int run_exact_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, c
 // (their CTAs exit at once for every other frame).  GROAN_FLAG_EXACT_ONLY runs the reference-order passes alone.
 int run_get_center(groan_gpu_ctx *ctx, const Group &g, bool weighted, float *out) {
     const int *flags = nullptr;
-    if (ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
+    if (ctx->occ_center_quad > 0 && quad_center_ok(ctx, g) && ctx->batch_tric) {
+        // triclinic extension: the single pass on the ring in the sheared picture, then -- like behind the gather kernel -- the
+        // reference-order passes over the frames it flagged (they exit at once for every other frame)
+        if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
+            typedef QuadCfg<false, kQuadCenterStages, kQuadCenterThreads> C;
+            dim3 grid(blocks_per_frame_quad(g.n, ctx->n_frames, ctx->occ_center_quad, C::kAtoms), (unsigned)ctx->n_frames);
+            FallbackPlan fp = fallback_plan(ctx, g, true, weighted, out, false, nullptr, nullptr, false);
+            fp.enabled = 0;
+            if (weighted)
+                k_center_quad<true, true><<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials,
+                                                                                              ctx->d_tickets, out, ctx->d_flags, fp, nullptr, 0, nullptr);
+            else
+                k_center_quad<false, true><<<grid, kQuadCenterThreads, C::kBytes, ctx->compute>>>(frames_of_geom(ctx), view_of(g), ctx->d_partials,
+                                                                                               ctx->d_tickets, out, ctx->d_flags, fp, nullptr, 0, nullptr);
+            LAUNCHED();
+            flags = ctx->d_flags;
+        }
+    } else if (ctx->occ_center_quad > 0 && quad_center_ok(ctx, g)) {
         if (ctx->flags & GROAN_FLAG_EXACT_ONLY) return run_exact_center_quad(ctx, g, weighted, out, nullptr);
         if (skip_single_pass(ctx, g)) {
             int rc = mark_all_flagged(ctx);
@@ -759,6 +777,8 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         const int sq = (int)QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kBytes;
         CK(cudaFuncSetAttribute(k_center_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
         CK(cudaFuncSetAttribute(k_center_quad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaFuncSetAttribute(k_center_quad<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
+        CK(cudaFuncSetAttribute(k_center_quad<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
         CK(cudaFuncSetAttribute(k_trig_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, sq));
         CK(cudaFuncSetAttribute(k_cov_quad, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kBytes));

@@ -546,7 +546,11 @@ __device__ __forceinline__ double edge_sin(float x, float L) {
 // ext_pilot != nullptr: the EXACT pass -- the reference's second loop itself (iterators.rs:1237-1266): pilot = c0, the
 //   Bai-Breen estimate of the frame (k_trig_quad), result = c0 + mean(min-image displacement from c0).  No compactness is
 //   needed and nothing is flagged: this is what frames the single pass could not certify are re-done with.
-template <bool WEIGHTED>
+// TRIC: the triclinic extension -- every atom goes through Shear::to_u as it leaves shared memory (the
+//   sheared picture is an orthogonal periodic box, so everything after that is the orthogonal kernel) and the centre goes back
+//   through Shear::to_x; with an orthogonal box both maps are the identity bit for bit.  Single pass only (no ext_pilot, no
+//   sel): flagged frames are re-done by the host-launched reference-order passes, which know about the shear themselves.
+template <bool WEIGHTED, bool TRIC>
 __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets,
                                                                  float *out, int *flags, FallbackPlan fp, const int *sel, int sel_mode,
                                                                  const float *ext_pilot) {
@@ -578,14 +582,26 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
     const float *p0 = ext_pilot ? ext_pilot + (size_t)f * 3 : fr + (size_t)g.first * 3;
-    const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    Shear sh = {0.f, 0.f, 0.f};
+    if (TRIC) {
+        sh = fv.shear(f);
+        sh.to_u(p[0], p[1], p[2]);
+    }
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<false, kQuadCenterStages, kQuadCenterThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 smd = v3_zero(), ssin = v3_zero();
     float2 sm2 = make_float2(0.f, 0.f);
     QuadMinMax mm = {{3.0e38f, 3.0e38f, 3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
     stream_quads<false, kQuadCenterStages, kQuadCenterThreads>(fv, g, f, bg, nullptr, dyn_smem,
-                                           [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&)[4]) {
+                                           [&](uint32_t j, const float4 &l0, const float4 &l1, const float4 &l2, const float4 (&)[4]) {
+        float4 c0 = l0, c1 = l1, c2 = l2;
+        if (TRIC) { // atoms (c0.x c0.y c0.z) (c0.w c1.x c1.y) (c1.z c1.w c2.x) (c2.y c2.z c2.w) into the sheared picture
+            sh.to_u(c0.x, c0.y, c0.z);
+            sh.to_u(c0.w, c1.x, c1.y);
+            sh.to_u(c1.z, c1.w, c2.x);
+            sh.to_u(c2.y, c2.z, c2.w);
+        }
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
         if (WEIGHTED) {
@@ -614,8 +630,10 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
             const float *q = fr + ((size_t)g.first + i) * 3;
             const double m = WEIGHTED ? (double)__ldg(g.mass + i) : 1.0;
             if (WEIGHTED) tot[3] += m;
+            float xq[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)};
+            if (TRIC) sh.to_u(xq[0], xq[1], xq[2]);
             for (int k = 0; k < 3; k++) {
-                const float xk = __ldg(q + k), d = pilot_delta(xk, p[k], L[k], 1.0f / L[k]);
+                const float xk = xq[k], d = pilot_delta(xk, p[k], L[k], 1.0f / L[k]);
                 tot[k] += m * (double)d;
                 tot[4 + k] += edge_sin(xk, L[k]);
                 tmn[k] = fminf(tmn[k], d);
@@ -629,6 +647,7 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
         }
         int flag = 0;
         finish_center_sin(tot, WEIGHTED ? tot[3] : (double)g.n, tot + 4, tmn, tmx, p, L, g.n, out + f * 3, &flag);
+        if (TRIC) sh.to_x(out[f * 3], out[f * 3 + 1], out[f * 3 + 2]); // the centre back from the sheared picture
         if (sel_mode) {
             if (flag) flags[f] |= 2;
         } else {

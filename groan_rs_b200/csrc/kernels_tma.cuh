@@ -119,7 +119,7 @@ struct FallbackPlan {
 };
 
 // sel_mode 0: every frame of the batch; 1: frames with sel[f] != 0; 2: frames sel[0 .. gridDim.y)
-template <bool WEIGHTED>
+template <bool WEIGHTED, bool TRIC = false>
 __global__ void k_center_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets, float *out, int *flags, FallbackPlan fp,
                               const int *sel, int sel_mode, const float *ext_pilot);
 __global__ void k_trig_quad(FrameView fv, GroupView g, double *partials, unsigned int *tickets, float *c0_out, const int *sel, int sel_mode);
