@@ -128,13 +128,13 @@ int launch_second_tier(groan_gpu_ctx *ctx, const Group &g, float *d_center, Fall
     return GROAN_OK;
 }
 
-template <bool SAME_MASS, int CENTER>
+template <bool SAME_MASS, int CENTER, bool TRIC = false>
 int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, float *d_center, float *d_rmsd,
                        float *d_rot, FallbackPlan fp) {
     typedef QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads> C;
     if (ctx->n_atoms % 4 == 0 || ctx->n_frames == 1) {
         dim3 grid((unsigned)blocks_per_frame_quad(g.n, ctx->n_frames, 2, C::kAtoms), (unsigned)ctx->n_frames);
-        k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+        k_rmsd_quad<SAME_MASS, CENTER, TRIC><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(TRIC ? frames_of_geom(ctx) : frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
                                                                                        ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
                                                                                        ctx->d_flags, fp, nullptr);
         LAUNCHED();
@@ -149,7 +149,7 @@ int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, co
         nb = std::max<size_t>(1, std::min<size_t>(nb, kPartialSlots / ctx->n_frames));  // partial records are indexed by the frame number
         dim3 grid((unsigned)nb, (unsigned)counts[h]);
         fp.n_report = counts[h];
-        k_rmsd_quad<SAME_MASS, CENTER><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
+        k_rmsd_quad<SAME_MASS, CENTER, TRIC><<<grid, kQuadRmsdThreads, C::kBytes, ctx->compute>>>(TRIC ? frames_of_geom(ctx) : frames_of(ctx), view_of(g), rv, d_pq, ctx->d_partials,
                                                                                        ctx->d_tickets, d_center, d_rmsd, d_rot, ctx->d_cen,
                                                                                        ctx->d_flags, fp, ctx->d_head_list + offsets[h]);
         LAUNCHED();
@@ -162,6 +162,10 @@ int launch_rmsd_quad_t(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, co
 int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, const QuadRef &d_pq, bool same_mass, int center_mode,
                      float *d_center, float *d_rmsd, float *d_rot, const FallbackPlan &fp) {
 #define GO(SM, CM) return launch_rmsd_quad_t<SM, CM>(ctx, g, rv, d_pq, d_center, d_rmsd, d_rot, fp)
+    if (center_mode == 3) { // triclinic extension: RMSD only, in the sheared picture (k_rmsd_quad<., 0, TRIC>)
+        if (same_mass) return launch_rmsd_quad_t<true, 0, true>(ctx, g, rv, d_pq, d_center, d_rmsd, d_rot, fp);
+        return launch_rmsd_quad_t<false, 0, true>(ctx, g, rv, d_pq, d_center, d_rmsd, d_rot, fp);
+    }
     if (same_mass) {
         if (center_mode == 0) GO(true, 0);
         if (center_mode == 1) GO(true, 1);
@@ -174,9 +178,9 @@ int launch_rmsd_quad(groan_gpu_ctx *ctx, const Group &g, const RefView &rv, cons
 #undef GO
 }
 
-template <bool SAME_MASS, int CENTER>
+template <bool SAME_MASS, int CENTER, bool TRIC = false>
 int set_quad_attr(groan_gpu_ctx *ctx) {
-    CK(cudaFuncSetAttribute(k_rmsd_quad<SAME_MASS, CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(k_rmsd_quad<SAME_MASS, CENTER, TRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kBytes));
     return GROAN_OK;
 }
@@ -613,8 +617,10 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
     float *d_center = center ? target_of<float>(center, ctx->d_cen2) : nullptr;
     bool center_done = false, device_fallback = false, second_tier = false;
     const bool qx = quad_ok(ctx, *g);  // contiguous group on the ring: fast and exact passes of kernels_quad.cuh
+    // triclinic extension: the single pass on the ring in the sheared picture; the exact passes stay with the gather kernels
+    const bool qt = !qx && ctx->batch_tric && quad_center_ok(ctx, *g) && !(ctx->flags & GROAN_FLAG_EXACT_ONLY);
     QuadRef qr;
-    if (qx) {
+    if (qx || qt) {
         rc = ensure_quad_ref(ctx, R, *g, &qr);
         if (rc) return rc;
     }
@@ -632,6 +638,12 @@ int rmsd_common(groan_gpu_ctx *ctx, int gid, float *rmsd, float *rot, bool fit, 
         flags = ctx->d_flags;
         center_done = fused;
         second_tier = fused;
+    } else if (qt) {
+        FallbackPlan fp = fallback_plan(ctx, *g, false, false, nullptr, true, d_rmsd, d_rot, false, &qr);
+        fp.enabled = 0;  // flagged frames: the host-launched reference-order passes below, gated by the flags
+        rc = launch_rmsd_quad(ctx, *g, rv, qr, R.same_mass, 3, nullptr, d_rmsd, d_rot, fp);
+        if (rc) return rc;
+        flags = ctx->d_flags;
     } else if (!(ctx->flags & GROAN_FLAG_EXACT_ONLY)) {
         // single pass: COM, covariance and RMSD sums relative to a pilot atom (kernels_rmsd.cuh)
         const int nbf = blocks_per_frame_fast(g->n, ctx->n_frames, ctx->occ_rmsd);
@@ -788,6 +800,8 @@ int groan_gpu_create(int device, size_t n_atoms, size_t max_frames, groan_gpu_ct
         if (!qrc) qrc = set_quad_attr<true, 1>(ctx);
         if (!qrc) qrc = set_quad_attr<true, 2>(ctx);
         if (!qrc) qrc = set_quad_attr<false, 0>(ctx);
+        if (!qrc) qrc = set_quad_attr<true, 0, true>(ctx);
+        if (!qrc) qrc = set_quad_attr<false, 0, true>(ctx);
         if (qrc) return qrc;
         return GROAN_OK;
     }();

@@ -665,7 +665,11 @@ __global__ void __launch_bounds__(kQuadCenterThreads, 3) k_center_quad(FrameView
 // canonical sums after the fold: [0..25] as kFastSums (kernels_rmsd.cuh), then (CENTER) [26..28] sum d, [29..31] sum d^2 (unweighted)
 constexpr int kQuadSums = kFastSums + 6;
 
-template <bool SAME_MASS, int CENTER>
+// TRIC (CENTER = 0 only): the triclinic extension, like k_rmsd_fast -- coordinates into the sheared
+//   picture (Shear::to_u) as they leave shared memory, minimum image and compactness there, the displacement back to Cartesian
+//   (Shear::to_x: a linear map, and sums of Cartesian displacements are what Kabsch needs) before the sums.  Identity bit for
+//   bit on an orthogonal box.  Flagged frames are re-done by the host-launched reference-order passes.
+template <bool SAME_MASS, int CENTER, bool TRIC = false>
 __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv, GroupView g, RefView ref, QuadRef ref_pq, double *partials,
                                                                unsigned int *tickets, float *center_out, float *rmsd_out, float *rot_out,
                                                                float *com_out, int *flags, FallbackPlan fp, const int *sel) {
@@ -679,7 +683,13 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
     fv.lengths(f, L[0], L[1], L[2]);
     const float *fr = fv.frame(f);
     const float *p0 = fr + (size_t)g.first * 3;
-    const float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    static_assert(!TRIC || CENTER == 0, "the triclinic variant is the RMSD-only kernel");
+    float p[3] = {__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2)};
+    Shear sh = {0.f, 0.f, 0.f};
+    if (TRIC) {
+        sh = fv.shear(f);
+        sh.to_u(p[0], p[1], p[2]);
+    }
     const QuadConst qc = quad_constants(p, L, reinterpret_cast<float *>(dyn_smem + QuadCfg<true, kQuadRmsdStages, kQuadRmsdThreads>::kConstOff));
     const BodyGeom bg = body_geom(fv, g, f);
     V3 h[3], hw[3], swd = v3_zero(), smd = v3_zero();
@@ -703,7 +713,7 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         sq = __ffma2_rn(wd.b, d.b, sq);
         sq = __ffma2_rn(wd.c, d.c, sq);
         if (CENTER) v3_add(sdv, d);
-        quad_minmax(mm, d);
+        if (!TRIC) quad_minmax(mm, d);
         if (!SAME_MASS) {
             const float2 m = make_float2(__ldg(g.mass + i), __ldg(g.mass + i + 1));
             v3_fma(smd, m, d); // sum m is a constant of the group: ref.sum_m_target, no accumulator
@@ -715,9 +725,24 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
         cqv.c = __ffma2_rn(d.c, d.c, cqv.c);
     };
     stream_quads_warp<kQuadRmsdStages, kQuadRmsdThreads>(fv, g, f, bg, ref_pq.v[bg.head], dyn_smem,
-                                        [&](uint32_t j, const float4 &c0, const float4 &c1, const float4 &c2, const float4 (&r)[4]) {
+                                        [&](uint32_t j, const float4 &l0, const float4 &l1, const float4 &l2, const float4 (&r)[4]) {
+        float4 c0 = l0, c1 = l1, c2 = l2;
+        if (TRIC) { // atoms (c0.x c0.y c0.z) (c0.w c1.x c1.y) (c1.z c1.w c2.x) (c2.y c2.z c2.w) into the sheared picture
+            sh.to_u(c0.x, c0.y, c0.z);
+            sh.to_u(c0.w, c1.x, c1.y);
+            sh.to_u(c1.z, c1.w, c2.x);
+            sh.to_u(c2.y, c2.z, c2.w);
+        }
         V3 d01, d23;
         quad_deltas(qc, c0, c1, c2, d01, d23);
+        if (TRIC) { // the extent is certified in the sheared picture, the sums are formed with Cartesian displacements
+            quad_minmax(mm, d01);
+            quad_minmax(mm, d23);
+            sh.to_x(d01.a.x, d01.a.y, d01.b.x);
+            sh.to_x(d01.b.y, d01.c.x, d01.c.y);
+            sh.to_x(d23.a.x, d23.a.y, d23.b.x);
+            sh.to_x(d23.b.y, d23.c.x, d23.c.y);
+        }
         atom_pair(d01, r[0], r[1], bg.head + j);
         if (CENTER) moments(d01);
         atom_pair(d23, r[2], r[3], bg.head + j + 2);
@@ -749,11 +774,16 @@ __global__ void __launch_bounds__(kQuadRmsdThreads, 2) k_rmsd_quad(FrameView fv,
             const float4 r = ref_at(ref.pc, i);
             const double pcd[3] = {(double)r.x, (double)r.y, (double)r.z}, w = (double)r.w;
             double d[3];
+            float xq[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, dq[3];
+            if (TRIC) sh.to_u(xq[0], xq[1], xq[2]);
             for (int k = 0; k < 3; k++) {
-                const float xk = __ldg(q + k), dk = pilot_delta(xk, p[k], L[k], 1.0f / L[k]);
-                d[k] = (double)dk;
-                tmn[k] = fminf(tmn[k], dk);
-                tmx[k] = fmaxf(tmx[k], dk);
+                dq[k] = pilot_delta(xq[k], p[k], L[k], 1.0f / L[k]);
+                tmn[k] = fminf(tmn[k], dq[k]);
+                tmx[k] = fmaxf(tmx[k], dq[k]);
+            }
+            if (TRIC) sh.to_x(dq[0], dq[1], dq[2]);
+            for (int k = 0; k < 3; k++) {
+                d[k] = (double)dq[k];
                 if (CENTER) {
                     tot[KS - 6 + k] += d[k];
                     tot[KS - 3 + k] += d[k] * d[k];

@@ -506,34 +506,33 @@ def test_triclinic_centre_and_rmsd_blob_and_orthogonal_identity():
         e, _ = orc.tric_calc_rmsd_x64(ref_xyz, idx, box, masses[idx], wrapped[f], idx, boxes[f])
         assert abs(float(rm[f]) - e) <= TOL_RMSD, (f, rm[f], e)
         assert np.abs(cen_g[f] - orc.tric_get_center_x64(wrapped[f], idx, boxes[f])).max() <= TOL_CENTER
-    # (i): frame 3 (orthogonal box) inside the mixed batch == the same frame through the orthogonal code.  The centre of a large
-    # contiguous group runs on the ring in both cases (k_center_quad with and without the shear), the RMSD through the gather
-    # kernels (GROAN_FLAG_NO_TMA selects them for the orthogonal batch too).
-    oq = g.System(n, masses=masses, max_frames=F)  # the same batch size: the same grids, hence the same order of the partial sums
-    oq.set_frames(wrapped, np.tile(orth, (F, 1)))
-    oq.group_create_from_indices("G", idx)
-    assert np.array_equal(bits(oq.group_get_center("G")[3]), bits(cen_g[3]))
-    assert np.array_equal(bits(oq.group_get_com("G")[3]), bits(com_g[3]))
-    oq.close()
-    # ... and the gather kernels of the triclinic path (index-list group) against the orthogonal gather kernels
-    s.set_flags(g.FLAG_TRICLINIC | g.FLAG_NO_TMA)
-    cen_n, com_n = s.group_get_center("G"), s.group_get_com("G")
-    s.set_flags(g.FLAG_TRICLINIC)
-    assert np.abs(cen_n - cen_g).max() <= 4e-6 and np.abs(com_n - com_g).max() <= 4e-6  # ring against gather, every frame
-    cen_g, com_g = cen_n, com_n
-    o = g.System(n, masses=masses, max_frames=F)
-    o.set_flags(g.FLAG_NO_TMA)
-    o.set_frames(wrapped, np.tile(orth, (F, 1)))
-    o.group_create_from_indices("G", idx)
+    # (i): frame 3 (orthogonal box) inside the mixed batch == the same frame through the orthogonal code, bit for bit.  A large
+    # contiguous group runs on the rings in both cases (k_center_quad / k_rmsd_quad with and without the shear) ...
     oref = g.System(n, masses=masses)
     oref.set_frames(ref_xyz, orth.reshape(1, 9))
     oref.group_create_from_indices("G", idx)
     sref = g.System(n, masses=masses, triclinic=True)
     sref.set_frames(ref_xyz, orth.reshape(1, 9))
     sref.group_create_from_indices("G", idx)
-    rm_mixed = s.calc_rmsd(sref, "G")
-    assert np.array_equal(bits(o.group_get_center("G")[3]), bits(cen_g[3]))
-    assert np.array_equal(bits(o.group_get_com("G")[3]), bits(com_g[3]))
+    oq = g.System(n, masses=masses, max_frames=F)  # the same batch size: the same grids, hence the same order of the partial sums
+    oq.set_frames(wrapped, np.tile(orth, (F, 1)))
+    oq.group_create_from_indices("G", idx)
+    rm_ring = s.calc_rmsd(sref, "G")
+    assert np.array_equal(bits(oq.group_get_center("G")[3]), bits(cen_g[3]))
+    assert np.array_equal(bits(oq.group_get_com("G")[3]), bits(com_g[3]))
+    assert np.array_equal(bits(oq.calc_rmsd(oref, "G")[3:4]), bits(rm_ring[3:4]))
+    oq.close()
+    # ... and with GROAN_FLAG_NO_TMA through the gather kernels in both cases; ring and gather agree on every frame
+    s.set_flags(g.FLAG_TRICLINIC | g.FLAG_NO_TMA)
+    cen_n, com_n, rm_n, rm_mixed = s.group_get_center("G"), s.group_get_com("G"), s.calc_rmsd(ref, "G"), s.calc_rmsd(sref, "G")
+    s.set_flags(g.FLAG_TRICLINIC)
+    assert np.abs(cen_n - cen_g).max() <= 4e-6 and np.abs(com_n - com_g).max() <= 4e-6 and np.abs(rm_n - rm).max() <= 2e-6
+    o = g.System(n, masses=masses, max_frames=F)
+    o.set_flags(g.FLAG_NO_TMA)
+    o.set_frames(wrapped, np.tile(orth, (F, 1)))
+    o.group_create_from_indices("G", idx)
+    assert np.array_equal(bits(o.group_get_center("G")[3]), bits(cen_n[3]))
+    assert np.array_equal(bits(o.group_get_com("G")[3]), bits(com_n[3]))
     assert np.array_equal(bits(o.calc_rmsd(oref, "G")[3:4]), bits(rm_mixed[3:4]))
 
 
